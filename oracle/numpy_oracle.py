@@ -1,0 +1,324 @@
+"""TEST INFRASTRUCTURE ONLY -- numpy restatement of the reference's cost-volume and
+disparity-regression algorithms (babiking/realtime_stereo_matcher, mounted read-only at
+/root/reference in the build container).  Not product code; see ``oracle/__init__.py``.
+
+Every function states the reference ``file:line`` it follows.  The arithmetic of the
+reference lives in PyTorch ATen (torch 2.11.0+cu128 is the environment pin; the reference
+has no requirements file), so float reductions are only order-equivalent, not
+bit-equivalent, to ATen: copies, the difference volume, argmin and every reduction on
+dyadic inputs (k/8) are bit-exact, the rest is pinned to the committed golden vectors
+(``tests/golden``) within the tolerances written in ``tests/tolerances.py``.
+
+Conventions: out-of-range entries (x < d) stay at the fill value and
+take part in the regression; "soft-argmin" is softmax(+cost) expectation; layouts are
+exactly the reference's and are never normalised.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+__all__ = [
+    "concat_volume", "concat_volume_bwd",
+    "interweave", "interweave_bwd",
+    "inner_product_volume", "inner_product_volume_bwd",
+    "groupwise_volume", "groupwise_volume_bwd", "groupwise_pointwise",
+    "difference_volume", "difference_volume_bwd",
+    "softmax_d", "soft_argmax", "soft_argmax_bwd", "hard_argmin", "hard_argmax",
+    "linear_axis_table", "trilinear_upsample", "trilinear_upsample_bwd",
+    "v4_tail", "v4_tail_bwd", "inner_product_soft_argmax",
+]
+
+
+def _acc(a, acc_dtype):
+    return a.astype(acc_dtype if acc_dtype is not None else a.dtype, copy=False)
+
+
+# --------------------------------------------------------------------------- concatenate
+def concat_volume(left, right, max_disparity):
+    """(N,C,H,W)x2 -> (N,2C,H,W,D).  cost_volume/concatenate.py:11-41.
+
+    V[:, :C, y, x, d] = L[:, :, y, x] and V[:, C:, y, x, d] = R[:, :, y, x-d] for x >= d,
+    zero for x < d in both halves (concatenate.py:27-39).  d >= W leaves zeros.
+    """
+    n, c, h, w = left.shape
+    vol = np.zeros((n, 2 * c, h, w, max_disparity), dtype=left.dtype)
+    for d in range(min(max_disparity, w)):
+        vol[:, :c, :, d:, d] = left[:, :, :, d:]
+        vol[:, c:, :, d:, d] = right[:, :, :, : w - d]
+    return vol
+
+
+def concat_volume_bwd(gvol, acc_dtype=None):
+    """Adjoint of :func:`concat_volume` (autograd through concatenate.py:33-39).
+
+    gL[c,x] = sum_{d<=min(x,D-1)} gV[c,x,d];  gR[c,x'] = sum_{d<D, x'+d<W} gV[C+c,x'+d,d].
+    """
+    n, c2, h, w, dmax = gvol.shape
+    c = c2 // 2
+    g = _acc(gvol, acc_dtype)
+    gl = np.zeros((n, c, h, w), dtype=g.dtype)
+    gr = np.zeros((n, c, h, w), dtype=g.dtype)
+    for d in range(min(dmax, w)):
+        gl[:, :, :, d:] += g[:, :c, :, d:, d]
+        gr[:, :, :, : w - d] += g[:, c:, :, d:, d]
+    return gl.astype(gvol.dtype), gr.astype(gvol.dtype)
+
+
+# ---------------------------------------------------------------------------- interweave
+def interweave(left, right):
+    """(N,C,H,W)x2 -> (N,2C,H,W), even channels = left, odd = right.
+
+    cost_volume/interweave.py:10-22 and its twin interweave_tensors,
+    model/mobile_stereo_net_v4.py:17-23.
+    """
+    n, c, h, w = left.shape
+    out = np.zeros((n, 2 * c, h, w), dtype=left.dtype)
+    out[:, 0::2] = left
+    out[:, 1::2] = right
+    return out
+
+
+def interweave_bwd(gout):
+    """gL = gV[:, 0::2], gR = gV[:, 1::2] (autograd through interweave.py:18-19)."""
+    return np.ascontiguousarray(gout[:, 0::2]), np.ascontiguousarray(gout[:, 1::2])
+
+
+# ------------------------------------------------------------- inner product / correlation
+def inner_product_volume(left, right, max_disparity, mean=False, acc_dtype=np.float32,
+                         out_dtype=None):
+    """(N,C,H,W)x2 -> (N,D,H,W):  V[n,d,y,x] = s * sum_c L[n,c,y,x] R[n,c,y,x-d], x >= d.
+
+    s = 1: TorchInnerProductCost.forward, cost_volume/inner_product.py:29-41 (channel sum).
+    s = 1/C (``mean=True``): make_correlation_volume, model/mobile_disp_net_c.py:188-205
+    (channel mean, applied as a division of the accumulated sum, like ``Tensor.mean``).
+    Accumulates in ``acc_dtype`` (fp32 like ATen's reduction), output cast to
+    ``out_dtype`` (default: dtype of ``left``).
+    """
+    n, c, h, w = left.shape
+    out_dtype = out_dtype or left.dtype
+    l = _acc(left, acc_dtype)
+    r = _acc(right, acc_dtype)
+    vol = np.zeros((n, max_disparity, h, w), dtype=l.dtype)
+    for d in range(min(max_disparity, w)):
+        s = np.sum(l[:, :, :, d:] * r[:, :, :, : w - d], axis=1)
+        vol[:, d, :, d:] = s / c if mean else s
+    return vol.astype(out_dtype)
+
+
+def inner_product_volume_bwd(gvol, left, right, mean=False, acc_dtype=np.float32):
+    """Adjoint of :func:`inner_product_volume` (SURVEY.md 8a "Backward contracts").
+
+    gL[c,x] = s * sum_{d<=x} gV[d,x] R[c,x-d];  gR[c,x'] = s * sum_{d,x'+d<W} gV[d,x'+d] L[c,x'+d].
+    """
+    n, c, h, w = left.shape
+    dmax = gvol.shape[1]
+    g = _acc(gvol, acc_dtype)
+    l = _acc(left, acc_dtype)
+    r = _acc(right, acc_dtype)
+    gl = np.zeros_like(l)
+    gr = np.zeros_like(r)
+    for d in range(min(dmax, w)):
+        gd = g[:, d, :, d:][:, None]  # (N,1,H,W-d)
+        gl[:, :, :, d:] += gd * r[:, :, :, : w - d]
+        gr[:, :, :, : w - d] += gd * l[:, :, :, d:]
+    if mean:
+        gl = gl / c
+        gr = gr / c
+    return gl.astype(left.dtype), gr.astype(right.dtype)
+
+
+# ----------------------------------------------------------------------------- groupwise
+def groupwise_pointwise(left, right, n_groups, acc_dtype=np.float32):
+    """(N,C,H,W)x2 -> (N,G,H,W): per-group channel mean of L*R.
+
+    TorchGroupwiseCost.groupwise, cost_volume/groupwise.py:12-22; groups are contiguous
+    channel blocks of C//G; AssertionError when C % G != 0 (groupwise.py:15-17).
+    """
+    n, c, h, w = left.shape
+    assert c % n_groups == 0, f"groupwise cost channel ({c}) % #groups ({n_groups}) != 0."
+    cpg = c // n_groups
+    prod = _acc(left, acc_dtype) * _acc(right, acc_dtype)
+    return prod.reshape(n, n_groups, cpg, h, w).sum(axis=2) / cpg
+
+
+def groupwise_volume(left, right, n_groups, max_disparity, acc_dtype=np.float32,
+                     out_dtype=np.float32):
+    """(N,C,H,W)x2 -> (N,G,H,W,D).  cost_volume/groupwise.py:24-56.
+
+    V[n,g,y,x,d] = (1/cpg) sum_{c in g} L[n,c,y,x] R[n,c,y,x-d], x >= d, zero elsewhere.
+    The reference allocates the output without dtype/device (groupwise.py:39), so it is
+    always fp32; ``out_dtype`` defaults to that.
+    """
+    n, c, h, w = left.shape
+    vol = np.zeros((n, n_groups, h, w, max_disparity), dtype=out_dtype)
+    for d in range(min(max_disparity, w)):
+        vol[:, :, :, d:, d] = groupwise_pointwise(
+            left[:, :, :, d:], right[:, :, :, : w - d], n_groups, acc_dtype)
+    return vol
+
+
+def groupwise_volume_bwd(gvol, left, right, n_groups, acc_dtype=np.float32):
+    """Adjoint of :func:`groupwise_volume`: inner-product adjoint with per-group gV, s=1/cpg."""
+    n, c, h, w = left.shape
+    dmax = gvol.shape[-1]
+    cpg = c // n_groups
+    g = _acc(gvol, acc_dtype)
+    l = _acc(left, acc_dtype)
+    r = _acc(right, acc_dtype)
+    gl = np.zeros_like(l)
+    gr = np.zeros_like(r)
+    for d in range(min(dmax, w)):
+        gd = np.repeat(g[:, :, :, d:, d], cpg, axis=1)  # (N,C,H,W-d)
+        gl[:, :, :, d:] += gd * r[:, :, :, : w - d]
+        gr[:, :, :, : w - d] += gd * l[:, :, :, d:]
+    return (gl / cpg).astype(left.dtype), (gr / cpg).astype(right.dtype)
+
+
+# ---------------------------------------------------------------------------- difference
+def difference_volume(left, right, max_disp):
+    """(N,C,H,W)x2 -> (N,C,D,H,W): L - R shifted by d, fill value 1.0 for x < d.
+
+    make_cost_volume, model/mobile_stereo_net.py:8-27 (identical copies in
+    model/mobile_stereo_net_v2.py:8-27 and model/mobile_stereo_net_v3.py:9-28).
+    """
+    n, c, h, w = left.shape
+    vol = np.ones((n, c, max_disp, h, w), dtype=left.dtype)
+    for d in range(min(max_disp, w)):
+        vol[:, :, d, :, d:] = left[:, :, :, d:] - right[:, :, :, : w - d]
+    return vol
+
+
+def difference_volume_bwd(gvol, acc_dtype=None):
+    """gL[c,x] = sum_{d<=x} gV[c,d,x];  gR[c,x'] = -sum_{d,x'+d<W} gV[c,d,x'+d]."""
+    n, c, dmax, h, w = gvol.shape
+    g = _acc(gvol, acc_dtype)
+    gl = np.zeros((n, c, h, w), dtype=g.dtype)
+    gr = np.zeros((n, c, h, w), dtype=g.dtype)
+    for d in range(min(dmax, w)):
+        gl[:, :, :, d:] += g[:, :, d, :, d:]
+        gr[:, :, :, : w - d] -= g[:, :, d, :, d:]
+    return gl.astype(gvol.dtype), gr.astype(gvol.dtype)
+
+
+# ---------------------------------------------------------------------------- regression
+def softmax_d(cost, acc_dtype=np.float32):
+    """softmax over axis 1 (the disparity axis), F.softmax(cost, dim=1) as used at
+    model/mobile_stereo_net.py:144, mobile_stereo_net_v4.py:517, mobile_disp_net_c.py:218."""
+    c = _acc(cost, acc_dtype)
+    m = np.max(c, axis=1, keepdims=True)
+    e = np.exp(c - m)
+    return e / np.sum(e, axis=1, keepdims=True)
+
+
+def soft_argmax(cost, acc_dtype=np.float32, keepdim=False):
+    """(N,D,H,W) -> (N,H,W) [or (N,1,H,W)]:  E = sum_d d * softmax_d(+cost).
+
+    Inline form model/mobile_stereo_net.py:144-147 (= v2 :217-220, v3 :321-324);
+    disparity_regression of probabilities model/mobile_stereo_net_v4.py:10-14;
+    disparity_regression of logits model/mobile_disp_net_c.py:208-220.
+    Softmax of +cost, fill-value entries take part (F8).
+    """
+    p = softmax_d(cost, acc_dtype)
+    d = np.arange(cost.shape[1], dtype=p.dtype).reshape(1, -1, 1, 1)
+    e = np.sum(p * d, axis=1, keepdims=keepdim)
+    return e.astype(cost.dtype)
+
+
+def soft_argmax_bwd(gout, cost, acc_dtype=np.float32):
+    """gcost[d] = g * p[d] * (d - E) (softmax + expectation adjoint)."""
+    p = softmax_d(cost, acc_dtype)
+    d = np.arange(cost.shape[1], dtype=p.dtype).reshape(1, -1, 1, 1)
+    e = np.sum(p * d, axis=1, keepdims=True)
+    g = _acc(gout, acc_dtype).reshape(cost.shape[0], 1, cost.shape[2], cost.shape[3])
+    return (g * p * (d - e)).astype(cost.dtype)
+
+
+def hard_argmin(cost):
+    """(N,D,H,W) -> (N,H,W) int64 = torch.argmin(cost, dim=1) semantics.
+
+    Not in the reference: first index on ties, NaN counts as the minimum
+    (first NaN wins), int64 result.  numpy.argmin has the same rules.
+    """
+    return np.argmin(cost, axis=1).astype(np.int64)
+
+
+def hard_argmax(cost):
+    """torch.argmax(cost, dim=1): first index on ties, first NaN wins, int64."""
+    return np.argmax(cost, axis=1).astype(np.int64)
+
+
+# ------------------------------------------------------------------------- v4 tail
+def linear_axis_table(n_in, n_out):
+    """Source indices and weights of F.interpolate(mode='trilinear', align_corners=False)
+    along one axis, as ATen computes them in fp32: scale = in/out,
+    src = max(scale*(dst+0.5)-0.5, 0), i0 = floor(src), i1 = i0 + (i0 < in-1), w1 = src-i0.
+    Used by model/mobile_stereo_net_v4.py:513-516 (and :476-506 in training).
+    """
+    scale = np.float32(n_in) / np.float32(n_out)
+    dst = np.arange(n_out, dtype=np.float32)
+    src = scale * (dst + np.float32(0.5)) - np.float32(0.5)
+    src = np.maximum(src, np.float32(0.0)).astype(np.float32)
+    i0 = np.minimum(src.astype(np.int64), n_in - 1)
+    i1 = i0 + (i0 < n_in - 1)
+    w1 = np.clip(src - i0.astype(np.float32), 0.0, 1.0).astype(np.float32)
+    w0 = (np.float32(1.0) - w1).astype(np.float32)
+    return i0, i1, w0, w1
+
+
+def trilinear_upsample(cost, out_d, out_h, out_w, acc_dtype=np.float32):
+    """(N,Dc,Hc,Wc) -> (N,out_d,out_h,out_w): F.interpolate(cost[:,None], [D,H,W],
+    mode='trilinear') squeezed, model/mobile_stereo_net_v4.py:512-516 (separable lerps)."""
+    c = _acc(cost, acc_dtype)
+    n, dc, hc, wc = c.shape
+    x0, x1, wx0, wx1 = linear_axis_table(wc, out_w)
+    y0, y1, wy0, wy1 = linear_axis_table(hc, out_h)
+    d0, d1, wd0, wd1 = linear_axis_table(dc, out_d)
+    wx0, wx1, wy0, wy1, wd0, wd1 = (a.astype(c.dtype) for a in (wx0, wx1, wy0, wy1, wd0, wd1))
+    t = c[:, :, :, x0] * wx0 + c[:, :, :, x1] * wx1                       # (N,Dc,Hc,W)
+    t = t[:, :, y0, :] * wy0[:, None] + t[:, :, y1, :] * wy1[:, None]     # (N,Dc,H,W)
+    t = t[:, d0] * wd0[:, None, None] + t[:, d1] * wd1[:, None, None]     # (N,D,H,W)
+    return t
+
+
+def trilinear_upsample_bwd(gfine, dc, hc, wc, acc_dtype=np.float32):
+    """Transpose of :func:`trilinear_upsample` (UpsampleTrilinear3DBackward)."""
+    g = _acc(gfine, acc_dtype)
+    n, od, oh, ow = g.shape
+    x0, x1, wx0, wx1 = linear_axis_table(wc, ow)
+    y0, y1, wy0, wy1 = linear_axis_table(hc, oh)
+    d0, d1, wd0, wd1 = linear_axis_table(dc, od)
+    wx0, wx1, wy0, wy1, wd0, wd1 = (a.astype(g.dtype) for a in (wx0, wx1, wy0, wy1, wd0, wd1))
+    td = np.zeros((n, dc, oh, ow), dtype=g.dtype)
+    np.add.at(td, (slice(None), d0), g * wd0[:, None, None])
+    np.add.at(td, (slice(None), d1), g * wd1[:, None, None])
+    ty = np.zeros((n, dc, hc, ow), dtype=g.dtype)
+    np.add.at(ty, (slice(None), slice(None), y0), td * wy0[:, None])
+    np.add.at(ty, (slice(None), slice(None), y1), td * wy1[:, None])
+    tx = np.zeros((n, dc, hc, wc), dtype=g.dtype)
+    np.add.at(tx, (slice(None), slice(None), slice(None), x0), ty * wx0)
+    np.add.at(tx, (slice(None), slice(None), slice(None), x1), ty * wx1)
+    return tx
+
+
+def v4_tail(cost, maxdisp, out_h, out_w, acc_dtype=np.float32):
+    """(B,Dc,Hc,Wc) -> (B,out_h,out_w): trilinear upsample to (maxdisp,H,W), softmax over
+    D, expectation.  Eval head model/mobile_stereo_net_v4.py:511-518 (training heads
+    :471-506 are four copies).  The caller negates (:520)."""
+    fine = trilinear_upsample(cost, maxdisp, out_h, out_w, acc_dtype)
+    return soft_argmax(fine.astype(np.float32 if acc_dtype == np.float32 else acc_dtype),
+                       acc_dtype).astype(cost.dtype)
+
+
+def v4_tail_bwd(gout, cost, maxdisp, out_h, out_w, acc_dtype=np.float32):
+    """Adjoint of :func:`v4_tail` with respect to the coarse cost."""
+    fine = trilinear_upsample(cost, maxdisp, out_h, out_w, acc_dtype)
+    gfine = soft_argmax_bwd(gout, fine, acc_dtype)
+    n, dc, hc, wc = cost.shape
+    return trilinear_upsample_bwd(gfine, dc, hc, wc, acc_dtype).astype(cost.dtype)
+
+
+def inner_product_soft_argmax(left, right, max_disparity, mean=False, acc_dtype=np.float32):
+    """Composition used by the fused no-volume kernel: inner_product_volume followed by
+    soft_argmax and hard_argmax/argmin on the fp32 volume (never rounded to the input dtype)."""
+    vol = inner_product_volume(left, right, max_disparity, mean, acc_dtype, out_dtype=acc_dtype)
+    return soft_argmax(vol, acc_dtype), hard_argmin(vol), hard_argmax(vol)

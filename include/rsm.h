@@ -1,0 +1,160 @@
+/*
+ * rsm.h -- C ABI of librsm_b200.so: B200 (sm_100a) kernels for the stereo-matching hot path
+ * of babiking/realtime_stereo_matcher (cost-volume construction + disparity regression).
+ *
+ * The reference has no FFI / plugin registry: its boundary for this path is plain Python
+ * call signatures.  Each entry point below names the reference function it
+ * replaces (file:line relative to the reference checkout).  The Python mirror of those
+ * signatures lives in realtime_stereo_matcher_b200/ and is the only caller; the binding a
+ * maintainer of the reference would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers on `device`; nothing is allocated, freed or
+ *     synchronised inside the library; work is enqueued on `stream` (a cudaStream_t passed
+ *     as void*; NULL = the legacy default stream) and the call returns immediately.
+ *   - inputs are borrowed and never written; outputs are dense (contiguous) tensors in the
+ *     reference's own layouts, fully overwritten (fill-value regions included).
+ *   - feature maps may be non-contiguous views (the v4 forward passes width-cropped slices,
+ *     model/mobile_stereo_net_v4.py:446): they are described by rsm_feat with strides in
+ *     ELEMENTS.
+ *   - return value: RSM_OK (0) or an rsm_status code; rsm_last_error(code) returns a
+ *     static description (plus the CUDA error text of the calling thread's last failure).
+ *   - no global mutable state; safe to call concurrently from several host threads on
+ *     different devices (the reference trains under nn.DataParallel, train_stereo.py:139).
+ *   - there is NO CPU fallback.
+ */
+#ifndef RSM_B200_H_
+#define RSM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSM_VERSION 100 /* major*10000 + minor*100 + patch */
+
+typedef enum rsm_dtype {
+  RSM_F32 = 0,
+  RSM_F16 = 1,
+  RSM_BF16 = 2
+} rsm_dtype;
+
+typedef enum rsm_status {
+  RSM_OK = 0,
+  RSM_ERR_INVALID_SHAPE = 1,    /* negative / inconsistent sizes, C % G != 0, index overflow */
+  RSM_ERR_UNSUPPORTED_DTYPE = 2,
+  RSM_ERR_NULL_POINTER = 3,
+  RSM_ERR_CUDA = 4,             /* a CUDA runtime call or launch failed */
+  RSM_ERR_MISALIGNED = 5,       /* dense output / gradient pointer not aligned to its element */
+  RSM_ERR_UNSUPPORTED_CONFIG = 6
+} rsm_status;
+
+/* how a correlation is normalised over the reduced channels */
+typedef enum rsm_reduce {
+  RSM_REDUCE_SUM = 0,  /* TorchInnerProductCost: torch.sum(dim=1), cost_volume/inner_product.py:38-40 */
+  RSM_REDUCE_MEAN = 1  /* make_correlation_volume / groupwise: .mean(), mobile_disp_net_c.py:197-201 */
+} rsm_reduce;
+
+/* a (N,C,H,W) feature map on the device, strides in elements */
+typedef struct rsm_feat {
+  const void* data;
+  int64_t stride_n, stride_c, stride_h, stride_w;
+} rsm_feat;
+
+/* optional outputs of the regression kernels; any pointer may be NULL (not produced) */
+typedef struct rsm_regress_out {
+  void* soft;        /* (N,H,W) expectation sum_d d*softmax_d(+cost), dtype = cost dtype   */
+  int64_t* argmin;   /* (N,H,W) torch.argmin(cost, 1): first index on ties, NaN wins       */
+  int64_t* argmax;   /* (N,H,W) torch.argmax(cost, 1)                                       */
+  float* lse;        /* (N,H,W) fp32 log-sum-exp over D, saved for the backward pass        */
+} rsm_regress_out;
+
+int rsm_version(void);
+const char* rsm_last_error(int code);
+
+/* ---- concatenate volume: TorchConcatenateCost.forward, cost_volume/concatenate.py:11-41
+ * out (N,2C,H,W,D): out[:, :C,y,x,d] = L[:,:,y,x], out[:, C:,y,x,d] = R[:,:,y,x-d] for x>=d, else 0 */
+int rsm_concat_fwd(rsm_feat left, rsm_feat right, void* out, int64_t N, int64_t C, int64_t H,
+                   int64_t W, int64_t D, int dtype, int device, void* stream);
+/* adjoint (autograd through concatenate.py:33-39): gout (N,2C,H,W,D) -> gleft, gright (N,C,H,W) */
+int rsm_concat_bwd(const void* gout, void* gleft, void* gright, int64_t N, int64_t C, int64_t H,
+                   int64_t W, int64_t D, int dtype, int device, void* stream);
+
+/* ---- interweave: TorchInterweaveCost.forward, cost_volume/interweave.py:10-22 and
+ * interweave_tensors, model/mobile_stereo_net_v4.py:17-23.  out (N,2C,H,W), even ch = L, odd = R */
+int rsm_interweave_fwd(rsm_feat left, rsm_feat right, void* out, int64_t N, int64_t C, int64_t H,
+                       int64_t W, int dtype, int device, void* stream);
+int rsm_interweave_bwd(const void* gout, void* gleft, void* gright, int64_t N, int64_t C,
+                       int64_t H, int64_t W, int dtype, int device, void* stream);
+
+/* ---- inner product / correlation: TorchInnerProductCost.forward, cost_volume/inner_product.py:11-42
+ * (reduce = SUM) and make_correlation_volume, model/mobile_disp_net_c.py:188-205 (reduce = MEAN).
+ * out (N,D,H,W) = s * sum_c L[c,x] R[c,x-d] for x>=d, else 0; fp32 accumulation */
+int rsm_inner_fwd(rsm_feat left, rsm_feat right, void* out, int64_t N, int64_t C, int64_t H,
+                  int64_t W, int64_t D, int reduce, int in_dtype, int out_dtype, int device,
+                  void* stream);
+/* gout (N,D,H,W) dense in out_dtype; gleft/gright (N,C,H,W) dense in in_dtype; either may be NULL */
+int rsm_inner_bwd(const void* gout, rsm_feat left, rsm_feat right, void* gleft, void* gright,
+                  int64_t N, int64_t C, int64_t H, int64_t W, int64_t D, int reduce, int in_dtype,
+                  int out_dtype, int device, void* stream);
+
+/* ---- group-wise correlation: TorchGroupwiseCost.forward / .groupwise, cost_volume/groupwise.py:12-56
+ * out (N,G,H,W,D) = (1/(C/G)) * sum_{c in group g} L[c,x] R[c,x-d] for x>=d, else 0 */
+int rsm_groupwise_fwd(rsm_feat left, rsm_feat right, void* out, int64_t N, int64_t C, int64_t H,
+                      int64_t W, int64_t D, int64_t G, int in_dtype, int out_dtype, int device,
+                      void* stream);
+int rsm_groupwise_bwd(const void* gout, rsm_feat left, rsm_feat right, void* gleft, void* gright,
+                      int64_t N, int64_t C, int64_t H, int64_t W, int64_t D, int64_t G,
+                      int in_dtype, int out_dtype, int device, void* stream);
+
+/* ---- difference volume: make_cost_volume, model/mobile_stereo_net.py:8-27 (= v2 :8-27, v3 :9-28)
+ * out (N,C,D,H,W) = L[c,y,x] - R[c,y,x-d] for x>=d, else `fill` (the reference uses 1.0) */
+int rsm_difference_fwd(rsm_feat left, rsm_feat right, void* out, int64_t N, int64_t C, int64_t H,
+                       int64_t W, int64_t D, float fill, int dtype, int device, void* stream);
+int rsm_difference_bwd(const void* gout, void* gleft, void* gright, int64_t N, int64_t C,
+                       int64_t H, int64_t W, int64_t D, int dtype, int device, void* stream);
+
+/* ---- disparity regression over a dense (N,D,H,W) cost: softmax(+cost) expectation
+ * (model/mobile_stereo_net.py:144-147, mobile_stereo_net_v4.py:10-14 + :517,
+ * mobile_disp_net_c.py:208-220) and hard argmin / argmax (torch.argmin(cost, 1) semantics;
+ * not in the reference) in ONE pass over the volume */
+int rsm_regress_fwd(const void* cost, int64_t N, int64_t D, int64_t H, int64_t W, int dtype,
+                    rsm_regress_out out, int device, void* stream);
+/* gcost[d] = gout * p[d] * (d - soft);  soft/lse from the forward call; gout (N,H,W) in dtype */
+int rsm_regress_bwd(const void* gout, const void* cost, const void* soft, const float* lse,
+                    void* gcost, int64_t N, int64_t D, int64_t H, int64_t W, int dtype,
+                    int device, void* stream);
+
+/* ---- expectation of given probabilities: disparity_regression(x, maxdisp),
+ * model/mobile_stereo_net_v4.py:10-14 (x is already softmax-ed): out (N,H,W) = sum_d d * prob[d] */
+int rsm_expect_fwd(const void* prob, void* out, int64_t N, int64_t D, int64_t H, int64_t W, int dtype,
+                   int device, void* stream);
+/* gprob[d] = gout * d */
+int rsm_expect_bwd(const void* gout, void* gprob, int64_t N, int64_t D, int64_t H, int64_t W, int dtype,
+                   int device, void* stream);
+
+/* ---- MobileStereoNetV4 head: F.interpolate(cost[:,None], [D,H,W], 'trilinear') -> softmax ->
+ * disparity_regression, model/mobile_stereo_net_v4.py:511-518 (training heads :471-506), fused:
+ * cost (B,Dc,Hc,Wc) dense -> (B,H,W) without materialising the (B,D,H,W) tensor */
+int rsm_upsample_regress_fwd(const void* cost, int64_t B, int64_t Dc, int64_t Hc, int64_t Wc,
+                             int64_t D, int64_t H, int64_t W, int dtype, rsm_regress_out out,
+                             int device, void* stream);
+/* bytes of scratch the backward needs (a (B,Dc,H,W) fp32 tensor) */
+int64_t rsm_upsample_regress_bwd_workspace(int64_t B, int64_t Dc, int64_t H, int64_t W);
+int rsm_upsample_regress_bwd(const void* gout, const void* cost, const void* soft,
+                             const float* lse, void* gcost, void* workspace, int64_t B,
+                             int64_t Dc, int64_t Hc, int64_t Wc, int64_t D, int64_t H, int64_t W,
+                             int dtype, int device, void* stream);
+
+/* ---- fused build + regress: inner product / correlation volume reduced on chip to the
+ * soft-argmax disparity and hard argmin / argmax; the (N,D,H,W) volume never reaches HBM.
+ * out.soft is fp32 here (the volume stays in the fp32 accumulator); out.lse optional */
+int rsm_inner_regress_fwd(rsm_feat left, rsm_feat right, int64_t N, int64_t C, int64_t H,
+                          int64_t W, int64_t D, int reduce, int in_dtype, rsm_regress_out out,
+                          int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSM_B200_H_ */

@@ -1,0 +1,109 @@
+// Shared device/host helpers for librsm_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rsm.h"
+
+namespace rsm {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+// ----------------------------------------------------------------------------- host side
+// thread-local detail of the last CUDA failure (read by rsm_last_error)
+void set_cuda_error(cudaError_t e, const char* where);
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != device && cudaSetDevice(device) != cudaSuccess) ok = false;
+    want = device;
+  }
+  ~DeviceGuard() {
+    if (ok && prev != want) cudaSetDevice(prev);
+  }
+  int want = -1;
+};
+
+inline int finish_launch(const char* where) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_cuda_error(e, where);
+    return RSM_ERR_CUDA;
+  }
+  return RSM_OK;
+}
+
+inline bool valid_dtype(int dt) { return dt == RSM_F32 || dt == RSM_F16 || dt == RSM_BF16; }
+inline int dtype_size(int dt) { return dt == RSM_F32 ? 4 : 2; }
+inline bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// dispatch a generic lambda on a runtime dtype: f(T{}) with T in {float, __half, __nv_bfloat16}
+#define RSM_DISPATCH_DTYPE(dt, T, ...)                           \
+  [&]() -> int {                                                 \
+    switch (dt) {                                                \
+      case RSM_F32: { using T = float; return __VA_ARGS__(); }   \
+      case RSM_F16: { using T = __half; return __VA_ARGS__(); }  \
+      case RSM_BF16: { using T = __nv_bfloat16; return __VA_ARGS__(); } \
+      default: return (int)RSM_ERR_UNSUPPORTED_DTYPE;            \
+    }                                                            \
+  }()
+
+// ---------------------------------------------------------------------------- device side
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// 16-byte vector of T
+template <typename T> struct Vec16 {
+  static constexpr int N = 16 / sizeof(T);
+  union {
+    uint4 raw;
+    T v[N];
+  };
+};
+
+template <typename T> __device__ __forceinline__ Vec16<T> ldg16(const T* p) {
+  Vec16<T> r;
+  r.raw = __ldg(reinterpret_cast<const uint4*>(p));
+  return r;
+}
+// streaming (evict-first) 16-byte load / store for data touched exactly once
+template <typename T> __device__ __forceinline__ Vec16<T> ldcs16(const T* p) {
+  Vec16<T> r;
+  r.raw = __ldcs(reinterpret_cast<const uint4*>(p));
+  return r;
+}
+template <typename T> __device__ __forceinline__ void stcs16(T* p, const Vec16<T>& v) {
+  __stcs(reinterpret_cast<uint4*>(p), v.raw);
+}
+template <typename T> __device__ __forceinline__ void st16(T* p, const Vec16<T>& v) {
+  *reinterpret_cast<uint4*>(p) = v.raw;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+struct FeatView {  // device-side copy of rsm_feat
+  const void* data;
+  int64_t sn, sc, sh, sw;
+};
+inline FeatView view_of(const rsm_feat& f) { return FeatView{f.data, f.stride_n, f.stride_c, f.stride_h, f.stride_w}; }
+
+}  // namespace rsm

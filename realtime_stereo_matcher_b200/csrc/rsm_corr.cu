@@ -1,0 +1,459 @@
+// Correlation volumes (inner product / mean correlation / group-wise correlation), their adjoints,
+// and the fused correlation -> soft-argmax/argmin kernel that never writes the volume.
+//
+// Forward tiling (SIMT, fp32 accumulate): a CTA owns one epipolar row segment of TX=64 pixels of one
+// (n, y, group) and a chunk of up to 64 disparities.  Channel chunks of the left row segment and of
+// the right row window [x0-d_hi, x0+TX) are staged in shared memory once and reused by every
+// (x, d) pair of the tile; each thread accumulates a 4(x) x 8(d) register tile from 4 LDS.128 per
+// channel (one left quad + a 12-wide right window), i.e. 8 FMA per shared-memory word.
+#include <math.h>
+
+#include "rsm_common.cuh"
+
+namespace rsm {
+
+constexpr int TX = 64;       // pixels per CTA tile
+constexpr int XT = 4;        // pixels per thread
+constexpr int DT = 8;        // disparities per thread
+constexpr int NTX = TX / XT; // 16 threads along x
+constexpr int MAX_NTD = 8;   // <= 64 disparities per CTA chunk (volume kernels)
+constexpr int CK = 16;       // channels per shared-memory stage
+
+enum Layout { LAYOUT_NDHW = 0, LAYOUT_NGHWD = 1 };
+
+struct CorrGeom {
+  int C, H, W, D, G, cpg;
+  int ntd;        // threads along d  (blockDim.x = NTX * ntd)
+  int dchp;       // disparities covered by a CTA chunk = DT * ntd
+  int xtiles;     // ceil(W / TX)
+  int mean;       // divide by cpg
+};
+
+// ---- stage CK channels of the left segment and right window as fp32 in shared memory
+template <typename Tin>
+__device__ __forceinline__ void stage_rows(const FeatView& L, const FeatView& R, int64_t n, int cbase, int cend,
+                                           int y, int x0, int rbase, int rw, float* sL, float* sR, int W) {
+  const Tin* __restrict__ pl = reinterpret_cast<const Tin*>(L.data) + n * L.sn + (int64_t)y * L.sh;
+  const Tin* __restrict__ pr = reinterpret_cast<const Tin*>(R.data) + n * R.sn + (int64_t)y * R.sh;
+  for (int e = threadIdx.x; e < CK * TX; e += blockDim.x) {
+    const int c = e / TX, xx = e - c * TX;
+    const int x = x0 + xx, cc = cbase + c;
+    sL[e] = (cc < cend && x < W) ? to_f(__ldg(pl + (int64_t)cc * L.sc + (int64_t)x * L.sw)) : 0.f;
+  }
+  for (int e = threadIdx.x; e < CK * rw; e += blockDim.x) {
+    const int c = e / rw, j = e - c * rw;
+    const int x = rbase + j, cc = cbase + c;
+    sR[e] = (cc < cend && x >= 0 && x < W) ? to_f(__ldg(pr + (int64_t)cc * R.sc + (int64_t)x * R.sw)) : 0.f;
+  }
+}
+
+// ---- accumulate the 4x8 register tile over the staged channels
+__device__ __forceinline__ void tile_fma(const float* sL, const float* sR, int rw, int tx, int wstart, int nch,
+                                         float (&acc)[XT][DT]) {
+#pragma unroll 4
+  for (int c = 0; c < nch; ++c) {
+    const float4 l4 = *reinterpret_cast<const float4*>(sL + c * TX + XT * tx);
+    const float4* wp = reinterpret_cast<const float4*>(sR + c * rw + wstart);
+    const float4 w0 = wp[0], w1 = wp[1], w2 = wp[2];
+    const float l[XT] = {l4.x, l4.y, l4.z, l4.w};
+    const float w[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
+#pragma unroll
+    for (int i = 0; i < XT; ++i)
+#pragma unroll
+      for (int j = 0; j < DT; ++j) acc[i][j] = fmaf(l[i], w[8 + i - j], acc[i][j]);
+  }
+}
+
+template <typename Tout, int NV> struct PackOut;  // NV consecutive outputs
+template <> struct PackOut<float, 4> {
+  static __device__ __forceinline__ void store(float* p, const float* v) {
+    __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+  }
+};
+template <> struct PackOut<__half, 4> {
+  static __device__ __forceinline__ void store(__half* p, const float* v) {
+    union { uint2 u; __half2 h[2]; } t;
+    t.h[0] = __floats2half2_rn(v[0], v[1]); t.h[1] = __floats2half2_rn(v[2], v[3]);
+    __stcs(reinterpret_cast<uint2*>(p), t.u);
+  }
+};
+template <> struct PackOut<__nv_bfloat16, 4> {
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float* v) {
+    union { uint2 u; __nv_bfloat162 h[2]; } t;
+    t.h[0] = __floats2bfloat162_rn(v[0], v[1]); t.h[1] = __floats2bfloat162_rn(v[2], v[3]);
+    __stcs(reinterpret_cast<uint2*>(p), t.u);
+  }
+};
+
+// ======================================================================= volume forward
+template <typename Tin, typename Tout, int LAYOUT>
+__global__ void __launch_bounds__(NTX * MAX_NTD)
+corr_fwd_kernel(FeatView L, FeatView R, Tout* __restrict__ out, CorrGeom g) {
+  extern __shared__ __align__(16) float smem[];
+  const int rw = TX + g.dchp;
+  float* sL = smem;
+  float* sR = smem + CK * TX;
+
+  int64_t bid = blockIdx.x;
+  const int xt = (int)(bid % g.xtiles); bid /= g.xtiles;
+  const int y = (int)(bid % g.H); bid /= g.H;
+  const int grp = (int)(bid % g.G);
+  const int64_t n = bid / g.G;
+  const int x0 = xt * TX;
+  const int dc0 = blockIdx.y * g.dchp;
+  const int tx = threadIdx.x % NTX, td = threadIdx.x / NTX;
+  const int rbase = x0 - dc0 - g.dchp;
+  const int wstart = g.dchp + XT * tx - DT * td - DT;
+
+  float acc[XT][DT];
+#pragma unroll
+  for (int i = 0; i < XT; ++i)
+#pragma unroll
+    for (int j = 0; j < DT; ++j) acc[i][j] = 0.f;
+
+  const int cbeg = grp * g.cpg, cend = cbeg + g.cpg;
+  for (int c0 = cbeg; c0 < cend; c0 += CK) {
+    __syncthreads();
+    stage_rows<Tin>(L, R, n, c0, cend, y, x0, rbase, rw, sL, sR, g.W);
+    __syncthreads();
+    tile_fma(sL, sR, rw, tx, wstart, min(CK, cend - c0), acc);
+  }
+
+  const float cnt = g.mean ? (float)g.cpg : 1.f;
+  const int xb = x0 + XT * tx, db = dc0 + DT * td;
+#pragma unroll
+  for (int i = 0; i < XT; ++i)
+#pragma unroll
+    for (int j = 0; j < DT; ++j) acc[i][j] = (xb + i >= db + j) ? acc[i][j] / cnt : 0.f;
+
+  if constexpr (LAYOUT == LAYOUT_NDHW) {
+    const bool vec = (g.W % XT == 0);  // then xb + 3 < W whenever xb < W and the address is 4-aligned
+    if (xb >= g.W) return;
+#pragma unroll
+    for (int j = 0; j < DT; ++j) {
+      const int d = db + j;
+      if (d >= g.D) break;
+      Tout* p = out + (((int64_t)n * g.D + d) * g.H + y) * g.W + xb;
+      if (vec) {
+        const float v[4] = {acc[0][j], acc[1][j], acc[2][j], acc[3][j]};
+        PackOut<Tout, 4>::store(p, v);
+      } else {
+#pragma unroll
+        for (int i = 0; i < XT; ++i)
+          if (xb + i < g.W) p[i] = from_f<Tout>(acc[i][j]);
+      }
+    }
+  } else {
+    const bool vec = (g.D % 4 == 0);   // then db + 4k + 3 < D whenever db + 4k < D
+    if (db >= g.D) return;
+#pragma unroll
+    for (int i = 0; i < XT; ++i) {
+      const int x = xb + i;
+      if (x >= g.W) break;
+      Tout* p = out + ((((int64_t)n * g.G + grp) * g.H + y) * g.W + x) * g.D + db;
+      if (vec) {
+        PackOut<Tout, 4>::store(p, &acc[i][0]);
+        if (db + 4 < g.D) PackOut<Tout, 4>::store(p + 4, &acc[i][4]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < DT; ++j)
+          if (db + j < g.D) p[j] = from_f<Tout>(acc[i][j]);
+      }
+    }
+  }
+}
+
+// ======================================================================= volume adjoint
+// One thread per (n,c,y,x); atomic-free gather over d (SURVEY.md 8a backward contracts):
+//   gL[c,x]  = s * sum_{d<=min(x,D-1)}       gV[g(c),d,x]    * R[c,x-d]
+//   gR[c,x'] = s * sum_{d<=min(D-1,W-1-x')}  gV[g(c),d,x'+d] * L[c,x'+d]
+template <typename Tin, typename Tout, int LAYOUT>
+__global__ void __launch_bounds__(256)
+corr_bwd_kernel(const Tout* __restrict__ gout, FeatView L, FeatView R, Tin* __restrict__ gl,
+                Tin* __restrict__ gr, int64_t total, CorrGeom g) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
+  const int x = (int)(i % g.W);
+  const int y = (int)((i / g.W) % g.H);
+  const int c = (int)((i / ((int64_t)g.W * g.H)) % g.C);
+  const int64_t n = i / ((int64_t)g.W * g.H * g.C);
+  const int grp = c / g.cpg;
+  const Tin* __restrict__ pl = reinterpret_cast<const Tin*>(L.data) + n * L.sn + (int64_t)c * L.sc + (int64_t)y * L.sh;
+  const Tin* __restrict__ pr = reinterpret_cast<const Tin*>(R.data) + n * R.sn + (int64_t)c * R.sc + (int64_t)y * R.sh;
+  // address of gV[d, x]:  base + d * sd + x * sx
+  int64_t base, sd, sx;
+  if constexpr (LAYOUT == LAYOUT_NDHW) {
+    base = ((int64_t)n * g.D * g.H + y) * g.W; sd = (int64_t)g.H * g.W; sx = 1;
+  } else {
+    base = (((int64_t)n * g.G + grp) * g.H + y) * (int64_t)g.W * g.D; sd = 1; sx = g.D;
+  }
+  const float cnt = g.mean ? (float)g.cpg : 1.f;
+  if (gl) {
+    float s = 0.f;
+    const int dl = min(x, g.D - 1);
+    for (int d = 0; d <= dl; ++d)
+      s = fmaf(to_f(__ldg(gout + base + d * sd + x * sx)), to_f(__ldg(pr + (int64_t)(x - d) * R.sw)), s);
+    gl[i] = from_f<Tin>(s / cnt);
+  }
+  if (gr) {
+    float s = 0.f;
+    const int dr = min(g.D - 1, g.W - 1 - x);
+    for (int d = 0; d <= dr; ++d)
+      s = fmaf(to_f(__ldg(gout + base + d * sd + (x + d) * sx)), to_f(__ldg(pl + (int64_t)(x + d) * L.sw)), s);
+    gr[i] = from_f<Tin>(s / cnt);
+  }
+}
+
+// ============================================================ fused correlation -> regression
+struct Best {   // (value, index) with torch arg-extremum ordering
+  float v; int i;
+};
+template <bool MIN> __device__ __forceinline__ Best better(Best a, Best b) {
+  const bool an = a.v != a.v, bn = b.v != b.v;
+  if (an || bn) {
+    if (an && bn) return a.i < b.i ? a : b;
+    return an ? a : b;
+  }
+  if (MIN ? (a.v < b.v) : (a.v > b.v)) return a;
+  if (MIN ? (a.v > b.v) : (a.v < b.v)) return b;
+  return a.i < b.i ? a : b;
+}
+template <bool MIN> __device__ __forceinline__ Best warp_best(Best a) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Best b;
+    b.v = __shfl_xor_sync(0xffffffffu, a.v, o);
+    b.i = __shfl_xor_sync(0xffffffffu, a.i, o);
+    a = better<MIN>(a, b);
+  }
+  return a;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// The CTA covers ALL disparities of a TX-pixel row segment (blockDim = NTX * ceil(D/8) <= 1024),
+// parks the fp32 tile in shared memory and reduces each pixel's D values with one warp:
+// max -> (sum exp, sum d*exp) -> argmin/argmax, so the (N,D,H,W) volume never reaches HBM.
+template <typename Tin, int MAXT>
+__global__ void __launch_bounds__(MAXT)
+inner_regress_fwd_kernel(FeatView L, FeatView R, float* __restrict__ soft, int64_t* __restrict__ amin,
+                         int64_t* __restrict__ amax, float* __restrict__ lse, CorrGeom g) {
+  extern __shared__ __align__(16) float smem[];
+  const int rw = TX + g.dchp;
+  const int dp = g.dchp + 1;                 // odd pitch of the parked tile sV[x][d]
+  float* sL = smem;
+  float* sR = sL + CK * TX;
+  float* sV = sR + CK * rw;
+
+  int64_t bid = blockIdx.x;
+  const int xt = (int)(bid % g.xtiles); bid /= g.xtiles;
+  const int y = (int)(bid % g.H);
+  const int64_t n = bid / g.H;
+  const int x0 = xt * TX;
+  const int tx = threadIdx.x % NTX, td = threadIdx.x / NTX;
+  const int rbase = x0 - g.dchp;
+  const int wstart = g.dchp + XT * tx - DT * td - DT;
+
+  float acc[XT][DT];
+#pragma unroll
+  for (int i = 0; i < XT; ++i)
+#pragma unroll
+    for (int j = 0; j < DT; ++j) acc[i][j] = 0.f;
+  for (int c0 = 0; c0 < g.C; c0 += CK) {
+    __syncthreads();
+    stage_rows<Tin>(L, R, n, c0, g.C, y, x0, rbase, rw, sL, sR, g.W);
+    __syncthreads();
+    tile_fma(sL, sR, rw, tx, wstart, min(CK, g.C - c0), acc);
+  }
+  const float cnt = g.mean ? (float)g.C : 1.f;
+  const int xb = XT * tx, db = DT * td;
+#pragma unroll
+  for (int i = 0; i < XT; ++i)
+#pragma unroll
+    for (int j = 0; j < DT; ++j)
+      sV[(xb + i) * dp + db + j] = (x0 + xb + i >= db + j) ? acc[i][j] / cnt : 0.f;
+  __syncthreads();
+
+  constexpr float kLog2e = 1.4426950408889634f;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int xx = warp; xx < TX; xx += nwarps) {
+    const int x = x0 + xx;
+    if (x >= g.W) break;
+    const float* col = sV + xx * dp;
+    float m = -INFINITY;
+    Best bmin{INFINITY, 0x7fffffff}, bmax{-INFINITY, 0x7fffffff};
+    for (int d = lane; d < g.D; d += 32) {
+      const float v = col[d];
+      m = fmaxf(m, v);
+      bmin = better<true>(bmin, Best{v, d});
+      bmax = better<false>(bmax, Best{v, d});
+    }
+    m = warp_max(m);
+    float s = 0.f, ws = 0.f;
+    for (int d = lane; d < g.D; d += 32) {
+      float e;
+      const float t = fmaf(col[d], kLog2e, -m * kLog2e);
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+      s += e;
+      ws = fmaf((float)d, e, ws);
+    }
+    s = warp_sum(s);
+    ws = warp_sum(ws);
+    bmin = warp_best<true>(bmin);
+    bmax = warp_best<false>(bmax);
+    if (lane == 0) {
+      const int64_t o = ((int64_t)n * g.H + y) * g.W + x;
+      if (soft) soft[o] = ws / s;
+      if (lse) lse[o] = m + __logf(s);
+      if (amin) amin[o] = bmin.i;
+      if (amax) amax[o] = bmax.i;
+    }
+  }
+}
+
+static bool grid_ok(int64_t blocks) { return blocks >= 0 && blocks <= 2147483647LL; }
+
+static int make_geom(int64_t N, int64_t C, int64_t H, int64_t W, int64_t D, int64_t G, int mean, bool all_d,
+                     CorrGeom& g) {
+  if (N < 0 || C < 0 || H < 0 || W < 0 || D < 0 || G <= 0) return RSM_ERR_INVALID_SHAPE;
+  if (C % G != 0) return RSM_ERR_INVALID_SHAPE;
+  if (C > (1 << 24) || H > (1 << 24) || W > (1 << 24) || D > (1 << 24)) return RSM_ERR_INVALID_SHAPE;
+  g.C = (int)C; g.H = (int)H; g.W = (int)W; g.D = (int)D; g.G = (int)G; g.cpg = (int)(C / G);
+  const int need = (int)ceil_div(D > 0 ? D : 1, DT);
+  g.ntd = all_d ? need : (need < MAX_NTD ? need : MAX_NTD);
+  g.dchp = g.ntd * DT;
+  g.xtiles = (int)ceil_div(W > 0 ? W : 1, TX);
+  g.mean = mean;
+  return RSM_OK;
+}
+
+template <typename Tin, typename Tout, int LAYOUT>
+static int launch_fwd(const rsm_feat& left, const rsm_feat& right, void* out, int64_t N, const CorrGeom& g,
+                      cudaStream_t st, const char* where) {
+  const int64_t bx = N * g.G * g.H * g.xtiles;
+  const int64_t by = ceil_div(g.D, g.dchp);
+  if (!grid_ok(bx) || by > 65535) return RSM_ERR_INVALID_SHAPE;
+  const size_t smem = (size_t)(CK * TX + CK * (TX + g.dchp)) * sizeof(float);
+  corr_fwd_kernel<Tin, Tout, LAYOUT><<<dim3((unsigned)bx, (unsigned)by), NTX * g.ntd, smem, st>>>(
+      view_of(left), view_of(right), (Tout*)out, g);
+  return finish_launch(where);
+}
+
+template <typename Tin, typename Tout, int LAYOUT>
+static int launch_bwd(const void* gout, const rsm_feat& left, const rsm_feat& right, void* gl, void* gr,
+                      int64_t N, const CorrGeom& g, cudaStream_t st, const char* where) {
+  const int64_t total = N * g.C * g.H * g.W;
+  if (!grid_ok(ceil_div(total, 256))) return RSM_ERR_INVALID_SHAPE;
+  corr_bwd_kernel<Tin, Tout, LAYOUT><<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(
+      (const Tout*)gout, view_of(left), view_of(right), (Tin*)gl, (Tin*)gr, total, g);
+  return finish_launch(where);
+}
+
+// dispatch on (in_dtype, out_dtype): outputs are either the input dtype or fp32
+#define RSM_DISPATCH_IO(in_dt, out_dt, Tin, Tout, ...)                                   \
+  [&]() -> int {                                                                         \
+    if (out_dt != in_dt && out_dt != RSM_F32) return (int)RSM_ERR_UNSUPPORTED_DTYPE;     \
+    return RSM_DISPATCH_DTYPE(in_dt, Tin, [&]() -> int {                                 \
+      if (out_dt == RSM_F32) { using Tout = float; return __VA_ARGS__(); }               \
+      using Tout = Tin;                                                                  \
+      return __VA_ARGS__();                                                              \
+    });                                                                                  \
+  }()
+
+}  // namespace rsm
+
+using namespace rsm;
+
+#define RSM_COMMON_CHECKS(dtype)                                         \
+  if (!valid_dtype(dtype)) return RSM_ERR_UNSUPPORTED_DTYPE;             \
+  DeviceGuard guard(device);                                             \
+  if (!guard.ok) { set_cuda_error(cudaGetLastError(), __func__); return RSM_ERR_CUDA; } \
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+
+extern "C" int rsm_inner_fwd(rsm_feat left, rsm_feat right, void* out, int64_t N, int64_t C, int64_t H,
+                             int64_t W, int64_t D, int reduce, int in_dtype, int out_dtype, int device,
+                             void* stream) {
+  CorrGeom g;
+  if (int rc = make_geom(N, C, H, W, D, 1, reduce == RSM_REDUCE_MEAN, false, g)) return rc;
+  if (N * H * W * D == 0) return RSM_OK;
+  if (!out || (C > 0 && (!left.data || !right.data))) return RSM_ERR_NULL_POINTER;
+  RSM_COMMON_CHECKS(in_dtype)
+  if (!valid_dtype(out_dtype)) return RSM_ERR_UNSUPPORTED_DTYPE;
+  if (!aligned_to(out, dtype_size(out_dtype) * 4) && W % 4 == 0) return RSM_ERR_MISALIGNED;
+  return RSM_DISPATCH_IO(in_dtype, out_dtype, Tin, Tout, [&]() -> int {
+    return launch_fwd<Tin, Tout, LAYOUT_NDHW>(left, right, out, N, g, st, "rsm_inner_fwd");
+  });
+}
+
+extern "C" int rsm_inner_bwd(const void* gout, rsm_feat left, rsm_feat right, void* gleft, void* gright,
+                             int64_t N, int64_t C, int64_t H, int64_t W, int64_t D, int reduce,
+                             int in_dtype, int out_dtype, int device, void* stream) {
+  CorrGeom g;
+  if (int rc = make_geom(N, C, H, W, D, 1, reduce == RSM_REDUCE_MEAN, false, g)) return rc;
+  if (N * C * H * W == 0) return RSM_OK;
+  if (!left.data || !right.data || (D > 0 && !gout)) return RSM_ERR_NULL_POINTER;
+  if (!gleft && !gright) return RSM_OK;
+  RSM_COMMON_CHECKS(in_dtype)
+  if (!valid_dtype(out_dtype)) return RSM_ERR_UNSUPPORTED_DTYPE;
+  return RSM_DISPATCH_IO(in_dtype, out_dtype, Tin, Tout, [&]() -> int {
+    return launch_bwd<Tin, Tout, LAYOUT_NDHW>(gout, left, right, gleft, gright, N, g, st, "rsm_inner_bwd");
+  });
+}
+
+extern "C" int rsm_groupwise_fwd(rsm_feat left, rsm_feat right, void* out, int64_t N, int64_t C, int64_t H,
+                                 int64_t W, int64_t D, int64_t G, int in_dtype, int out_dtype, int device,
+                                 void* stream) {
+  CorrGeom g;
+  if (int rc = make_geom(N, C, H, W, D, G, 1, false, g)) return rc;
+  if (N * G * H * W * D == 0) return RSM_OK;
+  if (!out || (C > 0 && (!left.data || !right.data))) return RSM_ERR_NULL_POINTER;
+  RSM_COMMON_CHECKS(in_dtype)
+  if (!valid_dtype(out_dtype)) return RSM_ERR_UNSUPPORTED_DTYPE;
+  if (!aligned_to(out, dtype_size(out_dtype) * 4) && D % 4 == 0) return RSM_ERR_MISALIGNED;
+  return RSM_DISPATCH_IO(in_dtype, out_dtype, Tin, Tout, [&]() -> int {
+    return launch_fwd<Tin, Tout, LAYOUT_NGHWD>(left, right, out, N, g, st, "rsm_groupwise_fwd");
+  });
+}
+
+extern "C" int rsm_groupwise_bwd(const void* gout, rsm_feat left, rsm_feat right, void* gleft, void* gright,
+                                 int64_t N, int64_t C, int64_t H, int64_t W, int64_t D, int64_t G,
+                                 int in_dtype, int out_dtype, int device, void* stream) {
+  CorrGeom g;
+  if (int rc = make_geom(N, C, H, W, D, G, 1, false, g)) return rc;
+  if (N * C * H * W == 0) return RSM_OK;
+  if (!left.data || !right.data || (D > 0 && !gout)) return RSM_ERR_NULL_POINTER;
+  if (!gleft && !gright) return RSM_OK;
+  RSM_COMMON_CHECKS(in_dtype)
+  if (!valid_dtype(out_dtype)) return RSM_ERR_UNSUPPORTED_DTYPE;
+  return RSM_DISPATCH_IO(in_dtype, out_dtype, Tin, Tout, [&]() -> int {
+    return launch_bwd<Tin, Tout, LAYOUT_NGHWD>(gout, left, right, gleft, gright, N, g, st, "rsm_groupwise_bwd");
+  });
+}
+
+extern "C" int rsm_inner_regress_fwd(rsm_feat left, rsm_feat right, int64_t N, int64_t C, int64_t H,
+                                     int64_t W, int64_t D, int reduce, int in_dtype, rsm_regress_out out,
+                                     int device, void* stream) {
+  CorrGeom g;
+  if (D <= 0) return RSM_ERR_INVALID_SHAPE;
+  if (int rc = make_geom(N, C, H, W, D, 1, reduce == RSM_REDUCE_MEAN, true, g)) return rc;
+  if (N * H * W == 0) return RSM_OK;
+  if (C > 0 && (!left.data || !right.data)) return RSM_ERR_NULL_POINTER;
+  if (NTX * g.ntd > 1024) return RSM_ERR_UNSUPPORTED_CONFIG;  // D <= 512
+  RSM_COMMON_CHECKS(in_dtype)
+  const int64_t bx = N * g.H * g.xtiles;
+  if (!grid_ok(bx)) return RSM_ERR_INVALID_SHAPE;
+  const size_t smem = (size_t)(CK * TX + CK * (TX + g.dchp) + TX * (g.dchp + 1)) * sizeof(float);
+  return RSM_DISPATCH_DTYPE(in_dtype, Tin, [&]() -> int {
+    auto k = (NTX * g.ntd <= 512) ? inner_regress_fwd_kernel<Tin, 512> : inner_regress_fwd_kernel<Tin, 1024>;
+    if (smem > 48 * 1024) {
+      if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return finish_launch("rsm_inner_regress_fwd(attr)");
+    }
+    k<<<(unsigned)bx, NTX * g.ntd, smem, st>>>(view_of(left), view_of(right), (float*)out.soft, out.argmin,
+                                               out.argmax, out.lse, g);
+    return finish_launch("rsm_inner_regress_fwd");
+  });
+}

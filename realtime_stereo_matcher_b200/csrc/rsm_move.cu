@@ -1,0 +1,326 @@
+// Data-movement volumes: concatenate, interweave, difference (forward + adjoint).
+// All three are HBM-write bound: the kernels stage the tiny inputs on chip and
+// emit coalesced 128-bit stores of the output in the reference's own layout.
+#include "rsm_common.cuh"
+
+namespace rsm {
+
+constexpr int kThreads = 256;
+
+template <typename T> __device__ __forceinline__ T zero_of() { return from_f<T>(0.f); }
+
+// ===================================================================== concatenate forward
+// One CTA per output row (n, ch, y): the W source values go to shared memory once, then the
+// row's W*D outputs (contiguous, D innermost) are written with VEC-wide stores.  The (x, d)
+// decomposition of the running vector index is advanced incrementally (no division in the loop).
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kThreads)
+concat_fwd_kernel(FeatView L, FeatView R, T* __restrict__ out, int C, int H, int W, int D) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* srow = reinterpret_cast<T*>(smem_raw);
+
+  const int64_t row = blockIdx.x;
+  const int y = (int)(row % H);
+  const int ch = (int)((row / H) % (2 * C));
+  const int64_t n = row / ((int64_t)H * 2 * C);
+  const bool right = ch >= C;
+  const int c = right ? ch - C : ch;
+  const FeatView& F = right ? R : L;
+  const T* __restrict__ src = reinterpret_cast<const T*>(F.data) + n * F.sn + c * F.sc + y * F.sh;
+  for (int x = threadIdx.x; x < W; x += kThreads) srow[x] = __ldg(src + (int64_t)x * F.sw);
+  __syncthreads();
+
+  T* __restrict__ orow = out + row * (int64_t)W * D;
+  const int DQ = D / VEC;
+  const int nvec = W * DQ;
+  const int xstep = kThreads / DQ, dstep = kThreads % DQ;
+  int v = threadIdx.x;
+  int x = v / DQ, dq = v - x * DQ;
+  const T zero = zero_of<T>();
+  for (; v < nvec; v += kThreads) {
+    const int d0 = dq * VEC;
+    T vals[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const int d = d0 + j;
+      const int xs = right ? x - d : x;
+      vals[j] = (d <= x) ? srow[xs] : zero;
+    }
+    if constexpr (VEC * sizeof(T) == 16) {
+      Vec16<T> o;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) o.v[j] = vals[j];
+      stcs16(orow + (int64_t)v * VEC, o);
+    } else {
+      static_assert(VEC == 1, "scalar fallback only");
+      __stcs(orow + v, vals[0]);
+    }
+    x += xstep;
+    dq += dstep;
+    if (dq >= DQ) { dq -= DQ; ++x; }
+  }
+}
+
+// ===================================================================== concatenate adjoint
+// gL[c,x] = sum_{d<=min(x,D-1)} gV[c,x,d];  gR[c,x'] = sum_{d<D, x'+d<W} gV[C+c,x'+d,d].
+// One thread per (n,c,y,x): atomic-free, fp32 accumulation in ascending d.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+concat_bwd_kernel(const T* __restrict__ gout, T* __restrict__ gl, T* __restrict__ gr, int64_t total,
+                  int C, int H, int W, int D) {
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= total) return;
+  const int x = (int)(i % W);
+  const int y = (int)((i / W) % H);
+  const int c = (int)((i / ((int64_t)W * H)) % C);
+  const int64_t n = i / ((int64_t)W * H * C);
+  const int64_t rowL = ((n * 2 * C + c) * H + y) * (int64_t)W;        // in units of D
+  const int64_t rowR = ((n * 2 * C + C + c) * H + y) * (int64_t)W;
+  float sl = 0.f, sr = 0.f;
+  const T* pl = gout + (rowL + x) * D;
+  const int dl = min(x, D - 1);
+  for (int d = 0; d <= dl; ++d) sl += to_f(__ldg(pl + d));
+  const int dr = min(D - 1, W - 1 - x);
+  const T* pr = gout + (rowR + x) * D;
+  for (int d = 0; d <= dr; ++d) sr += to_f(__ldg(pr + (int64_t)d * (D + 1)));
+  gl[i] = from_f<T>(sl);
+  gr[i] = from_f<T>(sr);
+}
+
+// ============================================================================= interweave
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kThreads)
+interweave_fwd_kernel(FeatView L, FeatView R, T* __restrict__ out, int64_t total_vec, int C, int H,
+                      int W) {
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= total_vec) return;
+  const int WV = W / VEC;
+  const int xv = (int)(i % WV);
+  const int y = (int)((i / WV) % H);
+  const int ch = (int)((i / ((int64_t)WV * H)) % (2 * C));
+  const int64_t n = i / ((int64_t)WV * H * 2 * C);
+  const FeatView& F = (ch & 1) ? R : L;
+  const T* src = reinterpret_cast<const T*>(F.data) + n * F.sn + (int64_t)(ch >> 1) * F.sc + y * F.sh;
+  if constexpr (VEC > 1) {
+    Vec16<T> v = ldcs16(src + (int64_t)xv * VEC);
+    stcs16(out + i * VEC, v);
+  } else {
+    out[i] = __ldg(src + (int64_t)xv * F.sw);
+  }
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kThreads)
+interweave_bwd_kernel(const T* __restrict__ gout, T* __restrict__ gl, T* __restrict__ gr,
+                      int64_t total_vec, int C, int64_t plane_vec) {
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= total_vec) return;
+  const int64_t p = i % plane_vec;                       // vector inside an (H,W) plane
+  const int ch = (int)((i / plane_vec) % (2 * C));
+  const int64_t n = i / (plane_vec * 2 * C);
+  T* dst = ((ch & 1) ? gr : gl) + ((n * C + (ch >> 1)) * plane_vec + p) * VEC;
+  if constexpr (VEC > 1) {
+    stcs16(dst, ldcs16(gout + i * VEC));
+  } else {
+    *dst = gout[i];
+  }
+}
+
+// ============================================================================= difference
+// out (N,C,D,H,W): one thread per VEC consecutive x.  Inputs are D times smaller than the
+// output and are served by L1/L2; the 128-bit output stores are the HBM stream.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kThreads)
+difference_fwd_kernel(FeatView L, FeatView R, T* __restrict__ out, int64_t total_vec, int C, int H,
+                      int W, int D, float fill) {
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= total_vec) return;
+  const int WV = W / VEC;
+  const int xv = (int)(i % WV);
+  const int y = (int)((i / WV) % H);
+  const int d = (int)((i / ((int64_t)WV * H)) % D);
+  const int c = (int)((i / ((int64_t)WV * H * D)) % C);
+  const int64_t n = i / ((int64_t)WV * H * D * C);
+  const T* pl = reinterpret_cast<const T*>(L.data) + n * L.sn + c * L.sc + y * L.sh;
+  const T* pr = reinterpret_cast<const T*>(R.data) + n * R.sn + c * R.sc + y * R.sh;
+  const T fillv = from_f<T>(fill);
+  T vals[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    const int x = xv * VEC + j;
+    vals[j] = (x >= d) ? from_f<T>(to_f(__ldg(pl + (int64_t)x * L.sw)) - to_f(__ldg(pr + (int64_t)(x - d) * R.sw)))
+                       : fillv;
+  }
+  if constexpr (VEC * sizeof(T) == 16) {
+    Vec16<T> o;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) o.v[j] = vals[j];
+    stcs16(out + i * VEC, o);
+  } else {
+    out[i] = vals[0];
+  }
+}
+
+// gL[c,x] = sum_{d<=x} gV[c,d,x];  gR[c,x'] = -sum_{d, x'+d<W} gV[c,d,x'+d]
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+difference_bwd_kernel(const T* __restrict__ gout, T* __restrict__ gl, T* __restrict__ gr,
+                      int64_t total, int C, int H, int W, int D) {
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= total) return;
+  const int x = (int)(i % W);
+  const int y = (int)((i / W) % H);
+  const int64_t nc = i / ((int64_t)W * H);
+  const int64_t plane = (int64_t)H * W;
+  const T* p = gout + nc * D * plane + (int64_t)y * W + x;
+  float sl = 0.f, sr = 0.f;
+  const int dl = min(x, D - 1);
+  for (int d = 0; d <= dl; ++d) sl += to_f(__ldg(p + d * plane));
+  const int dr = min(D - 1, W - 1 - x);
+  for (int d = 0; d <= dr; ++d) sr -= to_f(__ldg(p + d * plane + d));
+  gl[i] = from_f<T>(sl);
+  gr[i] = from_f<T>(sr);
+}
+
+// ------------------------------------------------------------------------------- helpers
+static bool feat_vec_ok(const rsm_feat& f, int vec, int esize) {
+  return f.stride_w == 1 && f.stride_n % vec == 0 && f.stride_c % vec == 0 && f.stride_h % vec == 0 &&
+         aligned_to(f.data, (size_t)vec * esize);
+}
+static bool grid_ok(int64_t blocks) { return blocks >= 0 && blocks <= 2147483647LL; }
+
+}  // namespace rsm
+
+using namespace rsm;
+
+#define RSM_COMMON_CHECKS(dtype)                                         \
+  if (!valid_dtype(dtype)) return RSM_ERR_UNSUPPORTED_DTYPE;             \
+  DeviceGuard guard(device);                                             \
+  if (!guard.ok) { set_cuda_error(cudaGetLastError(), __func__); return RSM_ERR_CUDA; } \
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+
+extern "C" int rsm_concat_fwd(rsm_feat left, rsm_feat right, void* out, int64_t N, int64_t C,
+                              int64_t H, int64_t W, int64_t D, int dtype, int device, void* stream) {
+  if (N < 0 || C < 0 || H < 0 || W < 0 || D < 0) return RSM_ERR_INVALID_SHAPE;
+  if (N * C * H * W * D == 0) return RSM_OK;
+  if (!left.data || !right.data || !out) return RSM_ERR_NULL_POINTER;
+  RSM_COMMON_CHECKS(dtype)
+  if (W * D > 2147483647LL || !grid_ok(N * 2 * C * H)) return RSM_ERR_INVALID_SHAPE;
+  if (!aligned_to(out, dtype_size(dtype))) return RSM_ERR_MISALIGNED;
+  return RSM_DISPATCH_DTYPE(dtype, T, [&]() -> int {
+    constexpr int VEC = 16 / sizeof(T);
+    const size_t smem = (size_t)W * sizeof(T);
+    if (smem > 200 * 1024) return (int)RSM_ERR_UNSUPPORTED_CONFIG;
+    const dim3 grid((unsigned)(N * 2 * C * H));
+    if (D % VEC == 0 && aligned_to(out, 16)) {
+      auto k = concat_fwd_kernel<T, VEC>;
+      if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      k<<<grid, kThreads, smem, st>>>(view_of(left), view_of(right), (T*)out, (int)C, (int)H, (int)W, (int)D);
+    } else {
+      auto k = concat_fwd_kernel<T, 1>;
+      if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      k<<<grid, kThreads, smem, st>>>(view_of(left), view_of(right), (T*)out, (int)C, (int)H, (int)W, (int)D);
+    }
+    return finish_launch("rsm_concat_fwd");
+  });
+}
+
+extern "C" int rsm_concat_bwd(const void* gout, void* gleft, void* gright, int64_t N, int64_t C,
+                              int64_t H, int64_t W, int64_t D, int dtype, int device, void* stream) {
+  if (N < 0 || C < 0 || H < 0 || W < 0 || D < 0) return RSM_ERR_INVALID_SHAPE;
+  const int64_t total = N * C * H * W;
+  if (total == 0) return RSM_OK;
+  if (!gleft || !gright || (D > 0 && !gout)) return RSM_ERR_NULL_POINTER;
+  RSM_COMMON_CHECKS(dtype)
+  if (!grid_ok(ceil_div(total, kThreads))) return RSM_ERR_INVALID_SHAPE;
+  return RSM_DISPATCH_DTYPE(dtype, T, [&]() -> int {
+    concat_bwd_kernel<T><<<(unsigned)ceil_div(total, kThreads), kThreads, 0, st>>>(
+        (const T*)gout, (T*)gleft, (T*)gright, total, (int)C, (int)H, (int)W, (int)D);
+    return finish_launch("rsm_concat_bwd");
+  });
+}
+
+extern "C" int rsm_interweave_fwd(rsm_feat left, rsm_feat right, void* out, int64_t N, int64_t C,
+                                  int64_t H, int64_t W, int dtype, int device, void* stream) {
+  if (N < 0 || C < 0 || H < 0 || W < 0) return RSM_ERR_INVALID_SHAPE;
+  if (N * C * H * W == 0) return RSM_OK;
+  if (!left.data || !right.data || !out) return RSM_ERR_NULL_POINTER;
+  RSM_COMMON_CHECKS(dtype)
+  return RSM_DISPATCH_DTYPE(dtype, T, [&]() -> int {
+    constexpr int VEC = 16 / sizeof(T);
+    const bool vec = W % VEC == 0 && feat_vec_ok(left, VEC, sizeof(T)) && feat_vec_ok(right, VEC, sizeof(T)) &&
+                     aligned_to(out, 16);
+    const int64_t total = N * 2 * C * H * (vec ? W / VEC : W);
+    if (!grid_ok(ceil_div(total, kThreads))) return (int)RSM_ERR_INVALID_SHAPE;
+    const unsigned blocks = (unsigned)ceil_div(total, kThreads);
+    if (vec)
+      interweave_fwd_kernel<T, VEC><<<blocks, kThreads, 0, st>>>(view_of(left), view_of(right), (T*)out, total,
+                                                                 (int)C, (int)H, (int)W);
+    else
+      interweave_fwd_kernel<T, 1><<<blocks, kThreads, 0, st>>>(view_of(left), view_of(right), (T*)out, total,
+                                                               (int)C, (int)H, (int)W);
+    return finish_launch("rsm_interweave_fwd");
+  });
+}
+
+extern "C" int rsm_interweave_bwd(const void* gout, void* gleft, void* gright, int64_t N, int64_t C,
+                                  int64_t H, int64_t W, int dtype, int device, void* stream) {
+  if (N < 0 || C < 0 || H < 0 || W < 0) return RSM_ERR_INVALID_SHAPE;
+  if (N * C * H * W == 0) return RSM_OK;
+  if (!gout || !gleft || !gright) return RSM_ERR_NULL_POINTER;
+  RSM_COMMON_CHECKS(dtype)
+  return RSM_DISPATCH_DTYPE(dtype, T, [&]() -> int {
+    constexpr int VEC = 16 / sizeof(T);
+    const int64_t plane = H * W;
+    const bool vec = plane % VEC == 0 && aligned_to(gout, 16) && aligned_to(gleft, 16) && aligned_to(gright, 16);
+    const int64_t plane_vec = vec ? plane / VEC : plane;
+    const int64_t total = N * 2 * C * plane_vec;
+    if (!grid_ok(ceil_div(total, kThreads))) return (int)RSM_ERR_INVALID_SHAPE;
+    const unsigned blocks = (unsigned)ceil_div(total, kThreads);
+    if (vec)
+      interweave_bwd_kernel<T, VEC><<<blocks, kThreads, 0, st>>>((const T*)gout, (T*)gleft, (T*)gright, total,
+                                                                 (int)C, plane_vec);
+    else
+      interweave_bwd_kernel<T, 1><<<blocks, kThreads, 0, st>>>((const T*)gout, (T*)gleft, (T*)gright, total,
+                                                               (int)C, plane_vec);
+    return finish_launch("rsm_interweave_bwd");
+  });
+}
+
+extern "C" int rsm_difference_fwd(rsm_feat left, rsm_feat right, void* out, int64_t N, int64_t C,
+                                  int64_t H, int64_t W, int64_t D, float fill, int dtype, int device,
+                                  void* stream) {
+  if (N < 0 || C < 0 || H < 0 || W < 0 || D < 0) return RSM_ERR_INVALID_SHAPE;
+  if (N * C * H * W * D == 0) return RSM_OK;
+  if (!left.data || !right.data || !out) return RSM_ERR_NULL_POINTER;
+  RSM_COMMON_CHECKS(dtype)
+  return RSM_DISPATCH_DTYPE(dtype, T, [&]() -> int {
+    constexpr int VEC = 16 / sizeof(T);
+    const bool vec = W % VEC == 0 && aligned_to(out, 16);
+    const int64_t total = N * C * D * H * (vec ? W / VEC : W);
+    if (!grid_ok(ceil_div(total, kThreads))) return (int)RSM_ERR_INVALID_SHAPE;
+    const unsigned blocks = (unsigned)ceil_div(total, kThreads);
+    if (vec)
+      difference_fwd_kernel<T, VEC><<<blocks, kThreads, 0, st>>>(view_of(left), view_of(right), (T*)out, total,
+                                                                 (int)C, (int)H, (int)W, (int)D, fill);
+    else
+      difference_fwd_kernel<T, 1><<<blocks, kThreads, 0, st>>>(view_of(left), view_of(right), (T*)out, total,
+                                                               (int)C, (int)H, (int)W, (int)D, fill);
+    return finish_launch("rsm_difference_fwd");
+  });
+}
+
+extern "C" int rsm_difference_bwd(const void* gout, void* gleft, void* gright, int64_t N, int64_t C,
+                                  int64_t H, int64_t W, int64_t D, int dtype, int device, void* stream) {
+  if (N < 0 || C < 0 || H < 0 || W < 0 || D < 0) return RSM_ERR_INVALID_SHAPE;
+  const int64_t total = N * C * H * W;
+  if (total == 0) return RSM_OK;
+  if (!gleft || !gright || (D > 0 && !gout)) return RSM_ERR_NULL_POINTER;
+  RSM_COMMON_CHECKS(dtype)
+  if (!grid_ok(ceil_div(total, kThreads))) return RSM_ERR_INVALID_SHAPE;
+  return RSM_DISPATCH_DTYPE(dtype, T, [&]() -> int {
+    difference_bwd_kernel<T><<<(unsigned)ceil_div(total, kThreads), kThreads, 0, st>>>(
+        (const T*)gout, (T*)gleft, (T*)gright, total, (int)C, (int)H, (int)W, (int)D);
+    return finish_launch("rsm_difference_bwd");
+  });
+}

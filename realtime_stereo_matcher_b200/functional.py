@@ -1,0 +1,393 @@
+"""Functional form of the hot path: every op is one C-ABI call into librsm_b200.so, with forward
+and backward wired into autograd so the reference's train_stereo.py keeps working.
+
+Shapes/layouts are the reference's: concat (N,2C,H,W,D), interweave (N,2C,H,W),
+inner/correlation (N,D,H,W), groupwise (N,G,H,W,D), difference (N,C,D,H,W).  Out-of-range
+entries (x < d) hold the fill value and take part in the regression (F8); the regression is
+softmax(+cost) (F9).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch.amp import custom_bwd, custom_fwd
+
+from . import _lib as L
+
+
+def _check_pair(left: torch.Tensor, right: torch.Tensor) -> Tuple[int, int, int, int, int]:
+    if left.dim() != 4 or right.dim() != 4:
+        raise ValueError(f"expected (N,C,H,W) feature maps, got {tuple(left.shape)} and {tuple(right.shape)}")
+    if left.shape != right.shape:
+        raise RuntimeError(f"left {tuple(left.shape)} and right {tuple(right.shape)} feature shapes differ")
+    if left.dtype != right.dtype:
+        raise TypeError(f"left ({left.dtype}) and right ({right.dtype}) dtypes differ")
+    dev = L.require_cuda(left, right)
+    n, c, h, w = left.shape
+    return dev, n, c, h, w
+
+
+def _dense(t: torch.Tensor) -> torch.Tensor:
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# --------------------------------------------------------------------------- concatenate
+class _Concat(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda")
+    def forward(ctx, left, right, max_disparity):
+        dev, n, c, h, w = _check_pair(left, right)
+        d = int(max_disparity)
+        out = torch.empty((n, 2 * c, h, w, d), dtype=left.dtype, device=left.device)
+        L.check(L.load().rsm_concat_fwd(L.feat(left), L.feat(right), out.data_ptr(), n, c, h, w, d,
+                                        L.dtype_code(left), dev, L.stream_ptr(dev)), "rsm_concat_fwd")
+        ctx.dims = (dev, n, c, h, w, d)
+        return out
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, gout):
+        dev, n, c, h, w, d = ctx.dims
+        gout = _dense(gout)
+        gl = torch.empty((n, c, h, w), dtype=gout.dtype, device=gout.device)
+        gr = torch.empty_like(gl)
+        L.check(L.load().rsm_concat_bwd(gout.data_ptr(), gl.data_ptr(), gr.data_ptr(), n, c, h, w, d,
+                                        L.dtype_code(gout), dev, L.stream_ptr(dev)), "rsm_concat_bwd")
+        return gl, gr, None
+
+
+def concat_volume(left, right, max_disparity):
+    """TorchConcatenateCost.forward (reference cost_volume/concatenate.py:11-41)."""
+    return _Concat.apply(left, right, max_disparity)
+
+
+# ---------------------------------------------------------------------------- interweave
+class _Interweave(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda")
+    def forward(ctx, left, right):
+        dev, n, c, h, w = _check_pair(left, right)
+        out = torch.empty((n, 2 * c, h, w), dtype=left.dtype, device=left.device)
+        L.check(L.load().rsm_interweave_fwd(L.feat(left), L.feat(right), out.data_ptr(), n, c, h, w,
+                                            L.dtype_code(left), dev, L.stream_ptr(dev)), "rsm_interweave_fwd")
+        ctx.dims = (dev, n, c, h, w)
+        return out
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, gout):
+        dev, n, c, h, w = ctx.dims
+        gout = _dense(gout)
+        gl = torch.empty((n, c, h, w), dtype=gout.dtype, device=gout.device)
+        gr = torch.empty_like(gl)
+        L.check(L.load().rsm_interweave_bwd(gout.data_ptr(), gl.data_ptr(), gr.data_ptr(), n, c, h, w,
+                                            L.dtype_code(gout), dev, L.stream_ptr(dev)), "rsm_interweave_bwd")
+        return gl, gr
+
+
+def interweave(left, right):
+    """TorchInterweaveCost.forward / interweave_tensors (interweave.py:10-22, mobile_stereo_net_v4.py:17-23)."""
+    return _Interweave.apply(left, right)
+
+
+# ------------------------------------------------------------- inner product / correlation
+def _out_dtype(left: torch.Tensor, out_dtype: Optional[torch.dtype]) -> torch.dtype:
+    out_dtype = out_dtype or left.dtype
+    if out_dtype not in (left.dtype, torch.float32):
+        raise TypeError(f"out_dtype must be the input dtype or float32, got {out_dtype}")
+    return out_dtype
+
+
+class _Inner(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda")
+    def forward(ctx, left, right, max_disparity, mean, out_dtype):
+        dev, n, c, h, w = _check_pair(left, right)
+        d = int(max_disparity)
+        odt = _out_dtype(left, out_dtype)
+        out = torch.empty((n, d, h, w), dtype=odt, device=left.device)
+        red = L.RSM_REDUCE_MEAN if mean else L.RSM_REDUCE_SUM
+        L.check(L.load().rsm_inner_fwd(L.feat(left), L.feat(right), out.data_ptr(), n, c, h, w, d, red,
+                                       L.dtype_code(left), L.dtype_code(out), dev, L.stream_ptr(dev)),
+                "rsm_inner_fwd")
+        ctx.save_for_backward(left, right)
+        ctx.dims = (dev, n, c, h, w, d, red, odt)
+        return out
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, gout):
+        left, right = ctx.saved_tensors
+        dev, n, c, h, w, d, red, odt = ctx.dims
+        gout = _dense(gout.to(odt))
+        gl = torch.empty((n, c, h, w), dtype=left.dtype, device=left.device) if ctx.needs_input_grad[0] else None
+        gr = torch.empty((n, c, h, w), dtype=left.dtype, device=left.device) if ctx.needs_input_grad[1] else None
+        L.check(L.load().rsm_inner_bwd(gout.data_ptr(), L.feat(left), L.feat(right), L.ptr(gl), L.ptr(gr),
+                                       n, c, h, w, d, red, L.dtype_code(left), L.dtype_code(gout), dev,
+                                       L.stream_ptr(dev)), "rsm_inner_bwd")
+        return gl, gr, None, None, None
+
+
+def inner_product_volume(left, right, max_disparity, mean=False, out_dtype=None):
+    """TorchInnerProductCost.forward (inner_product.py:11-42; channel sum) or, with ``mean=True``,
+    make_correlation_volume (mobile_disp_net_c.py:188-205; channel mean).  fp32 accumulation."""
+    return _Inner.apply(left, right, max_disparity, bool(mean), out_dtype)
+
+
+# ----------------------------------------------------------------------------- groupwise
+class _Groupwise(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda")
+    def forward(ctx, left, right, n_groups, max_disparity, out_dtype):
+        dev, n, c, h, w = _check_pair(left, right)
+        g, d = int(n_groups), int(max_disparity)
+        # same check and message as the reference (cost_volume/groupwise.py:15-17)
+        assert c % g == 0, f"groupwise cost channel ({c}) % #groups ({g}) != 0."
+        odt = _out_dtype(left, out_dtype)
+        out = torch.empty((n, g, h, w, d), dtype=odt, device=left.device)
+        L.check(L.load().rsm_groupwise_fwd(L.feat(left), L.feat(right), out.data_ptr(), n, c, h, w, d, g,
+                                           L.dtype_code(left), L.dtype_code(out), dev, L.stream_ptr(dev)),
+                "rsm_groupwise_fwd")
+        ctx.save_for_backward(left, right)
+        ctx.dims = (dev, n, c, h, w, d, g, odt)
+        return out
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, gout):
+        left, right = ctx.saved_tensors
+        dev, n, c, h, w, d, g, odt = ctx.dims
+        gout = _dense(gout.to(odt))
+        gl = torch.empty((n, c, h, w), dtype=left.dtype, device=left.device) if ctx.needs_input_grad[0] else None
+        gr = torch.empty((n, c, h, w), dtype=left.dtype, device=left.device) if ctx.needs_input_grad[1] else None
+        L.check(L.load().rsm_groupwise_bwd(gout.data_ptr(), L.feat(left), L.feat(right), L.ptr(gl), L.ptr(gr),
+                                           n, c, h, w, d, g, L.dtype_code(left), L.dtype_code(gout), dev,
+                                           L.stream_ptr(dev)), "rsm_groupwise_bwd")
+        return gl, gr, None, None, None
+
+
+def groupwise_volume(left, right, n_groups, max_disparity, out_dtype=None):
+    """TorchGroupwiseCost.forward (groupwise.py:24-56).  The volume is returned on ``left.device``
+    in ``left.dtype`` (pass ``out_dtype=torch.float32`` for the reference's always-fp32 output;
+    the reference's CPU placement is its bug)."""
+    return _Groupwise.apply(left, right, n_groups, max_disparity, out_dtype)
+
+
+def groupwise_pointwise(left, right, n_groups):
+    """TorchGroupwiseCost.groupwise (groupwise.py:12-22): (N,G,H,W) = the d=0 slice."""
+    return groupwise_volume(left, right, n_groups, 1)[..., 0]
+
+
+# ---------------------------------------------------------------------------- difference
+class _Difference(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda")
+    def forward(ctx, left, right, max_disp, fill):
+        dev, n, c, h, w = _check_pair(left, right)
+        d = int(max_disp)
+        out = torch.empty((n, c, d, h, w), dtype=left.dtype, device=left.device)
+        L.check(L.load().rsm_difference_fwd(L.feat(left), L.feat(right), out.data_ptr(), n, c, h, w, d,
+                                            float(fill), L.dtype_code(left), dev, L.stream_ptr(dev)),
+                "rsm_difference_fwd")
+        ctx.dims = (dev, n, c, h, w, d)
+        return out
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, gout):
+        dev, n, c, h, w, d = ctx.dims
+        gout = _dense(gout)
+        gl = torch.empty((n, c, h, w), dtype=gout.dtype, device=gout.device)
+        gr = torch.empty_like(gl)
+        L.check(L.load().rsm_difference_bwd(gout.data_ptr(), gl.data_ptr(), gr.data_ptr(), n, c, h, w, d,
+                                            L.dtype_code(gout), dev, L.stream_ptr(dev)), "rsm_difference_bwd")
+        return gl, gr, None, None
+
+
+def difference_volume(left, right, max_disp, fill=1.0):
+    """make_cost_volume of MobileStereoNet v1-v3 (mobile_stereo_net.py:8-27): L - R shifted, fill 1.0."""
+    return _Difference.apply(left, right, max_disp, fill)
+
+
+# ---------------------------------------------------------------------------- regression
+def _regress_outputs(shape, dtype, device, soft, argmin, argmax, lse):
+    n, h, w = shape
+    so = torch.empty((n, h, w), dtype=dtype, device=device) if soft else None
+    mi = torch.empty((n, h, w), dtype=torch.int64, device=device) if argmin else None
+    ma = torch.empty((n, h, w), dtype=torch.int64, device=device) if argmax else None
+    ls = torch.empty((n, h, w), dtype=torch.float32, device=device) if lse else None
+    return so, mi, ma, ls, L.RsmRegressOut(L.ptr(so), L.ptr(mi), L.ptr(ma), L.ptr(ls))
+
+
+def _check_cost(cost):
+    if cost.dim() != 4:
+        raise ValueError(f"expected a (N,D,H,W) cost volume, got {tuple(cost.shape)}")
+    if cost.shape[1] == 0:
+        raise ValueError("cost volume has an empty disparity axis")
+    return L.require_cuda(cost)
+
+
+class _Regress(torch.autograd.Function):
+    """soft-argmax + hard argmin + hard argmax in ONE pass over the volume."""
+
+    @staticmethod
+    @custom_fwd(device_type="cuda")
+    def forward(ctx, cost, want_argmin, want_argmax):
+        dev = _check_cost(cost)
+        cost = _dense(cost)
+        n, d, h, w = cost.shape
+        need_grad = ctx.needs_input_grad[0]
+        so, mi, ma, ls, out = _regress_outputs((n, h, w), cost.dtype, cost.device, True, want_argmin,
+                                               want_argmax, need_grad)
+        L.check(L.load().rsm_regress_fwd(cost.data_ptr(), n, d, h, w, L.dtype_code(cost), out, dev,
+                                         L.stream_ptr(dev)), "rsm_regress_fwd")
+        if need_grad:
+            ctx.save_for_backward(cost, so, ls)
+        ctx.dims = (dev, n, d, h, w)
+        empty = torch.empty(0, dtype=torch.int64, device=cost.device)
+        mi = mi if mi is not None else empty
+        ma = ma if ma is not None else empty
+        ctx.mark_non_differentiable(mi, ma)
+        return so, mi, ma
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, gsoft, _gmi, _gma):
+        cost, so, ls = ctx.saved_tensors
+        dev, n, d, h, w = ctx.dims
+        gsoft = _dense(gsoft.to(cost.dtype))
+        gcost = torch.empty_like(cost)
+        L.check(L.load().rsm_regress_bwd(gsoft.data_ptr(), cost.data_ptr(), so.data_ptr(), ls.data_ptr(),
+                                         gcost.data_ptr(), n, d, h, w, L.dtype_code(cost), dev,
+                                         L.stream_ptr(dev)), "rsm_regress_bwd")
+        return gcost, None, None
+
+
+def regress(cost, argmin=True, argmax=True):
+    """One pass over a (N,D,H,W) cost -> (soft (N,H,W), argmin (N,H,W) int64, argmax (N,H,W) int64).
+
+    soft = sum_d d * softmax_d(+cost) (reference mobile_stereo_net.py:144-147); argmin/argmax follow
+    torch.argmin/argmax(cost, 1): first index on ties, NaN is the extremum."""
+    so, mi, ma = _Regress.apply(cost, bool(argmin), bool(argmax))
+    return so, (mi if argmin else None), (ma if argmax else None)
+
+
+def soft_argmax(cost, keepdim=False):
+    """sum_d d * softmax_d(+cost): (N,D,H,W) -> (N,H,W), or (N,1,H,W) with ``keepdim``."""
+    so, _, _ = _Regress.apply(cost, False, False)
+    return so.unsqueeze(1) if keepdim else so
+
+
+def hard_argmin(cost):
+    """torch.argmin(cost, dim=1) for a (N,D,H,W) cost, int64."""
+    dev = _check_cost(cost)
+    cost = _dense(cost.detach())
+    n, d, h, w = cost.shape
+    _, mi, _, _, out = _regress_outputs((n, h, w), cost.dtype, cost.device, False, True, False, False)
+    L.check(L.load().rsm_regress_fwd(cost.data_ptr(), n, d, h, w, L.dtype_code(cost), out, dev,
+                                     L.stream_ptr(dev)), "rsm_regress_fwd")
+    return mi
+
+
+def hard_argmax(cost):
+    """torch.argmax(cost, dim=1) for a (N,D,H,W) cost, int64."""
+    dev = _check_cost(cost)
+    cost = _dense(cost.detach())
+    n, d, h, w = cost.shape
+    _, _, ma, _, out = _regress_outputs((n, h, w), cost.dtype, cost.device, False, False, True, False)
+    L.check(L.load().rsm_regress_fwd(cost.data_ptr(), n, d, h, w, L.dtype_code(cost), out, dev,
+                                     L.stream_ptr(dev)), "rsm_regress_fwd")
+    return ma
+
+
+class _Expect(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda")
+    def forward(ctx, prob):
+        dev = _check_cost(prob)
+        prob = _dense(prob)
+        n, d, h, w = prob.shape
+        out = torch.empty((n, h, w), dtype=prob.dtype, device=prob.device)
+        L.check(L.load().rsm_expect_fwd(prob.data_ptr(), out.data_ptr(), n, d, h, w, L.dtype_code(prob), dev,
+                                        L.stream_ptr(dev)), "rsm_expect_fwd")
+        ctx.dims = (dev, n, d, h, w)
+        return out
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, gout):
+        dev, n, d, h, w = ctx.dims
+        gout = _dense(gout)
+        gp = torch.empty((n, d, h, w), dtype=gout.dtype, device=gout.device)
+        L.check(L.load().rsm_expect_bwd(gout.data_ptr(), gp.data_ptr(), n, d, h, w, L.dtype_code(gout), dev,
+                                        L.stream_ptr(dev)), "rsm_expect_bwd")
+        return gp
+
+
+def expectation(prob):
+    """sum_d d * prob[:, d] for already-normalised probabilities (mobile_stereo_net_v4.py:10-14)."""
+    return _Expect.apply(prob)
+
+
+# -------------------------------------------------------------------------- v4 head
+class _UpsampleRegress(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda")
+    def forward(ctx, cost, maxdisp, out_h, out_w, want_argmin, want_argmax):
+        dev = _check_cost(cost)
+        cost = _dense(cost)
+        b, dc, hc, wc = cost.shape
+        d, h, w = int(maxdisp), int(out_h), int(out_w)
+        need_grad = ctx.needs_input_grad[0]
+        so, mi, ma, ls, out = _regress_outputs((b, h, w), cost.dtype, cost.device, True, want_argmin,
+                                               want_argmax, need_grad)
+        L.check(L.load().rsm_upsample_regress_fwd(cost.data_ptr(), b, dc, hc, wc, d, h, w, L.dtype_code(cost),
+                                                  out, dev, L.stream_ptr(dev)), "rsm_upsample_regress_fwd")
+        if need_grad:
+            ctx.save_for_backward(cost, so, ls)
+        ctx.dims = (dev, b, dc, hc, wc, d, h, w)
+        empty = torch.empty(0, dtype=torch.int64, device=cost.device)
+        mi = mi if mi is not None else empty
+        ma = ma if ma is not None else empty
+        ctx.mark_non_differentiable(mi, ma)
+        return so, mi, ma
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, gsoft, _gmi, _gma):
+        cost, so, ls = ctx.saved_tensors
+        dev, b, dc, hc, wc, d, h, w = ctx.dims
+        gsoft = _dense(gsoft.to(cost.dtype))
+        gcost = torch.empty_like(cost)
+        nbytes = L.load().rsm_upsample_regress_bwd_workspace(b, dc, h, w)
+        work = torch.empty(nbytes // 4, dtype=torch.float32, device=cost.device)
+        L.check(L.load().rsm_upsample_regress_bwd(gsoft.data_ptr(), cost.data_ptr(), so.data_ptr(),
+                                                  ls.data_ptr(), gcost.data_ptr(), work.data_ptr(), b, dc, hc,
+                                                  wc, d, h, w, L.dtype_code(cost), dev, L.stream_ptr(dev)),
+                "rsm_upsample_regress_bwd")
+        return gcost, None, None, None, None, None
+
+
+def upsample_regress(cost, maxdisp, out_h, out_w, argmin=False, argmax=False):
+    """MobileStereoNetV4 head (mobile_stereo_net_v4.py:511-518), fused: trilinear upsample of the coarse
+    (B,Dc,Hc,Wc) cost to (maxdisp,out_h,out_w) -> softmax over D -> expectation, (B,H,W).
+    Optionally also the hard argmin/argmax over the upsampled volume."""
+    so, mi, ma = _UpsampleRegress.apply(cost, maxdisp, out_h, out_w, bool(argmin), bool(argmax))
+    if not argmin and not argmax:
+        return so
+    return so, (mi if argmin else None), (ma if argmax else None)
+
+
+# --------------------------------------------------------------- fused build + regress
+def inner_product_regress(left, right, max_disparity, mean=False, argmin=True, argmax=True):
+    """Inner-product / correlation volume reduced on chip to (soft fp32, argmin, argmax); the
+    (N,D,H,W) volume is never written to HBM.  Inference only (no autograd)."""
+    dev, n, c, h, w = _check_pair(left, right)
+    d = int(max_disparity)
+    so, mi, ma, _, out = _regress_outputs((n, h, w), torch.float32, left.device, True, argmin, argmax, False)
+    red = L.RSM_REDUCE_MEAN if mean else L.RSM_REDUCE_SUM
+    L.check(L.load().rsm_inner_regress_fwd(L.feat(left.detach()), L.feat(right.detach()), n, c, h, w, d, red,
+                                           L.dtype_code(left), out, dev, L.stream_ptr(dev)),
+            "rsm_inner_regress_fwd")
+    return so, mi, ma

@@ -1,0 +1,54 @@
+"""Model-local hot-path functions of the reference under their own names and signatures
+(SURVEY.md 8b).  The reference models look these up as module globals at call time, so
+``patch.patch_reference()`` can swap them in without touching weights or state_dict keys.
+"""
+from __future__ import annotations
+
+from . import functional as F_rsm
+
+
+def make_cost_volume(left, right, max_disp):
+    """model/mobile_stereo_net.py:8-27 (= mobile_stereo_net_v2.py:8-27, mobile_stereo_net_v3.py:9-28):
+    (N,C,H,W) x2 -> (N,C,max_disp,H,W) difference volume, out-of-range region filled with 1.0."""
+    return F_rsm.difference_volume(left, right, max_disp, fill=1.0)
+
+
+def make_correlation_volume(l_fmap, r_fmap, max_disp):
+    """model/mobile_disp_net_c.py:188-205: (N,C,H,W) x2 -> (N,max_disp,H,W) channel-MEAN correlation."""
+    return F_rsm.inner_product_volume(l_fmap, r_fmap, max_disp, mean=True)
+
+
+def interweave_tensors(refimg_fea, targetimg_fea):
+    """model/mobile_stereo_net_v4.py:17-23: (B,C,H,W) x2 -> (B,2C,H,W), even = ref, odd = target.
+    Accepts the width-cropped, non-contiguous slices the v4 forward passes (:446)."""
+    return F_rsm.interweave(refimg_fea, targetimg_fea)
+
+
+def disparity_regression_v4(x, maxdisp):
+    """model/mobile_stereo_net_v4.py:10-14: x holds PROBABILITIES (already softmax-ed);
+    returns sum_d d * x[:, d] as (N,H,W)."""
+    assert len(x.shape) == 4
+    assert x.shape[1] == maxdisp, f"disparity axis ({x.shape[1]}) != maxdisp ({maxdisp})"
+    return F_rsm.expectation(x)
+
+
+def disparity_regression_dispnetc(corr_volume, max_disp):
+    """model/mobile_disp_net_c.py:208-220: corr_volume holds LOGITS; softmax over dim 1 then
+    expectation, returned as (N,1,H,W)."""
+    assert len(corr_volume.shape) == 4, "#dimensions of correlation volume != 4."
+    assert corr_volume.shape[1] == max_disp, f"#channels of correlation volume != max_disparity ({max_disp})."
+    return F_rsm.soft_argmax(corr_volume, keepdim=True)
+
+
+def softmax_regression(cost_volume, keepdim=True):
+    """The inline regression of MobileStereoNet v1-v3 (mobile_stereo_net.py:144-147,
+    mobile_stereo_net_v2.py:217-220, mobile_stereo_net_v3.py:321-324): softmax(dim=1) ->
+    sum(x * arange(D)), one fused pass."""
+    return F_rsm.soft_argmax(cost_volume, keepdim=keepdim)
+
+
+def v4_head(cost, maxdisp, out_h, out_w):
+    """The MobileStereoNetV4 head (mobile_stereo_net_v4.py:511-518; training heads :471-506):
+    F.interpolate(cost[:,None], [maxdisp,H,W], 'trilinear') -> softmax -> disparity_regression,
+    without materialising the (B,maxdisp,H,W) tensor.  Returns (B,H,W)."""
+    return F_rsm.upsample_regress(cost, maxdisp, out_h, out_w)

@@ -1,0 +1,150 @@
+"""Swap the reference's hot path for the B200 kernels, in place, without touching weights.
+
+    import realtime_stereo_matcher_b200 as rsm
+    rsm.patch_reference()            # reference checkout must be importable (sys.path)
+    net = model.build_model(cfg["model"]).cuda()     # the reference's own factory
+    net(left, right)                 # cost volumes + regression now run in librsm_b200.so
+
+Two levels:
+  1. module-global functions the reference models resolve at call time
+     (make_cost_volume, make_correlation_volume, interweave_tensors, disparity_regression) and the
+     four ``cost_volume.*`` classes are replaced by the mirrors in this package;
+  2. with ``fuse=True`` the model ``forward`` methods are replaced by the glue below, which calls
+     the SAME sub-modules in the same order (state_dict keys and numerics of every conv stack are
+     untouched) but routes the inline ``F.softmax -> arange -> sum`` regression of v1-v3 and the
+     ``F.interpolate(trilinear) -> softmax -> disparity_regression`` head of v4 through the fused
+     single-pass kernels.
+"""
+from __future__ import annotations
+
+import importlib
+from typing import Dict, List, Tuple
+
+import torch.nn.functional as F
+
+from . import cost_volume as cv_mirror
+from . import model_functions as mf
+
+_SAVED: List[Tuple[object, str, object]] = []
+
+
+def _set(obj, name, value):
+    _SAVED.append((obj, name, getattr(obj, name)))
+    setattr(obj, name, value)
+
+
+# ------------------------------------------------------------------ fused forward glue
+def _normalise_and_pad(self, l_img, r_img):
+    # mobile_stereo_net.py:121-130 (same in v2 :194-203, v3 :296-305)
+    l_img = (2.0 * (l_img / 255.0) - 1.0).contiguous()
+    r_img = (2.0 * (r_img / 255.0) - 1.0).contiguous()
+    h, w = l_img.shape[2:]
+    pad = (0, (self.align - w % self.align) % self.align, 0, (self.align - h % self.align) % self.align)
+    return F.pad(l_img, pad), F.pad(r_img, pad), h, w
+
+
+def _refine_outputs(x, steps, l_img, h, w):
+    # mobile_stereo_net.py:149-159: refine, rescale to full resolution, crop, negate
+    outs = []
+    for step in steps:
+        x = step(x)
+        outs.append(F.interpolate(x * (l_img.size(3) / x.size(3)), l_img.shape[2:])[:, :, :h, :w])
+    return [-1.0 * o for o in outs]
+
+
+def forward_v1(self, left_img, right_img):
+    """MobileStereoNet.forward (mobile_stereo_net.py:120-159) with the fused hot path."""
+    l_img, r_img, h, w = _normalise_and_pad(self, left_img, right_img)
+    lf, rf = self.feature_extractor(l_img), self.feature_extractor(r_img)
+    cost = self.cost_filter(mf.make_cost_volume(lf, rf, self.max_disp)).squeeze(1)
+    x = mf.softmax_regression(cost, keepdim=True)
+    return _refine_outputs(x, [lambda t, r=r: r(t, l_img) for r in self.refine_layer], l_img, h, w)
+
+
+def forward_v2(self, left_img, right_img):
+    """MobileStereoNetV2.forward (mobile_stereo_net_v2.py:193-232) with the fused hot path."""
+    l_img, r_img, h, w = _normalise_and_pad(self, left_img, right_img)
+    lf, rf = self.feature_extractor(l_img), self.feature_extractor(r_img)
+    cost = self.cost_filter(mf.make_cost_volume(lf, rf, self.max_disp)).squeeze(1)
+    x = mf.softmax_regression(cost, keepdim=True)
+    return _refine_outputs(x, [lambda t, r=r: r(t, l_img, r_img) for r in self.refine_layer], l_img, h, w)
+
+
+def forward_v3(self, l_img, r_img):
+    """MobileStereoNetV3.forward (mobile_stereo_net_v3.py:295-336) with the fused hot path."""
+    l_img, r_img, h, w = _normalise_and_pad(self, l_img, r_img)
+    lfs, rfs = self.feature_extractor(l_img), self.feature_extractor(r_img)
+    cost = self.cost_filter(mf.make_cost_volume(lfs[0], rfs[0], self.max_disp)).squeeze(1)
+    x = mf.softmax_regression(cost, keepdim=True)
+    steps = [lambda t, r=r, i=i: r(t, lfs[i + 1], rfs[i + 1]) for i, r in enumerate(self.refine_layers)]
+    return _refine_outputs(x, steps, l_img, h, w)
+
+
+def forward_v4(self, L, R):
+    """MobileStereoNetV4.forward (mobile_stereo_net_v4.py:432-524) with interweave and the
+    trilinear -> softmax -> expectation head on the fused kernels."""
+    L = (2.0 * (L / 255.0) - 1.0).contiguous()
+    R = (2.0 * (R / 255.0) - 1.0).contiguous()
+    featL = self.preconv11(self.feature_extraction(L))
+    featR = self.preconv11(self.feature_extraction(R))
+    B, C, H, W = featL.shape
+    volume = featL.new_zeros([B, self.num_groups, self.volume_size, H, W])
+    for i in range(self.volume_size):   # per-disparity learned volume (:444-458); SURVEY.md 8f-1 is next
+        x = mf.interweave_tensors(featL[:, :, :, i:], featR[:, :, :, : W - i])
+        x = self.volume11(self.conv3d(x.unsqueeze(1)).squeeze(2))
+        volume[:, :, i, :, i:] = x
+    volume = volume.squeeze(1)
+    cost0 = self.dres0(volume)
+    cost0 = self.dres1(cost0) + cost0
+    out1 = self.encoder_decoder1(cost0)
+    out2 = self.encoder_decoder2(out1)
+    out3 = self.encoder_decoder3(out2)
+    h, w = L.shape[2:]
+    if self.training:
+        costs = [self.classif0(cost0), self.classif1(out1), self.classif2(out2), self.classif3(out3)]
+    else:
+        costs = [self.classif3(out3)]
+    return [-1.0 * mf.v4_head(c, self.maxdisp, h, w).unsqueeze(1) for c in costs]
+
+
+# ---------------------------------------------------------------------------- patching
+def patch_reference(fuse: bool = True, model_package: str = "model", cost_volume_package: str = "cost_volume") -> Dict[str, List[str]]:
+    """Patch an importable reference checkout in place.  Returns what was patched.
+
+    Raises ImportError when the reference packages cannot be imported (nothing is patched)."""
+    done: Dict[str, List[str]] = {"functions": [], "classes": [], "forwards": []}
+    m1 = importlib.import_module(f"{model_package}.mobile_stereo_net")
+    m2 = importlib.import_module(f"{model_package}.mobile_stereo_net_v2")
+    m3 = importlib.import_module(f"{model_package}.mobile_stereo_net_v3")
+    m4 = importlib.import_module(f"{model_package}.mobile_stereo_net_v4")
+    mc = importlib.import_module(f"{model_package}.mobile_disp_net_c")
+    for m in (m1, m2, m3):
+        _set(m, "make_cost_volume", mf.make_cost_volume)
+        done["functions"].append(f"{m.__name__}.make_cost_volume")
+    _set(mc, "make_correlation_volume", mf.make_correlation_volume)
+    _set(mc, "disparity_regression", mf.disparity_regression_dispnetc)
+    _set(m4, "interweave_tensors", mf.interweave_tensors)
+    _set(m4, "disparity_regression", mf.disparity_regression_v4)
+    done["functions"] += [f"{mc.__name__}.make_correlation_volume", f"{mc.__name__}.disparity_regression",
+                          f"{m4.__name__}.interweave_tensors", f"{m4.__name__}.disparity_regression"]
+    try:
+        for sub, cls in (("concatenate", "TorchConcatenateCost"), ("interweave", "TorchInterweaveCost"),
+                         ("inner_product", "TorchInnerProductCost"), ("groupwise", "TorchGroupwiseCost")):
+            mod = importlib.import_module(f"{cost_volume_package}.{sub}")
+            _set(mod, cls, getattr(cv_mirror, cls))
+            done["classes"].append(f"{mod.__name__}.{cls}")
+    except ImportError:
+        pass  # cost_volume/ is imported by nothing in the reference: optional
+    if fuse:
+        for mod, cls, fwd in ((m1, "MobileStereoNet", forward_v1), (m2, "MobileStereoNetV2", forward_v2),
+                              (m3, "MobileStereoNetV3", forward_v3), (m4, "MobileStereoNetV4", forward_v4)):
+            _set(getattr(mod, cls), "forward", fwd)
+            done["forwards"].append(f"{mod.__name__}.{cls}.forward")
+    return done
+
+
+def unpatch_reference() -> None:
+    """Undo every patch_reference() call (restores the reference's own functions)."""
+    while _SAVED:
+        obj, name, value = _SAVED.pop()
+        setattr(obj, name, value)

@@ -1,0 +1,401 @@
+"""GPU parity suite (-m gpu): the CUDA path, called through the C ABI of librsm_b200.so, against
+(1) the committed golden vectors produced by executing the reference, (2) the numpy oracle on
+seeded inputs, (3) size-independent properties at BASELINE.json's full sizes.
+
+Bars (tests/tolerances.py): bit-exact for concatenate / interweave / difference, for hard
+argmin/argmax on a given volume and for every reduction on dyadic inputs; stated fp32 / 16-bit
+tolerances elsewhere.
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from golden_io import load, names, round_to
+from tolerances import (GRAD_RTOL, RTOL_16, V4_TAIL_ATOL, corr_atol_fp32, soft_argmax_atol)
+
+pytestmark = pytest.mark.gpu
+
+DT = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}
+
+
+@pytest.fixture(scope="module")
+def rsm():
+    import realtime_stereo_matcher_b200 as m
+    m.load_library()  # fail loudly if the extension is missing
+    return m
+
+
+def dev(a, dname="fp32", grad=False):
+    t = torch.from_numpy(np.ascontiguousarray(a)).to("cuda").to(DT[dname])
+    return t.requires_grad_(grad)
+
+
+def host(t):
+    return t.detach().float().cpu().numpy()
+
+
+def close(a, b, atol, rtol=0.0):
+    np.testing.assert_allclose(host(a) if torch.is_tensor(a) else a, b, atol=atol, rtol=rtol)
+
+
+def equal(a, b):
+    if torch.is_tensor(a):
+        a = a.cpu().numpy() if a.dtype == torch.int64 else host(a)
+    np.testing.assert_array_equal(a, b)
+
+
+# ------------------------------------------------------------------ golden vectors: volumes
+@pytest.mark.parametrize("name", names("vol_"))
+def test_volume_goldens(rsm, name):
+    g, m = load(name)
+    dn, d, ng, c = m["dtype"], m["D"], m["G"], m["C"]
+    exact = m["kind"] == "dyadic"
+    lmax, rmax = np.abs(g["left"]).max(), np.abs(g["right"]).max()
+
+    def fresh():
+        return dev(g["left"], dn, True), dev(g["right"], dn, True)
+
+    # --- pure data movement: bit exact, forward and backward
+    for op, fn in (("concat", lambda a, b: rsm.TorchConcatenateCost(d)(a, b)),
+                   ("interweave", lambda a, b: rsm.TorchInterweaveCost()(a, b)),
+                   ("interweave_v4", rsm.interweave_tensors),
+                   ("difference", lambda a, b: rsm.make_cost_volume(a, b, d))):
+        l, r = fresh()
+        out = fn(l, r)
+        assert out.dtype == DT[dn] and out.is_contiguous()
+        equal(out, g[f"{op}.out"])
+        out.backward(dev(g[f"{op}.gout"], dn))
+        if dn == "fp32":
+            tol = 0.0 if op.startswith("interweave") else GRAD_RTOL * np.sqrt(d)
+            close(l.grad, g[f"{op}.gleft"], tol)
+            close(r.grad, g[f"{op}.gright"], tol)
+    # --- reductions
+    if dn == "fp32":
+        atol, rtol = (0.0 if exact else corr_atol_fp32(c, lmax, rmax)), 0.0
+    else:
+        atol, rtol = RTOL_16[dn] * np.sqrt(c) * lmax * rmax, RTOL_16[dn] * 2
+    gs = GRAD_RTOL * np.sqrt(d) * max(lmax, rmax) * 4
+    for op, fn in (("inner", lambda a, b: rsm.TorchInnerProductCost(d)(a, b)),
+                   ("corr_mean", lambda a, b: rsm.make_correlation_volume(a, b, d)),
+                   ("groupwise", lambda a, b: rsm.TorchGroupwiseCost(ng, d, out_dtype=torch.float32)(a, b))):
+        l, r = fresh()
+        out = fn(l, r)
+        close(out, g[f"{op}.out"], atol, rtol)
+        if dn == "fp32":
+            out.backward(dev(g[f"{op}.gout"]))
+            close(l.grad, g[f"{op}.gleft"], gs)
+            close(r.grad, g[f"{op}.gright"], gs)
+
+
+def test_noncontiguous_slices(rsm):
+    """v4 passes width-cropped non-contiguous views (mobile_stereo_net_v4.py:446)."""
+    g, m = load("noncontig_interweave")
+    i = m["i"]
+    fl, fr = dev(g["featL"]), dev(g["featR"])
+    a, b = fl[:, :, :, i:], fr[:, :, :, :-i]
+    assert not a.is_contiguous()
+    equal(rsm.interweave_tensors(a, b), g["out"])
+    equal(rsm.TorchConcatenateCost(5)(a, b), g["concat"])
+    close(rsm.TorchInnerProductCost(5)(a, b), g["inner"], 1e-5)
+
+
+# --------------------------------------------------------------- golden vectors: regression
+@pytest.mark.parametrize("name", names("regress_"))
+def test_regression_goldens(rsm, name):
+    g, m = load(name)
+    dn = m.get("dtype", "fp32")
+    cost = dev(g["cost"], dn, "e" in g and dn == "fp32")
+    soft, amin, amax = rsm.regress(cost)
+    equal(amin, g["argmin"])
+    equal(amax, g["argmax"])
+    equal(rsm.hard_argmin(cost), g["argmin"])
+    equal(rsm.hard_argmax(cost), g["argmax"])
+    if "e" not in g:
+        return
+    atol = soft_argmax_atol(m["D"]) if dn == "fp32" else RTOL_16[dn] * m["D"]
+    close(soft, g["e"], atol)
+    close(rsm.disparity_regression_dispnetc(cost, m["D"]), g["e_keepdim"], atol)
+    close(rsm.disparity_regression_v4(torch.softmax(cost.detach().float(), 1).to(DT[dn]), m["D"]), g["e"],
+          atol * (4 if dn != "fp32" else 1))
+    if dn == "fp32":
+        rsm.disparity_regression_dispnetc(cost, m["D"]).backward(dev(g["gout"]))
+        close(cost.grad, g["gcost"], GRAD_RTOL * m["D"])
+
+
+@pytest.mark.parametrize("name", names("tail_"))
+def test_v4_tail_goldens(rsm, name):
+    g, m = load(name)
+    cost = dev(g["cost"], "fp32", True)
+    pred, amin, amax = rsm.upsample_regress(cost, m["D"], m["H"], m["W"], argmin=True, argmax=True)
+    close(pred, g["pred"], V4_TAIL_ATOL)
+    pred.backward(dev(g["gout"]))
+    close(cost.grad, g["gcost"], GRAD_RTOL * m["D"])
+    # hard extrema over the upsampled volume: identical wherever the top-2 gap is resolvable
+    fine = g["fine"]
+    srt = np.sort(fine, axis=1)
+    ok_max = (srt[:, -1] - srt[:, -2]) > 1e-4
+    ok_min = (srt[:, 1] - srt[:, 0]) > 1e-4
+    assert np.array_equal(amax.cpu().numpy()[ok_max], g["argmax"][ok_max])
+    assert np.array_equal(amin.cpu().numpy()[ok_min], g["argmin"][ok_min])
+
+
+# ------------------------------------------------------------- golden vectors: call sites
+def test_callsite_v1(rsm):
+    g, m = load("callsite_v1")
+    equal(rsm.make_cost_volume(dev(g["lf"]), dev(g["rf"]), m["max_disp"]), g["volume"])
+    close(rsm.softmax_regression(dev(g["filtered"])), g["regressed"], soft_argmax_atol(m["max_disp"]))
+
+
+def test_callsite_dispnetc(rsm):
+    g, m = load("callsite_dispnetc")
+    c = g["lf"].shape[1]
+    atol = corr_atol_fp32(c, np.abs(g["lf"]).max(), np.abs(g["rf"]).max())
+    close(rsm.make_correlation_volume(dev(g["lf"]), dev(g["rf"]), m["max_disp"]), g["volume"], atol)
+
+
+def test_callsite_v4(rsm):
+    g, m = load("callsite_v4")
+    for k in range(m["n_iw"]):
+        equal(rsm.interweave_tensors(dev(g[f"iw{k}.a"]), dev(g[f"iw{k}.b"])), g[f"iw{k}.out"])
+    pred = rsm.v4_head(dev(g["cost3"]), m["maxdisp"], m["H"], m["W"])
+    close(-pred.unsqueeze(1), g["final"], V4_TAIL_ATOL)
+
+
+# ------------------------------------------------------------------ oracle on seeded inputs
+SHAPES = [  # N, C, H, W, D, G
+    (2, 32, 12, 156, 24, 8),     # cfg1-like feature shape
+    (1, 64, 9, 240, 48, 16),     # cfg2-like row
+    (1, 32, 6, 312, 48, 8),      # cfg3-like row
+    (1, 12, 5, 67, 19, 3),       # nothing divisible by 4
+    (1, 20, 3, 130, 70, 5),      # D > 64: two disparity chunks
+    (3, 5, 4, 9, 13, 5),         # D > W
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("dn", ["fp32", "bf16", "fp16"])
+def test_volumes_vs_oracle(rsm, shape, dn):
+    n, c, h, w, d, ng = shape
+    rng = np.random.default_rng(1234)
+    l = round_to(rng.standard_normal((n, c, h, w)).astype(np.float32), dn)
+    r = round_to(rng.standard_normal((n, c, h, w)).astype(np.float32), dn)
+    L, R = dev(l, dn), dev(r, dn)
+    equal(rsm.concat_volume(L, R, d), oracle.concat_volume(l, r, d))
+    equal(rsm.interweave(L, R), oracle.interweave(l, r))
+    equal(rsm.difference_volume(L, R, d), round_to(oracle.difference_volume(l, r, d), dn))
+    lmax, rmax = np.abs(l).max(), np.abs(r).max()
+    if dn == "fp32":
+        atol, rtol = corr_atol_fp32(c, lmax, rmax), 0.0
+    else:   # fp32 oracle on the same rounded inputs; only the output cast differs
+        atol, rtol = 1e-5 * np.sqrt(c) * lmax * rmax, RTOL_16[dn]
+    close(rsm.inner_product_volume(L, R, d), oracle.inner_product_volume(l, r, d, out_dtype=np.float32), atol, rtol)
+    close(rsm.inner_product_volume(L, R, d, mean=True),
+          oracle.inner_product_volume(l, r, d, mean=True, out_dtype=np.float32), atol, rtol)
+    close(rsm.groupwise_volume(L, R, ng, d, out_dtype=torch.float32), oracle.groupwise_volume(l, r, ng, d),
+          corr_atol_fp32(c // ng, lmax, rmax))
+
+
+@pytest.mark.parametrize("shape", SHAPES[:4])
+def test_dyadic_bit_exact(rsm, shape):
+    """k/8 inputs: fp32 sums are exact, so every reduction must match the oracle bit for bit,
+    and so must the fused build + argmin."""
+    n, c, h, w, d, ng = shape
+    rng = np.random.default_rng(7)
+    l = (rng.integers(-8, 9, (n, c, h, w)) / 8.0).astype(np.float32)
+    r = (rng.integers(-8, 9, (n, c, h, w)) / 8.0).astype(np.float32)
+    L, R = dev(l), dev(r)
+    vol = oracle.inner_product_volume(l, r, d)
+    equal(rsm.inner_product_volume(L, R, d), vol)
+    equal(rsm.groupwise_volume(L, R, ng, d), oracle.groupwise_volume(l, r, ng, d))
+    soft, amin, amax = rsm.inner_product_regress(L, R, d)
+    equal(amin, oracle.hard_argmin(vol))
+    equal(amax, oracle.hard_argmax(vol))
+    close(soft, oracle.soft_argmax(vol), soft_argmax_atol(d))
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_volume_grads_vs_oracle(rsm, shape):
+    n, c, h, w, d, ng = shape
+    rng = np.random.default_rng(99)
+    l = rng.standard_normal((n, c, h, w)).astype(np.float32)
+    r = rng.standard_normal((n, c, h, w)).astype(np.float32)
+    gs = GRAD_RTOL * np.sqrt(d) * 16
+    for fn, ofn, oshape in (
+        (lambda a, b: rsm.concat_volume(a, b, d), lambda g_: oracle.concat_volume_bwd(g_), (n, 2 * c, h, w, d)),
+        (lambda a, b: rsm.difference_volume(a, b, d), lambda g_: oracle.difference_volume_bwd(g_), (n, c, d, h, w)),
+        (lambda a, b: rsm.inner_product_volume(a, b, d), lambda g_: oracle.inner_product_volume_bwd(g_, l, r), (n, d, h, w)),
+        (lambda a, b: rsm.inner_product_volume(a, b, d, mean=True),
+         lambda g_: oracle.inner_product_volume_bwd(g_, l, r, mean=True), (n, d, h, w)),
+        (lambda a, b: rsm.groupwise_volume(a, b, ng, d), lambda g_: oracle.groupwise_volume_bwd(g_, l, r, ng),
+         (n, ng, h, w, d)),
+    ):
+        gout = rng.standard_normal(oshape).astype(np.float32)
+        L, R = dev(l, grad=True), dev(r, grad=True)
+        fn(L, R).backward(dev(gout))
+        gl, gr = ofn(gout)
+        close(L.grad, gl, gs)
+        close(R.grad, gr, gs)
+
+
+@pytest.mark.parametrize("shape", [(2, 24, 12, 40), (1, 192, 8, 60), (1, 48, 5, 33), (1, 7, 3, 5), (2, 1, 2, 2)])
+@pytest.mark.parametrize("dn", ["fp32", "bf16", "fp16"])
+def test_regress_vs_oracle(rsm, shape, dn):
+    n, d, h, w = shape
+    rng = np.random.default_rng(5)
+    cost = round_to((rng.standard_normal(shape) * 4).astype(np.float32), dn)
+    soft, amin, amax = rsm.regress(dev(cost, dn))
+    equal(amin, oracle.hard_argmin(cost))     # bit exact on the given volume
+    equal(amax, oracle.hard_argmax(cost))
+    atol = soft_argmax_atol(d) if dn == "fp32" else RTOL_16[dn] * d
+    close(soft, oracle.soft_argmax(cost), atol)
+    if dn == "fp32":
+        c = dev(cost, grad=True)
+        gout = rng.standard_normal((n, h, w)).astype(np.float32)
+        rsm.soft_argmax(c).backward(dev(gout))
+        close(c.grad, oracle.soft_argmax_bwd(gout, cost), GRAD_RTOL * d)
+
+
+def test_regress_ties_everywhere(rsm):
+    """integer-valued costs: massive ties, first occurrence must win at every pixel."""
+    rng = np.random.default_rng(3)
+    cost = rng.integers(-2, 3, (2, 37, 9, 20)).astype(np.float32)
+    _, amin, amax = rsm.regress(dev(cost))
+    equal(amin, oracle.hard_argmin(cost))
+    equal(amax, oracle.hard_argmax(cost))
+
+
+@pytest.mark.parametrize("geom", [(1, 48, 6, 10, 192, 24, 40), (2, 12, 5, 7, 48, 20, 28), (1, 5, 3, 4, 13, 7, 10),
+                                  (1, 9, 8, 8, 9, 4, 4)])
+def test_v4_tail_vs_oracle(rsm, geom):
+    b, dc, hc, wc, d, h, w = geom
+    rng = np.random.default_rng(11)
+    cost = (rng.standard_normal((b, dc, hc, wc)) * 3).astype(np.float32)
+    c = dev(cost, grad=True)
+    pred = rsm.upsample_regress(c, d, h, w)
+    close(pred, oracle.v4_tail(cost, d, h, w), V4_TAIL_ATOL)
+    gout = rng.standard_normal((b, h, w)).astype(np.float32)
+    pred.backward(dev(gout))
+    close(c.grad, oracle.v4_tail_bwd(gout, cost, d, h, w), GRAD_RTOL * d)
+
+
+@pytest.mark.parametrize("shape", [(1, 16, 4, 100, 48), (2, 64, 3, 70, 192), (1, 8, 2, 33, 24)])
+@pytest.mark.parametrize("mean", [False, True])
+def test_fused_inner_regress_vs_oracle(rsm, shape, mean):
+    n, c, h, w, d = shape
+    rng = np.random.default_rng(21)
+    l = rng.standard_normal((n, c, h, w)).astype(np.float32)
+    r = rng.standard_normal((n, c, h, w)).astype(np.float32)
+    soft, amin, amax = rsm.inner_product_regress(dev(l), dev(r), d, mean=mean)
+    vol = oracle.inner_product_volume(l, r, d, mean=mean)
+    close(soft, oracle.soft_argmax(vol), soft_argmax_atol(d) * 4)
+    # accumulation order differs from the oracle, so near-ties may flip: report, bound at 0.1 %
+    mism = (amax.cpu().numpy() != oracle.hard_argmax(vol)).mean()
+    assert mism < 1e-3, f"fused argmax mismatch rate {mism}"
+
+
+# -------------------------------------------------- full-size properties (BASELINE configs)
+def test_fullsize_concat_groupwise_properties(rsm):
+    """cfg3 shapes per GPU (N=2 here to bound memory): every disparity slice of the volume equals
+    the shifted inputs; checked with torch ops on the device."""
+    n, c, h, w, d, ng = 2, 32, 96, 312, 48, 8
+    gen = torch.Generator(device="cuda").manual_seed(1234)
+    L = torch.randn((n, c, h, w), device="cuda", generator=gen)
+    R = torch.randn((n, c, h, w), device="cuda", generator=gen)
+    vol = rsm.concat_volume(L, R, d)
+    gw = rsm.groupwise_volume(L, R, ng, d)
+    for dd in (0, 1, 17, 47):
+        assert torch.equal(vol[:, :c, :, dd:, dd], L[:, :, :, dd:])
+        assert torch.equal(vol[:, c:, :, dd:, dd], R[:, :, :, : w - dd])
+        assert vol[:, :, :, :dd, dd].abs().sum().item() == 0.0
+        ref = (L[:, :, :, dd:] * R[:, :, :, : w - dd]).view(n, ng, c // ng, h, w - dd).mean(2)
+        torch.testing.assert_close(gw[:, :, :, dd:, dd], ref, atol=2e-5, rtol=0)
+        assert gw[:, :, :, :dd, dd].abs().sum().item() == 0.0
+    # checksum of checksums: sum over d of the left half = L * min(x+1, D)
+    cnt = torch.clamp(torch.arange(w, device="cuda") + 1, max=d).float()
+    torch.testing.assert_close(vol[:, :c].sum(-1), L * cnt, atol=1e-4, rtol=1e-5)
+
+
+def test_fullsize_correlation_cfg2(rsm):
+    """cfg2: (N,64,144,240), D=48 mean correlation (N=4 here), against torch ops on the device."""
+    n, c, h, w, d = 4, 64, 144, 240, 48
+    gen = torch.Generator(device="cuda").manual_seed(1234)
+    L = torch.randn((n, c, h, w), device="cuda", generator=gen)
+    R = torch.randn((n, c, h, w), device="cuda", generator=gen)
+    vol = rsm.make_correlation_volume(L, R, d)
+    for dd in (0, 5, 47):
+        ref = (L[:, :, :, dd:] * R[:, :, :, : w - dd]).mean(1)
+        torch.testing.assert_close(vol[:, dd, :, dd:], ref, atol=2e-5, rtol=0)
+        assert vol[:, dd, :, :dd].abs().sum().item() == 0.0
+
+
+def test_fullsize_regression_cfg5(rsm):
+    """cfg5: one (192,1080,1920) fp32 volume: argmin/argmax bit-exact vs torch on the device,
+    soft-argmax within tolerance, invariance under a constant shift of the cost."""
+    gen = torch.Generator(device="cuda").manual_seed(1234)
+    cost = torch.randn((1, 192, 1080, 1920), device="cuda", generator=gen) * 4
+    soft, amin, amax = rsm.regress(cost)
+    assert torch.equal(amin, torch.argmin(cost, 1))
+    assert torch.equal(amax, torch.argmax(cost, 1))
+    ref = (torch.softmax(cost, 1) * torch.arange(192, device="cuda").view(1, -1, 1, 1)).sum(1)
+    torch.testing.assert_close(soft, ref, atol=soft_argmax_atol(192), rtol=0)
+    soft2 = rsm.soft_argmax(cost + 3.0)
+    torch.testing.assert_close(soft2, soft, atol=soft_argmax_atol(192), rtol=0)
+
+
+def test_fullsize_v4_tail_cfg3(rsm):
+    """cfg3 tail: (2,48,96,312) -> (2,384,1248) against interpolate+softmax on the device."""
+    gen = torch.Generator(device="cuda").manual_seed(1234)
+    cost = torch.randn((2, 48, 96, 312), device="cuda", generator=gen) * 3
+    pred = rsm.v4_head(cost, 192, 384, 1248)
+    fine = torch.nn.functional.interpolate(cost.unsqueeze(1), [192, 384, 1248], mode="trilinear").squeeze(1)
+    ref = (torch.softmax(fine, 1) * torch.arange(192, device="cuda").view(1, -1, 1, 1)).sum(1)
+    torch.testing.assert_close(pred, ref, atol=V4_TAIL_ATOL, rtol=0)
+
+
+# ------------------------------------------------------------------------ error behaviour
+def test_errors(rsm):
+    x = torch.zeros((1, 6, 2, 8), device="cuda")
+    with pytest.raises(AssertionError, match="groupwise cost channel"):   # groupwise.py:15-17
+        rsm.TorchGroupwiseCost(4, 3)(x, x)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        rsm.concat_volume(x.cpu(), x.cpu(), 2)
+    with pytest.raises(TypeError):
+        rsm.concat_volume(x.double(), x.double(), 2)
+    with pytest.raises(RuntimeError):
+        rsm.concat_volume(x, x[:, :3], 2)
+    assert str(rsm.TorchInnerProductCost(4)) == "TorchInnerProductCost | aijk,aijh->ajkh"
+    assert str(rsm.TorchInterweaveCost()) == "TorchInterweaveCost"
+    assert rsm.concat_volume(x[:0], x[:0], 2).shape == (0, 12, 2, 8, 2)   # empty batch
+
+
+def test_streams_and_autocast(rsm):
+    """ops enqueue on the caller's current stream and accept autocast's fp16 features (F11)."""
+    s = torch.cuda.Stream()
+    L = torch.randn((1, 8, 4, 32), device="cuda")
+    with torch.cuda.stream(s):
+        with torch.autocast("cuda", dtype=torch.float16):
+            v = rsm.inner_product_volume(L.half(), L.half(), 4)
+    s.synchronize()
+    assert v.dtype == torch.float16
+    ref = oracle.inner_product_volume(host(L.half()), host(L.half()), 4, out_dtype=np.float32)
+    close(v, ref, 1e-2, RTOL_16["fp16"])
+
+
+def test_epe_delta_synthetic(rsm):
+    """EPE of the soft-argmax disparity on a synthetic pair (right = left shifted by a known
+    disparity) for the CUDA path vs the oracle path: the delta must be negligible."""
+    rng = np.random.default_rng(0)
+    n, c, h, w, d, true_d = 1, 16, 8, 96, 24, 7
+    l = rng.standard_normal((n, c, h, w)).astype(np.float32)
+    r = np.zeros_like(l)
+    r[..., : w - true_d] = l[..., true_d:]
+    vol = rsm.inner_product_volume(dev(l), dev(r), d)
+    ours = host(rsm.soft_argmax(vol * 4.0))
+    ref = oracle.soft_argmax(oracle.inner_product_volume(l, r, d) * 4.0)
+    valid = np.zeros((n, h, w), bool)
+    valid[..., d:] = True
+    epe_ours = np.abs(ours - true_d)[valid].mean()
+    epe_ref = np.abs(ref - true_d)[valid].mean()
+    assert abs(epe_ours - epe_ref) < 1e-4, (epe_ours, epe_ref)
+    assert epe_ours < 0.5

@@ -323,7 +323,8 @@ static int make_geom(int64_t N, int64_t C, int64_t H, int64_t W, int64_t D, int6
   if (C > (1 << 24) || H > (1 << 24) || W > (1 << 24) || D > (1 << 24)) return RSM_ERR_INVALID_SHAPE;
   g.C = (int)C; g.H = (int)H; g.W = (int)W; g.D = (int)D; g.G = (int)G; g.cpg = (int)(C / G);
   const int need = (int)ceil_div(D > 0 ? D : 1, DT);
-  g.ntd = all_d ? need : (need < MAX_NTD ? need : MAX_NTD);
+  // the fused kernel reduces with full-warp shuffles: keep blockDim = 16 * ntd a multiple of 32
+  g.ntd = all_d ? ((need + 1) & ~1) : (need < MAX_NTD ? need : MAX_NTD);
   g.dchp = g.ntd * DT;
   g.xtiles = (int)ceil_div(W > 0 ? W : 1, TX);
   g.mean = mean;

@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 
 #include "rsm.h"
@@ -99,6 +100,26 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// running first-occurrence argmin / argmax with torch semantics (NaN is the extremum)
+struct ArgTrack {
+  float minv = INFINITY, maxv = -INFINITY;
+  int mini = 0, maxi = 0;
+  __device__ __forceinline__ void update(float v, int d) {
+    const bool vnan = v != v;
+    if ((v < minv) || (vnan && minv == minv)) { minv = v; mini = d; }
+    if ((v > maxv) || (vnan && maxv == maxv)) { maxv = v; maxi = d; }
+  }
+};
 
 struct FeatView {  // device-side copy of rsm_feat
   const void* data;

@@ -2,58 +2,69 @@
 // and the fused correlation -> soft-argmax/argmin kernel that never writes the volume.
 //
 // Forward tiling (SIMT, fp32 accumulate): a CTA owns one epipolar row segment of TX=64 pixels of one
-// (n, y, group) and a chunk of up to 64 disparities.  Channel chunks of the left row segment and of
-// the right row window [x0-d_hi, x0+TX) are staged in shared memory once and reused by every
-// (x, d) pair of the tile; each thread accumulates a 4(x) x 8(d) register tile from 4 LDS.128 per
-// channel (one left quad + a 12-wide right window), i.e. 8 FMA per shared-memory word.
+// (n, y), a chunk of up to 64 disparities and a SLAB of up to 32 channels: either a slice of one big
+// group (inner product: the CTA walks all slabs of the channel axis) or several whole small groups
+// (group-wise: the CTA emits one output tile per group from a single staging pass).  The slab of
+// the left segment and of the right window [x0-d_hi, x0+TX) is staged in shared memory as fp32
+// once; each thread accumulates a 4(x) x 8(d) register tile from 4 LDS.128 per channel (one left
+// quad + a 12-wide right window): 8 FMA per shared-memory word.  The lane order follows the
+// output layout so that stores coalesce: x-fastest for (N,D,H,W), d-fastest with 256-bit stores
+// (STG.E.ENL2.256) for the D-innermost (N,G,H,W,D).
 #include <math.h>
 
 #include "rsm_common.cuh"
 
 namespace rsm {
 
-constexpr int TX = 64;       // pixels per CTA tile
-constexpr int XT = 4;        // pixels per thread
-constexpr int DT = 8;        // disparities per thread
-constexpr int NTX = TX / XT; // 16 threads along x
-constexpr int MAX_NTD = 8;   // <= 64 disparities per CTA chunk (volume kernels)
-constexpr int CK = 16;       // channels per shared-memory stage
+constexpr int TX = 64;        // pixels per CTA tile
+constexpr int XT = 4;         // pixels per thread
+constexpr int DT = 8;         // disparities per thread
+constexpr int NTX = TX / XT;  // 16 threads along x
+constexpr int MAX_NTD = 8;    // <= 64 disparities per CTA chunk (volume kernels)
+constexpr int CKMAX = 32;     // channels per shared-memory slab
 
 enum Layout { LAYOUT_NDHW = 0, LAYOUT_NGHWD = 1 };
 
 struct CorrGeom {
   int C, H, W, D, G, cpg;
-  int ntd;        // threads along d  (blockDim.x = NTX * ntd)
-  int dchp;       // disparities covered by a CTA chunk = DT * ntd
-  int xtiles;     // ceil(W / TX)
-  int mean;       // divide by cpg
+  int ntd;      // threads along d  (blockDim.x = NTX * ntd)
+  int dchp;     // disparities covered by a CTA chunk = DT * ntd
+  int xtiles;   // ceil(W / TX)
+  int mean;     // divide by cpg
+  int gpb;      // groups per CTA (small groups share one staging pass)
+  int gblocks;  // ceil(G / gpb)
+  int pow2;     // cpg is a power of two: the mean is an exact multiply
 };
 
-// ---- stage CK channels of the left segment and right window as fp32 in shared memory
+// ---- stage `nch` channels [c0, c0+nch) of the left segment and right window as fp32
 template <typename Tin>
-__device__ __forceinline__ void stage_rows(const FeatView& L, const FeatView& R, int64_t n, int cbase, int cend,
-                                           int y, int x0, int rbase, int rw, float* sL, float* sR, int W) {
-  const Tin* __restrict__ pl = reinterpret_cast<const Tin*>(L.data) + n * L.sn + (int64_t)y * L.sh;
-  const Tin* __restrict__ pr = reinterpret_cast<const Tin*>(R.data) + n * R.sn + (int64_t)y * R.sh;
-  for (int e = threadIdx.x; e < CK * TX; e += blockDim.x) {
-    const int c = e / TX, xx = e - c * TX;
-    const int x = x0 + xx, cc = cbase + c;
-    sL[e] = (cc < cend && x < W) ? to_f(__ldg(pl + (int64_t)cc * L.sc + (int64_t)x * L.sw)) : 0.f;
-  }
-  for (int e = threadIdx.x; e < CK * rw; e += blockDim.x) {
-    const int c = e / rw, j = e - c * rw;
-    const int x = rbase + j, cc = cbase + c;
-    sR[e] = (cc < cend && x >= 0 && x < W) ? to_f(__ldg(pr + (int64_t)cc * R.sc + (int64_t)x * R.sw)) : 0.f;
+__device__ __forceinline__ void stage_slab(const FeatView& L, const FeatView& R, int64_t n, int y, int c0, int nch,
+                                           int x0, int rbase, int rw, float* sL, float* sR, int W) {
+  const Tin* __restrict__ pl = reinterpret_cast<const Tin*>(L.data) + n * L.sn + (int64_t)y * L.sh + (int64_t)c0 * L.sc;
+  const Tin* __restrict__ pr = reinterpret_cast<const Tin*>(R.data) + n * R.sn + (int64_t)y * R.sh + (int64_t)c0 * R.sc;
+  const int span = TX + rw;   // per channel: TX left values then rw right values
+  for (int c = 0; c < nch; ++c) {
+    for (int e = threadIdx.x; e < span; e += blockDim.x) {
+      if (e < TX) {
+        const int x = x0 + e;
+        sL[c * TX + e] = (x < W) ? to_f(__ldg(pl + (int64_t)c * L.sc + (int64_t)x * L.sw)) : 0.f;
+      } else {
+        const int j = e - TX, x = rbase + j;
+        sR[c * rw + j] = (x >= 0 && x < W) ? to_f(__ldg(pr + (int64_t)c * R.sc + (int64_t)x * R.sw)) : 0.f;
+      }
+    }
   }
 }
 
-// ---- accumulate the 4x8 register tile over the staged channels
-__device__ __forceinline__ void tile_fma(const float* sL, const float* sR, int rw, int tx, int wstart, int nch,
-                                         float (&acc)[XT][DT]) {
+// ---- accumulate the 4x8 register tile over staged channels [cofs, cofs+nch)
+__device__ __forceinline__ void tile_fma(const float* sL, const float* sR, int rw, int tx, int wstart, int cofs,
+                                         int nch, float (&acc)[XT][DT]) {
+  const float* pl = sL + cofs * TX + XT * tx;
+  const float* pw = sR + cofs * rw + wstart;
 #pragma unroll 4
   for (int c = 0; c < nch; ++c) {
-    const float4 l4 = *reinterpret_cast<const float4*>(sL + c * TX + XT * tx);
-    const float4* wp = reinterpret_cast<const float4*>(sR + c * rw + wstart);
+    const float4 l4 = *reinterpret_cast<const float4*>(pl + c * TX);
+    const float4* wp = reinterpret_cast<const float4*>(pw + c * rw);
     const float4 w0 = wp[0], w1 = wp[1], w2 = wp[2];
     const float l[XT] = {l4.x, l4.y, l4.z, l4.w};
     const float w[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
@@ -64,79 +75,74 @@ __device__ __forceinline__ void tile_fma(const float* sL, const float* sR, int r
   }
 }
 
-template <typename Tout, int NV> struct PackOut;  // NV consecutive outputs
-template <> struct PackOut<float, 4> {
-  static __device__ __forceinline__ void store(float* p, const float* v) {
-    __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
-  }
-};
-template <> struct PackOut<__half, 4> {
-  static __device__ __forceinline__ void store(__half* p, const float* v) {
-    union { uint2 u; __half2 h[2]; } t;
-    t.h[0] = __floats2half2_rn(v[0], v[1]); t.h[1] = __floats2half2_rn(v[2], v[3]);
-    __stcs(reinterpret_cast<uint2*>(p), t.u);
-  }
-};
-template <> struct PackOut<__nv_bfloat16, 4> {
-  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float* v) {
-    union { uint2 u; __nv_bfloat162 h[2]; } t;
-    t.h[0] = __floats2bfloat162_rn(v[0], v[1]); t.h[1] = __floats2bfloat162_rn(v[2], v[3]);
-    __stcs(reinterpret_cast<uint2*>(p), t.u);
-  }
-};
+// ---- vector stores of consecutive outputs (streaming: the volume is written once, read later)
+__device__ __forceinline__ void store4(float* p, const float* v) {
+  __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+}
+__device__ __forceinline__ void store4(__half* p, const float* v) {
+  union { uint2 u; __half2 h[2]; } t;
+  t.h[0] = __floats2half2_rn(v[0], v[1]); t.h[1] = __floats2half2_rn(v[2], v[3]);
+  __stcs(reinterpret_cast<uint2*>(p), t.u);
+}
+__device__ __forceinline__ void store4(__nv_bfloat16* p, const float* v) {
+  union { uint2 u; __nv_bfloat162 h[2]; } t;
+  t.h[0] = __floats2bfloat162_rn(v[0], v[1]); t.h[1] = __floats2bfloat162_rn(v[2], v[3]);
+  __stcs(reinterpret_cast<uint2*>(p), t.u);
+}
+// 8 consecutive outputs: one 256-bit store for fp32 (32-byte aligned), one 128-bit store for 16-bit
+__device__ __forceinline__ void store8(float* p, const float* v) {
+  asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+               "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void store8(__half* p, const float* v) {
+  union { uint4 u; __half2 h[4]; } t;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) t.h[k] = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+  __stcs(reinterpret_cast<uint4*>(p), t.u);
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float* v) {
+  union { uint4 u; __nv_bfloat162 h[4]; } t;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) t.h[k] = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+  __stcs(reinterpret_cast<uint4*>(p), t.u);
+}
 
-// ======================================================================= volume forward
-template <typename Tin, typename Tout, int LAYOUT>
-__global__ void __launch_bounds__(NTX * MAX_NTD)
-corr_fwd_kernel(FeatView L, FeatView R, Tout* __restrict__ out, CorrGeom g) {
-  extern __shared__ __align__(16) float smem[];
-  const int rw = TX + g.dchp;
-  float* sL = smem;
-  float* sR = smem + CK * TX;
-
-  int64_t bid = blockIdx.x;
-  const int xt = (int)(bid % g.xtiles); bid /= g.xtiles;
-  const int y = (int)(bid % g.H); bid /= g.H;
-  const int grp = (int)(bid % g.G);
-  const int64_t n = bid / g.G;
-  const int x0 = xt * TX;
-  const int dc0 = blockIdx.y * g.dchp;
-  const int tx = threadIdx.x % NTX, td = threadIdx.x / NTX;
-  const int rbase = x0 - dc0 - g.dchp;
-  const int wstart = g.dchp + XT * tx - DT * td - DT;
-
-  float acc[XT][DT];
+// ---- scale, zero the x < d triangle and store one finished 4x8 tile of group `grp`
+template <typename Tout, int LAYOUT>
+__device__ __forceinline__ void store_tile(float (&acc)[XT][DT], Tout* __restrict__ out, const CorrGeom& g, int64_t n,
+                                           int grp, int y, int xb, int db, bool vec) {
+  if (g.mean) {
+    if (g.pow2) {
+      const float inv = 1.f / (float)g.cpg;   // exact: identical to the division
+#pragma unroll
+      for (int i = 0; i < XT; ++i)
+#pragma unroll
+        for (int j = 0; j < DT; ++j) acc[i][j] *= inv;
+    } else {
+      const float cnt = (float)g.cpg;
+#pragma unroll
+      for (int i = 0; i < XT; ++i)
+#pragma unroll
+        for (int j = 0; j < DT; ++j) acc[i][j] = acc[i][j] / cnt;
+    }
+  }
 #pragma unroll
   for (int i = 0; i < XT; ++i)
 #pragma unroll
-    for (int j = 0; j < DT; ++j) acc[i][j] = 0.f;
-
-  const int cbeg = grp * g.cpg, cend = cbeg + g.cpg;
-  for (int c0 = cbeg; c0 < cend; c0 += CK) {
-    __syncthreads();
-    stage_rows<Tin>(L, R, n, c0, cend, y, x0, rbase, rw, sL, sR, g.W);
-    __syncthreads();
-    tile_fma(sL, sR, rw, tx, wstart, min(CK, cend - c0), acc);
-  }
-
-  const float cnt = g.mean ? (float)g.cpg : 1.f;
-  const int xb = x0 + XT * tx, db = dc0 + DT * td;
-#pragma unroll
-  for (int i = 0; i < XT; ++i)
-#pragma unroll
-    for (int j = 0; j < DT; ++j) acc[i][j] = (xb + i >= db + j) ? acc[i][j] / cnt : 0.f;
+    for (int j = 0; j < DT; ++j)
+      if (xb + i < db + j) acc[i][j] = 0.f;   // the reference leaves zeros where x < d
 
   if constexpr (LAYOUT == LAYOUT_NDHW) {
-    const bool vec = (g.W % XT == 0);  // then xb + 3 < W whenever xb < W and the address is 4-aligned
     if (xb >= g.W) return;
 #pragma unroll
     for (int j = 0; j < DT; ++j) {
       const int d = db + j;
       if (d >= g.D) break;
       Tout* p = out + (((int64_t)n * g.D + d) * g.H + y) * g.W + xb;
-      if (vec) {
+      if (vec) {   // W % 4 == 0: xb + 3 < W and the address is aligned
         const float v[4] = {acc[0][j], acc[1][j], acc[2][j], acc[3][j]};
-        PackOut<Tout, 4>::store(p, v);
+        store4(p, v);
       } else {
 #pragma unroll
         for (int i = 0; i < XT; ++i)
@@ -144,21 +150,74 @@ corr_fwd_kernel(FeatView L, FeatView R, Tout* __restrict__ out, CorrGeom g) {
       }
     }
   } else {
-    const bool vec = (g.D % 4 == 0);   // then db + 4k + 3 < D whenever db + 4k < D
     if (db >= g.D) return;
 #pragma unroll
     for (int i = 0; i < XT; ++i) {
       const int x = xb + i;
       if (x >= g.W) break;
       Tout* p = out + ((((int64_t)n * g.G + grp) * g.H + y) * g.W + x) * g.D + db;
-      if (vec) {
-        PackOut<Tout, 4>::store(p, &acc[i][0]);
-        if (db + 4 < g.D) PackOut<Tout, 4>::store(p + 4, &acc[i][4]);
+      if (vec) {   // D % 8 == 0: db + 7 < D and the address is aligned
+        store8(p, &acc[i][0]);
       } else {
 #pragma unroll
         for (int j = 0; j < DT; ++j)
           if (db + j < g.D) p[j] = from_f<Tout>(acc[i][j]);
       }
+    }
+  }
+}
+
+// ======================================================================= volume forward
+template <typename Tin, typename Tout, int LAYOUT>
+__global__ void __launch_bounds__(NTX * MAX_NTD)
+corr_fwd_kernel(FeatView L, FeatView R, Tout* __restrict__ out, CorrGeom g, int vec) {
+  extern __shared__ __align__(16) float smem[];
+  const int rw = TX + g.dchp;
+  float* sL = smem;
+  float* sR = smem + CKMAX * TX;
+
+  int64_t bid = blockIdx.x;
+  const int xt = (int)(bid % g.xtiles); bid /= g.xtiles;
+  const int gb = (int)(bid % g.gblocks); bid /= g.gblocks;
+  const int y = (int)(bid % g.H);
+  const int64_t n = bid / g.H;
+  const int x0 = xt * TX;
+  const int dc0 = blockIdx.y * g.dchp;
+  int tx, td;
+  if constexpr (LAYOUT == LAYOUT_NDHW) { tx = threadIdx.x % NTX; td = threadIdx.x / NTX; }
+  else { td = threadIdx.x % g.ntd; tx = threadIdx.x / g.ntd; }
+  const int rbase = x0 - dc0 - g.dchp;
+  const int wstart = g.dchp + XT * tx - DT * td - DT;
+  const int xb = x0 + XT * tx, db = dc0 + DT * td;
+
+  float acc[XT][DT];
+  const int g0 = gb * g.gpb, g1 = min(g.G, g0 + g.gpb);
+  if (g.cpg >= CKMAX) {
+    // one (big) group per CTA: walk its channels slab by slab into the same accumulators
+#pragma unroll
+    for (int i = 0; i < XT; ++i)
+#pragma unroll
+      for (int j = 0; j < DT; ++j) acc[i][j] = 0.f;
+    const int cbeg = g0 * g.cpg, cend = cbeg + g.cpg;
+    for (int c0 = cbeg; c0 < cend; c0 += CKMAX) {
+      const int nch = min(CKMAX, cend - c0);
+      __syncthreads();
+      stage_slab<Tin>(L, R, n, y, c0, nch, x0, rbase, rw, sL, sR, g.W);
+      __syncthreads();
+      tile_fma(sL, sR, rw, tx, wstart, 0, nch, acc);
+    }
+    store_tile<Tout, LAYOUT>(acc, out, g, n, g0, y, xb, db, vec);
+  } else {
+    // several small groups per CTA: one staging pass, one output tile per group
+    stage_slab<Tin>(L, R, n, y, g0 * g.cpg, (g1 - g0) * g.cpg, x0, rbase, rw, sL, sR, g.W);
+    __syncthreads();
+    for (int grp = g0; grp < g1; ++grp) {
+#pragma unroll
+      for (int i = 0; i < XT; ++i)
+#pragma unroll
+        for (int j = 0; j < DT; ++j) acc[i][j] = 0.f;
+      tile_fma(sL, sR, rw, tx, wstart, (grp - g0) * g.cpg, g.cpg, acc);
+      store_tile<Tout, LAYOUT>(acc, out, g, n, grp, y, xb, db, vec);
     }
   }
 }
@@ -245,8 +304,8 @@ inner_regress_fwd_kernel(FeatView L, FeatView R, float* __restrict__ soft, int64
   const int rw = TX + g.dchp;
   const int dp = g.dchp + 1;                 // odd pitch of the parked tile sV[x][d]
   float* sL = smem;
-  float* sR = sL + CK * TX;
-  float* sV = sR + CK * rw;
+  float* sR = sL + CKMAX * TX;
+  float* sV = sR + CKMAX * rw;
 
   int64_t bid = blockIdx.x;
   const int xt = (int)(bid % g.xtiles); bid /= g.xtiles;
@@ -262,11 +321,12 @@ inner_regress_fwd_kernel(FeatView L, FeatView R, float* __restrict__ soft, int64
   for (int i = 0; i < XT; ++i)
 #pragma unroll
     for (int j = 0; j < DT; ++j) acc[i][j] = 0.f;
-  for (int c0 = 0; c0 < g.C; c0 += CK) {
+  for (int c0 = 0; c0 < g.C; c0 += CKMAX) {
+    const int nch = min(CKMAX, g.C - c0);
     __syncthreads();
-    stage_rows<Tin>(L, R, n, c0, g.C, y, x0, rbase, rw, sL, sR, g.W);
+    stage_slab<Tin>(L, R, n, y, c0, nch, x0, rbase, rw, sL, sR, g.W);
     __syncthreads();
-    tile_fma(sL, sR, rw, tx, wstart, min(CK, g.C - c0), acc);
+    tile_fma(sL, sR, rw, tx, wstart, 0, nch, acc);
   }
   const float cnt = g.mean ? (float)g.C : 1.f;
   const int xb = XT * tx, db = DT * td;
@@ -328,18 +388,24 @@ static int make_geom(int64_t N, int64_t C, int64_t H, int64_t W, int64_t D, int6
   g.dchp = g.ntd * DT;
   g.xtiles = (int)ceil_div(W > 0 ? W : 1, TX);
   g.mean = mean;
+  g.gpb = (g.cpg >= CKMAX || g.cpg == 0) ? 1 : (CKMAX / g.cpg < g.G ? CKMAX / g.cpg : g.G);
+  g.gblocks = (int)ceil_div(g.G, g.gpb);
+  g.pow2 = g.cpg > 0 && (g.cpg & (g.cpg - 1)) == 0;
   return RSM_OK;
 }
 
 template <typename Tin, typename Tout, int LAYOUT>
 static int launch_fwd(const rsm_feat& left, const rsm_feat& right, void* out, int64_t N, const CorrGeom& g,
                       cudaStream_t st, const char* where) {
-  const int64_t bx = N * g.G * g.H * g.xtiles;
+  const int64_t bx = N * g.gblocks * g.H * g.xtiles;
   const int64_t by = ceil_div(g.D, g.dchp);
   if (!grid_ok(bx) || by > 65535) return RSM_ERR_INVALID_SHAPE;
-  const size_t smem = (size_t)(CK * TX + CK * (TX + g.dchp)) * sizeof(float);
+  const size_t smem = (size_t)(CKMAX * TX + CKMAX * (TX + g.dchp)) * sizeof(float);
+  // vector stores need the run length to divide evenly and the base pointer aligned to the vector
+  const int vec = (LAYOUT == LAYOUT_NDHW) ? (g.W % 4 == 0 && aligned_to(out, 4 * sizeof(Tout)))
+                                          : (g.D % 8 == 0 && aligned_to(out, 8 * sizeof(Tout)));
   corr_fwd_kernel<Tin, Tout, LAYOUT><<<dim3((unsigned)bx, (unsigned)by), NTX * g.ntd, smem, st>>>(
-      view_of(left), view_of(right), (Tout*)out, g);
+      view_of(left), view_of(right), (Tout*)out, g, vec);
   return finish_launch(where);
 }
 
@@ -383,7 +449,7 @@ extern "C" int rsm_inner_fwd(rsm_feat left, rsm_feat right, void* out, int64_t N
   if (!out || (C > 0 && (!left.data || !right.data))) return RSM_ERR_NULL_POINTER;
   RSM_COMMON_CHECKS(in_dtype)
   if (!valid_dtype(out_dtype)) return RSM_ERR_UNSUPPORTED_DTYPE;
-  if (!aligned_to(out, dtype_size(out_dtype) * 4) && W % 4 == 0) return RSM_ERR_MISALIGNED;
+  if (!aligned_to(out, dtype_size(out_dtype))) return RSM_ERR_MISALIGNED;
   return RSM_DISPATCH_IO(in_dtype, out_dtype, Tin, Tout, [&]() -> int {
     return launch_fwd<Tin, Tout, LAYOUT_NDHW>(left, right, out, N, g, st, "rsm_inner_fwd");
   });
@@ -413,7 +479,7 @@ extern "C" int rsm_groupwise_fwd(rsm_feat left, rsm_feat right, void* out, int64
   if (!out || (C > 0 && (!left.data || !right.data))) return RSM_ERR_NULL_POINTER;
   RSM_COMMON_CHECKS(in_dtype)
   if (!valid_dtype(out_dtype)) return RSM_ERR_UNSUPPORTED_DTYPE;
-  if (!aligned_to(out, dtype_size(out_dtype) * 4) && D % 4 == 0) return RSM_ERR_MISALIGNED;
+  if (!aligned_to(out, dtype_size(out_dtype))) return RSM_ERR_MISALIGNED;
   return RSM_DISPATCH_IO(in_dtype, out_dtype, Tin, Tout, [&]() -> int {
     return launch_fwd<Tin, Tout, LAYOUT_NGHWD>(left, right, out, N, g, st, "rsm_groupwise_fwd");
   });
@@ -446,7 +512,7 @@ extern "C" int rsm_inner_regress_fwd(rsm_feat left, rsm_feat right, int64_t N, i
   RSM_COMMON_CHECKS(in_dtype)
   const int64_t bx = N * g.H * g.xtiles;
   if (!grid_ok(bx)) return RSM_ERR_INVALID_SHAPE;
-  const size_t smem = (size_t)(CK * TX + CK * (TX + g.dchp) + TX * (g.dchp + 1)) * sizeof(float);
+  const size_t smem = (size_t)(CKMAX * TX + CKMAX * (TX + g.dchp) + TX * (g.dchp + 1)) * sizeof(float);
   return RSM_DISPATCH_DTYPE(in_dtype, Tin, [&]() -> int {
     auto k = (NTX * g.ntd <= 512) ? inner_regress_fwd_kernel<Tin, 512> : inner_regress_fwd_kernel<Tin, 1024>;
     if (smem > 48 * 1024) {

@@ -43,15 +43,22 @@ __device__ __forceinline__ void stage_slab(const FeatView& L, const FeatView& R,
   const Tin* __restrict__ pl = reinterpret_cast<const Tin*>(L.data) + n * L.sn + (int64_t)y * L.sh + (int64_t)c0 * L.sc;
   const Tin* __restrict__ pr = reinterpret_cast<const Tin*>(R.data) + n * R.sn + (int64_t)y * R.sh + (int64_t)c0 * R.sc;
   const int span = TX + rw;   // per channel: TX left values then rw right values
-  for (int c = 0; c < nch; ++c) {
-    for (int e = threadIdx.x; e < span; e += blockDim.x) {
-      if (e < TX) {
-        const int x = x0 + e;
-        sL[c * TX + e] = (x < W) ? to_f(__ldg(pl + (int64_t)c * L.sc + (int64_t)x * L.sw)) : 0.f;
-      } else {
-        const int j = e - TX, x = rbase + j;
-        sR[c * rw + j] = (x >= 0 && x < W) ? to_f(__ldg(pr + (int64_t)c * R.sc + (int64_t)x * R.sw)) : 0.f;
-      }
+  constexpr int U = 8;        // independent loads in flight per thread
+  for (int e = threadIdx.x; e < span; e += blockDim.x) {
+    const bool left = e < TX;
+    const int x = left ? x0 + e : rbase + (e - TX);
+    const bool valid = x >= 0 && x < W;
+    const Tin* __restrict__ p = left ? pl + (int64_t)x * L.sw : pr + (int64_t)x * R.sw;
+    const int64_t cs = left ? L.sc : R.sc;
+    float* dst = left ? sL + e : sR + (e - TX);
+    const int pitch = left ? TX : rw;
+    for (int c = 0; c < nch; c += U) {
+      float v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) v[u] = (valid && c + u < nch) ? to_f(__ldg(p + (c + u) * cs)) : 0.f;
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (c + u < nch) dst[(c + u) * pitch] = v[u];
     }
   }
 }

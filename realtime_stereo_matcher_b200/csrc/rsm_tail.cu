@@ -66,13 +66,25 @@ template <typename T>
 __device__ __forceinline__ void stage_tile(const T* __restrict__ cost_b, const TailSmem& sm, const TailGeom& g,
                                            int cy0, int cx0) {
   const int per = g.FH * g.FW;
-  for (int k = 0; k < g.Dc; ++k) {
-    const T* __restrict__ plane = cost_b + (int64_t)k * g.Hc * g.Wc;
-    for (int r = threadIdx.x; r < per; r += kTX * kTY) {
-      const int fy = r / g.FW, fx = r - fy * g.FW;
-      const int cy = min(cy0 + fy, g.Hc - 1), cx = min(cx0 + fx, g.Wc - 1);
-      sm.foot[k * per + r] = to_f(__ldg(plane + (int64_t)cy * g.Wc + cx));
+  const int tot = g.Dc * per;
+  const int64_t plane = (int64_t)g.Hc * g.Wc;
+  constexpr int U = 8, NT = kTX * kTY;   // U independent loads in flight per thread
+  for (int e0 = threadIdx.x; e0 < tot; e0 += U * NT) {
+    float v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int e = e0 + u * NT;
+      v[u] = 0.f;
+      if (e < tot) {
+        const int k = e / per, r = e - k * per;
+        const int fy = r / g.FW, fx = r - fy * g.FW;
+        const int cy = min(cy0 + fy, g.Hc - 1), cx = min(cx0 + fx, g.Wc - 1);
+        v[u] = to_f(__ldg(cost_b + k * plane + (int64_t)cy * g.Wc + cx));
+      }
     }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (e0 + u * NT < tot) sm.foot[e0 + u * NT] = v[u];
   }
   if (!g.fast4) {
     for (int d = threadIdx.x; d < g.D; d += kTX * kTY) {

@@ -38,24 +38,29 @@ struct TailGeom {
   int Dc, Hc, Wc, D, H, W;
   int FH, FW;        // coarse rows / cols a tile can touch (upper bound)
   int fast4;         // D == 4 * Dc
+  int cached;        // per-pixel slice values are parked in shared memory (Dc * 256 floats fit)
   float sd, sh, sw;  // in/out scale per axis
 };
 
-// shared memory: [ footprint Dc*FH*FW | w1tab D | dstart Dc+1 | i0tab D ]  (tables: generic ratio only)
+// shared memory: [ footprint Dc*FH*FW | slices Dc*256 (if cached) | w1tab D | dstart Dc+1 | i0tab D ]
+// (tables: generic ratio only)
 struct TailSmem {
   float* foot;
+  float* slices;   // slices[k * 256 + tid]: bilinear slice value c_k of this thread's pixel
   float* w1tab;
   int* dstart;
   int* i0tab;
   __device__ __forceinline__ TailSmem(float* base, const TailGeom& g) {
     foot = base;
-    w1tab = base + g.Dc * g.FH * g.FW;
+    slices = base + g.Dc * g.FH * g.FW;
+    w1tab = slices + (g.cached ? g.Dc * kTX * kTY : 0);
     dstart = reinterpret_cast<int*>(w1tab + g.D);
     i0tab = dstart + g.Dc + 1;
   }
 };
 static size_t tail_smem_bytes(const TailGeom& g) {
   size_t n = (size_t)g.Dc * g.FH * g.FW;
+  if (g.cached) n += (size_t)g.Dc * kTX * kTY;
   if (!g.fast4) n += (size_t)g.D + g.Dc + 1 + g.D;
   return n * sizeof(float);
 }
@@ -120,12 +125,36 @@ struct Taps {
   }
 };
 
+// slice values of one pixel: evaluated once (pass 1) and, when they fit, parked in shared memory so
+// that pass 2 is one LDS per slice instead of 4 LDS + 6 flops
+template <bool CACHED>
+struct SliceSrc {
+  const Taps& tp;
+  const float* foot;
+  float* mine;   // &slices[tid]
+  int per;
+  __device__ __forceinline__ float max_and_park(int Dc) const {
+    float M = -INFINITY;
+    const float* s = foot;
+    float* dst = mine;
+    for (int k = 0; k < Dc; ++k, s += per, dst += kTX * kTY) {
+      const float c = tp.slice(s);
+      M = fmaxf(M, c);
+      if (CACHED) *dst = c;
+    }
+    return M;
+  }
+  __device__ __forceinline__ float get(int k) const {
+    return CACHED ? mine[k * (kTX * kTY)] : tp.slice(foot + k * per);
+  }
+};
+
 struct NoTrack {
   __device__ __forceinline__ void update(float, int) {}
 };
 
 // ===================================================================================== forward
-template <typename T, bool FAST4, bool WANT_ARG>
+template <typename T, bool FAST4, bool WANT_ARG, bool CACHED>
 __global__ void __launch_bounds__(kTX * kTY)
 upsample_regress_fwd_kernel(const T* __restrict__ cost, T* __restrict__ soft, int64_t* __restrict__ amin,
                             int64_t* __restrict__ amax, float* __restrict__ lse, TailGeom g) {
@@ -140,18 +169,17 @@ upsample_regress_fwd_kernel(const T* __restrict__ cost, T* __restrict__ soft, in
   if (x >= g.W || y >= g.H) return;
 
   const Taps tp(x, y, cx0, cy0, g);
-  const int per = g.FH * g.FW;
+  const SliceSrc<CACHED> src{tp, sm.foot, sm.slices + threadIdx.x, g.FH * g.FW};
   // pass 1: stabiliser.  Every fine value is a convex combination of slice values, so their max
   // bounds it (and is attained within |c_{k+1}-c_k|/8 for the x4 head).
-  float M = -INFINITY;
-  for (int k = 0; k < g.Dc; ++k) M = fmaxf(M, tp.slice(sm.foot + k * per));
+  const float M = src.max_and_park(g.Dc);
   const float Ml = M * kLog2e;
 
   // pass 2: intervals in ascending d.  Slices are pre-scaled: cs = c*log2(e) - M*log2(e), so
   // exp(f - M) = ex2(lerp(cs0, cs1)).  The arg-extrema are tracked on the (monotone) scaled values.
   float s = 0.f, ws = 0.f;
   typename std::conditional<WANT_ARG, ArgTrack, NoTrack>::type trk;
-  float cs0 = fmaf(tp.slice(sm.foot), kLog2e, -Ml);
+  float cs0 = fmaf(src.get(0), kLog2e, -Ml);
   if constexpr (FAST4) {
     {   // d' = 0, 1 sit on slice 0
       const float e = fast_exp2(cs0);
@@ -160,7 +188,7 @@ upsample_regress_fwd_kernel(const T* __restrict__ cost, T* __restrict__ soft, in
     }
     float base = 2.f;   // first fine index of the interval, 4k + 2
     for (int k = 0; k + 1 < g.Dc; ++k) {
-      const float cs1 = fmaf(tp.slice(sm.foot + (k + 1) * per), kLog2e, -Ml);
+      const float cs1 = fmaf(src.get(k + 1), kLog2e, -Ml);
       const float dl = cs1 - cs0;
       const float f0 = fmaf(0.125f, dl, cs0), f1 = fmaf(0.375f, dl, cs0);
       const float f2 = fmaf(0.625f, dl, cs0), f3 = fmaf(0.875f, dl, cs0);
@@ -184,7 +212,7 @@ upsample_regress_fwd_kernel(const T* __restrict__ cost, T* __restrict__ soft, in
     }
   } else {
     for (int k = 0; k < g.Dc; ++k) {
-      const float cs1 = (k + 1 < g.Dc) ? fmaf(tp.slice(sm.foot + (k + 1) * per), kLog2e, -Ml) : cs0;
+      const float cs1 = (k + 1 < g.Dc) ? fmaf(src.get(k + 1), kLog2e, -Ml) : cs0;
       const float dl = cs1 - cs0;
       const int dend = sm.dstart[k + 1];
       for (int d = sm.dstart[k]; d < dend; ++d) {
@@ -333,6 +361,7 @@ static int make_geom(int64_t Dc, int64_t Hc, int64_t Wc, int64_t D, int64_t H, i
   g.FH = (int)fminf((float)Hc, ceilf(kTY * g.sh) + 2.f);
   g.FW = (int)fminf((float)Wc, ceilf(kTX * g.sw) + 2.f);
   g.fast4 = (D == 4 * Dc) ? 1 : 0;
+  g.cached = (Dc * kTX * kTY * sizeof(float) <= 96 * 1024) ? 1 : 0;
   smem = tail_smem_bytes(g);
   if (smem > 200 * 1024) return RSM_ERR_UNSUPPORTED_CONFIG;
   return RSM_OK;
@@ -351,7 +380,8 @@ using namespace rsm;
 template <typename T, bool FAST4, bool WANT_ARG>
 static int launch_tail_fwd(const void* cost, const rsm_regress_out& out, const TailGeom& g, size_t smem, dim3 grid,
                            cudaStream_t st) {
-  auto k = upsample_regress_fwd_kernel<T, FAST4, WANT_ARG>;
+  auto k = g.cached ? upsample_regress_fwd_kernel<T, FAST4, WANT_ARG, true>
+                    : upsample_regress_fwd_kernel<T, FAST4, WANT_ARG, false>;
   if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k<<<grid, kTX * kTY, smem, st>>>((const T*)cost, (T*)out.soft, out.argmin, out.argmax, out.lse, g);
   return finish_launch("rsm_upsample_regress_fwd");
@@ -393,6 +423,8 @@ extern "C" int rsm_upsample_regress_bwd(const void* gout, const void* cost, cons
   size_t smem;
   if (int rc = make_geom(Dc, Hc, Wc, D, H, W, g, smem)) return rc;
   if (B == 0) return RSM_OK;
+  g.cached = 0;   // the adjoint evaluates every slice exactly once: nothing to park
+  smem = tail_smem_bytes(g);
   if (!gout || !cost || !soft || !lse || !gcost || !workspace) return RSM_ERR_NULL_POINTER;
   if (B > 65535) return RSM_ERR_INVALID_SHAPE;
   RSM_COMMON_CHECKS(dtype)

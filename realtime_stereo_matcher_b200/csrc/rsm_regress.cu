@@ -8,10 +8,81 @@
 namespace rsm {
 
 // ============================================================================ regress fwd
-// One thread owns VEC consecutive pixels and streams the D values of each (coalesced 16-byte
-// loads across the warp, stride H*W between disparities), DCH disparities per step so that one
-// rescale exp serves DCH value exps and DCH independent loads are in flight.
-template <typename T, int VEC, int DCH>
+// One thread owns VEC consecutive pixels and streams their D values (coalesced vector loads across
+// the warp, stride H*W between disparities), DCH disparities per step: DCH independent loads in
+// flight, one rescale exp per DCH value exps (chunked online softmax).  The arg-extrema follow
+// torch.argmin/argmax: first index on ties (strict compares in ascending d) and NaN as the
+// extremum -- NaNs only raise a flag in the hot loop; flagged pixels (rare) are re-scanned for
+// their first NaN at the end.
+template <typename T, int VEC>
+__device__ __forceinline__ void load_vec(const T* __restrict__ p, float (&v)[VEC]) {
+  if constexpr (VEC * sizeof(T) == 16) {
+    Vec16<T> t = ldcs16(p);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) v[j] = to_f(t.v[j]);
+  } else if constexpr (VEC * sizeof(T) == 8) {
+    union { uint2 raw; T e[VEC]; } t;
+    t.raw = __ldcs(reinterpret_cast<const uint2*>(p));
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) v[j] = to_f(t.e[j]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) v[j] = to_f(__ldcs(p + j));
+  }
+}
+
+template <int VEC, bool SOFT, bool ARG>
+struct RegressState {
+  float m[VEC], s[VEC], ws[VEC];
+  float minv[VEC], maxv[VEC];
+  int mini[VEC], maxi[VEC];
+  bool nan[VEC];
+  __device__ __forceinline__ RegressState() {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      m[j] = -INFINITY; s[j] = 0.f; ws[j] = 0.f;
+      minv[j] = INFINITY; maxv[j] = -INFINITY; mini[j] = 0; maxi[j] = 0; nan[j] = false;
+    }
+  }
+  // consume disparities d0 .. d0+CNT-1 held in v[k][j]
+  template <int DCH>
+  __device__ __forceinline__ void consume(const float (&v)[DCH][VEC], int d0, int cnt) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      if constexpr (SOFT) {
+        float cm = v[0][j];
+#pragma unroll
+        for (int k = 1; k < DCH; ++k)
+          if (k < cnt) cm = fmaxf(cm, v[k][j]);
+        const float mn = fmaxf(m[j], cm);
+        const float mnl = mn * kLog2e;
+        // exp(m - mn); nothing seen yet (m = -inf): s = ws = 0 and the scale is irrelevant
+        const float a = (m[j] == -INFINITY) ? 0.f : fast_exp2(fmaf(m[j], kLog2e, -mnl));
+        float sj = s[j] * a, wj = ws[j] * a;
+#pragma unroll
+        for (int k = 0; k < DCH; ++k)
+          if (k < cnt) {
+            const float e = fast_exp2(fmaf(v[k][j], kLog2e, -mnl));
+            sj += e;
+            wj = fmaf((float)(d0 + k), e, wj);
+          }
+        m[j] = mn; s[j] = sj; ws[j] = wj;
+      }
+      if constexpr (ARG) {
+#pragma unroll
+        for (int k = 0; k < DCH; ++k)
+          if (k < cnt) {
+            const float x = v[k][j];
+            if (x < minv[j]) { minv[j] = x; mini[j] = d0 + k; }
+            if (x > maxv[j]) { maxv[j] = x; maxi[j] = d0 + k; }
+            nan[j] |= (x != x);
+          }
+      }
+    }
+  }
+};
+
+template <typename T, int VEC, int DCH, bool SOFT, bool ARG>
 __global__ void __launch_bounds__(256)
 regress_fwd_kernel(const T* __restrict__ cost, T* __restrict__ soft, int64_t* __restrict__ amin,
                    int64_t* __restrict__ amax, float* __restrict__ lse, int64_t pix_vec_per_img,
@@ -22,58 +93,44 @@ regress_fwd_kernel(const T* __restrict__ cost, T* __restrict__ soft, int64_t* __
   const int64_t p = (i - n * pix_vec_per_img) * VEC;
   const T* __restrict__ base = cost + n * D * HW + p;
 
-  float m[VEC], s[VEC], ws[VEC];
-  ArgTrack trk[VEC];
+  RegressState<VEC, SOFT, ARG> st;
+  int d0 = 0;
+  for (; d0 + DCH <= D; d0 += DCH) {      // full chunks: no bounds checks
+    float v[DCH][VEC];
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) { m[j] = -INFINITY; s[j] = 0.f; ws[j] = 0.f; }
-
-  for (int d0 = 0; d0 < D; d0 += DCH) {
+    for (int k = 0; k < DCH; ++k) load_vec<T, VEC>(base + (int64_t)(d0 + k) * HW, v[k]);
+    st.template consume<DCH>(v, d0, DCH);
+  }
+  if (d0 < D) {                            // ragged tail
     float v[DCH][VEC];
 #pragma unroll
     for (int k = 0; k < DCH; ++k) {
-      if (d0 + k < D) {
-        if constexpr (VEC * sizeof(T) == 16) {
-          Vec16<T> t = ldcs16(base + (int64_t)(d0 + k) * HW);
+      if (d0 + k < D) load_vec<T, VEC>(base + (int64_t)(d0 + k) * HW, v[k]);
+      else {
 #pragma unroll
-          for (int j = 0; j < VEC; ++j) v[k][j] = to_f(t.v[j]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < VEC; ++j) v[k][j] = to_f(__ldcs(base + (int64_t)(d0 + k) * HW + j));
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) v[k][j] = -INFINITY;
+        for (int j = 0; j < VEC; ++j) v[k][j] = 0.f;
       }
     }
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      float cm = v[0][j];
-#pragma unroll
-      for (int k = 1; k < DCH; ++k) cm = fmaxf(cm, v[k][j]);
-      const float mn = fmaxf(m[j], cm);
-      const float mnl = mn * kLog2e;
-      // exp(m - mn); when both are -inf (nothing seen yet) the scale is irrelevant: s = ws = 0
-      const float a = (m[j] == -INFINITY) ? 0.f : fast_exp2(m[j] * kLog2e - mnl);
-      float sj = s[j] * a, wj = ws[j] * a;
-#pragma unroll
-      for (int k = 0; k < DCH; ++k) {
-        if (d0 + k < D) {
-          const float e = fast_exp2(fmaf(v[k][j], kLog2e, -mnl));
-          sj += e;
-          wj = fmaf((float)(d0 + k), e, wj);
-          trk[j].update(v[k][j], d0 + k);
-        }
-      }
-      m[j] = mn; s[j] = sj; ws[j] = wj;
-    }
+    st.template consume<DCH>(v, d0, D - d0);
   }
   const int64_t o = n * HW + p;
 #pragma unroll
   for (int j = 0; j < VEC; ++j) {
-    if (soft) soft[o + j] = from_f<T>(ws[j] / s[j]);
-    if (lse) lse[o + j] = m[j] + __logf(s[j]);
-    if (amin) amin[o + j] = trk[j].mini;
-    if (amax) amax[o + j] = trk[j].maxi;
+    if constexpr (SOFT) {
+      if (soft) soft[o + j] = from_f<T>(st.ws[j] / st.s[j]);
+      if (lse) lse[o + j] = st.m[j] + __logf(st.s[j]);
+    }
+    if constexpr (ARG) {
+      int mi = st.mini[j], ma = st.maxi[j];
+      if (st.nan[j]) {                     // torch: NaN is both the minimum and the maximum; first one wins
+        for (int d = 0; d < D; ++d) {
+          const float x = to_f(base[(int64_t)d * HW + j]);
+          if (x != x) { mi = ma = d; break; }
+        }
+      }
+      if (amin) amin[o + j] = mi;
+      if (amax) amax[o + j] = ma;
+    }
   }
 }
 
@@ -190,19 +247,26 @@ extern "C" int rsm_regress_fwd(const void* cost, int64_t N, int64_t D, int64_t H
   if (D > 2147483647LL) return RSM_ERR_INVALID_SHAPE;
   RSM_COMMON_CHECKS(dtype)
   return RSM_DISPATCH_DTYPE(dtype, T, [&]() -> int {
-    constexpr int VEC = 16 / sizeof(T);
+    constexpr int VEC = 4;   // 16-byte loads for fp32, 8-byte loads for 16-bit: same register budget
     const int64_t HW = H * W;
-    const bool vec = HW % VEC == 0 && aligned_to(cost, 16);
+    const bool vec = HW % VEC == 0 && aligned_to(cost, VEC * sizeof(T));
     const int64_t pv = vec ? HW / VEC : HW;
     const int64_t total = N * pv;
     if (!grid_ok(ceil_div(total, 256))) return (int)RSM_ERR_INVALID_SHAPE;
     const unsigned blocks = (unsigned)ceil_div(total, 256);
-    if (vec)
-      regress_fwd_kernel<T, VEC, (sizeof(T) == 4 ? 8 : 4)><<<blocks, 256, 0, st>>>(
-          (const T*)cost, (T*)out.soft, out.argmin, out.argmax, out.lse, pv, total, (int)D, HW);
-    else
-      regress_fwd_kernel<T, 1, 8><<<blocks, 256, 0, st>>>((const T*)cost, (T*)out.soft, out.argmin, out.argmax,
-                                                          out.lse, pv, total, (int)D, HW);
+    const bool want_soft = out.soft || out.lse, want_arg = out.argmin || out.argmax;
+    auto launch = [&](auto kern) {
+      kern<<<blocks, 256, 0, st>>>((const T*)cost, (T*)out.soft, out.argmin, out.argmax, out.lse, pv, total, (int)D, HW);
+    };
+    if (vec) {
+      if (want_soft && want_arg) launch(regress_fwd_kernel<T, 4, 4, true, true>);
+      else if (want_soft) launch(regress_fwd_kernel<T, 4, 8, true, false>);
+      else launch(regress_fwd_kernel<T, 4, 8, false, true>);
+    } else {
+      if (want_soft && want_arg) launch(regress_fwd_kernel<T, 1, 8, true, true>);
+      else if (want_soft) launch(regress_fwd_kernel<T, 1, 8, true, false>);
+      else launch(regress_fwd_kernel<T, 1, 8, false, true>);
+    }
     return finish_launch("rsm_regress_fwd");
   });
 }

@@ -1,0 +1,178 @@
+#!/usr/bin/env python
+"""Per-kernel roofline sweep over the BASELINE.json configs.
+
+Each op is timed alone with CUDA events on the launching stream, L2 flushed (a 512 MB memset)
+before every timed launch, median of `--iters` launches after 3 warm-ups.  achieved GB/s uses the
+ALGORITHMIC bytes (each input element read once, each output element written once); the fraction
+is against MEASURED_PEAKS.json hbm_gbs.  One JSON object per line on stdout.
+
+    python tools/sweep.py [--iters 10] [--only cfg3]
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import realtime_stereo_matcher_b200 as rsm  # noqa: E402
+
+DT = {"f32": torch.float32, "bf16": torch.bfloat16, "f16": torch.float16}
+PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
+    os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+_flush = None
+
+
+def flush_l2():
+    global _flush
+    if _flush is None:
+        _flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+    _flush.zero_()
+
+
+def timed(fn, iters):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        flush_l2()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return statistics.median(ts)
+
+
+def report(cfg, op, dtype, shape, ms, nbytes, flops=0):
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    rec = {"cfg": cfg, "op": op, "dtype": dtype, "shape": shape, "ms": round(ms, 5), "algorithmic_bytes": nbytes,
+           "GBps": round(gbs, 1), "frac_of_measured_hbm": round(gbs / PEAK, 3)}
+    if flops:
+        rec["TFLOPs"] = round(flops / (ms * 1e-3) / 1e12, 2)
+    print(json.dumps(rec), flush=True)
+
+
+def feats(n, c, h, w, dt):
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    return (torch.randn((n, c, h, w), device="cuda", generator=g).to(DT[dt]),
+            torch.randn((n, c, h, w), device="cuda", generator=g).to(DT[dt]))
+
+
+def sweep_volumes(cfg, n, c, h, w, d, g, dtypes, iters, ops):
+    for dt in dtypes:
+        e = 2 if dt != "f32" else 4
+        L, R = feats(n, c, h, w, dt)
+        fin = 2 * n * c * h * w * e
+        shp = dict(N=n, C=c, H=h, W=w, D=d, G=g)
+        with torch.no_grad():
+            if "concat" in ops:
+                report(cfg, "concat_fwd", dt, shp, timed(lambda: rsm.concat_volume(L, R, d), iters), fin + 2 * n * c * h * w * d * e)
+            if "interweave" in ops:
+                report(cfg, "interweave_fwd", dt, shp, timed(lambda: rsm.interweave(L, R), iters), 2 * fin)
+            if "difference" in ops:
+                report(cfg, "difference_fwd", dt, shp, timed(lambda: rsm.difference_volume(L, R, d), iters), fin + n * c * d * h * w * e)
+            if "groupwise" in ops:
+                report(cfg, "groupwise_fwd", dt, shp, timed(lambda: rsm.groupwise_volume(L, R, g, d), iters),
+                       fin + n * g * h * w * d * e, 2 * n * c * h * w * d)
+            if "inner" in ops:
+                report(cfg, "inner_mean_fwd", dt, shp, timed(lambda: rsm.inner_product_volume(L, R, d, mean=True), iters),
+                       fin + n * d * h * w * e, 2 * n * c * h * w * d)
+            if "fused" in ops and d <= 512:
+                report(cfg, "inner_regress_fused_fwd", dt, shp, timed(lambda: rsm.inner_product_regress(L, R, d), iters),
+                       fin + n * h * w * 20, 2 * n * c * h * w * d)
+        if "bwd" in ops:
+            Lg, Rg = L.clone().requires_grad_(True), R.clone().requires_grad_(True)
+            for name, fn, nb in (
+                ("concat_bwd", lambda: rsm.concat_volume(Lg, Rg, d), 2 * n * c * h * w * d * e + fin),
+                ("groupwise_bwd", lambda: rsm.groupwise_volume(Lg, Rg, g, d), n * g * h * w * d * e + 2 * fin),
+                ("inner_mean_bwd", lambda: rsm.inner_product_volume(Lg, Rg, d, mean=True), n * d * h * w * e + 2 * fin),
+            ):
+                if name.split("_")[0] not in ops:
+                    continue
+                out = fn()
+                go = torch.randn_like(out)
+                report(cfg, name, dt, shp, timed(lambda: torch.autograd.grad(out, (Lg, Rg), go, retain_graph=True), iters), nb)
+                del out, go
+        del L, R
+        torch.cuda.empty_cache()
+
+
+def sweep_regress(cfg, n, d, h, w, dtypes, iters):
+    for dt in dtypes:
+        e = 2 if dt != "f32" else 4
+        g = torch.Generator(device="cuda").manual_seed(1234)
+        cost = (torch.randn((n, d, h, w), device="cuda", generator=g) * 4).to(DT[dt])
+        shp = dict(N=n, D=d, H=h, W=w)
+        with torch.no_grad():
+            report(cfg, "regress_fwd(soft+argmin+argmax)", dt, shp, timed(lambda: rsm.regress(cost), iters),
+                   n * d * h * w * e + n * h * w * (e + 16))
+            report(cfg, "soft_argmax_fwd", dt, shp, timed(lambda: rsm.soft_argmax(cost), iters), n * d * h * w * e + n * h * w * e)
+            report(cfg, "hard_argmin_fwd", dt, shp, timed(lambda: rsm.hard_argmin(cost), iters), n * d * h * w * e + n * h * w * 8)
+        cg = cost.requires_grad_(True)
+        out = rsm.soft_argmax(cg)
+        go = torch.randn_like(out)
+        report(cfg, "soft_argmax_bwd", dt, shp, timed(lambda: torch.autograd.grad(out, cg, go, retain_graph=True), iters),
+               2 * n * d * h * w * e + 3 * n * h * w * 4)
+        del cost, cg, out, go
+        torch.cuda.empty_cache()
+
+
+def sweep_tail(cfg, b, dc, hc, wc, iters):
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    cost = torch.randn((b, dc, hc, wc), device="cuda", generator=g) * 3
+    d, h, w = 4 * dc, 4 * hc, 4 * wc
+    shp = dict(B=b, Dc=dc, Hc=hc, Wc=wc, D=d, H=h, W=w)
+    nb = b * dc * hc * wc * 4 + b * h * w * 4
+    with torch.no_grad():
+        ms = timed(lambda: rsm.v4_head(cost, d, h, w), iters)
+        report(cfg, "v4_head_fwd", "f32", {**shp, "Gexp_per_s": round(b * d * h * w / (ms * 1e-3) / 1e9, 1)}, ms, nb)
+        report(cfg, "v4_head_fwd+argmin+argmax", "f32", shp,
+               timed(lambda: rsm.upsample_regress(cost, d, h, w, argmin=True, argmax=True), iters), nb + b * h * w * 16)
+        # the unfused 4-kernel path this replaces (stock torch on the same device), for the speed-up figure
+        def unfused():
+            fine = torch.nn.functional.interpolate(cost.unsqueeze(1), [d, h, w], mode="trilinear").squeeze(1)
+            p = torch.softmax(fine, 1)
+            return (p * torch.arange(d, device="cuda", dtype=p.dtype).view(1, -1, 1, 1)).sum(1)
+        if b * d * h * w * 4 * 3 < 60e9:
+            report(cfg, "v4_head_unfused_torch(reference op sequence on GPU)", "f32", shp, timed(unfused, max(3, iters // 3)), nb)
+    cg = cost.requires_grad_(True)
+    out = rsm.v4_head(cg, d, h, w)
+    go = torch.randn_like(out)
+    report(cfg, "v4_head_bwd", "f32", shp, timed(lambda: torch.autograd.grad(out, cg, go, retain_graph=True), iters),
+           nb + 2 * b * dc * h * w * 4)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--only", default="")
+    a = ap.parse_args()
+    want = lambda c: not a.only or c in a.only.split(",")
+    rsm.load_library()
+    if want("cfg1"):
+        sweep_volumes("cfg1", 1, 32, 48, 156, 24, 8, ["f32"], a.iters, {"difference", "bwd"})
+        sweep_regress("cfg1", 1, 24, 48, 156, ["f32"], a.iters)
+    if want("cfg2"):
+        for c in (16, 64):
+            sweep_volumes("cfg2", 32, c, 144, 240, 48, 1, ["f32", "bf16"], a.iters, {"inner", "fused", "bwd"})
+    if want("cfg3"):
+        sweep_volumes("cfg3", 8, 32, 96, 312, 48, 8, ["f32", "bf16"], a.iters, {"concat", "groupwise", "interweave", "bwd"})
+        sweep_tail("cfg3", 8, 48, 96, 312, a.iters)
+        sweep_regress("cfg3", 8, 192, 384, 1248, ["f32"], a.iters)
+    if want("cfg4"):
+        for c, g, d in ((32, 8, 48), (64, 16, 96), (128, 32, 192)):
+            sweep_volumes("cfg4", 1, c, 270, 480, d, g, ["f32", "bf16"], a.iters, {"concat", "groupwise", "inner", "fused"})
+    if want("cfg5"):
+        sweep_regress("cfg5", 1, 192, 1080, 1920, ["f32", "bf16"], a.iters)
+        sweep_regress("cfg5", 4, 192, 1080, 1920, ["f32"], a.iters)
+        sweep_tail("cfg5", 1, 48, 270, 480, a.iters)
+
+
+if __name__ == "__main__":
+    main()

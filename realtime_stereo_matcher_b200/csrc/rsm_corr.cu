@@ -52,6 +52,19 @@ __device__ __forceinline__ void stage_slab(const FeatView& L, const FeatView& R,
     const int64_t cs = left ? L.sc : R.sc;
     float* dst = left ? sL + e : sR + (e - TX);
     const int pitch = left ? TX : rw;
+    if constexpr (sizeof(Tin) == 4) {
+      // fp32 features: asynchronous global->shared copies (LDGSTS), all of the thread's loads in
+      // flight at once, zero-fill (src-size 0) outside the image; completed by cp_async_wait_all()
+      const uint32_t sdst = (uint32_t)__cvta_generic_to_shared(dst);
+      const Tin* src = valid ? p : reinterpret_cast<const Tin*>(L.data);
+      const int64_t step = valid ? cs : 0;
+      const int nbytes = valid ? 4 : 0;
+      for (int c = 0; c < nch; ++c)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sdst + (uint32_t)(c * pitch * 4)),
+                     "l"(src + c * step), "r"(nbytes)
+                     : "memory");
+      continue;
+    }
     for (int c = 0; c < nch; c += U) {
       float v[U];
 #pragma unroll
@@ -61,6 +74,7 @@ __device__ __forceinline__ void stage_slab(const FeatView& L, const FeatView& R,
         if (c + u < nch) dst[(c + u) * pitch] = v[u];
     }
   }
+  if constexpr (sizeof(Tin) == 4) asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
 // ---- accumulate the 4x8 register tile over staged channels [cofs, cofs+nch)

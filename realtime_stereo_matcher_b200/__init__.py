@@ -15,6 +15,7 @@ from .functional import (concat_volume, difference_volume, expectation, groupwis
 from .model_functions import (disparity_regression_dispnetc, disparity_regression_v4, interweave_tensors,
                               make_correlation_volume, make_cost_volume, softmax_regression, v4_head)
 from .patch import patch_reference, unpatch_reference
+from .pipeline import HostPipeline
 from .sharding import all_gather_metrics, shard_range
 
 __version__ = "0.1.0"

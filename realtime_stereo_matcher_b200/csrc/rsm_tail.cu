@@ -4,11 +4,14 @@
 // exp per fine disparity), not by HBM, so the work per fine disparity is stripped
 // to: one FMA (lerp along d of two pre-scaled coarse slices), one ex2, and the two accumulations.
 //
-// Per output pixel the 4 bilinear taps of every coarse slice are combined ONCE per slice
-// ("slice value" c_k); fine disparities are then visited interval by interval: all d' whose
-// source index i0(d') equals k interpolate between c_k and c_{k+1}.  For the x4 head
-// (D == 4*Dc) the intervals are regular -- weights 1/8,3/8,5/8,7/8 -- and the inner loop is fully
-// unrolled with constant weights; other ratios use per-CTA tables in shared memory.
+// The interpolation is separable and is evaluated in that order per CTA (32x8 output pixels):
+//   1. the coarse footprint of the tile is staged in shared memory (raw[k][fy][fx]);
+//   2. it is interpolated along x ONCE for the tile's 32 output columns (rows[k][fy][tx]);
+//   3. each thread (one pixel) gets slice value c_k with one y-lerp of two conflict-free LDS;
+//   4. fine disparities are visited interval by interval: all d' whose source index i0(d') equals
+//      k interpolate between c_k and c_{k+1}.  For the x4 head (D == 4*Dc) the intervals are
+//      regular -- weights 1/8,3/8,5/8,7/8 -- and the loop body is fully unrolled with constant
+//      weights; other ratios use per-CTA index/weight tables in shared memory.
 #include <type_traits>
 
 #include "rsm_common.cuh"
@@ -32,73 +35,79 @@ __device__ __forceinline__ Lin lin_index(int o, float scale, int n_in) {
   return r;
 }
 
-constexpr int kTX = 32, kTY = 8;  // fine-pixel tile of one CTA (256 threads, one pixel each)
+constexpr int kTX = 32, kTY = 8;   // fine-pixel tile of one CTA (256 threads, one pixel each)
+constexpr int kNT = kTX * kTY;
 
 struct TailGeom {
   int Dc, Hc, Wc, D, H, W;
   int FH, FW;        // coarse rows / cols a tile can touch (upper bound)
   int fast4;         // D == 4 * Dc
-  int cached;        // per-pixel slice values are parked in shared memory (Dc * 256 floats fit)
   float sd, sh, sw;  // in/out scale per axis
 };
 
-// shared memory: [ footprint Dc*FH*FW | slices Dc*256 (if cached) | w1tab D | dstart Dc+1 | i0tab D ]
-// (tables: generic ratio only)
+// shared memory: [ rows Dc*FH*32 | raw Dc*FH*FW | w1tab D | dstart Dc+1 | i0tab D ]  (tables: generic ratio)
 struct TailSmem {
-  float* foot;
-  float* slices;   // slices[k * 256 + tid]: bilinear slice value c_k of this thread's pixel
+  float* rows;
+  float* raw;
   float* w1tab;
   int* dstart;
   int* i0tab;
   __device__ __forceinline__ TailSmem(float* base, const TailGeom& g) {
-    foot = base;
-    slices = base + g.Dc * g.FH * g.FW;
-    w1tab = slices + (g.cached ? g.Dc * kTX * kTY : 0);
+    rows = base;
+    raw = rows + g.Dc * g.FH * kTX;
+    w1tab = raw + g.Dc * g.FH * g.FW;
     dstart = reinterpret_cast<int*>(w1tab + g.D);
     i0tab = dstart + g.Dc + 1;
   }
 };
 static size_t tail_smem_bytes(const TailGeom& g) {
-  size_t n = (size_t)g.Dc * g.FH * g.FW;
-  if (g.cached) n += (size_t)g.Dc * kTX * kTY;
+  size_t n = (size_t)g.Dc * g.FH * (kTX + g.FW);
   if (!g.fast4) n += (size_t)g.D + g.Dc + 1 + g.D;
   return n * sizeof(float);
 }
 
-// stage the coarse footprint of this tile as fp32: foot[k][fy][fx], rows cy0.., cols cx0..; and,
-// for generic ratios, the per-fine-disparity tables.  Ends with __syncthreads().
+// Steps 1 + 2 (+ tables).  Ends with __syncthreads().
 template <typename T>
 __device__ __forceinline__ void stage_tile(const T* __restrict__ cost_b, const TailSmem& sm, const TailGeom& g,
                                            int cy0, int cx0) {
+  // ---- 1. raw footprint: thread -> (r = tid % 64, k = tid / 64 + 4j); no divisions in the loop
   const int per = g.FH * g.FW;
-  const int tot = g.Dc * per;
   const int64_t plane = (int64_t)g.Hc * g.Wc;
-  constexpr int U = 8, NT = kTX * kTY;   // U independent loads in flight per thread
-  for (int e0 = threadIdx.x; e0 < tot; e0 += U * NT) {
-    float v[U];
+  for (int r = threadIdx.x & 63; r < per; r += 64) {
+    const int fy = r / g.FW, fx = r - fy * g.FW;
+    const int cy = min(cy0 + fy, g.Hc - 1), cx = min(cx0 + fx, g.Wc - 1);
+    const T* __restrict__ src = cost_b + (int64_t)cy * g.Wc + cx;
+    constexpr int U = 4;
+    for (int k0 = threadIdx.x >> 6; k0 < g.Dc; k0 += 4 * U) {
+      float v[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int e = e0 + u * NT;
-      v[u] = 0.f;
-      if (e < tot) {
-        const int k = e / per, r = e - k * per;
-        const int fy = r / g.FW, fx = r - fy * g.FW;
-        const int cy = min(cy0 + fy, g.Hc - 1), cx = min(cx0 + fx, g.Wc - 1);
-        v[u] = to_f(__ldg(cost_b + k * plane + (int64_t)cy * g.Wc + cx));
-      }
+      for (int u = 0; u < U; ++u) v[u] = (k0 + 4 * u < g.Dc) ? to_f(__ldg(src + (k0 + 4 * u) * plane)) : 0.f;
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (k0 + 4 * u < g.Dc) sm.raw[(k0 + 4 * u) * per + r] = v[u];
     }
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-      if (e0 + u * NT < tot) sm.foot[e0 + u * NT] = v[u];
   }
   if (!g.fast4) {
-    for (int d = threadIdx.x; d < g.D; d += kTX * kTY) {
+    for (int d = threadIdx.x; d < g.D; d += kNT) {
       const Lin ld = lin_index(d, g.sd, g.Dc);
       sm.w1tab[d] = ld.w1;
       sm.i0tab[d] = ld.i0;
     }
-    __syncthreads();
-    for (int k = threadIdx.x; k <= g.Dc; k += kTX * kTY) {   // dstart[k] = #{d : i0(d) < k}
+  }
+  __syncthreads();
+  // ---- 2. interpolate along x for this tile's 32 columns: rows[(k*FH + fy)*32 + tx]
+  {
+    const int tx = threadIdx.x & (kTX - 1);
+    const Lin lx = lin_index(blockIdx.x * kTX + tx, g.sw, g.Wc);
+    const int a0 = min(lx.i0 - cx0, g.FW - 1), a1 = min(lx.i1 - cx0, g.FW - 1);
+    const int npair = g.Dc * g.FH;          // (k, fy) pairs; raw row of pair p starts at p * FW
+    for (int p = threadIdx.x >> 5; p < npair; p += kNT / kTX) {
+      const float* rr = sm.raw + p * g.FW;
+      sm.rows[p * kTX + tx] = lx.w0 * rr[a0] + lx.w1 * rr[a1];
+    }
+  }
+  if (!g.fast4) {
+    for (int k = threadIdx.x; k <= g.Dc; k += kNT) {   // dstart[k] = #{d : i0(d) < k}
       int lo = 0, hi = g.D;
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
@@ -110,43 +119,21 @@ __device__ __forceinline__ void stage_tile(const T* __restrict__ cost_b, const T
   __syncthreads();
 }
 
-// bilinear taps of one output pixel inside the staged footprint
-struct Taps {
-  int o00, o01, o10, o11;
-  float wx0, wx1, wy0, wy1;
-  __device__ __forceinline__ Taps(int x, int y, int cx0, int cy0, const TailGeom& g) {
-    const Lin ly = lin_index(y, g.sh, g.Hc), lx = lin_index(x, g.sw, g.Wc);
-    o00 = (ly.i0 - cy0) * g.FW + (lx.i0 - cx0); o01 = (ly.i0 - cy0) * g.FW + (lx.i1 - cx0);
-    o10 = (ly.i1 - cy0) * g.FW + (lx.i0 - cx0); o11 = (ly.i1 - cy0) * g.FW + (lx.i1 - cx0);
-    wx0 = lx.w0; wx1 = lx.w1; wy0 = ly.w0; wy1 = ly.w1;
+// Step 3: the y-lerp of one output pixel; slice k is at base + k * stride
+struct SliceY {
+  const float* p0;   // rows + (y0 - cy0) * 32 + tx
+  const float* p1;   // rows + (y1 - cy0) * 32 + tx
+  float wy0, wy1;
+  int stride;        // FH * 32
+  __device__ __forceinline__ SliceY(const TailSmem& sm, const TailGeom& g, int y, int cy0) {
+    const Lin ly = lin_index(y, g.sh, g.Hc);
+    const int tx = threadIdx.x & (kTX - 1);
+    p0 = sm.rows + min(ly.i0 - cy0, g.FH - 1) * kTX + tx;
+    p1 = sm.rows + min(ly.i1 - cy0, g.FH - 1) * kTX + tx;
+    wy0 = ly.w0; wy1 = ly.w1;
+    stride = g.FH * kTX;
   }
-  __device__ __forceinline__ float slice(const float* s) const {
-    return wy0 * (wx0 * s[o00] + wx1 * s[o01]) + wy1 * (wx0 * s[o10] + wx1 * s[o11]);
-  }
-};
-
-// slice values of one pixel: evaluated once (pass 1) and, when they fit, parked in shared memory so
-// that pass 2 is one LDS per slice instead of 4 LDS + 6 flops
-template <bool CACHED>
-struct SliceSrc {
-  const Taps& tp;
-  const float* foot;
-  float* mine;   // &slices[tid]
-  int per;
-  __device__ __forceinline__ float max_and_park(int Dc) const {
-    float M = -INFINITY;
-    const float* s = foot;
-    float* dst = mine;
-    for (int k = 0; k < Dc; ++k, s += per, dst += kTX * kTY) {
-      const float c = tp.slice(s);
-      M = fmaxf(M, c);
-      if (CACHED) *dst = c;
-    }
-    return M;
-  }
-  __device__ __forceinline__ float get(int k) const {
-    return CACHED ? mine[k * (kTX * kTY)] : tp.slice(foot + k * per);
-  }
+  __device__ __forceinline__ float get(int k) const { return wy0 * p0[k * stride] + wy1 * p1[k * stride]; }
 };
 
 struct NoTrack {
@@ -154,32 +141,31 @@ struct NoTrack {
 };
 
 // ===================================================================================== forward
-template <typename T, bool FAST4, bool WANT_ARG, bool CACHED>
-__global__ void __launch_bounds__(kTX * kTY)
+template <typename T, bool FAST4, bool WANT_ARG>
+__global__ void __launch_bounds__(kNT)
 upsample_regress_fwd_kernel(const T* __restrict__ cost, T* __restrict__ soft, int64_t* __restrict__ amin,
                             int64_t* __restrict__ amax, float* __restrict__ lse, TailGeom g) {
   extern __shared__ __align__(16) float smem_f[];
   const TailSmem sm(smem_f, g);
   const int b = blockIdx.z;
-  const int tx = threadIdx.x % kTX, ty = threadIdx.x / kTX;
-  const int x = blockIdx.x * kTX + tx, y = blockIdx.y * kTY + ty;
+  const int x = blockIdx.x * kTX + (threadIdx.x & (kTX - 1)), y = blockIdx.y * kTY + threadIdx.x / kTX;
   const int cy0 = lin_index(blockIdx.y * kTY, g.sh, g.Hc).i0;
   const int cx0 = lin_index(blockIdx.x * kTX, g.sw, g.Wc).i0;
   stage_tile(cost + (int64_t)b * g.Dc * g.Hc * g.Wc, sm, g, cy0, cx0);
   if (x >= g.W || y >= g.H) return;
 
-  const Taps tp(x, y, cx0, cy0, g);
-  const SliceSrc<CACHED> src{tp, sm.foot, sm.slices + threadIdx.x, g.FH * g.FW};
+  const SliceY sl(sm, g, y, cy0);
   // pass 1: stabiliser.  Every fine value is a convex combination of slice values, so their max
   // bounds it (and is attained within |c_{k+1}-c_k|/8 for the x4 head).
-  const float M = src.max_and_park(g.Dc);
+  float M = -INFINITY;
+  for (int k = 0; k < g.Dc; ++k) M = fmaxf(M, sl.get(k));
   const float Ml = M * kLog2e;
 
   // pass 2: intervals in ascending d.  Slices are pre-scaled: cs = c*log2(e) - M*log2(e), so
   // exp(f - M) = ex2(lerp(cs0, cs1)).  The arg-extrema are tracked on the (monotone) scaled values.
   float s = 0.f, ws = 0.f;
   typename std::conditional<WANT_ARG, ArgTrack, NoTrack>::type trk;
-  float cs0 = fmaf(src.get(0), kLog2e, -Ml);
+  float cs0 = fmaf(sl.get(0), kLog2e, -Ml);
   if constexpr (FAST4) {
     {   // d' = 0, 1 sit on slice 0
       const float e = fast_exp2(cs0);
@@ -188,7 +174,7 @@ upsample_regress_fwd_kernel(const T* __restrict__ cost, T* __restrict__ soft, in
     }
     float base = 2.f;   // first fine index of the interval, 4k + 2
     for (int k = 0; k + 1 < g.Dc; ++k) {
-      const float cs1 = fmaf(src.get(k + 1), kLog2e, -Ml);
+      const float cs1 = fmaf(sl.get(k + 1), kLog2e, -Ml);
       const float dl = cs1 - cs0;
       const float f0 = fmaf(0.125f, dl, cs0), f1 = fmaf(0.375f, dl, cs0);
       const float f2 = fmaf(0.625f, dl, cs0), f3 = fmaf(0.875f, dl, cs0);
@@ -212,7 +198,7 @@ upsample_regress_fwd_kernel(const T* __restrict__ cost, T* __restrict__ soft, in
     }
   } else {
     for (int k = 0; k < g.Dc; ++k) {
-      const float cs1 = (k + 1 < g.Dc) ? fmaf(src.get(k + 1), kLog2e, -Ml) : cs0;
+      const float cs1 = (k + 1 < g.Dc) ? fmaf(sl.get(k + 1), kLog2e, -Ml) : cs0;
       const float dl = cs1 - cs0;
       const int dend = sm.dstart[k + 1];
       for (int d = sm.dstart[k]; d < dend; ++d) {
@@ -240,28 +226,26 @@ upsample_regress_fwd_kernel(const T* __restrict__ cost, T* __restrict__ soft, in
 // Deterministic (no atomics): intervals are visited in order, so slice k is complete once
 // interval k has been processed.
 template <typename T>
-__global__ void __launch_bounds__(kTX * kTY)
+__global__ void __launch_bounds__(kNT)
 upsample_regress_bwd_cols_kernel(const T* __restrict__ gout, const T* __restrict__ cost,
                                  const T* __restrict__ soft, const float* __restrict__ lse,
                                  float* __restrict__ wsp, TailGeom g) {
   extern __shared__ __align__(16) float smem_f[];
   const TailSmem sm(smem_f, g);
   const int b = blockIdx.z;
-  const int tx = threadIdx.x % kTX, ty = threadIdx.x / kTX;
-  const int x = blockIdx.x * kTX + tx, y = blockIdx.y * kTY + ty;
+  const int x = blockIdx.x * kTX + (threadIdx.x & (kTX - 1)), y = blockIdx.y * kTY + threadIdx.x / kTX;
   const int cy0 = lin_index(blockIdx.y * kTY, g.sh, g.Hc).i0;
   const int cx0 = lin_index(blockIdx.x * kTX, g.sw, g.Wc).i0;
   stage_tile(cost + (int64_t)b * g.Dc * g.Hc * g.Wc, sm, g, cy0, cx0);
   if (x >= g.W || y >= g.H) return;
 
-  const Taps tp(x, y, cx0, cy0, g);
-  const int per = g.FH * g.FW;
+  const SliceY sl(sm, g, y, cy0);
   const int64_t o = ((int64_t)b * g.H + y) * g.W + x;
   const float go = to_f(gout[o]), E = to_f(soft[o]), l2 = lse[o] * kLog2e;
   const int64_t plane = (int64_t)g.H * g.W;
   float* __restrict__ col = wsp + (int64_t)b * g.Dc * plane + (int64_t)y * g.W + x;
 
-  float cs0 = fmaf(tp.slice(sm.foot), kLog2e, -l2);
+  float cs0 = fmaf(sl.get(0), kLog2e, -l2);
   float acc0 = 0.f;   // gradient of slice k accumulated so far
   if (g.fast4) {
     {
@@ -270,7 +254,7 @@ upsample_regress_bwd_cols_kernel(const T* __restrict__ gout, const T* __restrict
     }
     float base = 2.f;
     for (int k = 0; k + 1 < g.Dc; ++k) {
-      const float cs1 = fmaf(tp.slice(sm.foot + (k + 1) * per), kLog2e, -l2);
+      const float cs1 = fmaf(sl.get(k + 1), kLog2e, -l2);
       const float dl = cs1 - cs0;
       float acc1 = 0.f;
 #pragma unroll
@@ -281,7 +265,7 @@ upsample_regress_bwd_cols_kernel(const T* __restrict__ gout, const T* __restrict
         acc0 = fmaf(1.f - w, gf, acc0);
         acc1 = fmaf(w, gf, acc1);
       }
-      col[(int64_t)k * plane] = acc0;
+      __stcs(col + (int64_t)k * plane, acc0);
       acc0 = acc1;
       base += 4.f;
       cs0 = cs1;
@@ -289,11 +273,11 @@ upsample_regress_bwd_cols_kernel(const T* __restrict__ gout, const T* __restrict
     {
       const float p = fast_exp2(cs0);
       acc0 += go * p * (((float)(g.D - 2) - E) + ((float)(g.D - 1) - E));
-      col[(int64_t)(g.Dc - 1) * plane] = acc0;
+      __stcs(col + (int64_t)(g.Dc - 1) * plane, acc0);
     }
   } else {
     for (int k = 0; k < g.Dc; ++k) {
-      const float cs1 = (k + 1 < g.Dc) ? fmaf(tp.slice(sm.foot + (k + 1) * per), kLog2e, -l2) : cs0;
+      const float cs1 = (k + 1 < g.Dc) ? fmaf(sl.get(k + 1), kLog2e, -l2) : cs0;
       const float dl = cs1 - cs0;
       float acc1 = 0.f;
       const int dend = sm.dstart[k + 1];
@@ -361,7 +345,6 @@ static int make_geom(int64_t Dc, int64_t Hc, int64_t Wc, int64_t D, int64_t H, i
   g.FH = (int)fminf((float)Hc, ceilf(kTY * g.sh) + 2.f);
   g.FW = (int)fminf((float)Wc, ceilf(kTX * g.sw) + 2.f);
   g.fast4 = (D == 4 * Dc) ? 1 : 0;
-  g.cached = (Dc * kTX * kTY * sizeof(float) <= 96 * 1024) ? 1 : 0;
   smem = tail_smem_bytes(g);
   if (smem > 200 * 1024) return RSM_ERR_UNSUPPORTED_CONFIG;
   return RSM_OK;
@@ -380,10 +363,9 @@ using namespace rsm;
 template <typename T, bool FAST4, bool WANT_ARG>
 static int launch_tail_fwd(const void* cost, const rsm_regress_out& out, const TailGeom& g, size_t smem, dim3 grid,
                            cudaStream_t st) {
-  auto k = g.cached ? upsample_regress_fwd_kernel<T, FAST4, WANT_ARG, true>
-                    : upsample_regress_fwd_kernel<T, FAST4, WANT_ARG, false>;
+  auto k = upsample_regress_fwd_kernel<T, FAST4, WANT_ARG>;
   if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k<<<grid, kTX * kTY, smem, st>>>((const T*)cost, (T*)out.soft, out.argmin, out.argmax, out.lse, g);
+  k<<<grid, kNT, smem, st>>>((const T*)cost, (T*)out.soft, out.argmin, out.argmax, out.lse, g);
   return finish_launch("rsm_upsample_regress_fwd");
 }
 
@@ -423,8 +405,6 @@ extern "C" int rsm_upsample_regress_bwd(const void* gout, const void* cost, cons
   size_t smem;
   if (int rc = make_geom(Dc, Hc, Wc, D, H, W, g, smem)) return rc;
   if (B == 0) return RSM_OK;
-  g.cached = 0;   // the adjoint evaluates every slice exactly once: nothing to park
-  smem = tail_smem_bytes(g);
   if (!gout || !cost || !soft || !lse || !gcost || !workspace) return RSM_ERR_NULL_POINTER;
   if (B > 65535) return RSM_ERR_INVALID_SHAPE;
   RSM_COMMON_CHECKS(dtype)
@@ -433,7 +413,7 @@ extern "C" int rsm_upsample_regress_bwd(const void* gout, const void* cost, cons
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const dim3 grid((unsigned)ceil_div(W, kTX), (unsigned)ceil_div(H, kTY), (unsigned)B);
     if (grid.y > 65535) return (int)RSM_ERR_INVALID_SHAPE;
-    k<<<grid, kTX * kTY, smem, st>>>((const T*)gout, (const T*)cost, (const T*)soft, lse, (float*)workspace, g);
+    k<<<grid, kNT, smem, st>>>((const T*)gout, (const T*)cost, (const T*)soft, lse, (float*)workspace, g);
     if (int rc = finish_launch("rsm_upsample_regress_bwd(cols)")) return rc;
     const int64_t total = B * Dc * Hc * Wc;
     if (!grid_ok(ceil_div(total, 256))) return (int)RSM_ERR_INVALID_SHAPE;

@@ -11,10 +11,14 @@
 // output layout so that stores coalesce: x-fastest for (N,D,H,W), d-fastest with 256-bit stores
 // (STG.E.ENL2.256) for the D-innermost (N,G,H,W,D).
 #include <math.h>
+#include <stdlib.h>
 
 #include "rsm_common.cuh"
 
 namespace rsm {
+
+int launch_inner_tc(const rsm_feat& left, const rsm_feat& right, void* out, int64_t N, int64_t C, int64_t H, int64_t W,
+                    int64_t D, int mean, int in_dtype, int out_dtype, cudaStream_t st);
 
 constexpr int TX = 64;        // pixels per CTA tile
 constexpr int XT = 4;         // pixels per thread
@@ -471,6 +475,13 @@ extern "C" int rsm_inner_fwd(rsm_feat left, rsm_feat right, void* out, int64_t N
   RSM_COMMON_CHECKS(in_dtype)
   if (!valid_dtype(out_dtype)) return RSM_ERR_UNSUPPORTED_DTYPE;
   if (!aligned_to(out, dtype_size(out_dtype))) return RSM_ERR_MISALIGNED;
+  // 16-bit features: banded per-row GEMM on the tcgen05 tensor cores (rsm_corr_tc.cu); fp32 features and
+  // shapes it does not cover (C % 16 != 0) use the SIMT kernel.  RSM_DISABLE_TC=1 forces SIMT (A/B runs).
+  const char* no_tc = getenv("RSM_DISABLE_TC");
+  if (!(no_tc && no_tc[0] == '1')) {
+    const int rc = launch_inner_tc(left, right, out, N, C, H, W, D, reduce == RSM_REDUCE_MEAN, in_dtype, out_dtype, st);
+    if (rc != RSM_ERR_UNSUPPORTED_CONFIG) return rc;
+  }
   return RSM_DISPATCH_IO(in_dtype, out_dtype, Tin, Tout, [&]() -> int {
     return launch_fwd<Tin, Tout, LAYOUT_NDHW>(left, right, out, N, g, st, "rsm_inner_fwd");
   });

@@ -32,6 +32,7 @@ struct TcGeom {
   int mean, pow2;
   int fmt;      // 0 = fp16, 1 = bf16 (UMMA a/b format)
   int tmem_cols;
+  int smem_main;  // bytes of max(operand buffers, skew buffer)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -76,30 +77,45 @@ __device__ __forceinline__ bool mbar_wait(uint32_t mbar, uint32_t phase) {
   return false;
 }
 
-// ---- stage nch channels of one operand: xs = first x of the tile, nxg = x-groups of 8
+// ---- stage nch channels of one operand: xs = first x of the tile, nxg = x-groups of 8.
+// thread -> (channel inside its K-group: 8 lanes write 128 contiguous bytes, x-group lane); all
+// K-groups of one x-group are loaded before any is stored (up to 8 independent 16-byte loads in flight)
+template <typename Tin>
+__device__ __forceinline__ uint4 load_chunk_slow(const Tin* __restrict__ src, int x, int W, int64_t sw) {
+  union { uint4 u; Tin e[8]; } tmp;
+  tmp.u = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (x + i >= 0 && x + i < W) tmp.e[i] = __ldg(src + (int64_t)(x + i) * sw);
+  return tmp.u;
+}
+
 template <typename Tin>
 __device__ __forceinline__ void stage_operand(const FeatView& F, int64_t n, int y, int c0, int nch, int xs, int nxg, int W,
                                               unsigned char* dst, bool fast) {
-  const Tin* __restrict__ base = reinterpret_cast<const Tin*>(F.data) + n * F.sn + (int64_t)y * F.sh;
-  const int nchunk = nch * nxg;   // 16-byte chunks: (c, x-group)
-  for (int q = threadIdx.x; q < nchunk; q += blockDim.x) {
-    const int cl = q & 7;                 // channel inside its K-group: fastest -> conflict-free 128 B per 8 lanes
-    const int t = q >> 3;
-    const int xg = t % nxg, cg = t / nxg;
-    const int c = c0 + 8 * cg + cl, x = xs + 8 * xg;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    const Tin* src = base + (int64_t)c * F.sc;
-    if (fast && x >= 0 && x + 8 <= W) {
-      v = __ldg(reinterpret_cast<const uint4*>(src + x));
-    } else {
-      union { uint4 u; Tin e[8]; } tmp;
-      tmp.u = v;
+  const int cl = threadIdx.x & 7, xl = threadIdx.x >> 3, nxl = blockDim.x >> 3;
+  const int ncg = nch >> 3;
+  const Tin* __restrict__ base =
+      reinterpret_cast<const Tin*>(F.data) + n * F.sn + (int64_t)y * F.sh + (int64_t)(c0 + cl) * F.sc;
+  for (int xg = xl; xg < nxg; xg += nxl) {
+    const int x = xs + 8 * xg;
+    const bool inside = fast && x >= 0 && x + 8 <= W;
+    const bool empty = x + 8 <= 0 || x >= W;
+    for (int cg0 = 0; cg0 < ncg; cg0 += 8) {
+      uint4 v[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (x + i >= 0 && x + i < W) tmp.e[i] = __ldg(src + (int64_t)(x + i) * F.sw);
-      v = tmp.u;
+      for (int u = 0; u < 8; ++u) {
+        v[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (cg0 + u < ncg && !empty) {
+          const Tin* src = base + (int64_t)(8 * (cg0 + u)) * F.sc;
+          v[u] = inside ? __ldg(reinterpret_cast<const uint4*>(src + x)) : load_chunk_slow<Tin>(src, x, W, F.sw);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (cg0 + u < ncg)
+          *reinterpret_cast<uint4*>(dst + ((size_t)((cg0 + u) * nxg + xg) * 8 + cl) * 16) = v[u];
     }
-    *reinterpret_cast<uint4*>(dst + ((size_t)(cg * nxg + xg) * 8 + cl) * 16) = v;
   }
 }
 
@@ -109,8 +125,9 @@ inner_tc_fwd_kernel(FeatView L, FeatView R, Tout* __restrict__ out, TcGeom g, in
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* sA = smem_raw;                                   // TC_KC * TC_TM * 2 bytes
   unsigned char* sB = sA + TC_KC * TC_TM * 2;                      // TC_KC * ncol * 2 bytes
-  float* skew = reinterpret_cast<float*>(sB + (size_t)TC_KC * g.ncol * 2);   // 128 * pitch floats
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(skew + (size_t)TC_TM * g.pitch);
+  float* skew = reinterpret_cast<float*>(smem_raw);                // 128 * pitch floats, ALIASES the operand
+                                                                   // buffers (free once the last MMA committed)
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + g.smem_main);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -225,7 +242,9 @@ static int launch_inner_tc_typed(const rsm_feat& left, const rsm_feat& right, vo
   g.tmem_cols = g.ncol <= 128 ? 128 : 256;
   const int64_t bx = N * H * g.xtiles, by = ceil_div(D, g.dch);
   if (bx <= 0 || bx > 2147483647LL || by > 65535) return RSM_ERR_INVALID_SHAPE;
-  const size_t smem = (size_t)TC_KC * TC_TM * 2 + (size_t)TC_KC * g.ncol * 2 + (size_t)TC_TM * g.pitch * 4 + 16;
+  const size_t ops = (size_t)TC_KC * TC_TM * 2 + (size_t)TC_KC * g.ncol * 2, skw = (size_t)TC_TM * g.pitch * 4;
+  g.smem_main = (int)(((ops > skw ? ops : skw) + 15) / 16 * 16);
+  const size_t smem = (size_t)g.smem_main + 16;
   auto k = inner_tc_fwd_kernel<Tin, Tout>;
   if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return finish_launch("rsm_inner_fwd(tc attr)");

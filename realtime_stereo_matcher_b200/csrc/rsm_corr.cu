@@ -19,6 +19,8 @@ namespace rsm {
 
 int launch_inner_tc(const rsm_feat& left, const rsm_feat& right, void* out, int64_t N, int64_t C, int64_t H, int64_t W,
                     int64_t D, int mean, int in_dtype, int out_dtype, cudaStream_t st);
+int launch_inner_regress_tc(const rsm_feat& left, const rsm_feat& right, int64_t N, int64_t C, int64_t H, int64_t W,
+                            int64_t D, int mean, int in_dtype, const rsm_regress_out& out, cudaStream_t st);
 
 constexpr int TX = 64;        // pixels per CTA tile
 constexpr int XT = 4;         // pixels per thread
@@ -542,6 +544,13 @@ extern "C" int rsm_inner_regress_fwd(rsm_feat left, rsm_feat right, int64_t N, i
   if (C > 0 && (!left.data || !right.data)) return RSM_ERR_NULL_POINTER;
   if (NTX * g.ntd > 1024) return RSM_ERR_UNSUPPORTED_CONFIG;  // D <= 512
   RSM_COMMON_CHECKS(in_dtype)
+  {
+    const char* no_tc = getenv("RSM_DISABLE_TC");
+    if (!(no_tc && no_tc[0] == '1')) {   // 16-bit features, D <= 128: tcgen05 tiles reduced straight out of TMEM
+      const int rc = launch_inner_regress_tc(left, right, N, C, H, W, D, reduce == RSM_REDUCE_MEAN, in_dtype, out, st);
+      if (rc != RSM_ERR_UNSUPPORTED_CONFIG) return rc;
+    }
+  }
   const int64_t bx = N * g.H * g.xtiles;
   if (!grid_ok(bx)) return RSM_ERR_INVALID_SHAPE;
   const size_t smem = (size_t)(CKMAX * TX + CKMAX * (TX + g.dchp) + TX * (g.dchp + 1)) * sizeof(float);

@@ -1,43 +1,64 @@
-// Inner-product / correlation volume on the 5th-gen tensor cores (tcgen05) for 16-bit features.
+// Inner-product / correlation on the 5th-gen tensor cores (tcgen05) for 16-bit features: the
+// (N,D,H,W) volume (EPI_VOLUME) or, fused, the soft-argmax / argmin / argmax of it without ever
+// writing the volume (EPI_REGRESS).
 //
 // Per epipolar row the correlation is the band  0 <= x - x' < D  of the W x W product
 // P[x, x'] = sum_c L[c, x] * R[c, x']  (the reference's own einsum hint, cost_volume/inner_product.py:33-34).
-// A CTA owns TM = 128 left pixels x0.. of one (n, y) and a chunk of DCH <= 128 disparities dc0..:
+// A tile = TM = 128 left pixels x0.. of one (n, y) and a chunk of DCH <= 128 disparities dc0..:
 //     D_tmem[r, j] = sum_c L[c, x0 + r] * R[c, xr0 + j],   xr0 = x0 - dc0 - DCH,  j in [0, 128 + DCH)
 // is ONE tcgen05.mma per 16 channels (M = 128, N = 128 + DCH, K = 16, both operands MN-major in shared
-// memory, fp32 accumulators in TMEM, issued by one thread).  The wanted value for disparity
-// dc0 + dl of pixel x0 + r sits at column j = r + DCH - dl: a diagonal band.  Each epilogue warp
-// (TMEM lanes 32w..32w+31) pulls the DCH + 32 columns that cover its lanes with tcgen05.ld, parks
-// them in a padded shared-memory row per lane, and reads them back skewed so that for every
-// disparity the 32 lanes store 32 consecutive x of the (N,D,H,W) volume.
+// memory, fp32 accumulators in TMEM, issued by one thread).  The value for disparity dc0 + dl of
+// pixel x0 + r sits at column j = r + DCH - dl: a diagonal band.
 //
-// Operand staging is done with ordinary vector loads (the features may be strided views and the
-// right window needs zero fill on both sides); the canonical no-swizzle MN-major core-matrix
-// layout is written directly:  addr(x, c) = ((c/8) * (T/8) + x/8) * 128 + (c%8) * 16 + (x%8) * 2.
-#include <stdlib.h>
-
+// Persistent, warp-specialised CTA (256 threads, one per SM), tiles strided over the grid:
+//   warps 4-7  loaders: stage the operand slab (<= 64 channels) of the next k-chunk into one of two
+//              shared-memory stages with 16-byte loads (features may be strided views; the right window
+//              is zero-filled on both sides), writing the canonical no-swizzle MN-major core-matrix
+//              layout directly:  addr(x, c) = ((c/8) * (T/8) + x/8) * 128 + (c%8) * 16 + (x%8) * 2;
+//              thread 128 then issues the UMMAs and commits them to mbarriers;
+//   warps 0-3  epilogue: TMEM lane quadrant w; tcgen05.ld the DCH + 32 columns covering its lanes and
+//              either park them in a padded shared-memory row per lane and read them back skewed, so
+//              that for every disparity 32 lanes store 32 consecutive x (EPI_VOLUME), or reduce them in
+//              registers with a chunked online softmax + arg-extrema (EPI_REGRESS).
+// Two TMEM accumulator buffers and two operand stages decouple the roles: the loaders run up to two
+// k-chunks / one tile ahead of the epilogue.  mbarriers: smem_empty[2] (UMMA commit -> loaders),
+// tmem_full[2] (UMMA commit -> epilogue), tmem_empty[2] (128 epilogue threads -> UMMA issuer).
 #include "rsm_common.cuh"
 
 namespace rsm {
 
-constexpr int TC_TM = 128;   // UMMA M: left pixels per CTA
-constexpr int TC_KC = 64;    // channels per shared-memory stage
+constexpr int TC_TM = 128;        // UMMA M: left pixels per tile
+constexpr int TC_KC = 64;         // channels per shared-memory stage
+constexpr int TC_THREADS = 256;
+enum { EPI_VOLUME = 0, EPI_REGRESS = 1 };
 
 struct TcGeom {
   int C, H, W, D;
-  int dch;      // disparities per CTA chunk (multiple of 16, <= 128)
-  int ncol;     // UMMA N = TC_TM + dch
-  int pitch;    // floats per lane row of the skew buffer
-  int xtiles;   // ceil(W / TC_TM)
+  int dch;        // disparities per tile chunk (multiple of 16, <= 128)
+  int ncol;       // UMMA N = TC_TM + dch
+  int pitch;      // floats per lane row of the skew buffer
+  int xtiles;     // ceil(W / TC_TM)
+  int dchunks;    // ceil(D / dch)
   int mean, pow2;
-  int fmt;      // 0 = fp16, 1 = bf16 (UMMA a/b format)
-  int tmem_cols;
-  int smem_main;  // bytes of max(operand buffers, skew buffer)
+  int fmt;        // 0 = fp16, 1 = bf16 (UMMA a/b format)
+  int tmem_buf;   // TMEM columns per accumulator buffer (128 or 256)
+  int stage_bytes;
+  int64_t rows;   // N * H
+  int64_t tiles;  // rows * xtiles * dchunks
+};
+
+struct RegressPtrs {
+  float* soft;
+  int64_t* amin;
+  int64_t* amax;
+  float* lse;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// shared-memory matrix descriptor, SWIZZLE_NONE, version 1 (cute::UMMA::SmemDescriptor bit layout)
+// shared-memory matrix descriptor, SWIZZLE_NONE, version 1 (cute::UMMA::SmemDescriptor bit layout).
+// MN-major operands: SBO = stride between 8-element groups along M/N, LBO = stride between 8-row groups
+// along K (verified on B200 against the oracle; the swapped assignment produces garbage).
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
@@ -53,6 +74,9 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_commit(uint32_t mbar) {   // implies tcgen05.fence::before_thread_sync
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+}
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
@@ -63,23 +87,26 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "memory");
 }
 
-// wait for completion of the given phase of an mbarrier; bounded so a protocol bug cannot hang the GPU
-__device__ __forceinline__ bool mbar_wait(uint32_t mbar, uint32_t phase) {
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+}
+// wait for completion of the phase with the given parity; bounded so a protocol bug cannot hang the GPU
+__device__ __forceinline__ bool mbar_wait(uint32_t mbar, uint32_t parity) {
   for (int it = 0; it < (1 << 22); ++it) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(mbar), "r"(phase)
+        : "r"(mbar), "r"(parity)
         : "memory");
     if (ok) return true;
   }
   return false;
 }
 
-// ---- stage nch channels of one operand: xs = first x of the tile, nxg = x-groups of 8.
-// thread -> (channel inside its K-group: 8 lanes write 128 contiguous bytes, x-group lane); all
-// K-groups of one x-group are loaded before any is stored (up to 8 independent 16-byte loads in flight)
 template <typename Tin>
 __device__ __forceinline__ uint4 load_chunk_slow(const Tin* __restrict__ src, int x, int W, int64_t sw) {
   union { uint4 u; Tin e[8]; } tmp;
@@ -90,10 +117,13 @@ __device__ __forceinline__ uint4 load_chunk_slow(const Tin* __restrict__ src, in
   return tmp.u;
 }
 
+// ---- stage nch channels of one operand with the 128 loader threads (lt = 0..127): xs = first x of the
+// tile, nxg = x-groups of 8.  thread -> (channel inside its K-group: 8 lanes write 128 contiguous bytes,
+// x-group lane); all K-groups of an x-group are loaded before any is stored (<= 8 loads in flight).
 template <typename Tin>
 __device__ __forceinline__ void stage_operand(const FeatView& F, int64_t n, int y, int c0, int nch, int xs, int nxg, int W,
-                                              unsigned char* dst, bool fast) {
-  const int cl = threadIdx.x & 7, xl = threadIdx.x >> 3, nxl = blockDim.x >> 3;
+                                              unsigned char* dst, bool fast, int lt) {
+  const int cl = lt & 7, xl = lt >> 3, nxl = 16;
   const int ncg = nch >> 3;
   const Tin* __restrict__ base =
       reinterpret_cast<const Tin*>(F.data) + n * F.sn + (int64_t)y * F.sh + (int64_t)(c0 + cl) * F.sc;
@@ -119,114 +149,191 @@ __device__ __forceinline__ void stage_operand(const FeatView& F, int64_t n, int 
   }
 }
 
-template <typename Tin, typename Tout>
-__global__ void __launch_bounds__(128)
-inner_tc_fwd_kernel(FeatView L, FeatView R, Tout* __restrict__ out, TcGeom g, int fast) {
+struct TileCoord {
+  int64_t n;
+  int y, x0, dc0;
+};
+__device__ __forceinline__ TileCoord tile_coord(int64_t t, const TcGeom& g) {
+  TileCoord c;
+  const int xt = (int)(t % g.xtiles); t /= g.xtiles;
+  const int64_t row = t % g.rows;
+  const int dchunk = (int)(t / g.rows);
+  c.n = row / g.H;
+  c.y = (int)(row % g.H);
+  c.x0 = xt * TC_TM;
+  c.dc0 = dchunk * g.dch;
+  return c;
+}
+
+template <typename Tin, typename Tout, int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, TcGeom g, int fast) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  unsigned char* sA = smem_raw;                                   // TC_KC * TC_TM * 2 bytes
-  unsigned char* sB = sA + TC_KC * TC_TM * 2;                      // TC_KC * ncol * 2 bytes
-  float* skew = reinterpret_cast<float*>(smem_raw);                // 128 * pitch floats, ALIASES the operand
-                                                                   // buffers (free once the last MMA committed)
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + g.smem_main);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+  unsigned char* stage0 = smem_raw;                                   // 2 x { A: KC*128*2 | B: KC*ncol*2 }
+  float* skew = reinterpret_cast<float*>(smem_raw + 2 * (size_t)g.stage_bytes);   // 128 * pitch floats (EPI_VOLUME)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(skew) +
+                                               (EPI == EPI_VOLUME ? (size_t)TC_TM * g.pitch * 4 : 0));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  const uint32_t smem_empty = smem_u32(bars), tmem_full = smem_u32(bars + 2), tmem_empty = smem_u32(bars + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int64_t bid = blockIdx.x;
-  const int xt = (int)(bid % g.xtiles); bid /= g.xtiles;
-  const int y = (int)(bid % g.H);
-  const int64_t n = bid / g.H;
-  const int x0 = xt * TC_TM;
-  const int dc0 = blockIdx.y * g.dch;
-  const int xr0 = x0 - dc0 - g.dch;
-
-  // ---- one-time setup: TMEM allocation (warp 0), mbarrier (thread 0)
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)g.tmem_cols)
+                 "r"((uint32_t)(2 * g.tmem_buf))
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (threadIdx.x == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)) : "memory");
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_empty + 8 * i, 1);
+      mbar_init(tmem_full + 8 * i, 1);
+      mbar_init(tmem_empty + 8 * i, 128);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  const int nk = (g.C + TC_KC - 1) / TC_KC;
 
-  // instruction descriptor: D = f32, A/B = fmt, both MN-major, N = ncol, M = 128
-  const uint32_t idesc = (1u << 4) | ((uint32_t)g.fmt << 7) | ((uint32_t)g.fmt << 10) | (1u << 15) | (1u << 16) |
-                         ((uint32_t)(g.ncol >> 3) << 17) | ((uint32_t)(TC_TM >> 4) << 24);
-  const uint32_t sbo = 128;                              // next 8-pixel group along M / N
-  const uint32_t lboA = (TC_TM / 8) * 128;               // next 8-channel group along K
-  const uint32_t lboB = (uint32_t)(g.ncol / 8) * 128;
-
-  uint32_t phase = 0;
-  bool ok = true;
-  for (int c0 = 0; c0 < g.C; c0 += TC_KC) {
-    const int nch = min(TC_KC, g.C - c0);
-    stage_operand<Tin>(L, n, y, c0, nch, x0, TC_TM / 8, g.W, sA, fast);
-    stage_operand<Tin>(R, n, y, c0, nch, xr0, g.ncol / 8, g.W, sB, fast);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (UMMA)
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      for (int ks = 0; ks < nch / 16; ++ks) {
-        // descriptor fields (cute make_umma_desc<Major::MN>, SWIZZLE_NONE): SBO = stride between 8-element
-        // groups along M/N, LBO = stride between 8-row groups along K
-        // (verified on B200 against the oracle; the swapped assignment produces garbage)
-        const uint64_t adesc = umma_desc(smem_u32(sA) + ks * 2 * lboA, lboA, sbo);
-        const uint64_t bdesc = umma_desc(smem_u32(sB) + ks * 2 * lboB, lboB, sbo);
-        umma_f16(tmem_base, adesc, bdesc, idesc, (c0 > 0 || ks > 0) ? 1u : 0u);
+  if (warp >= 4) {
+    // =========================================================== loaders (+ UMMA issue by lt == 0)
+    const int lt = threadIdx.x - 128;
+    const uint32_t idesc = (1u << 4) | ((uint32_t)g.fmt << 7) | ((uint32_t)g.fmt << 10) | (1u << 15) | (1u << 16) |
+                           ((uint32_t)(g.ncol >> 3) << 17) | ((uint32_t)(TC_TM >> 4) << 24);
+    const uint32_t sbo = 128, lboA = (TC_TM / 8) * 128, lboB = (uint32_t)(g.ncol / 8) * 128;
+    uint32_t it = 0, use = 0;   // k-chunks staged so far; tiles processed so far
+    for (int64_t t = blockIdx.x; t < g.tiles; t += gridDim.x, ++use) {
+      const TileCoord tc = tile_coord(t, g);
+      const int xr0 = tc.x0 - tc.dc0 - g.dch;
+      const uint32_t buf = use & 1;
+      for (int kc = 0; kc < nk; ++kc, ++it) {
+        const uint32_t s = it & 1;
+        unsigned char* sA = stage0 + (size_t)s * g.stage_bytes;
+        unsigned char* sB = sA + TC_KC * TC_TM * 2;
+        const int c0 = kc * TC_KC, nch = min(TC_KC, g.C - c0);
+        mbar_wait(smem_empty + 8 * s, ((it >> 1) & 1) ^ 1);        // UMMAs that read this stage have completed
+        stage_operand<Tin>(L, tc.n, tc.y, c0, nch, tc.x0, TC_TM / 8, g.W, sA, fast, lt);
+        stage_operand<Tin>(R, tc.n, tc.y, c0, nch, xr0, g.ncol / 8, g.W, sB, fast, lt);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (UMMA)
+        asm volatile("bar.sync 1, 128;" ::: "memory");                 // all four loader warps
+        if (lt == 0) {
+          if (kc == 0) mbar_wait(tmem_empty + 8 * buf, ((use >> 1) & 1) ^ 1);   // epilogue drained this buffer
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          for (int ks = 0; ks < nch / 16; ++ks) {
+            const uint64_t adesc = umma_desc(smem_u32(sA) + ks * 2 * lboA, lboA, sbo);
+            const uint64_t bdesc = umma_desc(smem_u32(sB) + ks * 2 * lboB, lboB, sbo);
+            umma_f16(tmem_base + buf * g.tmem_buf, adesc, bdesc, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+          }
+          umma_commit(smem_empty + 8 * s);
+          if (kc == nk - 1) umma_commit(tmem_full + 8 * buf);
+        }
       }
-      // completion of all MMAs issued so far -> mbarrier (implies tcgen05.fence::before_thread_sync)
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar))
-                   : "memory");
     }
-    ok = mbar_wait(smem_u32(mbar), phase) && ok;   // operands consumed: smem may be restaged, TMEM is current
-    phase ^= 1;
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  }
+  } else {
+    // ================================================================================= epilogue
+    const float inv = 1.f / (float)g.C, cnt = (float)g.C;
+    const int ncw = g.dch + 32;
+    uint32_t use = 0;
+    for (int64_t t = blockIdx.x; t < g.tiles; t += gridDim.x, ++use) {
+      const TileCoord tc = tile_coord(t, g);
+      const uint32_t buf = use & 1;
+      const bool ok = mbar_wait(tmem_full + 8 * buf, (use >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + buf * g.tmem_buf + ((uint32_t)(32 * warp) << 16) + (uint32_t)(32 * warp);
+      const int x = tc.x0 + 32 * warp + lane;
+      const int dmax = min(g.dch, g.D - tc.dc0);
 
-  // ---- epilogue: lane r = 32*warp + lane owns pixel x0 + r; columns [32*warp, 32*warp + dch + 32)
-  float* row = skew + (size_t)(32 * warp + lane) * g.pitch;
-  const int ncw = g.dch + 32;
-  for (int cb = 0; cb < ncw; cb += 16) {
-    uint32_t r[16];
-    tmem_ld16(tmem_base + ((uint32_t)(32 * warp) << 16) + (uint32_t)(32 * warp + cb), r);
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if constexpr (EPI == EPI_VOLUME) {
+        float* row = skew + (size_t)(32 * warp + lane) * g.pitch;
+        for (int cb = 0; cb < ncw; cb += 16) {
+          uint32_t r[16];
+          tmem_ld16(taddr + cb, r);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-    for (int i = 0; i < 16; i += 4)
-      *reinterpret_cast<uint4*>(row + cb + i) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
-  }
-  __syncwarp();
-  const int x = x0 + 32 * warp + lane;
-  const float inv = 1.f / (float)g.C, cnt = (float)g.C;
-  if (x < g.W) {
-    const int dmax = min(g.dch, g.D - dc0);
-    Tout* __restrict__ o = out + (((int64_t)n * g.D + dc0) * g.H + y) * g.W + x;
-    const int64_t dstride = (int64_t)g.H * g.W;
-    for (int dl = 0; dl < dmax; ++dl) {
-      float v = ok ? row[lane + g.dch - dl] : __int_as_float(0x7fc00000);
-      if (g.mean) v = g.pow2 ? v * inv : v / cnt;
-      if (x < dc0 + dl) v = 0.f;                       // the reference leaves zeros where x < d
-      o[dl * dstride] = from_f<Tout>(v);
+          for (int i = 0; i < 16; i += 4)
+            *reinterpret_cast<uint4*>(row + cb + i) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(tmem_empty + 8 * buf);                 // this thread is done with the TMEM buffer
+        __syncwarp();
+        if (x < g.W) {
+          Tout* __restrict__ o = out + (((int64_t)tc.n * g.D + tc.dc0) * g.H + tc.y) * g.W + x;
+          const int64_t dstride = (int64_t)g.H * g.W;
+          for (int dl = 0; dl < dmax; ++dl) {
+            float v = ok ? row[lane + g.dch - dl] : __int_as_float(0x7fc00000);
+            if (g.mean) v = g.pow2 ? v * inv : v / cnt;
+            if (x < tc.dc0 + dl) v = 0.f;                   // the reference leaves zeros where x < d
+            __stcs(o + dl * dstride, from_f<Tout>(v));
+          }
+        }
+        __syncwarp();                                       // rows are reused by the next tile
+      } else {
+        // fused regression: column jj of this lane's window holds disparity dl = lane + dch - jj.
+        // Columns are visited in ascending jj = DESCENDING disparity, so ties resolve to the smaller
+        // index with >= / <= updates (torch: first occurrence); NaNs raise a flag and win.
+        float m = -INFINITY, s = 0.f, ws = 0.f;
+        float minv = INFINITY, maxv = -INFINITY;
+        int mini = 0, maxi = 0, nani = 0x7fffffff;
+        for (int cb = 0; cb < ncw; cb += 16) {
+          uint32_t r[16];
+          tmem_ld16(taddr + cb, r);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          float v[16];
+          float gm = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int dl = lane + g.dch - (cb + i);
+            float f = __uint_as_float(r[i]);
+            if (g.mean) f = g.pow2 ? f * inv : f / cnt;
+            if (x < tc.dc0 + dl) f = 0.f;                   // fill value takes part in the regression (F8)
+            const bool valid = dl >= 0 && dl < dmax;
+            v[i] = valid ? f : -INFINITY;
+            gm = fmaxf(gm, v[i]);
+            if (valid) {
+              if (f <= minv) { minv = f; mini = dl; }
+              if (f >= maxv) { maxv = f; maxi = dl; }
+              if (f != f) nani = min(nani, dl);
+            }
+          }
+          const float mn = fmaxf(m, gm);
+          if (mn > -INFINITY) {
+            const float mnl = mn * kLog2e;
+            const float a = (m == -INFINITY) ? 0.f : fast_exp2(fmaf(m, kLog2e, -mnl));
+            s *= a; ws *= a;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float e = fast_exp2(fmaf(v[i], kLog2e, -mnl));     // invalid: exp2(-inf) = 0
+              s += e;
+              ws = fmaf((float)(lane + g.dch - (cb + i)), e, ws);
+            }
+            m = mn;
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(tmem_empty + 8 * buf);
+        if (x < g.W) {
+          const int64_t o = ((int64_t)tc.n * g.H + tc.y) * g.W + x;
+          if (nani != 0x7fffffff) { mini = nani; maxi = nani; }
+          const float bad = __int_as_float(0x7fc00000);
+          if (rp.soft) rp.soft[o] = ok ? ws / s : bad;
+          if (rp.lse) rp.lse[o] = ok ? m + __logf(s) : bad;
+          if (rp.amin) rp.amin[o] = mini;
+          if (rp.amax) rp.amax[o] = maxi;
+        }
+      }
     }
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * g.tmem_buf))
                  : "memory");
 }
 
-// returns RSM_ERR_UNSUPPORTED_CONFIG when the tensor-core path does not apply (caller falls back to SIMT)
-template <typename Tin, typename Tout>
-static int launch_inner_tc_typed(const rsm_feat& left, const rsm_feat& right, void* out, int64_t N, int64_t C, int64_t H,
-                                 int64_t W, int64_t D, int mean, int fmt, cudaStream_t st) {
-  TcGeom g;
+static int tc_geom(int64_t N, int64_t C, int64_t H, int64_t W, int64_t D, int mean, int fmt, TcGeom& g) {
   g.C = (int)C; g.H = (int)H; g.W = (int)W; g.D = (int)D;
   const int d16 = (int)((D + 15) / 16 * 16);
   g.dch = d16 < 128 ? d16 : 128;
@@ -236,35 +343,61 @@ static int launch_inner_tc_typed(const rsm_feat& left, const rsm_feat& right, vo
   if ((p / 4) % 2 == 0) p += 4;
   g.pitch = p;
   g.xtiles = (int)ceil_div(W, TC_TM);
+  g.dchunks = (int)ceil_div(D, g.dch);
   g.mean = mean;
   g.pow2 = (C & (C - 1)) == 0;
   g.fmt = fmt;
-  g.tmem_cols = g.ncol <= 128 ? 128 : 256;
-  const int64_t bx = N * H * g.xtiles, by = ceil_div(D, g.dch);
-  if (bx <= 0 || bx > 2147483647LL || by > 65535) return RSM_ERR_INVALID_SHAPE;
-  const size_t ops = (size_t)TC_KC * TC_TM * 2 + (size_t)TC_KC * g.ncol * 2, skw = (size_t)TC_TM * g.pitch * 4;
-  g.smem_main = (int)(((ops > skw ? ops : skw) + 15) / 16 * 16);
-  const size_t smem = (size_t)g.smem_main + 16;
-  auto k = inner_tc_fwd_kernel<Tin, Tout>;
-  if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-    return finish_launch("rsm_inner_fwd(tc attr)");
-  auto vec_ok = [&](const rsm_feat& f) {
-    return f.stride_w == 1 && f.stride_n % 8 == 0 && f.stride_c % 8 == 0 && f.stride_h % 8 == 0 && aligned_to(f.data, 16);
-  };
-  const int fast = vec_ok(left) && vec_ok(right);   // 16-byte chunks start at multiples of 8 elements
-  k<<<dim3((unsigned)bx, (unsigned)by), 128, smem, st>>>(view_of(left), view_of(right), (Tout*)out, g, fast);
-  return finish_launch("rsm_inner_fwd(tcgen05)");
+  g.tmem_buf = g.ncol <= 128 ? 128 : 256;
+  g.stage_bytes = TC_KC * TC_TM * 2 + TC_KC * g.ncol * 2;
+  g.rows = N * H;
+  g.tiles = g.rows * g.xtiles * g.dchunks;
+  if (g.tiles <= 0 || g.tiles > (int64_t)1 << 40) return RSM_ERR_INVALID_SHAPE;
+  return RSM_OK;
 }
 
+static bool feat_vec8(const rsm_feat& f) {
+  return f.stride_w == 1 && f.stride_n % 8 == 0 && f.stride_c % 8 == 0 && f.stride_h % 8 == 0 && aligned_to(f.data, 16);
+}
+
+template <typename Tin, typename Tout, int EPI>
+static int launch_tc(const rsm_feat& left, const rsm_feat& right, void* out, RegressPtrs rp, const TcGeom& g,
+                     cudaStream_t st, const char* where) {
+  const size_t smem = 2 * (size_t)g.stage_bytes + (EPI == EPI_VOLUME ? (size_t)TC_TM * g.pitch * 4 : 0) + 64;
+  auto k = inner_tc_kernel<Tin, Tout, EPI>;
+  if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return finish_launch(where);
+  const int fast = feat_vec8(left) && feat_vec8(right);   // 16-byte chunks start at multiples of 8 elements
+  const unsigned grid = (unsigned)(g.tiles < kNumSMs ? g.tiles : kNumSMs);   // persistent: one CTA per SM
+  k<<<grid, TC_THREADS, smem, st>>>(view_of(left), view_of(right), (Tout*)out, rp, g, fast);
+  return finish_launch(where);
+}
+
+// returns RSM_ERR_UNSUPPORTED_CONFIG when the tensor-core path does not apply (caller falls back to SIMT)
 int launch_inner_tc(const rsm_feat& left, const rsm_feat& right, void* out, int64_t N, int64_t C, int64_t H, int64_t W,
                     int64_t D, int mean, int in_dtype, int out_dtype, cudaStream_t st) {
   if (in_dtype == RSM_F32 || C % 16 != 0 || C <= 0 || D <= 0) return RSM_ERR_UNSUPPORTED_CONFIG;
+  TcGeom g;
+  if (int rc = tc_geom(N, C, H, W, D, mean, in_dtype == RSM_F16 ? 0 : 1, g)) return rc;
+  const RegressPtrs none{nullptr, nullptr, nullptr, nullptr};
+  const char* where = "rsm_inner_fwd(tcgen05)";
   if (in_dtype == RSM_F16) {
-    if (out_dtype == RSM_F32) return launch_inner_tc_typed<__half, float>(left, right, out, N, C, H, W, D, mean, 0, st);
-    return launch_inner_tc_typed<__half, __half>(left, right, out, N, C, H, W, D, mean, 0, st);
+    if (out_dtype == RSM_F32) return launch_tc<__half, float, EPI_VOLUME>(left, right, out, none, g, st, where);
+    return launch_tc<__half, __half, EPI_VOLUME>(left, right, out, none, g, st, where);
   }
-  if (out_dtype == RSM_F32) return launch_inner_tc_typed<__nv_bfloat16, float>(left, right, out, N, C, H, W, D, mean, 1, st);
-  return launch_inner_tc_typed<__nv_bfloat16, __nv_bfloat16>(left, right, out, N, C, H, W, D, mean, 1, st);
+  if (out_dtype == RSM_F32) return launch_tc<__nv_bfloat16, float, EPI_VOLUME>(left, right, out, none, g, st, where);
+  return launch_tc<__nv_bfloat16, __nv_bfloat16, EPI_VOLUME>(left, right, out, none, g, st, where);
+}
+
+int launch_inner_regress_tc(const rsm_feat& left, const rsm_feat& right, int64_t N, int64_t C, int64_t H, int64_t W,
+                            int64_t D, int mean, int in_dtype, const rsm_regress_out& out, cudaStream_t st) {
+  // one disparity chunk must cover all D: the softmax state lives in the epilogue's registers
+  if (in_dtype == RSM_F32 || C % 16 != 0 || C <= 0 || D <= 0 || D > 128) return RSM_ERR_UNSUPPORTED_CONFIG;
+  TcGeom g;
+  if (int rc = tc_geom(N, C, H, W, D, mean, in_dtype == RSM_F16 ? 0 : 1, g)) return rc;
+  const RegressPtrs rp{(float*)out.soft, out.argmin, out.argmax, out.lse};
+  const char* where = "rsm_inner_regress_fwd(tcgen05)";
+  if (in_dtype == RSM_F16) return launch_tc<__half, float, EPI_REGRESS>(left, right, nullptr, rp, g, st, where);
+  return launch_tc<__nv_bfloat16, float, EPI_REGRESS>(left, right, nullptr, rp, g, st, where);
 }
 
 }  // namespace rsm

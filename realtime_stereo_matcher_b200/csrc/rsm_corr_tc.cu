@@ -29,14 +29,17 @@ namespace rsm {
 
 constexpr int TC_TM = 128;        // UMMA M: left pixels per tile
 constexpr int TC_KC = 64;         // channels per shared-memory stage
-constexpr int TC_THREADS = 256;
+constexpr int TC_EPI_WARPS = 8;    // warps 0-7: epilogue (two per TMEM lane quadrant)
+constexpr int TC_THREADS = 32 * TC_EPI_WARPS + 128;   // + warps 8-11: loaders
 enum { EPI_VOLUME = 0, EPI_REGRESS = 1 };
 
 struct TcGeom {
   int C, H, W, D;
   int dch;        // disparities per tile chunk (multiple of 16, <= 128)
   int ncol;       // UMMA N = TC_TM + dch
+  int ncw;        // TMEM columns an epilogue warp pulls: >= dch/2 + 32, multiple of 16
   int pitch;      // floats per lane row of the skew buffer
+  int epi_bytes;  // epilogue scratch: skew rows (volume) or partial softmax states (regress)
   int xtiles;     // ceil(W / TC_TM)
   int dchunks;    // ceil(D / dch)
   int mean, pow2;
@@ -170,9 +173,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, TcGeom g, int fast) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* stage0 = smem_raw;                                   // 2 x { A: KC*128*2 | B: KC*ncol*2 }
-  float* skew = reinterpret_cast<float*>(smem_raw + 2 * (size_t)g.stage_bytes);   // 128 * pitch floats (EPI_VOLUME)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(skew) +
-                                               (EPI == EPI_VOLUME ? (size_t)TC_TM * g.pitch * 4 : 0));
+  float* skew = reinterpret_cast<float*>(smem_raw + 2 * (size_t)g.stage_bytes);   // epilogue scratch (g.epi_bytes)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(skew) + g.epi_bytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
   const uint32_t smem_empty = smem_u32(bars), tmem_full = smem_u32(bars + 2), tmem_empty = smem_u32(bars + 4);
 
@@ -187,7 +189,7 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_empty + 8 * i, 1);
       mbar_init(tmem_full + 8 * i, 1);
-      mbar_init(tmem_empty + 8 * i, 128);
+      mbar_init(tmem_empty + 8 * i, 32 * TC_EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -197,9 +199,9 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
   const uint32_t tmem_base = *tmem_slot;
   const int nk = (g.C + TC_KC - 1) / TC_KC;
 
-  if (warp >= 4) {
+  if (warp >= TC_EPI_WARPS) {
     // =========================================================== loaders (+ UMMA issue by lt == 0)
-    const int lt = threadIdx.x - 128;
+    const int lt = threadIdx.x - 32 * TC_EPI_WARPS;
     const uint32_t idesc = (1u << 4) | ((uint32_t)g.fmt << 7) | ((uint32_t)g.fmt << 10) | (1u << 15) | (1u << 16) |
                            ((uint32_t)(g.ncol >> 3) << 17) | ((uint32_t)(TC_TM >> 4) << 24);
     const uint32_t sbo = 128, lboA = (TC_TM / 8) * 128, lboB = (uint32_t)(g.ncol / 8) * 128;
@@ -233,17 +235,23 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
     }
   } else {
     // ================================================================================= epilogue
+    // warp -> (TMEM lane quadrant q, disparity half hh): lanes 32q.., disparities [hh*dh, (hh+1)*dh).
+    // Disparity dl of lane t sits at column 32q + t + dch - dl; this warp's window starts at
+    // 32q + cs with cs = dch - (hh+1)*dh and is ncw columns wide (>= dh + 32, multiple of 16).
+    const int q = warp & 3, hh = warp >> 2;
+    const int dh = g.dch / 2, cs = g.dch - (hh + 1) * dh, ncw = g.ncw;
     const float inv = 1.f / (float)g.C, cnt = (float)g.C;
-    const int ncw = g.dch + 32;
+    const float nanv = __int_as_float(0x7fc00000);
     uint32_t use = 0;
     for (int64_t t = blockIdx.x; t < g.tiles; t += gridDim.x, ++use) {
       const TileCoord tc = tile_coord(t, g);
       const uint32_t buf = use & 1;
       const bool ok = mbar_wait(tmem_full + 8 * buf, (use >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t taddr = tmem_base + buf * g.tmem_buf + ((uint32_t)(32 * warp) << 16) + (uint32_t)(32 * warp);
-      const int x = tc.x0 + 32 * warp + lane;
+      const uint32_t taddr = tmem_base + buf * g.tmem_buf + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * q + cs);
+      const int x = tc.x0 + 32 * q + lane;
       const int dmax = min(g.dch, g.D - tc.dc0);
+      const int dlo = hh * dh, dhi = min((hh + 1) * dh, dmax);
 
       if constexpr (EPI == EPI_VOLUME) {
         float* row = skew + (size_t)(32 * warp + lane) * g.pitch;
@@ -259,23 +267,33 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
         mbar_arrive(tmem_empty + 8 * buf);                 // this thread is done with the TMEM buffer
         __syncwarp();
         if (x < g.W) {
+          const float* rp0 = row + lane + (hh + 1) * dh;     // value(dl) = rp0[-dl]
           Tout* __restrict__ o = out + (((int64_t)tc.n * g.D + tc.dc0) * g.H + tc.y) * g.W + x;
           const int64_t dstride = (int64_t)g.H * g.W;
-          for (int dl = 0; dl < dmax; ++dl) {
-            float v = ok ? row[lane + g.dch - dl] : __int_as_float(0x7fc00000);
+          auto fin = [&](float v, int dl) -> Tout {
+            if (!ok) v = nanv;
             if (g.mean) v = g.pow2 ? v * inv : v / cnt;
-            if (x < tc.dc0 + dl) v = 0.f;                   // the reference leaves zeros where x < d
-            __stcs(o + dl * dstride, from_f<Tout>(v));
+            return from_f<Tout>(x < tc.dc0 + dl ? 0.f : v);   // the reference leaves zeros where x < d
+          };
+          int dl = dlo;
+          for (; dl + 4 <= dhi; dl += 4) {                   // 4 independent LDS -> STG chains
+            const float v0 = rp0[-dl], v1 = rp0[-dl - 1], v2 = rp0[-dl - 2], v3 = rp0[-dl - 3];
+            __stcs(o + (int64_t)dl * dstride, fin(v0, dl));
+            __stcs(o + (int64_t)(dl + 1) * dstride, fin(v1, dl + 1));
+            __stcs(o + (int64_t)(dl + 2) * dstride, fin(v2, dl + 2));
+            __stcs(o + (int64_t)(dl + 3) * dstride, fin(v3, dl + 3));
           }
+          for (; dl < dhi; ++dl) __stcs(o + (int64_t)dl * dstride, fin(rp0[-dl], dl));
         }
         __syncwarp();                                       // rows are reused by the next tile
       } else {
-        // fused regression: column jj of this lane's window holds disparity dl = lane + dch - jj.
+        // fused regression: column jj of this warp's window holds disparity dl = lane + (hh+1)*dh - jj.
         // Columns are visited in ascending jj = DESCENDING disparity, so ties resolve to the smaller
         // index with >= / <= updates (torch: first occurrence); NaNs raise a flag and win.
         float m = -INFINITY, s = 0.f, ws = 0.f;
         float minv = INFINITY, maxv = -INFINITY;
-        int mini = 0, maxi = 0, nani = 0x7fffffff;
+        int mini = 0x7fffffff, maxi = 0x7fffffff, nani = 0x7fffffff;
+        const int dtop = lane + (hh + 1) * dh;
         for (int cb = 0; cb < ncw; cb += 16) {
           uint32_t r[16];
           tmem_ld16(taddr + cb, r);
@@ -284,11 +302,11 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
           float gm = -INFINITY;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const int dl = lane + g.dch - (cb + i);
+            const int dl = dtop - (cb + i);
             float f = __uint_as_float(r[i]);
             if (g.mean) f = g.pow2 ? f * inv : f / cnt;
             if (x < tc.dc0 + dl) f = 0.f;                   // fill value takes part in the regression (F8)
-            const bool valid = dl >= 0 && dl < dmax;
+            const bool valid = dl >= dlo && dl < dhi;
             v[i] = valid ? f : -INFINITY;
             gm = fmaxf(gm, v[i]);
             if (valid) {
@@ -306,19 +324,37 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
             for (int i = 0; i < 16; ++i) {
               const float e = fast_exp2(fmaf(v[i], kLog2e, -mnl));     // invalid: exp2(-inf) = 0
               s += e;
-              ws = fmaf((float)(lane + g.dch - (cb + i)), e, ws);
+              ws = fmaf((float)(dtop - (cb + i)), e, ws);
             }
             m = mn;
           }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         mbar_arrive(tmem_empty + 8 * buf);
-        if (x < g.W) {
-          const int64_t o = ((int64_t)tc.n * g.H + tc.y) * g.W + x;
+        // combine the two disparity halves of a quadrant: hh = 1 parks its state, hh = 0 merges and stores
+        float* part = skew + ((size_t)(use & 1) * 128 + 32 * q + lane) * 8;
+        if (hh == 1) {
+          part[0] = m; part[1] = s; part[2] = ws; part[3] = minv; part[4] = maxv;
+          part[5] = __int_as_float(mini); part[6] = __int_as_float(maxi); part[7] = __int_as_float(nani);
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+        if (hh == 0 && x < g.W) {
+          const float m2 = part[0], s2 = part[1], w2 = part[2], minv2 = part[3], maxv2 = part[4];
+          const int mini2 = __float_as_int(part[5]), maxi2 = __float_as_int(part[6]), nani2 = __float_as_int(part[7]);
+          const float M = fmaxf(m, m2);
+          const float a1 = (m == -INFINITY) ? 0.f : fast_exp2((m - M) * kLog2e);
+          const float a2 = (m2 == -INFINITY) ? 0.f : fast_exp2((m2 - M) * kLog2e);
+          const float S = s * a1 + s2 * a2, WS = ws * a1 + w2 * a2;
+          // the lower half holds the smaller indices: it wins ties
+          if (!(minv <= minv2) && mini2 != 0x7fffffff) mini = mini2;
+          if (mini == 0x7fffffff) mini = mini2;
+          if (!(maxv >= maxv2) && maxi2 != 0x7fffffff) maxi = maxi2;
+          if (maxi == 0x7fffffff) maxi = maxi2;
+          nani = min(nani, nani2);
           if (nani != 0x7fffffff) { mini = nani; maxi = nani; }
-          const float bad = __int_as_float(0x7fc00000);
-          if (rp.soft) rp.soft[o] = ok ? ws / s : bad;
-          if (rp.lse) rp.lse[o] = ok ? m + __logf(s) : bad;
+          const int64_t o = ((int64_t)tc.n * g.H + tc.y) * g.W + x;
+          if (rp.soft) rp.soft[o] = ok ? WS / S : nanv;
+          if (rp.lse) rp.lse[o] = ok ? M + __logf(S) : nanv;
           if (rp.amin) rp.amin[o] = mini;
           if (rp.amax) rp.amax[o] = maxi;
         }
@@ -338,9 +374,9 @@ static int tc_geom(int64_t N, int64_t C, int64_t H, int64_t W, int64_t D, int me
   const int d16 = (int)((D + 15) / 16 * 16);
   g.dch = d16 < 128 ? d16 : 128;
   g.ncol = TC_TM + g.dch;
-  int p = g.dch + 32;                    // pitch: >= dch + 32, multiple of 4 with an odd quotient (conflict-free
-  p = (p + 3) / 4 * 4;                   // 128-bit row writes and conflict-free skewed 32-bit reads)
-  if ((p / 4) % 2 == 0) p += 4;
+  g.ncw = (g.dch / 2 + 32 + 15) / 16 * 16;
+  int p = g.ncw;                         // pitch: >= ncw, multiple of 4 with an odd quotient (conflict-free
+  if ((p / 4) % 2 == 0) p += 4;          // 128-bit row writes and conflict-free skewed 32-bit reads)
   g.pitch = p;
   g.xtiles = (int)ceil_div(W, TC_TM);
   g.dchunks = (int)ceil_div(D, g.dch);
@@ -360,9 +396,11 @@ static bool feat_vec8(const rsm_feat& f) {
 }
 
 template <typename Tin, typename Tout, int EPI>
-static int launch_tc(const rsm_feat& left, const rsm_feat& right, void* out, RegressPtrs rp, const TcGeom& g,
+static int launch_tc(const rsm_feat& left, const rsm_feat& right, void* out, RegressPtrs rp, const TcGeom& g_in,
                      cudaStream_t st, const char* where) {
-  const size_t smem = 2 * (size_t)g.stage_bytes + (EPI == EPI_VOLUME ? (size_t)TC_TM * g.pitch * 4 : 0) + 64;
+  TcGeom g = g_in;
+  g.epi_bytes = EPI == EPI_VOLUME ? 32 * TC_EPI_WARPS * g.pitch * 4 : 2 * 128 * 8 * 4;
+  const size_t smem = 2 * (size_t)g.stage_bytes + (size_t)g.epi_bytes + 64;
   auto k = inner_tc_kernel<Tin, Tout, EPI>;
   if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return finish_launch(where);

@@ -122,7 +122,9 @@ __device__ __forceinline__ uint4 load_chunk_slow(const Tin* __restrict__ src, in
 
 // ---- stage nch channels of one operand with the 128 loader threads (lt = 0..127): xs = first x of the
 // tile, nxg = x-groups of 8.  thread -> (channel inside its K-group: 8 lanes write 128 contiguous bytes,
-// x-group lane); all K-groups of an x-group are loaded before any is stored (<= 8 loads in flight).
+// x-group lane).  Chunks inside the image go global -> shared with 16-byte cp.async (LDGSTS: no register
+// staging, every load of the stage in flight at once), chunks outside are zero-filled by the same
+// instruction (src-size 0); ragged / unaligned chunks take the synchronous element-wise path.
 template <typename Tin>
 __device__ __forceinline__ void stage_operand(const FeatView& F, int64_t n, int y, int c0, int nch, int xs, int nxg, int W,
                                               unsigned char* dst, bool fast, int lt) {
@@ -134,20 +136,19 @@ __device__ __forceinline__ void stage_operand(const FeatView& F, int64_t n, int 
     const int x = xs + 8 * xg;
     const bool inside = fast && x >= 0 && x + 8 <= W;
     const bool empty = x + 8 <= 0 || x >= W;
-    for (int cg0 = 0; cg0 < ncg; cg0 += 8) {
-      uint4 v[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        v[u] = make_uint4(0u, 0u, 0u, 0u);
-        if (cg0 + u < ncg && !empty) {
-          const Tin* src = base + (int64_t)(8 * (cg0 + u)) * F.sc;
-          v[u] = inside ? __ldg(reinterpret_cast<const uint4*>(src + x)) : load_chunk_slow<Tin>(src, x, W, F.sw);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u)
-        if (cg0 + u < ncg)
-          *reinterpret_cast<uint4*>(dst + ((size_t)((cg0 + u) * nxg + xg) * 8 + cl) * 16) = v[u];
+    unsigned char* d0 = dst + ((size_t)xg * 8 + cl) * 16;
+    if (inside || empty) {
+      const Tin* src = inside ? base + x : base;
+      const int64_t cstep = inside ? 8 * F.sc : 0;
+      const int nbytes = inside ? 16 : 0;
+      for (int cg = 0; cg < ncg; ++cg)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(d0 + (size_t)cg * nxg * 128)),
+                     "l"(src + cg * cstep), "r"(nbytes)
+                     : "memory");
+    } else {
+      for (int cg = 0; cg < ncg; ++cg)
+        *reinterpret_cast<uint4*>(d0 + (size_t)cg * nxg * 128) =
+            load_chunk_slow<Tin>(base + (int64_t)(8 * cg) * F.sc, x, W, F.sw);
     }
   }
 }
@@ -156,15 +157,19 @@ struct TileCoord {
   int64_t n;
   int y, x0, dc0;
 };
-__device__ __forceinline__ TileCoord tile_coord(int64_t t, const TcGeom& g) {
+// 32-bit arithmetic only (tiles < 2^31 is checked on the host): 64-bit divisions are ~150-instruction
+// dependent chains and this runs once per tile in every loader and epilogue warp
+__device__ __forceinline__ TileCoord tile_coord(int64_t t64, const TcGeom& g) {
   TileCoord c;
-  const int xt = (int)(t % g.xtiles); t /= g.xtiles;
-  const int64_t row = t % g.rows;
-  const int dchunk = (int)(t / g.rows);
-  c.n = row / g.H;
-  c.y = (int)(row % g.H);
-  c.x0 = xt * TC_TM;
-  c.dc0 = dchunk * g.dch;
+  uint32_t t = (uint32_t)t64;
+  const uint32_t xt = t % (uint32_t)g.xtiles; t /= (uint32_t)g.xtiles;
+  const uint32_t rows = (uint32_t)g.rows;
+  const uint32_t dchunk = t / rows, row = t - dchunk * rows;
+  const uint32_t n = row / (uint32_t)g.H;
+  c.n = n;
+  c.y = (int)(row - n * (uint32_t)g.H);
+  c.x0 = (int)xt * TC_TM;
+  c.dc0 = (int)dchunk * g.dch;
   return c;
 }
 
@@ -205,34 +210,54 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
     const uint32_t idesc = (1u << 4) | ((uint32_t)g.fmt << 7) | ((uint32_t)g.fmt << 10) | (1u << 15) | (1u << 16) |
                            ((uint32_t)(g.ncol >> 3) << 17) | ((uint32_t)(TC_TM >> 4) << 24);
     const uint32_t sbo = 128, lboA = (TC_TM / 8) * 128, lboB = (uint32_t)(g.ncol / 8) * 128;
-    uint32_t it = 0, use = 0;   // k-chunks staged so far; tiles processed so far
+    // Software pipeline over k-chunk jobs: the copies of job i+1 are issued (cp.async group) before the
+    // loaders wait for job i to land, so two stages of loads are in flight while the UMMAs of job i issue.
+    struct Job {
+      unsigned char* sA;
+      unsigned char* sB;
+      int nch, kc;
+      uint32_t s, buf, use;
+    };
+    auto complete = [&](const Job& j, bool newer_group_in_flight) {
+      if (newer_group_in_flight) asm volatile("cp.async.wait_group 1;" ::: "memory");
+      else asm volatile("cp.async.wait_group 0;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (UMMA)
+      asm volatile("bar.sync 1, 128;" ::: "memory");                 // all four loader warps
+      if (lt == 0) {
+        if (j.kc == 0) mbar_wait(tmem_empty + 8 * j.buf, ((j.use >> 1) & 1) ^ 1);   // epilogue drained this buffer
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int ks = 0; ks < j.nch / 16; ++ks) {
+          const uint64_t adesc = umma_desc(smem_u32(j.sA) + ks * 2 * lboA, lboA, sbo);
+          const uint64_t bdesc = umma_desc(smem_u32(j.sB) + ks * 2 * lboB, lboB, sbo);
+          umma_f16(tmem_base + j.buf * g.tmem_buf, adesc, bdesc, idesc, (j.kc > 0 || ks > 0) ? 1u : 0u);
+        }
+        umma_commit(smem_empty + 8 * j.s);
+        if (j.kc == nk - 1) umma_commit(tmem_full + 8 * j.buf);
+      }
+    };
+    uint32_t it = 0, use = 0;   // k-chunks issued so far; tiles started so far
+    Job prev{};
+    bool have_prev = false;
     for (int64_t t = blockIdx.x; t < g.tiles; t += gridDim.x, ++use) {
       const TileCoord tc = tile_coord(t, g);
       const int xr0 = tc.x0 - tc.dc0 - g.dch;
-      const uint32_t buf = use & 1;
       for (int kc = 0; kc < nk; ++kc, ++it) {
-        const uint32_t s = it & 1;
-        unsigned char* sA = stage0 + (size_t)s * g.stage_bytes;
-        unsigned char* sB = sA + TC_KC * TC_TM * 2;
-        const int c0 = kc * TC_KC, nch = min(TC_KC, g.C - c0);
-        mbar_wait(smem_empty + 8 * s, ((it >> 1) & 1) ^ 1);        // UMMAs that read this stage have completed
-        stage_operand<Tin>(L, tc.n, tc.y, c0, nch, tc.x0, TC_TM / 8, g.W, sA, fast, lt);
-        stage_operand<Tin>(R, tc.n, tc.y, c0, nch, xr0, g.ncol / 8, g.W, sB, fast, lt);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (UMMA)
-        asm volatile("bar.sync 1, 128;" ::: "memory");                 // all four loader warps
-        if (lt == 0) {
-          if (kc == 0) mbar_wait(tmem_empty + 8 * buf, ((use >> 1) & 1) ^ 1);   // epilogue drained this buffer
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          for (int ks = 0; ks < nch / 16; ++ks) {
-            const uint64_t adesc = umma_desc(smem_u32(sA) + ks * 2 * lboA, lboA, sbo);
-            const uint64_t bdesc = umma_desc(smem_u32(sB) + ks * 2 * lboB, lboB, sbo);
-            umma_f16(tmem_base + buf * g.tmem_buf, adesc, bdesc, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
-          }
-          umma_commit(smem_empty + 8 * s);
-          if (kc == nk - 1) umma_commit(tmem_full + 8 * buf);
-        }
+        Job cur;
+        cur.s = it & 1; cur.buf = use & 1; cur.use = use; cur.kc = kc;
+        cur.sA = stage0 + (size_t)cur.s * g.stage_bytes;
+        cur.sB = cur.sA + TC_KC * TC_TM * 2;
+        const int c0 = kc * TC_KC;
+        cur.nch = min(TC_KC, g.C - c0);
+        mbar_wait(smem_empty + 8 * cur.s, ((it >> 1) & 1) ^ 1);     // UMMAs that read this stage have completed
+        stage_operand<Tin>(L, tc.n, tc.y, c0, cur.nch, tc.x0, TC_TM / 8, g.W, cur.sA, fast, lt);
+        stage_operand<Tin>(R, tc.n, tc.y, c0, cur.nch, xr0, g.ncol / 8, g.W, cur.sB, fast, lt);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (have_prev) complete(prev, true);
+        prev = cur;
+        have_prev = true;
       }
     }
+    if (have_prev) complete(prev, false);
   } else {
     // ================================================================================= epilogue
     // warp -> (TMEM lane quadrant q, disparity half hh): lanes 32q.., disparities [hh*dh, (hh+1)*dh).
@@ -255,13 +280,19 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
 
       if constexpr (EPI == EPI_VOLUME) {
         float* row = skew + (size_t)(32 * warp + lane) * g.pitch;
-        for (int cb = 0; cb < ncw; cb += 16) {
-          uint32_t r[16];
-          tmem_ld16(taddr + cb, r);
+        for (int cb = 0; cb < ncw; cb += 64) {             // up to four 16-column loads in flight per wait
+          uint32_t r[4][16];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (cb + 16 * u < ncw) tmem_ld16(taddr + cb + 16 * u, r[u]);   // warp-uniform condition
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int i = 0; i < 16; i += 4)
-            *reinterpret_cast<uint4*>(row + cb + i) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
+          for (int u = 0; u < 4; ++u)
+            if (cb + 16 * u < ncw) {
+#pragma unroll
+              for (int i = 0; i < 16; i += 4)
+                *reinterpret_cast<uint4*>(row + cb + 16 * u + i) = make_uint4(r[u][i], r[u][i + 1], r[u][i + 2], r[u][i + 3]);
+            }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         mbar_arrive(tmem_empty + 8 * buf);                 // this thread is done with the TMEM buffer
@@ -387,7 +418,7 @@ static int tc_geom(int64_t N, int64_t C, int64_t H, int64_t W, int64_t D, int me
   g.stage_bytes = TC_KC * TC_TM * 2 + TC_KC * g.ncol * 2;
   g.rows = N * H;
   g.tiles = g.rows * g.xtiles * g.dchunks;
-  if (g.tiles <= 0 || g.tiles > (int64_t)1 << 40) return RSM_ERR_INVALID_SHAPE;
+  if (g.tiles <= 0 || g.tiles > 2147483647LL) return RSM_ERR_INVALID_SHAPE;
   return RSM_OK;
 }
 

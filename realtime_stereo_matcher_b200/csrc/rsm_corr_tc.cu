@@ -29,6 +29,7 @@ namespace rsm {
 
 constexpr int TC_TM = 128;        // UMMA M: left pixels per tile
 constexpr int TC_KC = 64;         // channels per shared-memory stage
+constexpr int TC_NSTAGE = 4;      // upper bound on operand stages (g.nstage = 2..4, whatever fits in shared memory)
 constexpr int TC_EPI_WARPS = 8;    // warps 0-7: epilogue (two per TMEM lane quadrant)
 constexpr int TC_THREADS = 32 * TC_EPI_WARPS + 128;   // + warps 8-11: loaders
 enum { EPI_VOLUME = 0, EPI_REGRESS = 1 };
@@ -46,6 +47,7 @@ struct TcGeom {
   int fmt;        // 0 = fp16, 1 = bf16 (UMMA a/b format)
   int tmem_buf;   // TMEM columns per accumulator buffer (128 or 256)
   int stage_bytes;
+  int nstage;     // operand stages in use: the loaders run up to nstage-1 k-chunks ahead of the UMMAs
   int64_t rows;   // N * H
   int64_t tiles;  // rows * xtiles * dchunks
 };
@@ -177,11 +179,12 @@ template <typename Tin, typename Tout, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, TcGeom g, int fast) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  unsigned char* stage0 = smem_raw;                                   // 2 x { A: KC*128*2 | B: KC*ncol*2 }
-  float* skew = reinterpret_cast<float*>(smem_raw + 2 * (size_t)g.stage_bytes);   // epilogue scratch (g.epi_bytes)
+  unsigned char* stage0 = smem_raw;                                   // NSTAGE x { A: KC*128*2 | B: KC*ncol*2 }
+  float* skew = reinterpret_cast<float*>(smem_raw + g.nstage * (size_t)g.stage_bytes);   // epilogue scratch
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(skew) + g.epi_bytes);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
-  const uint32_t smem_empty = smem_u32(bars), tmem_full = smem_u32(bars + 2), tmem_empty = smem_u32(bars + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + TC_NSTAGE + 4);
+  const uint32_t smem_empty = smem_u32(bars), tmem_full = smem_u32(bars + TC_NSTAGE),
+                 tmem_empty = smem_u32(bars + TC_NSTAGE + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0) {
@@ -191,8 +194,8 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (threadIdx.x == 0) {
+    for (int i = 0; i < TC_NSTAGE; ++i) mbar_init(smem_empty + 8 * i, 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(smem_empty + 8 * i, 1);
       mbar_init(tmem_full + 8 * i, 1);
       mbar_init(tmem_empty + 8 * i, 32 * TC_EPI_WARPS);
     }
@@ -210,17 +213,22 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
     const uint32_t idesc = (1u << 4) | ((uint32_t)g.fmt << 7) | ((uint32_t)g.fmt << 10) | (1u << 15) | (1u << 16) |
                            ((uint32_t)(g.ncol >> 3) << 17) | ((uint32_t)(TC_TM >> 4) << 24);
     const uint32_t sbo = 128, lboA = (TC_TM / 8) * 128, lboB = (uint32_t)(g.ncol / 8) * 128;
-    // Software pipeline over k-chunk jobs: the copies of job i+1 are issued (cp.async group) before the
-    // loaders wait for job i to land, so two stages of loads are in flight while the UMMAs of job i issue.
+    // Software pipeline over k-chunk jobs: the copies of jobs i+1 .. i+NSTAGE-1 are issued (one cp.async
+    // group each) before the loaders wait for job i to land, so NSTAGE-1 stages of loads cover the HBM
+    // latency while the UMMAs of job i issue.
     struct Job {
       unsigned char* sA;
       unsigned char* sB;
       int nch, kc;
       uint32_t s, buf, use;
     };
-    auto complete = [&](const Job& j, bool newer_group_in_flight) {
-      if (newer_group_in_flight) asm volatile("cp.async.wait_group 1;" ::: "memory");
-      else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    auto complete = [&](const Job& j, int newer_groups_in_flight) {
+      switch (newer_groups_in_flight) {   // wait_group takes an immediate
+        case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+      }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (UMMA)
       asm volatile("bar.sync 1, 128;" ::: "memory");                 // all four loader warps
       if (lt == 0) {
@@ -236,28 +244,30 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
       }
     };
     uint32_t it = 0, use = 0;   // k-chunks issued so far; tiles started so far
-    Job prev{};
-    bool have_prev = false;
+    Job ring[TC_NSTAGE];
+    const uint32_t nst = (uint32_t)g.nstage;
+    uint32_t done = 0;          // jobs completed (UMMAs issued) so far
     for (int64_t t = blockIdx.x; t < g.tiles; t += gridDim.x, ++use) {
       const TileCoord tc = tile_coord(t, g);
       const int xr0 = tc.x0 - tc.dc0 - g.dch;
       for (int kc = 0; kc < nk; ++kc, ++it) {
-        Job cur;
-        cur.s = it & 1; cur.buf = use & 1; cur.use = use; cur.kc = kc;
+        Job& cur = ring[it % nst];
+        cur.s = it % nst; cur.buf = use & 1; cur.use = use; cur.kc = kc;
         cur.sA = stage0 + (size_t)cur.s * g.stage_bytes;
         cur.sB = cur.sA + TC_KC * TC_TM * 2;
         const int c0 = kc * TC_KC;
         cur.nch = min(TC_KC, g.C - c0);
-        mbar_wait(smem_empty + 8 * cur.s, ((it >> 1) & 1) ^ 1);     // UMMAs that read this stage have completed
+        mbar_wait(smem_empty + 8 * cur.s, ((it / nst) & 1) ^ 1);   // UMMAs that read this stage completed
         stage_operand<Tin>(L, tc.n, tc.y, c0, cur.nch, tc.x0, TC_TM / 8, g.W, cur.sA, fast, lt);
         stage_operand<Tin>(R, tc.n, tc.y, c0, cur.nch, xr0, g.ncol / 8, g.W, cur.sB, fast, lt);
         asm volatile("cp.async.commit_group;" ::: "memory");
-        if (have_prev) complete(prev, true);
-        prev = cur;
-        have_prev = true;
+        if (it + 1 - done == nst) {           // pipeline full: retire the oldest job
+          complete(ring[done % nst], (int)nst - 1);
+          ++done;
+        }
       }
     }
-    if (have_prev) complete(prev, false);
+    for (; done < it; ++done) complete(ring[done % nst], (int)(it - done - 1));   // drain
   } else {
     // ================================================================================= epilogue
     // warp -> (TMEM lane quadrant q, disparity half hh): lanes 32q.., disparities [hh*dh, (hh+1)*dh).
@@ -278,92 +288,85 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
       const int dmax = min(g.dch, g.D - tc.dc0);
       const int dlo = hh * dh, dhi = min((hh + 1) * dh, dmax);
 
-      if constexpr (EPI == EPI_VOLUME) {
-        float* row = skew + (size_t)(32 * warp + lane) * g.pitch;
-        for (int cb = 0; cb < ncw; cb += 64) {             // up to four 16-column loads in flight per wait
-          uint32_t r[4][16];
+      // ---- TMEM -> one padded shared-memory row per lane (up to four 16-column loads in flight per wait)
+      float* row = skew + (size_t)(32 * warp + lane) * g.pitch;
+      for (int cb = 0; cb < ncw; cb += 64) {
+        uint32_t r[4][16];
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (cb + 16 * u < ncw) tmem_ld16(taddr + cb + 16 * u, r[u]);   // warp-uniform condition
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int u = 0; u < 4; ++u)
+          if (cb + 16 * u < ncw) tmem_ld16(taddr + cb + 16 * u, r[u]);   // warp-uniform condition
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (cb + 16 * u < ncw) {
+        for (int u = 0; u < 4; ++u)
+          if (cb + 16 * u < ncw) {
 #pragma unroll
-              for (int i = 0; i < 16; i += 4)
-                *reinterpret_cast<uint4*>(row + cb + 16 * u + i) = make_uint4(r[u][i], r[u][i + 1], r[u][i + 2], r[u][i + 3]);
-            }
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        mbar_arrive(tmem_empty + 8 * buf);                 // this thread is done with the TMEM buffer
-        __syncwarp();
-        if (x < g.W) {
-          const float* rp0 = row + lane + (hh + 1) * dh;     // value(dl) = rp0[-dl]
-          Tout* __restrict__ o = out + (((int64_t)tc.n * g.D + tc.dc0) * g.H + tc.y) * g.W + x;
-          const int64_t dstride = (int64_t)g.H * g.W;
-          auto fin = [&](float v, int dl) -> Tout {
-            if (!ok) v = nanv;
-            if (g.mean) v = g.pow2 ? v * inv : v / cnt;
-            return from_f<Tout>(x < tc.dc0 + dl ? 0.f : v);   // the reference leaves zeros where x < d
-          };
-          int dl = dlo;
-          for (; dl + 4 <= dhi; dl += 4) {                   // 4 independent LDS -> STG chains
-            const float v0 = rp0[-dl], v1 = rp0[-dl - 1], v2 = rp0[-dl - 2], v3 = rp0[-dl - 3];
-            __stcs(o + (int64_t)dl * dstride, fin(v0, dl));
-            __stcs(o + (int64_t)(dl + 1) * dstride, fin(v1, dl + 1));
-            __stcs(o + (int64_t)(dl + 2) * dstride, fin(v2, dl + 2));
-            __stcs(o + (int64_t)(dl + 3) * dstride, fin(v3, dl + 3));
+            for (int i = 0; i < 16; i += 4)
+              *reinterpret_cast<uint4*>(row + cb + 16 * u + i) = make_uint4(r[u][i], r[u][i + 1], r[u][i + 2], r[u][i + 3]);
           }
-          for (; dl < dhi; ++dl) __stcs(o + (int64_t)dl * dstride, fin(rp0[-dl], dl));
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(tmem_empty + 8 * buf);                   // this thread is done with the TMEM buffer
+      __syncwarp();
+      // ---- skewed read-back: value(dl) = rp0[-dl]; zeros where x < d, i.e. for dl >= dz
+      const float* rp0 = row + lane + (hh + 1) * dh;
+      const float mul = !ok ? nanv : (g.mean ? (g.pow2 ? inv : 1.f) : 1.f);   // NaN marks a pipeline fault
+      const bool divide = g.mean && !g.pow2;
+      const int dz = max(dlo, min(dhi, x - tc.dc0 + 1));    // [dlo, dz): values, [dz, dhi): fill
+
+      if constexpr (EPI == EPI_VOLUME) {
+        if (x < g.W) {
+          const int64_t dstride = (int64_t)g.H * g.W;
+          Tout* __restrict__ o = out + (((int64_t)tc.n * g.D + tc.dc0 + dlo) * g.H + tc.y) * g.W + x;
+          int dl = dlo;
+          if (!divide) {
+            for (; dl + 4 <= dz; dl += 4) {                  // 4 independent LDS -> STG chains
+              const float v0 = rp0[-dl], v1 = rp0[-dl - 1], v2 = rp0[-dl - 2], v3 = rp0[-dl - 3];
+              __stcs(o, from_f<Tout>(v0 * mul)); o += dstride;
+              __stcs(o, from_f<Tout>(v1 * mul)); o += dstride;
+              __stcs(o, from_f<Tout>(v2 * mul)); o += dstride;
+              __stcs(o, from_f<Tout>(v3 * mul)); o += dstride;
+            }
+          }
+          for (; dl < dz; ++dl, o += dstride) __stcs(o, from_f<Tout>(divide ? rp0[-dl] * mul / cnt : rp0[-dl] * mul));
+          const Tout zero = from_f<Tout>(0.f);
+          for (; dl < dhi; ++dl, o += dstride) __stcs(o, zero);
         }
-        __syncwarp();                                       // rows are reused by the next tile
       } else {
-        // fused regression: column jj of this warp's window holds disparity dl = lane + (hh+1)*dh - jj.
-        // Columns are visited in ascending jj = DESCENDING disparity, so ties resolve to the smaller
-        // index with >= / <= updates (torch: first occurrence); NaNs raise a flag and win.
+        // ---- fused regression over this warp's disparities in ascending order (first index wins ties)
         float m = -INFINITY, s = 0.f, ws = 0.f;
         float minv = INFINITY, maxv = -INFINITY;
         int mini = 0x7fffffff, maxi = 0x7fffffff, nani = 0x7fffffff;
-        const int dtop = lane + (hh + 1) * dh;
-        for (int cb = 0; cb < ncw; cb += 16) {
-          uint32_t r[16];
-          tmem_ld16(taddr + cb, r);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          float v[16];
+        for (int d0 = dlo; d0 < dhi; d0 += 8) {
+          float v[8];
           float gm = -INFINITY;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int dl = dtop - (cb + i);
-            float f = __uint_as_float(r[i]);
-            if (g.mean) f = g.pow2 ? f * inv : f / cnt;
-            if (x < tc.dc0 + dl) f = 0.f;                   // fill value takes part in the regression (F8)
-            const bool valid = dl >= dlo && dl < dhi;
-            v[i] = valid ? f : -INFINITY;
-            gm = fmaxf(gm, v[i]);
-            if (valid) {
-              if (f <= minv) { minv = f; mini = dl; }
-              if (f >= maxv) { maxv = f; maxi = dl; }
+          for (int k = 0; k < 8; ++k) {
+            const int dl = d0 + k;
+            float f = -INFINITY;
+            if (dl < dhi) {
+              f = dl < dz ? (divide ? rp0[-dl] * mul / cnt : rp0[-dl] * mul) : 0.f;   // fill takes part (F8)
+              if (f < minv) { minv = f; mini = dl; }
+              if (f > maxv) { maxv = f; maxi = dl; }
               if (f != f) nani = min(nani, dl);
             }
+            v[k] = f;
+            gm = fmaxf(gm, f);
           }
           const float mn = fmaxf(m, gm);
-          if (mn > -INFINITY) {
-            const float mnl = mn * kLog2e;
-            const float a = (m == -INFINITY) ? 0.f : fast_exp2(fmaf(m, kLog2e, -mnl));
-            s *= a; ws *= a;
+          const float mnl = mn * kLog2e;
+          const float a = (m == -INFINITY) ? 0.f : fast_exp2(fmaf(m, kLog2e, -mnl));
+          s *= a; ws *= a;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float e = fast_exp2(fmaf(v[i], kLog2e, -mnl));     // invalid: exp2(-inf) = 0
-              s += e;
-              ws = fmaf((float)(dtop - (cb + i)), e, ws);
-            }
-            m = mn;
+          for (int k = 0; k < 8; ++k) {
+            const float e = fast_exp2(fmaf(v[k], kLog2e, -mnl));       // past the end: exp2(-inf) = 0
+            s += e;
+            ws = fmaf((float)(tc.dc0 + d0 + k), e, ws);
           }
+          m = mn;
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        mbar_arrive(tmem_empty + 8 * buf);
         // combine the two disparity halves of a quadrant: hh = 1 parks its state, hh = 0 merges and stores
-        float* part = skew + ((size_t)(use & 1) * 128 + 32 * q + lane) * 8;
+        float* part = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(skew) + g.epi_bytes - 2 * 128 * 8 * 4) +
+                      ((size_t)(use & 1) * 128 + 32 * q + lane) * 8;
         if (hh == 1) {
           part[0] = m; part[1] = s; part[2] = ws; part[3] = minv; part[4] = maxv;
           part[5] = __int_as_float(mini); part[6] = __int_as_float(maxi); part[7] = __int_as_float(nani);
@@ -377,19 +380,18 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
           const float a2 = (m2 == -INFINITY) ? 0.f : fast_exp2((m2 - M) * kLog2e);
           const float S = s * a1 + s2 * a2, WS = ws * a1 + w2 * a2;
           // the lower half holds the smaller indices: it wins ties
-          if (!(minv <= minv2) && mini2 != 0x7fffffff) mini = mini2;
-          if (mini == 0x7fffffff) mini = mini2;
-          if (!(maxv >= maxv2) && maxi2 != 0x7fffffff) maxi = maxi2;
-          if (maxi == 0x7fffffff) maxi = maxi2;
+          if (minv2 < minv && mini2 != 0x7fffffff) mini = mini2;
+          if (maxv2 > maxv && maxi2 != 0x7fffffff) maxi = maxi2;
           nani = min(nani, nani2);
           if (nani != 0x7fffffff) { mini = nani; maxi = nani; }
           const int64_t o = ((int64_t)tc.n * g.H + tc.y) * g.W + x;
-          if (rp.soft) rp.soft[o] = ok ? WS / S : nanv;
-          if (rp.lse) rp.lse[o] = ok ? M + __logf(S) : nanv;
-          if (rp.amin) rp.amin[o] = mini;
-          if (rp.amax) rp.amax[o] = maxi;
+          if (rp.soft) rp.soft[o] = WS / S;
+          if (rp.lse) rp.lse[o] = M + __logf(S);
+          if (rp.amin) rp.amin[o] = tc.dc0 + mini;
+          if (rp.amax) rp.amax[o] = tc.dc0 + maxi;
         }
       }
+      __syncwarp();                                         // rows are reused by the next tile
     }
   }
 
@@ -430,8 +432,10 @@ template <typename Tin, typename Tout, int EPI>
 static int launch_tc(const rsm_feat& left, const rsm_feat& right, void* out, RegressPtrs rp, const TcGeom& g_in,
                      cudaStream_t st, const char* where) {
   TcGeom g = g_in;
-  g.epi_bytes = EPI == EPI_VOLUME ? 32 * TC_EPI_WARPS * g.pitch * 4 : 2 * 128 * 8 * 4;
-  const size_t smem = 2 * (size_t)g.stage_bytes + (size_t)g.epi_bytes + 64;
+  g.epi_bytes = 32 * TC_EPI_WARPS * g.pitch * 4 + (EPI == EPI_REGRESS ? 2 * 128 * 8 * 4 : 0);   // rows (+ partials)
+  g.nstage = TC_NSTAGE;
+  while (g.nstage > 2 && g.nstage * (size_t)g.stage_bytes + (size_t)g.epi_bytes + 128 > 220 * 1024) --g.nstage;
+  const size_t smem = g.nstage * (size_t)g.stage_bytes + (size_t)g.epi_bytes + 128;
   auto k = inner_tc_kernel<Tin, Tout, EPI>;
   if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return finish_launch(where);

@@ -399,3 +399,49 @@ def test_epe_delta_synthetic(rsm):
     epe_ref = np.abs(ref - true_d)[valid].mean()
     assert abs(epe_ours - epe_ref) < 1e-4, (epe_ours, epe_ref)
     assert epe_ours < 0.5
+
+
+# ----------------------------------------------------------- tcgen05 (tensor-core) paths
+@pytest.mark.parametrize("shape", [(1, 16, 3, 240, 48), (2, 64, 4, 240, 48), (1, 32, 2, 312, 48),
+                                   (1, 128, 2, 480, 192), (1, 16, 2, 67, 19), (1, 48, 2, 130, 130)])
+@pytest.mark.parametrize("dn", ["bf16", "fp16"])
+def test_tcgen05_inner_vs_oracle_and_simt(rsm, shape, dn, monkeypatch):
+    """16-bit features with C % 16 == 0 take the tcgen05 banded-GEMM kernel: check it against the fp32
+    oracle on the same rounded inputs AND against the SIMT kernel (RSM_DISABLE_TC=1)."""
+    n, c, h, w, d = shape
+    rng = np.random.default_rng(31)
+    l = round_to(rng.standard_normal((n, c, h, w)).astype(np.float32), dn)
+    r = round_to(rng.standard_normal((n, c, h, w)).astype(np.float32), dn)
+    L, R = dev(l, dn), dev(r, dn)
+    ref = oracle.inner_product_volume(l, r, d, mean=True, out_dtype=np.float32)
+    monkeypatch.delenv("RSM_DISABLE_TC", raising=False)
+    tc32 = rsm.inner_product_volume(L, R, d, mean=True, out_dtype=torch.float32)
+    tc16 = rsm.inner_product_volume(L, R, d, mean=True)
+    monkeypatch.setenv("RSM_DISABLE_TC", "1")
+    simt32 = rsm.inner_product_volume(L, R, d, mean=True, out_dtype=torch.float32)
+    atol = 1e-5 * np.sqrt(c) * np.abs(l).max() * np.abs(r).max()
+    close(tc32, ref, atol)
+    close(simt32, ref, atol)
+    close(tc16, ref, atol, RTOL_16[dn])
+
+
+@pytest.mark.parametrize("shape", [(1, 16, 3, 240, 48), (2, 64, 3, 240, 48), (1, 32, 2, 312, 24), (1, 64, 2, 480, 128)])
+def test_tcgen05_fused_regress(rsm, shape):
+    """Fused correlation -> soft-argmax / argmin / argmax straight out of TMEM (bf16 features)."""
+    n, c, h, w, d = shape
+    rng = np.random.default_rng(41)
+    l = round_to((rng.standard_normal((n, c, h, w)) * 0.5).astype(np.float32), "bf16")
+    r = round_to((rng.standard_normal((n, c, h, w)) * 0.5).astype(np.float32), "bf16")
+    soft, amin, amax = rsm.inner_product_regress(dev(l, "bf16"), dev(r, "bf16"), d)
+    vol = oracle.inner_product_volume(l, r, d, out_dtype=np.float32)
+    close(soft, oracle.soft_argmax(vol), soft_argmax_atol(d) * 4)
+    assert (amax.cpu().numpy() != oracle.hard_argmax(vol)).mean() < 1e-3
+    assert (amin.cpu().numpy() != oracle.hard_argmin(vol)).mean() < 1e-3
+    # dyadic inputs: exact sums -> bit-exact extrema, including the x < d fill region and ties
+    l = (rng.integers(-8, 9, (n, c, h, w)) / 8.0).astype(np.float32)
+    r = (rng.integers(-8, 9, (n, c, h, w)) / 8.0).astype(np.float32)
+    soft, amin, amax = rsm.inner_product_regress(dev(l, "bf16"), dev(r, "bf16"), d)
+    vol = oracle.inner_product_volume(l, r, d)
+    equal(amin, oracle.hard_argmin(vol))
+    equal(amax, oracle.hard_argmax(vol))
+    equal(rsm.inner_product_volume(dev(l, "bf16"), dev(r, "bf16"), d, out_dtype=torch.float32), vol)

@@ -1,0 +1,148 @@
+// Tiled adjoint of the correlation volumes (inner product / mean correlation / group-wise), SIMT fp32.
+//
+//   gL[c,x]  = s * sum_d gV[g(c), d, x]      * R[c, x - d]          (SIDE_LEFT)
+//   gR[c,x'] = s * sum_d gV[g(c), d, x' + d] * L[c, x' + d]         (SIDE_RIGHT)
+//
+// Same shape as the forward: a CTA owns a 64-pixel row segment of one (n, y) and a block of <= 32
+// channels of ONE group; per chunk of <= 64 disparities it stages the gradient tile gV[d][x] and the
+// other feature's window in shared memory as fp32, and every thread accumulates a 4(x) x 4(c)
+// register tile, walking the disparities four at a time so that all shared-memory reads are aligned
+// 128-bit loads (4-6 FMA per LDS.128).  Atomic-free and deterministic.
+#pragma once
+
+namespace rsm {
+
+constexpr int BW_TX = 64;    // pixels per CTA
+constexpr int BW_CB = 32;    // channels per CTA (<= one group)
+constexpr int BW_DCH = 64;   // disparities per staged chunk
+
+enum { SIDE_LEFT = 0, SIDE_RIGHT = 1 };
+
+// gradient element gV[d, x] of (n, group, y) in either output layout
+template <typename Tout, int LAYOUT>
+struct GradView {
+  const Tout* base;
+  int64_t sd, sx;
+  __device__ __forceinline__ GradView(const Tout* gout, const CorrGeom& g, int64_t n, int grp, int y) {
+    if constexpr (LAYOUT == LAYOUT_NDHW) {
+      base = gout + ((int64_t)n * g.D * g.H + y) * g.W; sd = (int64_t)g.H * g.W; sx = 1;
+    } else {
+      base = gout + (((int64_t)n * g.G + grp) * g.H + y) * (int64_t)g.W * g.D; sd = 1; sx = g.D;
+    }
+  }
+  __device__ __forceinline__ float at(int d, int x) const { return to_f(__ldg(base + d * sd + x * sx)); }
+};
+
+template <typename Tin, typename Tout, int LAYOUT, int SIDE>
+__global__ void __launch_bounds__(16 * (BW_CB / 4))
+corr_bwd_tiled_kernel(const Tout* __restrict__ gout, FeatView L, FeatView R, Tin* __restrict__ gdst, CorrGeom g,
+                      int cblocks, int cb_size) {
+  extern __shared__ __align__(16) float smem[];
+  // SIDE_LEFT : sG[BW_DCH][TX]          gradient rows x0..x0+TX;      sF = R window [x0-dc0-DCH, x0-dc0+TX)
+  // SIDE_RIGHT: sG[BW_DCH][TX + DCH]    gradient rows x0+dc0.. ;      sF = L window [x0+dc0, x0+dc0+TX+DCH)
+  constexpr int GW = SIDE == SIDE_LEFT ? BW_TX : BW_TX + BW_DCH;
+  constexpr int FW = BW_TX + BW_DCH;
+  float* sG = smem;
+  float* sF = smem + BW_DCH * GW;
+
+  int64_t bid = blockIdx.x;
+  const int xt = (int)(bid % g.xtiles); bid /= g.xtiles;
+  const int cb = (int)(bid % cblocks); bid /= cblocks;
+  const int y = (int)(bid % g.H);
+  const int64_t n = bid / g.H;
+  const int x0 = xt * BW_TX;
+  const int c0 = cb * cb_size;                 // first channel of this block (never straddles a group)
+  const int grp = c0 / g.cpg;
+  const int ncb = min(cb_size, g.C - c0);
+  const int tx = threadIdx.x & 15, tc = threadIdx.x >> 4;
+  const GradView<Tout, LAYOUT> gv(gout, g, n, grp, y);
+  const FeatView& F = SIDE == SIDE_LEFT ? R : L;
+  const Tin* __restrict__ pf = reinterpret_cast<const Tin*>(F.data) + n * F.sn + (int64_t)y * F.sh + (int64_t)c0 * F.sc;
+
+  float acc[4][4];   // [channel j][pixel i]
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+
+  for (int dc0 = 0; dc0 < g.D; dc0 += BW_DCH) {
+    __syncthreads();
+    // ---- stage the gradient tile (zero outside [0,D) x [0,W)) and the feature window (zero outside [0,W))
+    const int gx0 = SIDE == SIDE_LEFT ? x0 : x0 + dc0;
+    for (int e = threadIdx.x; e < BW_DCH * GW; e += blockDim.x) {
+      int dl, xx;
+      if constexpr (LAYOUT == LAYOUT_NDHW) { dl = e / GW; xx = e - dl * GW; }      // x fastest: coalesced rows
+      else { xx = e / BW_DCH; dl = e - xx * BW_DCH; }                              // d fastest: contiguous runs
+      const int d = dc0 + dl, x = gx0 + xx;
+      sG[dl * GW + xx] = (d < g.D && x < g.W) ? gv.at(d, x) : 0.f;
+    }
+    const int fx0 = SIDE == SIDE_LEFT ? x0 - dc0 - BW_DCH : x0 + dc0;
+    for (int e = threadIdx.x; e < ncb * FW; e += blockDim.x) {
+      const int c = e / FW, j = e - c * FW;
+      const int x = fx0 + j;
+      sF[c * FW + j] = (x >= 0 && x < g.W) ? to_f(__ldg(pf + (int64_t)c * F.sc + (int64_t)x * F.sw)) : 0.f;
+    }
+    __syncthreads();
+    if (4 * tc >= ncb) continue;
+    // ---- accumulate: disparities four at a time (d = dc0 + 4q + r)
+    for (int q = 0; q < BW_DCH / 4; ++q) {
+      if (dc0 + 4 * q >= g.D) break;
+      if constexpr (SIDE == SIDE_LEFT) {
+        float gq[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float4 t = *reinterpret_cast<const float4*>(sG + (4 * q + r) * GW + 4 * tx);
+          gq[r][0] = t.x; gq[r][1] = t.y; gq[r][2] = t.z; gq[r][3] = t.w;
+        }
+        // R[x - d]: window index = DCH + 4tx + i - 4q - r = (DCH + 4tx - 4q - 4) + (4 + i - r)
+        const int wb = BW_DCH + 4 * tx - 4 * q - 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4* wp = reinterpret_cast<const float4*>(sF + (4 * tc + j) * FW + wb);
+          const float4 w0 = wp[0], w1 = wp[1];
+          const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[j][i] = fmaf(gq[r][i], w[4 + i - r], acc[j][i]);
+        }
+      } else {
+        // u = x' + d: window index = 4tx + 4q + (i + r) in both sG (row d) and sF
+        const int wb = 4 * tx + 4 * q;
+        float p[4][8];   // p[r][k] = gV[d = 4q + r][wb + k]
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float4* gp = reinterpret_cast<const float4*>(sG + (4 * q + r) * GW + wb);
+          const float4 a = gp[0], b = gp[1];
+          p[r][0] = a.x; p[r][1] = a.y; p[r][2] = a.z; p[r][3] = a.w;
+          p[r][4] = b.x; p[r][5] = b.y; p[r][6] = b.z; p[r][7] = b.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4* lp = reinterpret_cast<const float4*>(sF + (4 * tc + j) * FW + wb);
+          const float4 l0 = lp[0], l1 = lp[1];
+          const float l[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[j][i] = fmaf(p[r][i + r], l[i + r], acc[j][i]);
+        }
+      }
+    }
+  }
+  // ---- scale and store (x contiguous)
+  const float cnt = g.mean ? (float)g.cpg : 1.f;
+  const int xb = x0 + 4 * tx;
+  if (xb >= g.W) return;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = c0 + 4 * tc + j;
+    if (4 * tc + j >= ncb) break;
+    Tin* o = gdst + (((int64_t)n * g.C + c) * g.H + y) * g.W + xb;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (xb + i < g.W) o[i] = from_f<Tin>(acc[j][i] / cnt);
+  }
+}
+
+}  // namespace rsm

@@ -10,19 +10,23 @@
 // memory, fp32 accumulators in TMEM, issued by one thread).  The value for disparity dc0 + dl of
 // pixel x0 + r sits at column j = r + DCH - dl: a diagonal band.
 //
-// Persistent, warp-specialised CTA (256 threads, one per SM), tiles strided over the grid:
-//   warps 4-7  loaders: stage the operand slab (<= 64 channels) of the next k-chunk into one of two
-//              shared-memory stages with 16-byte loads (features may be strided views; the right window
-//              is zero-filled on both sides), writing the canonical no-swizzle MN-major core-matrix
-//              layout directly:  addr(x, c) = ((c/8) * (T/8) + x/8) * 128 + (c%8) * 16 + (x%8) * 2;
-//              thread 128 then issues the UMMAs and commits them to mbarriers;
-//   warps 0-3  epilogue: TMEM lane quadrant w; tcgen05.ld the DCH + 32 columns covering its lanes and
-//              either park them in a padded shared-memory row per lane and read them back skewed, so
-//              that for every disparity 32 lanes store 32 consecutive x (EPI_VOLUME), or reduce them in
-//              registers with a chunked online softmax + arg-extrema (EPI_REGRESS).
-// Two TMEM accumulator buffers and two operand stages decouple the roles: the loaders run up to two
-// k-chunks / one tile ahead of the epilogue.  mbarriers: smem_empty[2] (UMMA commit -> loaders),
-// tmem_full[2] (UMMA commit -> epilogue), tmem_empty[2] (128 epilogue threads -> UMMA issuer).
+// Persistent, warp-specialised CTA (416 threads, one per SM); each CTA owns a contiguous range of tiles:
+//   warps 8-11 loaders: stage the operand slab (<= 64 channels) of a k-chunk into one of 2-4 shared-memory
+//              stages with 16-byte cp.async (features may be strided views; the right window is
+//              zero-filled on both sides by the same instruction), writing the canonical no-swizzle
+//              MN-major core-matrix layout directly:
+//                  addr(x, c) = ((c/8) * (T/8) + x/8) * 128 + (c%8) * 16 + (x%8) * 2;
+//              up to nstage-1 newer cp.async groups stay in flight behind the one being waited for;
+//   warp 12    UMMA issuer (one lane): waits smem_full / tmem_empty, issues the tcgen05.mma chain of the
+//              k-chunk, commits it to smem_empty (stage reusable) and tmem_full (accumulator ready);
+//   warps 0-7  epilogue, two warps per TMEM lane quadrant (each takes half of the disparities):
+//              tcgen05.ld the columns covering its lanes, park them in a padded shared-memory row per
+//              lane, read them back skewed so that for every disparity 32 lanes hold 32 consecutive x, then
+//              either store the (N,D,H,W) volume (EPI_VOLUME) or run the chunked online softmax +
+//              arg-extrema over them (EPI_REGRESS; the two halves of a quadrant merge through smem).
+// Two TMEM accumulator buffers decouple the UMMAs of tile t+1 from the epilogue of tile t.
+// mbarriers: smem_full[s] (128 loader arrivals), smem_empty[s] (UMMA commit), tmem_full[b] (UMMA commit),
+// tmem_empty[b] (256 epilogue arrivals).  All waits are bounded (a protocol bug yields NaNs, not a hang).
 #include "rsm_common.cuh"
 
 namespace rsm {
@@ -31,7 +35,7 @@ constexpr int TC_TM = 128;        // UMMA M: left pixels per tile
 constexpr int TC_KC = 64;         // channels per shared-memory stage
 constexpr int TC_NSTAGE = 4;      // upper bound on operand stages (g.nstage = 2..4, whatever fits in shared memory)
 constexpr int TC_EPI_WARPS = 8;    // warps 0-7: epilogue (two per TMEM lane quadrant)
-constexpr int TC_THREADS = 32 * TC_EPI_WARPS + 128;   // + warps 8-11: loaders
+constexpr int TC_THREADS = 32 * TC_EPI_WARPS + 128 + 32;   // + warps 8-11: loaders, warp 12: UMMA issuer
 enum { EPI_VOLUME = 0, EPI_REGRESS = 1 };
 
 struct TcGeom {
@@ -158,6 +162,9 @@ __device__ __forceinline__ void stage_operand(const FeatView& F, int64_t n, int 
 struct TileCoord {
   int64_t n;
   int y, x0, dc0;
+  int xt;
+  // next tile in (dchunk, n, y, xt) order, xt fastest: no divisions in the steady state
+  __device__ __forceinline__ void advance(const TcGeom& g);
 };
 // 32-bit arithmetic only (tiles < 2^31 is checked on the host): 64-bit divisions are ~150-instruction
 // dependent chains and this runs once per tile in every loader and epilogue warp
@@ -170,9 +177,19 @@ __device__ __forceinline__ TileCoord tile_coord(int64_t t64, const TcGeom& g) {
   const uint32_t n = row / (uint32_t)g.H;
   c.n = n;
   c.y = (int)(row - n * (uint32_t)g.H);
+  c.xt = (int)xt;
   c.x0 = (int)xt * TC_TM;
   c.dc0 = (int)dchunk * g.dch;
   return c;
+}
+__device__ __forceinline__ void TileCoord::advance(const TcGeom& g) {
+  if (++xt < g.xtiles) { x0 += TC_TM; return; }
+  xt = 0; x0 = 0;
+  if (++y < g.H) return;
+  y = 0;
+  if (++n < g.rows / g.H) return;
+  n = 0;
+  dc0 += g.dch;
 }
 
 template <typename Tin, typename Tout, int EPI>
@@ -182,9 +199,9 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
   unsigned char* stage0 = smem_raw;                                   // NSTAGE x { A: KC*128*2 | B: KC*ncol*2 }
   float* skew = reinterpret_cast<float*>(smem_raw + g.nstage * (size_t)g.stage_bytes);   // epilogue scratch
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(skew) + g.epi_bytes);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + TC_NSTAGE + 4);
-  const uint32_t smem_empty = smem_u32(bars), tmem_full = smem_u32(bars + TC_NSTAGE),
-                 tmem_empty = smem_u32(bars + TC_NSTAGE + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_NSTAGE + 4);
+  const uint32_t smem_empty = smem_u32(bars), smem_full = smem_u32(bars + TC_NSTAGE),
+                 tmem_full = smem_u32(bars + 2 * TC_NSTAGE), tmem_empty = smem_u32(bars + 2 * TC_NSTAGE + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0) {
@@ -194,7 +211,10 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < TC_NSTAGE; ++i) mbar_init(smem_empty + 8 * i, 1);
+    for (int i = 0; i < TC_NSTAGE; ++i) {
+      mbar_init(smem_empty + 8 * i, 1);        // one UMMA commit
+      mbar_init(smem_full + 8 * i, 128);       // every loader thread, after its copies landed
+    }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tmem_full + 8 * i, 1);
       mbar_init(tmem_empty + 8 * i, 32 * TC_EPI_WARPS);
@@ -206,23 +226,45 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   const int nk = (g.C + TC_KC - 1) / TC_KC;
+  // contiguous tile range of this CTA (neighbouring x tiles share most of their right window in L2)
+  const int64_t per = (g.tiles + gridDim.x - 1) / gridDim.x;
+  const int64_t t_beg = min((int64_t)blockIdx.x * per, g.tiles), t_end = min(t_beg + per, g.tiles);
 
-  if (warp >= TC_EPI_WARPS) {
-    // =========================================================== loaders (+ UMMA issue by lt == 0)
+  if (warp == TC_EPI_WARPS + 4) {
+    // ================================================================ UMMA issuer (one elected lane)
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | ((uint32_t)g.fmt << 7) | ((uint32_t)g.fmt << 10) | (1u << 15) | (1u << 16) |
+                             ((uint32_t)(g.ncol >> 3) << 17) | ((uint32_t)(TC_TM >> 4) << 24);
+      const uint32_t sbo = 128, lboA = (TC_TM / 8) * 128, lboB = (uint32_t)(g.ncol / 8) * 128;
+      const uint32_t nst = (uint32_t)g.nstage;
+      uint32_t it = 0, use = 0;
+      for (int64_t t = t_beg; t < t_end; ++t, ++use) {
+        const uint32_t buf = use & 1;
+        mbar_wait(tmem_empty + 8 * buf, ((use >> 1) & 1) ^ 1);            // epilogue drained this accumulator
+        for (int kc = 0; kc < nk; ++kc, ++it) {
+          const uint32_t s = it % nst;
+          const uint32_t sA = smem_u32(stage0 + (size_t)s * g.stage_bytes), sB = sA + TC_KC * TC_TM * 2;
+          const int nch = min(TC_KC, g.C - kc * TC_KC);
+          mbar_wait(smem_full + 8 * s, (it / nst) & 1);                   // operands of this k-chunk have landed
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          for (int ks = 0; ks < nch / 16; ++ks) {
+            const uint64_t adesc = umma_desc(sA + ks * 2 * lboA, lboA, sbo);
+            const uint64_t bdesc = umma_desc(sB + ks * 2 * lboB, lboB, sbo);
+            umma_f16(tmem_base + buf * g.tmem_buf, adesc, bdesc, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+          }
+          umma_commit(smem_empty + 8 * s);                                // stage reusable once these complete
+          if (kc == nk - 1) umma_commit(tmem_full + 8 * buf);             // accumulator ready for the epilogue
+        }
+      }
+    }
+  } else if (warp >= TC_EPI_WARPS) {
+    // ================================================================================== loaders
+    // One cp.async group per k-chunk job; up to nstage-1 newer groups stay in flight while the loaders
+    // wait for the oldest one to land, fence it for the async proxy and signal smem_full.  The loaders
+    // never wait on the UMMA issuer except for a free stage (smem_empty), nstage jobs later.
     const int lt = threadIdx.x - 32 * TC_EPI_WARPS;
-    const uint32_t idesc = (1u << 4) | ((uint32_t)g.fmt << 7) | ((uint32_t)g.fmt << 10) | (1u << 15) | (1u << 16) |
-                           ((uint32_t)(g.ncol >> 3) << 17) | ((uint32_t)(TC_TM >> 4) << 24);
-    const uint32_t sbo = 128, lboA = (TC_TM / 8) * 128, lboB = (uint32_t)(g.ncol / 8) * 128;
-    // Software pipeline over k-chunk jobs: the copies of jobs i+1 .. i+NSTAGE-1 are issued (one cp.async
-    // group each) before the loaders wait for job i to land, so NSTAGE-1 stages of loads cover the HBM
-    // latency while the UMMAs of job i issue.
-    struct Job {
-      unsigned char* sA;
-      unsigned char* sB;
-      int nch, kc;
-      uint32_t s, buf, use;
-    };
-    auto complete = [&](const Job& j, int newer_groups_in_flight) {
+    const uint32_t nst = (uint32_t)g.nstage;
+    auto landed = [&](uint32_t job, int newer_groups_in_flight) {
       switch (newer_groups_in_flight) {   // wait_group takes an immediate
         case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
         case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
@@ -230,44 +272,28 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
         default: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (UMMA)
-      asm volatile("bar.sync 1, 128;" ::: "memory");                 // all four loader warps
-      if (lt == 0) {
-        if (j.kc == 0) mbar_wait(tmem_empty + 8 * j.buf, ((j.use >> 1) & 1) ^ 1);   // epilogue drained this buffer
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        for (int ks = 0; ks < j.nch / 16; ++ks) {
-          const uint64_t adesc = umma_desc(smem_u32(j.sA) + ks * 2 * lboA, lboA, sbo);
-          const uint64_t bdesc = umma_desc(smem_u32(j.sB) + ks * 2 * lboB, lboB, sbo);
-          umma_f16(tmem_base + j.buf * g.tmem_buf, adesc, bdesc, idesc, (j.kc > 0 || ks > 0) ? 1u : 0u);
-        }
-        umma_commit(smem_empty + 8 * j.s);
-        if (j.kc == nk - 1) umma_commit(tmem_full + 8 * j.buf);
-      }
+      mbar_arrive(smem_full + 8 * (job % nst));
     };
-    uint32_t it = 0, use = 0;   // k-chunks issued so far; tiles started so far
-    Job ring[TC_NSTAGE];
-    const uint32_t nst = (uint32_t)g.nstage;
-    uint32_t done = 0;          // jobs completed (UMMAs issued) so far
-    for (int64_t t = blockIdx.x; t < g.tiles; t += gridDim.x, ++use) {
-      const TileCoord tc = tile_coord(t, g);
+    uint32_t it = 0, done = 0;   // k-chunk jobs issued / signalled so far
+    TileCoord tc = tile_coord(t_beg, g);
+    for (int64_t t = t_beg; t < t_end; ++t, tc.advance(g)) {
       const int xr0 = tc.x0 - tc.dc0 - g.dch;
       for (int kc = 0; kc < nk; ++kc, ++it) {
-        Job& cur = ring[it % nst];
-        cur.s = it % nst; cur.buf = use & 1; cur.use = use; cur.kc = kc;
-        cur.sA = stage0 + (size_t)cur.s * g.stage_bytes;
-        cur.sB = cur.sA + TC_KC * TC_TM * 2;
-        const int c0 = kc * TC_KC;
-        cur.nch = min(TC_KC, g.C - c0);
-        mbar_wait(smem_empty + 8 * cur.s, ((it / nst) & 1) ^ 1);   // UMMAs that read this stage completed
-        stage_operand<Tin>(L, tc.n, tc.y, c0, cur.nch, tc.x0, TC_TM / 8, g.W, cur.sA, fast, lt);
-        stage_operand<Tin>(R, tc.n, tc.y, c0, cur.nch, xr0, g.ncol / 8, g.W, cur.sB, fast, lt);
+        const uint32_t s = it % nst;
+        unsigned char* sA = stage0 + (size_t)s * g.stage_bytes;
+        unsigned char* sB = sA + TC_KC * TC_TM * 2;
+        const int c0 = kc * TC_KC, nch = min(TC_KC, g.C - c0);
+        mbar_wait(smem_empty + 8 * s, ((it / nst) & 1) ^ 1);       // UMMAs that read this stage have completed
+        stage_operand<Tin>(L, tc.n, tc.y, c0, nch, tc.x0, TC_TM / 8, g.W, sA, fast, lt);
+        stage_operand<Tin>(R, tc.n, tc.y, c0, nch, xr0, g.ncol / 8, g.W, sB, fast, lt);
         asm volatile("cp.async.commit_group;" ::: "memory");
-        if (it + 1 - done == nst) {           // pipeline full: retire the oldest job
-          complete(ring[done % nst], (int)nst - 1);
+        if (it + 1 - done == nst) {             // keep at most nstage-1 newer groups behind the oldest
+          landed(done, (int)nst - 1);
           ++done;
         }
       }
     }
-    for (; done < it; ++done) complete(ring[done % nst], (int)(it - done - 1));   // drain
+    for (; done < it; ++done) landed(done, (int)(it - done - 1));   // drain
   } else {
     // ================================================================================= epilogue
     // warp -> (TMEM lane quadrant q, disparity half hh): lanes 32q.., disparities [hh*dh, (hh+1)*dh).
@@ -278,8 +304,8 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
     const float inv = 1.f / (float)g.C, cnt = (float)g.C;
     const float nanv = __int_as_float(0x7fc00000);
     uint32_t use = 0;
-    for (int64_t t = blockIdx.x; t < g.tiles; t += gridDim.x, ++use) {
-      const TileCoord tc = tile_coord(t, g);
+    TileCoord tc = tile_coord(t_beg, g);
+    for (int64_t t = t_beg; t < t_end; ++t, ++use, tc.advance(g)) {
       const uint32_t buf = use & 1;
       const bool ok = mbar_wait(tmem_full + 8 * buf, (use >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -434,8 +460,8 @@ static int launch_tc(const rsm_feat& left, const rsm_feat& right, void* out, Reg
   TcGeom g = g_in;
   g.epi_bytes = 32 * TC_EPI_WARPS * g.pitch * 4 + (EPI == EPI_REGRESS ? 2 * 128 * 8 * 4 : 0);   // rows (+ partials)
   g.nstage = TC_NSTAGE;
-  while (g.nstage > 2 && g.nstage * (size_t)g.stage_bytes + (size_t)g.epi_bytes + 128 > 220 * 1024) --g.nstage;
-  const size_t smem = g.nstage * (size_t)g.stage_bytes + (size_t)g.epi_bytes + 128;
+  while (g.nstage > 2 && g.nstage * (size_t)g.stage_bytes + (size_t)g.epi_bytes + 160 > 220 * 1024) --g.nstage;
+  const size_t smem = g.nstage * (size_t)g.stage_bytes + (size_t)g.epi_bytes + 160;
   auto k = inner_tc_kernel<Tin, Tout, EPI>;
   if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return finish_launch(where);

@@ -355,49 +355,58 @@ inner_regress_fwd_kernel(FeatView L, FeatView R, float* __restrict__ soft, int64
     __syncthreads();
     tile_fma(sL, sR, rw, tx, wstart, 0, nch, acc);
   }
-  const float cnt = g.mean ? (float)g.C : 1.f;
+  const float cnt = g.mean ? (float)g.C : 1.f, inv = 1.f / cnt;
+  const bool pow2 = !g.mean || g.pow2;            // exact reciprocal: identical to the division
   const int xb = XT * tx, db = DT * td;
 #pragma unroll
   for (int i = 0; i < XT; ++i)
 #pragma unroll
     for (int j = 0; j < DT; ++j)
-      sV[(xb + i) * dp + db + j] = (x0 + xb + i >= db + j) ? acc[i][j] / cnt : 0.f;
+      sV[(xb + i) * dp + db + j] = (x0 + xb + i >= db + j) ? (pow2 ? acc[i][j] * inv : acc[i][j] / cnt) : 0.f;
   __syncthreads();
 
-  constexpr float kLog2e = 1.4426950408889634f;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (int xx = warp; xx < TX; xx += nwarps) {
+  // One thread per pixel column, walking its D values in ascending order from shared memory (odd pitch:
+  // conflict-free): chunked online softmax (one rescale exp per 8 values), strict compares so the
+  // first index wins ties, NaNs win through a flag -- torch.argmin/argmax semantics.
+  for (int xx = threadIdx.x; xx < TX; xx += blockDim.x) {
     const int x = x0 + xx;
-    if (x >= g.W) break;
+    if (x >= g.W) continue;
     const float* col = sV + xx * dp;
-    float m = -INFINITY;
-    Best bmin{INFINITY, 0x7fffffff}, bmax{-INFINITY, 0x7fffffff};
-    for (int d = lane; d < g.D; d += 32) {
-      const float v = col[d];
-      m = fmaxf(m, v);
-      bmin = better<true>(bmin, Best{v, d});
-      bmax = better<false>(bmax, Best{v, d});
+    float m = -INFINITY, s = 0.f, ws = 0.f, minv = INFINITY, maxv = -INFINITY;
+    int mini = 0, maxi = 0, nani = -1;
+    for (int d0 = 0; d0 < g.D; d0 += 8) {
+      float v[8];
+      float gm = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int d = d0 + k;
+        float f = -INFINITY;
+        if (d < g.D) {
+          f = col[d];
+          if (f < minv) { minv = f; mini = d; }
+          if (f > maxv) { maxv = f; maxi = d; }
+          if (f != f && nani < 0) nani = d;
+        }
+        v[k] = f;
+        gm = fmaxf(gm, f);
+      }
+      const float mn = fmaxf(m, gm), mnl = mn * kLog2e;
+      const float a = (m == -INFINITY) ? 0.f : fast_exp2(fmaf(m, kLog2e, -mnl));
+      s *= a; ws *= a;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float e = fast_exp2(fmaf(v[k], kLog2e, -mnl));     // past the end: exp2(-inf) = 0
+        s += e;
+        ws = fmaf((float)(d0 + k), e, ws);
+      }
+      m = mn;
     }
-    m = warp_max(m);
-    float s = 0.f, ws = 0.f;
-    for (int d = lane; d < g.D; d += 32) {
-      float e;
-      const float t = fmaf(col[d], kLog2e, -m * kLog2e);
-      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
-      s += e;
-      ws = fmaf((float)d, e, ws);
-    }
-    s = warp_sum(s);
-    ws = warp_sum(ws);
-    bmin = warp_best<true>(bmin);
-    bmax = warp_best<false>(bmax);
-    if (lane == 0) {
-      const int64_t o = ((int64_t)n * g.H + y) * g.W + x;
-      if (soft) soft[o] = ws / s;
-      if (lse) lse[o] = m + __logf(s);
-      if (amin) amin[o] = bmin.i;
-      if (amax) amax[o] = bmax.i;
-    }
+    if (nani >= 0) { mini = nani; maxi = nani; }
+    const int64_t o = ((int64_t)n * g.H + y) * g.W + x;
+    if (soft) soft[o] = ws / s;
+    if (lse) lse[o] = m + __logf(s);
+    if (amin) amin[o] = mini;
+    if (amax) amax[o] = maxi;
   }
 }
 

@@ -51,6 +51,7 @@ struct TcGeom {
   int fmt;        // 0 = fp16, 1 = bf16 (UMMA a/b format)
   int tmem_buf;   // TMEM columns per accumulator buffer (128 or 256)
   int stage_bytes;
+  int d_fastest;  // tile order: disparity chunk fastest (fused regress keeps per-pixel state across chunks)
   int nstage;     // operand stages in use: the loaders run up to nstage-1 k-chunks ahead of the UMMAs
   int64_t rows;   // N * H
   int64_t tiles;  // rows * xtiles * dchunks
@@ -171,6 +172,13 @@ struct TileCoord {
 __device__ __forceinline__ TileCoord tile_coord(int64_t t64, const TcGeom& g) {
   TileCoord c;
   uint32_t t = (uint32_t)t64;
+  if (g.d_fastest) {
+    const uint32_t dchunk = t % (uint32_t)g.dchunks; t /= (uint32_t)g.dchunks;
+    const uint32_t xt = t % (uint32_t)g.xtiles, row = t / (uint32_t)g.xtiles;
+    const uint32_t n = row / (uint32_t)g.H;
+    c.n = n; c.y = (int)(row - n * (uint32_t)g.H); c.xt = (int)xt; c.x0 = (int)xt * TC_TM; c.dc0 = (int)dchunk * g.dch;
+    return c;
+  }
   const uint32_t xt = t % (uint32_t)g.xtiles; t /= (uint32_t)g.xtiles;
   const uint32_t rows = (uint32_t)g.rows;
   const uint32_t dchunk = t / rows, row = t - dchunk * rows;
@@ -183,6 +191,16 @@ __device__ __forceinline__ TileCoord tile_coord(int64_t t64, const TcGeom& g) {
   return c;
 }
 __device__ __forceinline__ void TileCoord::advance(const TcGeom& g) {
+  if (g.d_fastest) {
+    dc0 += g.dch;
+    if (dc0 < g.D) return;
+    dc0 = 0;
+    if (++xt < g.xtiles) { x0 += TC_TM; return; }
+    xt = 0; x0 = 0;
+    if (++y < g.H) return;
+    y = 0; ++n;
+    return;
+  }
   if (++xt < g.xtiles) { x0 += TC_TM; return; }
   xt = 0; x0 = 0;
   if (++y < g.H) return;
@@ -227,7 +245,8 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
   const uint32_t tmem_base = *tmem_slot;
   const int nk = (g.C + TC_KC - 1) / TC_KC;
   // contiguous tile range of this CTA (neighbouring x tiles share most of their right window in L2)
-  const int64_t per = (g.tiles + gridDim.x - 1) / gridDim.x;
+  int64_t per = (g.tiles + gridDim.x - 1) / gridDim.x;
+  if (g.d_fastest) per = (per + g.dchunks - 1) / g.dchunks * g.dchunks;   // never split the chunks of one pixel tile
   const int64_t t_beg = min((int64_t)blockIdx.x * per, g.tiles), t_end = min(t_beg + per, g.tiles);
 
   if (warp == TC_EPI_WARPS + 4) {
@@ -304,6 +323,11 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
     const float inv = 1.f / (float)g.C, cnt = (float)g.C;
     const float nanv = __int_as_float(0x7fc00000);
     uint32_t use = 0;
+    // EPI_REGRESS: running softmax / arg-extrema state of this lane's pixel, carried across the disparity
+    // chunks of a tile (chunks of one pixel tile are consecutive: d-fastest tile order)
+    float m = -INFINITY, s = 0.f, ws = 0.f, minv = INFINITY, maxv = -INFINITY;
+    int mini = 0x7fffffff, maxi = 0x7fffffff, nani = 0x7fffffff;
+    uint32_t combines = 0;
     TileCoord tc = tile_coord(t_beg, g);
     for (int64_t t = t_beg; t < t_end; ++t, ++use, tc.advance(g)) {
       const uint32_t buf = use & 1;
@@ -359,9 +383,10 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
         }
       } else {
         // ---- fused regression over this warp's disparities in ascending order (first index wins ties)
-        float m = -INFINITY, s = 0.f, ws = 0.f;
-        float minv = INFINITY, maxv = -INFINITY;
-        int mini = 0x7fffffff, maxi = 0x7fffffff, nani = 0x7fffffff;
+        if (tc.dc0 == 0) {
+          m = -INFINITY; s = 0.f; ws = 0.f; minv = INFINITY; maxv = -INFINITY;
+          mini = 0x7fffffff; maxi = 0x7fffffff; nani = 0x7fffffff;
+        }
         for (int d0 = dlo; d0 < dhi; d0 += 8) {
           float v[8];
           float gm = -INFINITY;
@@ -371,9 +396,9 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
             float f = -INFINITY;
             if (dl < dhi) {
               f = dl < dz ? (divide ? rp0[-dl] * mul / cnt : rp0[-dl] * mul) : 0.f;   // fill takes part (F8)
-              if (f < minv) { minv = f; mini = dl; }
-              if (f > maxv) { maxv = f; maxi = dl; }
-              if (f != f) nani = min(nani, dl);
+              if (f < minv) { minv = f; mini = tc.dc0 + dl; }
+              if (f > maxv) { maxv = f; maxi = tc.dc0 + dl; }
+              if (f != f) nani = min(nani, tc.dc0 + dl);
             }
             v[k] = f;
             gm = fmaxf(gm, f);
@@ -390,9 +415,11 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
           }
           m = mn;
         }
-        // combine the two disparity halves of a quadrant: hh = 1 parks its state, hh = 0 merges and stores
+        // after the last chunk, combine the two warps of a quadrant: hh = 1 parks its state, hh = 0 merges
+        // and stores (equal values: the smaller index wins, as torch does)
+        if (tc.dc0 + g.dch < g.D) { __syncwarp(); continue; }
         float* part = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(skew) + g.epi_bytes - 2 * 128 * 8 * 4) +
-                      ((size_t)(use & 1) * 128 + 32 * q + lane) * 8;
+                      ((size_t)(combines++ & 1) * 128 + 32 * q + lane) * 8;
         if (hh == 1) {
           part[0] = m; part[1] = s; part[2] = ws; part[3] = minv; part[4] = maxv;
           part[5] = __int_as_float(mini); part[6] = __int_as_float(maxi); part[7] = __int_as_float(nani);
@@ -405,16 +432,15 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
           const float a1 = (m == -INFINITY) ? 0.f : fast_exp2((m - M) * kLog2e);
           const float a2 = (m2 == -INFINITY) ? 0.f : fast_exp2((m2 - M) * kLog2e);
           const float S = s * a1 + s2 * a2, WS = ws * a1 + w2 * a2;
-          // the lower half holds the smaller indices: it wins ties
-          if (minv2 < minv && mini2 != 0x7fffffff) mini = mini2;
-          if (maxv2 > maxv && maxi2 != 0x7fffffff) maxi = maxi2;
+          if (minv2 < minv || (minv2 == minv && mini2 < mini)) mini = mini2;
+          if (maxv2 > maxv || (maxv2 == maxv && maxi2 < maxi)) maxi = maxi2;
           nani = min(nani, nani2);
           if (nani != 0x7fffffff) { mini = nani; maxi = nani; }
           const int64_t o = ((int64_t)tc.n * g.H + tc.y) * g.W + x;
           if (rp.soft) rp.soft[o] = WS / S;
           if (rp.lse) rp.lse[o] = M + __logf(S);
-          if (rp.amin) rp.amin[o] = tc.dc0 + mini;
-          if (rp.amax) rp.amax[o] = tc.dc0 + maxi;
+          if (rp.amin) rp.amin[o] = mini;
+          if (rp.amax) rp.amax[o] = maxi;
         }
       }
       __syncwarp();                                         // rows are reused by the next tile
@@ -444,6 +470,7 @@ static int tc_geom(int64_t N, int64_t C, int64_t H, int64_t W, int64_t D, int me
   g.fmt = fmt;
   g.tmem_buf = g.ncol <= 128 ? 128 : 256;
   g.stage_bytes = TC_KC * TC_TM * 2 + TC_KC * g.ncol * 2;
+  g.d_fastest = 0;
   g.rows = N * H;
   g.tiles = g.rows * g.xtiles * g.dchunks;
   if (g.tiles <= 0 || g.tiles > 2147483647LL) return RSM_ERR_INVALID_SHAPE;
@@ -489,10 +516,10 @@ int launch_inner_tc(const rsm_feat& left, const rsm_feat& right, void* out, int6
 
 int launch_inner_regress_tc(const rsm_feat& left, const rsm_feat& right, int64_t N, int64_t C, int64_t H, int64_t W,
                             int64_t D, int mean, int in_dtype, const rsm_regress_out& out, cudaStream_t st) {
-  // one disparity chunk must cover all D: the softmax state lives in the epilogue's registers
-  if (in_dtype == RSM_F32 || C % 16 != 0 || C <= 0 || D <= 0 || D > 128) return RSM_ERR_UNSUPPORTED_CONFIG;
+  if (in_dtype == RSM_F32 || C % 16 != 0 || C <= 0 || D <= 0) return RSM_ERR_UNSUPPORTED_CONFIG;
   TcGeom g;
   if (int rc = tc_geom(N, C, H, W, D, mean, in_dtype == RSM_F16 ? 0 : 1, g)) return rc;
+  g.d_fastest = 1;   // the softmax state of a pixel lives in the epilogue's registers across its disparity chunks
   const RegressPtrs rp{(float*)out.soft, out.argmin, out.argmax, out.lse};
   const char* where = "rsm_inner_regress_fwd(tcgen05)";
   if (in_dtype == RSM_F16) return launch_tc<__half, float, EPI_REGRESS>(left, right, nullptr, rp, g, st, where);

@@ -425,7 +425,8 @@ def test_tcgen05_inner_vs_oracle_and_simt(rsm, shape, dn, monkeypatch):
     close(tc16, ref, atol, RTOL_16[dn])
 
 
-@pytest.mark.parametrize("shape", [(1, 16, 3, 240, 48), (2, 64, 3, 240, 48), (1, 32, 2, 312, 24), (1, 64, 2, 480, 128)])
+@pytest.mark.parametrize("shape", [(1, 16, 3, 240, 48), (2, 64, 3, 240, 48), (1, 32, 2, 312, 24), (1, 64, 2, 480, 128),
+                                   (1, 128, 2, 480, 192), (1, 32, 3, 200, 130)])
 def test_tcgen05_fused_regress(rsm, shape):
     """Fused correlation -> soft-argmax / argmin / argmax straight out of TMEM (bf16 features)."""
     n, c, h, w, d = shape

@@ -13,7 +13,7 @@ for (n,c,h,w,d) in [(1,16,2,128,16),(1,16,3,240,48),(2,64,5,240,48),(1,32,4,312,
         err=np.abs(out-ref).max(); nan=np.isnan(out).sum()
         print((n,c,h,w,d),dn,"maxerr",err,"nan",nan,"ref max",np.abs(ref).max(), flush=True)
 print("--- fused regress (tcgen05)")
-for (n,c,h,w,d) in [(1,16,2,128,16),(1,16,3,240,48),(2,64,5,240,48),(1,32,4,312,48),(1,64,2,480,128),(1,16,2,67,19)]:
+for (n,c,h,w,d) in [(1,16,2,128,16),(1,16,3,240,48),(2,64,5,240,48),(1,32,4,312,48),(1,64,2,480,128),(1,16,2,67,19),(1,128,2,480,192),(1,32,3,200,130),(2,16,2,300,260)]:
     for dn,dt in (("bf16",torch.bfloat16),):
         rng=np.random.default_rng(1)
         l=round_to(rng.standard_normal((n,c,h,w)).astype(np.float32)*0.5,dn); r=round_to(rng.standard_normal((n,c,h,w)).astype(np.float32)*0.5,dn)

@@ -176,9 +176,13 @@ upsample_regress_fwd_kernel(const T* __restrict__ cost, T* __restrict__ soft, in
     for (int k = 0; k + 1 < g.Dc; ++k) {
       const float cs1 = fmaf(sl.get(k + 1), kLog2e, -Ml);
       const float dl = cs1 - cs0;
-      const float f0 = fmaf(0.125f, dl, cs0), f1 = fmaf(0.375f, dl, cs0);
-      const float f2 = fmaf(0.625f, dl, cs0), f3 = fmaf(0.875f, dl, cs0);
-      const float e0 = fast_exp2(f0), e1 = fast_exp2(f1), e2 = fast_exp2(f2), e3 = fast_exp2(f3);
+      // the four fine values are equally spaced (f_j = f0 + j * dl/4), so their exponentials form a
+      // geometric progression: two ex2 (MUFU is the scarcest pipe here) + three multiplies instead of
+      // four ex2.  All f_j <= 0 (M is the max), so e_j <= 1; q is clamped so a flushed e0 never meets inf.
+      const float f0 = fmaf(0.125f, dl, cs0);
+      const float e0 = fast_exp2(f0), q = fast_exp2(fminf(0.25f * dl, 126.f));
+      const float e1 = e0 * q, e2 = e1 * q, e3 = e2 * q;
+      [[maybe_unused]] const float f1 = fmaf(0.375f, dl, cs0), f2 = fmaf(0.625f, dl, cs0), f3 = fmaf(0.875f, dl, cs0);
       const float S = (e0 + e1) + (e2 + e3);
       const float Tm = fmaf(3.f, e3, fmaf(2.f, e2, e1));   // sum_j j * e_j
       s += S;

@@ -35,13 +35,14 @@ __device__ __forceinline__ Lin lin_index(int o, float scale, int n_in) {
   return r;
 }
 
-constexpr int kTX = 32, kTY = 8;   // fine-pixel tile of one CTA (256 threads, one pixel each)
+constexpr int kTX = 32, kTY = 8;   // fine-pixel tile of one CTA (256 threads, one pixel each; 32x16 measured slower)
 constexpr int kNT = kTX * kTY;
 
 struct TailGeom {
   int Dc, Hc, Wc, D, H, W;
   int FH, FW;        // coarse rows / cols a tile can touch (upper bound)
   int fast4;         // D == 4 * Dc
+  int fastx;         // W == 4 * Wc
   float sd, sh, sw;  // in/out scale per axis
 };
 
@@ -77,14 +78,14 @@ __device__ __forceinline__ void stage_tile(const T* __restrict__ cost_b, const T
     const int fy = r / g.FW, fx = r - fy * g.FW;
     const int cy = min(cy0 + fy, g.Hc - 1), cx = min(cx0 + fx, g.Wc - 1);
     const T* __restrict__ src = cost_b + (int64_t)cy * g.Wc + cx;
-    constexpr int U = 4;
-    for (int k0 = threadIdx.x >> 6; k0 < g.Dc; k0 += 4 * U) {
+    constexpr int U = 4, KS = kNT / 64;   // KS slices are staged concurrently by the 64-thread groups
+    for (int k0 = threadIdx.x >> 6; k0 < g.Dc; k0 += KS * U) {
       float v[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) v[u] = (k0 + 4 * u < g.Dc) ? to_f(__ldg(src + (k0 + 4 * u) * plane)) : 0.f;
+      for (int u = 0; u < U; ++u) v[u] = (k0 + KS * u < g.Dc) ? to_f(__ldg(src + (k0 + KS * u) * plane)) : 0.f;
 #pragma unroll
       for (int u = 0; u < U; ++u)
-        if (k0 + 4 * u < g.Dc) sm.raw[(k0 + 4 * u) * per + r] = v[u];
+        if (k0 + KS * u < g.Dc) sm.raw[(k0 + KS * u) * per + r] = v[u];
     }
   }
   if (!g.fast4) {
@@ -96,7 +97,25 @@ __device__ __forceinline__ void stage_tile(const T* __restrict__ cost_b, const T
   }
   __syncthreads();
   // ---- 2. interpolate along x for this tile's 32 columns: rows[(k*FH + fy)*32 + tx]
-  {
+  if (g.fastx) {
+    // W == 4 * Wc: four consecutive output columns 4j..4j+3 need only raw[j-1], raw[j], raw[j+1] (clamped)
+    // with the constant weights of lin_index -- 3 LDS + one 128-bit store per 4 outputs
+    const int q = threadIdx.x & 7;                                  // column quad of the tile
+    const int j = (blockIdx.x * kTX) / 4 + q;                       // coarse column of outputs 4j+2, 4j+3
+    const int jm = min(max(j - 1, 0), g.Wc - 1), jc = min(j, g.Wc - 1), jp = min(j + 1, g.Wc - 1);
+    const int am = min(jm - cx0, g.FW - 1), ac = min(jc - cx0, g.FW - 1), ap = min(jp - cx0, g.FW - 1);
+    const int npair = g.Dc * g.FH;
+    for (int p = threadIdx.x >> 3; p < npair; p += kNT / 8) {
+      const float* rr = sm.raw + p * g.FW;
+      const float vm = rr[am], vc = rr[ac], vp = rr[ap];
+      float4 o;
+      o.x = 0.375f * vm + 0.625f * vc;
+      o.y = 0.125f * vm + 0.875f * vc;
+      o.z = 0.875f * vc + 0.125f * vp;
+      o.w = 0.625f * vc + 0.375f * vp;
+      *reinterpret_cast<float4*>(sm.rows + p * kTX + 4 * q) = o;
+    }
+  } else {
     const int tx = threadIdx.x & (kTX - 1);
     const Lin lx = lin_index(blockIdx.x * kTX + tx, g.sw, g.Wc);
     const int a0 = min(lx.i0 - cx0, g.FW - 1), a1 = min(lx.i1 - cx0, g.FW - 1);
@@ -349,6 +368,7 @@ static int make_geom(int64_t Dc, int64_t Hc, int64_t Wc, int64_t D, int64_t H, i
   g.FH = (int)fminf((float)Hc, ceilf(kTY * g.sh) + 2.f);
   g.FW = (int)fminf((float)Wc, ceilf(kTX * g.sw) + 2.f);
   g.fast4 = (D == 4 * Dc) ? 1 : 0;
+  g.fastx = (W == 4 * Wc) ? 1 : 0;
   smem = tail_smem_bytes(g);
   if (smem > 200 * 1024) return RSM_ERR_UNSUPPORTED_CONFIG;
   return RSM_OK;

@@ -115,6 +115,17 @@ int rsm_difference_fwd(rsm_feat left, rsm_feat right, void* out, int64_t N, int6
 int rsm_difference_bwd(const void* gout, void* gleft, void* gright, int64_t N, int64_t C,
                        int64_t H, int64_t W, int64_t D, int dtype, int device, void* stream);
 
+/* ---- shifted interweave stack (first step): every iteration of MobileStereoNetV4's
+ * per-disparity loop, model/mobile_stereo_net_v4.py:444-458, builds
+ * interweave_tensors(featL[..., i:], featR[..., :-i]); this entry point builds all D of them at once,
+ * full width, zero where x < d (so the zero padding the cropped convolutions saw is reproduced):
+ * out (D,N,2C,H,W): out[d,n,2c,y,x] = L[n,c,y,x], out[d,n,2c+1,y,x] = R[n,c,y,x-d] for x >= d, else 0 */
+int rsm_shift_interweave_fwd(rsm_feat left, rsm_feat right, void* out, int64_t N, int64_t C, int64_t H,
+                             int64_t W, int64_t D, int dtype, int device, void* stream);
+/* gleft[n,c,y,x] = sum_{d<=x} gout[d,n,2c,y,x];  gright[n,c,y,x'] = sum_{d, x'+d<W} gout[d,n,2c+1,y,x'+d] */
+int rsm_shift_interweave_bwd(const void* gout, void* gleft, void* gright, int64_t N, int64_t C,
+                             int64_t H, int64_t W, int64_t D, int dtype, int device, void* stream);
+
 /* ---- disparity regression over a dense (N,D,H,W) cost: softmax(+cost) expectation
  * (model/mobile_stereo_net.py:144-147, mobile_stereo_net_v4.py:10-14 + :517,
  * mobile_disp_net_c.py:208-220) and hard argmin / argmax (torch.argmin(cost, 1) semantics;

@@ -22,7 +22,7 @@ __all__ = [
     "interweave", "interweave_bwd",
     "inner_product_volume", "inner_product_volume_bwd",
     "groupwise_volume", "groupwise_volume_bwd", "groupwise_pointwise",
-    "difference_volume", "difference_volume_bwd",
+    "difference_volume", "difference_volume_bwd", "shift_interweave_volume", "shift_interweave_volume_bwd",
     "softmax_d", "soft_argmax", "soft_argmax_bwd", "hard_argmin", "hard_argmax",
     "linear_axis_table", "trilinear_upsample", "trilinear_upsample_bwd",
     "v4_tail", "v4_tail_bwd", "inner_product_soft_argmax",
@@ -198,6 +198,33 @@ def difference_volume_bwd(gvol, acc_dtype=None):
         gl[:, :, :, d:] += g[:, :, d, :, d:]
         gr[:, :, :, : w - d] -= g[:, :, d, :, d:]
     return gl.astype(gvol.dtype), gr.astype(gvol.dtype)
+
+
+# ------------------------------------------------------------- shifted interweave stack
+def shift_interweave_volume(left, right, max_disparity):
+    """(N,C,H,W)x2 -> (D,N,2C,H,W): out[d] = interweave(left, right shifted right by d), zero for x < d.
+
+    Iteration i of the MobileStereoNetV4 volume loop (model/mobile_stereo_net_v4.py:444-458) feeds
+    interweave_tensors(featL[..., i:], featR[..., :-i]) to its convolutions; out[i][..., i:] is exactly that
+    tensor and out[i][..., :i] = 0 reproduces the zero padding those cropped convolutions see."""
+    n, c, h, w = left.shape
+    out = np.zeros((max_disparity, n, 2 * c, h, w), dtype=left.dtype)
+    for d in range(min(max_disparity, w)):
+        out[d, :, 0::2, :, d:] = left[:, :, :, d:]
+        out[d, :, 1::2, :, d:] = right[:, :, :, : w - d]
+    return out
+
+
+def shift_interweave_volume_bwd(gout, acc_dtype=None):
+    """gL[c,x] = sum_{d<=x} g[d,2c,x];  gR[c,x'] = sum_{d, x'+d<W} g[d,2c+1,x'+d]."""
+    dmax, n, c2, h, w = gout.shape
+    g = _acc(gout, acc_dtype)
+    gl = np.zeros((n, c2 // 2, h, w), dtype=g.dtype)
+    gr = np.zeros_like(gl)
+    for d in range(min(dmax, w)):
+        gl[:, :, :, d:] += g[d, :, 0::2, :, d:]
+        gr[:, :, :, : w - d] += g[d, :, 1::2, :, d:]
+    return gl.astype(gout.dtype), gr.astype(gout.dtype)
 
 
 # ---------------------------------------------------------------------------- regression

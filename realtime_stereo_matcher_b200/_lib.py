@@ -43,6 +43,8 @@ SIGNATURES = {
     "rsm_groupwise_bwd": [vp, RsmFeat, RsmFeat, vp, vp, i64, i64, i64, i64, i64, i64, ci, ci, ci, vp],
     "rsm_difference_fwd": [RsmFeat, RsmFeat, vp, i64, i64, i64, i64, i64, cf, ci, ci, vp],
     "rsm_difference_bwd": [vp, vp, vp, i64, i64, i64, i64, i64, ci, ci, vp],
+    "rsm_shift_interweave_fwd": [RsmFeat, RsmFeat, vp, i64, i64, i64, i64, i64, ci, ci, vp],
+    "rsm_shift_interweave_bwd": [vp, vp, vp, i64, i64, i64, i64, i64, ci, ci, vp],
     "rsm_regress_fwd": [vp, i64, i64, i64, i64, ci, RsmRegressOut, ci, vp],
     "rsm_regress_bwd": [vp, vp, vp, vp, vp, i64, i64, i64, i64, ci, ci, vp],
     "rsm_expect_fwd": [vp, vp, i64, i64, i64, i64, ci, ci, vp],

@@ -210,6 +210,39 @@ def difference_volume(left, right, max_disp, fill=1.0):
     return _Difference.apply(left, right, max_disp, fill)
 
 
+# ------------------------------------------------------------- shifted interweave stack
+class _ShiftInterweave(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda")
+    def forward(ctx, left, right, max_disparity):
+        dev, n, c, h, w = _check_pair(left, right)
+        d = int(max_disparity)
+        out = torch.empty((d, n, 2 * c, h, w), dtype=left.dtype, device=left.device)
+        L.check(L.load().rsm_shift_interweave_fwd(L.feat(left), L.feat(right), out.data_ptr(), n, c, h, w, d,
+                                                  L.dtype_code(left), dev, L.stream_ptr(dev)),
+                "rsm_shift_interweave_fwd")
+        ctx.dims = (dev, n, c, h, w, d)
+        return out
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, gout):
+        dev, n, c, h, w, d = ctx.dims
+        gout = _dense(gout)
+        gl = torch.empty((n, c, h, w), dtype=gout.dtype, device=gout.device)
+        gr = torch.empty_like(gl)
+        L.check(L.load().rsm_shift_interweave_bwd(gout.data_ptr(), gl.data_ptr(), gr.data_ptr(), n, c, h, w, d,
+                                                  L.dtype_code(gout), dev, L.stream_ptr(dev)),
+                "rsm_shift_interweave_bwd")
+        return gl, gr, None
+
+
+def shift_interweave_volume(left, right, max_disparity):
+    """All iterations of MobileStereoNetV4's per-disparity loop input at once (mobile_stereo_net_v4.py:444-458):
+    out (D,N,2C,H,W), out[d] = interweave_tensors(left, right shifted by d), zero where x < d."""
+    return _ShiftInterweave.apply(left, right, max_disparity)
+
+
 # ---------------------------------------------------------------------------- regression
 def _regress_outputs(shape, dtype, device, soft, argmin, argmax, lse):
     n, h, w = shape

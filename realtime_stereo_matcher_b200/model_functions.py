@@ -24,6 +24,13 @@ def interweave_tensors(refimg_fea, targetimg_fea):
     return F_rsm.interweave(refimg_fea, targetimg_fea)
 
 
+def shift_interweave_stack(refimg_fea, targetimg_fea, volume_size):
+    """All ``volume_size`` inputs of the MobileStereoNetV4 per-disparity loop at once
+    (model/mobile_stereo_net_v4.py:444-458): (B,C,H,W) x2 -> (D,B,2C,H,W) with
+    out[i][..., i:] == interweave_tensors(ref[..., i:], target[..., :-i]) and zeros for x < i."""
+    return F_rsm.shift_interweave_volume(refimg_fea, targetimg_fea, volume_size)
+
+
 def disparity_regression_v4(x, maxdisp):
     """model/mobile_stereo_net_v4.py:10-14: x holds PROBABILITIES (already softmax-ed);
     returns sum_d d * x[:, d] as (N,H,W)."""

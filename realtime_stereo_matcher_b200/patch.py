@@ -80,6 +80,37 @@ def forward_v3(self, l_img, r_img):
     return _refine_outputs(x, steps, l_img, h, w)
 
 
+def v4_volume_batched(self, featL, featR, chunk=None):
+    """MobileStereoNetV4's per-disparity volume loop (mobile_stereo_net_v4.py:443-458) as ONE batched pass
+    (eval mode: BatchNorm is affine, so batching the 48 iterations is exact).  The 48 interweaved, shifted
+    inputs come from one kernel (rsm_shift_interweave_fwd) at full width with zeros where x < d; the
+    reference's convolutions on the cropped tensors see zero padding at the crop edge, which is reproduced
+    by zeroing the x < d columns again after every ReLU.  The convolutions stay the module's own (cuDNN)."""
+    import torch
+    B, C, H, W = featL.shape
+    D = self.volume_size
+    out = featL.new_zeros([B, D, H, W])
+    chunk = chunk or D
+    xs = torch.arange(W, device=featL.device)
+    for d0 in range(0, D, chunk):                       # optional chunking over disparities bounds memory
+        d1 = min(D, d0 + chunk)
+        if d0 == 0 and d1 == D:
+            x = mf.shift_interweave_stack(featL, featR, D)                       # (D,B,2C,H,W)
+        else:
+            x = mf.shift_interweave_stack(featL, featR, d1)[d0:d1]
+        nd = d1 - d0
+        keep = (xs[None, :] >= torch.arange(d0, d1, device=featL.device)[:, None]).to(featL.dtype)   # (nd,W)
+        keep = keep.repeat_interleave(B, dim=0)                                                      # (nd*B,W)
+        x = x.reshape(nd * B, 1, 2 * C, H, W)
+        for layer in self.conv3d:
+            x = layer(x)
+            if isinstance(layer, torch.nn.ReLU):
+                x = x * keep.view(nd * B, 1, 1, 1, W)
+        x = self.volume11(x.squeeze(2)) * keep.view(nd * B, 1, 1, W)                                 # (nd*B,1,H,W)
+        out[:, d0:d1] = x.view(nd, B, H, W).permute(1, 0, 2, 3)
+    return out
+
+
 def forward_v4(self, L, R):
     """MobileStereoNetV4.forward (mobile_stereo_net_v4.py:432-524) with interweave and the
     trilinear -> softmax -> expectation head on the fused kernels."""
@@ -88,12 +119,17 @@ def forward_v4(self, L, R):
     featL = self.preconv11(self.feature_extraction(L))
     featR = self.preconv11(self.feature_extraction(R))
     B, C, H, W = featL.shape
-    volume = featL.new_zeros([B, self.num_groups, self.volume_size, H, W])
-    for i in range(self.volume_size):   # per-disparity learned volume (:444-458); SURVEY.md 8f-1 is next
-        x = mf.interweave_tensors(featL[:, :, :, i:], featR[:, :, :, : W - i])
-        x = self.volume11(self.conv3d(x.unsqueeze(1)).squeeze(2))
-        volume[:, :, i, :, i:] = x
-    volume = volume.squeeze(1)
+    if self.training:
+        # BatchNorm3d normalises with the statistics of each iteration's own (cropped) batch, so the
+        # per-disparity loop (:444-458) is kept as it is, with the interweave on the kernels
+        volume = featL.new_zeros([B, self.num_groups, self.volume_size, H, W])
+        for i in range(self.volume_size):
+            x = mf.interweave_tensors(featL[:, :, :, i:], featR[:, :, :, : W - i])
+            x = self.volume11(self.conv3d(x.unsqueeze(1)).squeeze(2))
+            volume[:, :, i, :, i:] = x
+        volume = volume.squeeze(1)
+    else:
+        volume = v4_volume_batched(self, featL, featR)
     cost0 = self.dres0(volume)
     cost0 = self.dres1(cost0) + cost0
     out1 = self.encoder_decoder1(cost0)

@@ -37,6 +37,7 @@ def oracle_backed(monkeypatch):
     monkeypatch.setattr(F_rsm, "expectation",
                         lambda p: _t((_np(p) * np.arange(p.shape[1], dtype=np.float32).reshape(1, -1, 1, 1)).sum(1), p))
     monkeypatch.setattr(F_rsm, "upsample_regress", lambda c, d, h, w, argmin=False, argmax=False: _t(oracle.v4_tail(_np(c), d, h, w), c))
+    monkeypatch.setattr(F_rsm, "shift_interweave_volume", lambda l, r, d: _t(oracle.shift_interweave_volume(_np(l), _np(r), d), l))
     sys.path.insert(0, REF)
     yield
     from realtime_stereo_matcher_b200 import unpatch_reference

@@ -27,7 +27,9 @@ concat_fwd_kernel(FeatView L, FeatView R, T* __restrict__ out, int C, int H, int
   const int c = right ? ch - C : ch;
   const FeatView& F = right ? R : L;
   const T* __restrict__ src = reinterpret_cast<const T*>(F.data) + n * F.sn + c * F.sc + y * F.sh;
-  for (int x = threadIdx.x; x < W; x += kThreads) srow[x] = __ldg(src + (int64_t)x * F.sw);
+  // the right row is kept REVERSED (srow[k] = R[W-1-k]) so that the D-run of a pixel, R[x-d] for
+  // ascending d, is a run of ASCENDING shared-memory addresses starting at W-1-x+d0
+  for (int x = threadIdx.x; x < W; x += kThreads) srow[right ? W - 1 - x : x] = __ldg(src + (int64_t)x * F.sw);
   __syncthreads();
 
   T* __restrict__ orow = out + row * (int64_t)W * D;
@@ -39,21 +41,39 @@ concat_fwd_kernel(FeatView L, FeatView R, T* __restrict__ out, int C, int H, int
   const T zero = zero_of<T>();
   for (; v < nvec; v += kThreads) {
     const int d0 = dq * VEC;
-    T vals[VEC];
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      const int d = d0 + j;
-      const int xs = right ? x - d : x;
-      vals[j] = (d <= x) ? srow[xs] : zero;
-    }
     if constexpr (VEC * sizeof(T) == 16) {
       Vec16<T> o;
+      if (d0 + VEC - 1 <= x) {
+        // interior vector (~all of them): no per-element range checks
+        if (!right) {
+          const T v0 = srow[x];
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) o.v[j] = vals[j];
+          for (int j = 0; j < VEC; ++j) o.v[j] = v0;
+        } else {
+          const int b = W - 1 - x + d0;
+          if constexpr (sizeof(T) == 4) {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) o.v[j] = srow[b + j];
+          } else {
+            // eight 16-bit values from an arbitrary 2-byte offset: five aligned words + funnel shifts
+            const uint32_t* w32 = reinterpret_cast<const uint32_t*>(srow) + (b >> 1);
+            const uint32_t sh = (uint32_t)(b & 1) * 16u;
+            const uint32_t w0 = w32[0], w1 = w32[1], w2 = w32[2], w3 = w32[3], w4 = w32[4];
+            o.raw = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
+                               __funnelshift_r(w3, w4, sh));
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          const int d = d0 + j;
+          o.v[j] = (d <= x) ? srow[right ? W - 1 - x + d : x] : zero;
+        }
+      }
       stcs16(orow + (int64_t)v * VEC, o);
     } else {
       static_assert(VEC == 1, "scalar fallback only");
-      __stcs(orow + v, vals[0]);
+      __stcs(orow + v, (d0 <= x) ? srow[right ? W - 1 - x + d0 : x] : zero);
     }
     x += xstep;
     dq += dstep;
@@ -209,7 +229,7 @@ extern "C" int rsm_concat_fwd(rsm_feat left, rsm_feat right, void* out, int64_t 
   if (!aligned_to(out, dtype_size(dtype))) return RSM_ERR_MISALIGNED;
   return RSM_DISPATCH_DTYPE(dtype, T, [&]() -> int {
     constexpr int VEC = 16 / sizeof(T);
-    const size_t smem = (size_t)W * sizeof(T);
+    const size_t smem = (size_t)W * sizeof(T) + 16;   // + one spare vector: the 16-bit path reads a fifth word
     if (smem > 200 * 1024) return (int)RSM_ERR_UNSUPPORTED_CONFIG;
     const dim3 grid((unsigned)(N * 2 * C * H));
     if (D % VEC == 0 && aligned_to(out, 16)) {

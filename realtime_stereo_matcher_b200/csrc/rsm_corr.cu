@@ -40,15 +40,55 @@ struct CorrGeom {
   int gpb;      // groups per CTA (small groups share one staging pass)
   int gblocks;  // ceil(G / gpb)
   int pow2;     // cpg is a power of two: the mean is an exact multiply
+  int pairs;    // 16-bit features can be staged as aligned 4-byte pairs with cp.async
 };
+
+template <typename T> __device__ __forceinline__ float2 unpack2(uint32_t w);
+template <> __device__ __forceinline__ float2 unpack2<float>(uint32_t w) { return make_float2(0.f, 0.f); }   // unused
+template <> __device__ __forceinline__ float2 unpack2<__nv_bfloat16>(uint32_t w) {
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+template <> __device__ __forceinline__ float2 unpack2<__half>(uint32_t w) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&w));
+}
 
 // ---- stage `nch` channels [c0, c0+nch) of the left segment and right window as fp32
 template <typename Tin>
 __device__ __forceinline__ void stage_slab(const FeatView& L, const FeatView& R, int64_t n, int y, int c0, int nch,
-                                           int x0, int rbase, int rw, float* sL, float* sR, int W) {
+                                           int x0, int rbase, int rw, float* sL, float* sR, int W,
+                                           uint32_t* sRaw = nullptr) {
   const Tin* __restrict__ pl = reinterpret_cast<const Tin*>(L.data) + n * L.sn + (int64_t)y * L.sh + (int64_t)c0 * L.sc;
   const Tin* __restrict__ pr = reinterpret_cast<const Tin*>(R.data) + n * R.sn + (int64_t)y * R.sh + (int64_t)c0 * R.sc;
   const int span = TX + rw;   // per channel: TX left values then rw right values
+  if constexpr (sizeof(Tin) == 2) {
+    if (sRaw) {
+      // 16-bit features, pair-aligned: raw 4-byte pairs go global -> shared with cp.async (every load of the
+      // slab in flight at once, zero-fill outside the image), then one conversion pass widens them to fp32
+      const int hspan = span / 2;
+      for (int e = threadIdx.x; e < hspan; e += blockDim.x) {
+        const bool left = e < TX / 2;
+        const int x = left ? x0 + 2 * e : rbase + 2 * (e - TX / 2);
+        const bool valid = x >= 0 && x + 1 < W;
+        const Tin* src = valid ? (left ? pl + x : pr + x) : reinterpret_cast<const Tin*>(L.data);
+        const int64_t step = valid ? (left ? L.sc : R.sc) : 0;
+        const int nbytes = valid ? 4 : 0;
+        const uint32_t sdst = (uint32_t)__cvta_generic_to_shared(sRaw + e);
+        for (int c = 0; c < nch; ++c)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sdst + (uint32_t)(c * hspan * 4)),
+                       "l"(src + c * step), "r"(nbytes)
+                       : "memory");
+      }
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      __syncthreads();
+      for (int c = 0; c < nch; ++c)
+        for (int j = threadIdx.x; j < hspan; j += blockDim.x) {
+          const float2 f = unpack2<Tin>(sRaw[c * hspan + j]);
+          float* dst = j < TX / 2 ? sL + c * TX + 2 * j : sR + c * rw + 2 * (j - TX / 2);
+          *reinterpret_cast<float2*>(dst) = f;
+        }
+      return;
+    }
+  }
   constexpr int U = 8;        // independent loads in flight per thread
   for (int e = threadIdx.x; e < span; e += blockDim.x) {
     const bool left = e < TX;
@@ -202,6 +242,7 @@ corr_fwd_kernel(FeatView L, FeatView R, Tout* __restrict__ out, CorrGeom g, int 
   const int rw = TX + g.dchp;
   float* sL = smem;
   float* sR = smem + CKMAX * TX;
+  uint32_t* sRaw = g.pairs ? reinterpret_cast<uint32_t*>(sR + CKMAX * rw) : nullptr;
 
   int64_t bid = blockIdx.x;
   const int xt = (int)(bid % g.xtiles); bid /= g.xtiles;
@@ -229,14 +270,14 @@ corr_fwd_kernel(FeatView L, FeatView R, Tout* __restrict__ out, CorrGeom g, int 
     for (int c0 = cbeg; c0 < cend; c0 += CKMAX) {
       const int nch = min(CKMAX, cend - c0);
       __syncthreads();
-      stage_slab<Tin>(L, R, n, y, c0, nch, x0, rbase, rw, sL, sR, g.W);
+      stage_slab<Tin>(L, R, n, y, c0, nch, x0, rbase, rw, sL, sR, g.W, sRaw);
       __syncthreads();
       tile_fma(sL, sR, rw, tx, wstart, 0, nch, acc);
     }
     store_tile<Tout, LAYOUT>(acc, out, g, n, g0, y, xb, db, vec);
   } else {
     // several small groups per CTA: one staging pass, one output tile per group
-    stage_slab<Tin>(L, R, n, y, g0 * g.cpg, (g1 - g0) * g.cpg, x0, rbase, rw, sL, sR, g.W);
+    stage_slab<Tin>(L, R, n, y, g0 * g.cpg, (g1 - g0) * g.cpg, x0, rbase, rw, sL, sR, g.W, sRaw);
     __syncthreads();
     for (int grp = g0; grp < g1; ++grp) {
 #pragma unroll
@@ -427,16 +468,23 @@ static int make_geom(int64_t N, int64_t C, int64_t H, int64_t W, int64_t D, int6
   g.gpb = (g.cpg >= CKMAX || g.cpg == 0) ? 1 : (CKMAX / g.cpg < g.G ? CKMAX / g.cpg : g.G);
   g.gblocks = (int)ceil_div(g.G, g.gpb);
   g.pow2 = g.cpg > 0 && (g.cpg & (g.cpg - 1)) == 0;
+  g.pairs = 0;
   return RSM_OK;
 }
 
 template <typename Tin, typename Tout, int LAYOUT>
-static int launch_fwd(const rsm_feat& left, const rsm_feat& right, void* out, int64_t N, const CorrGeom& g,
+static int launch_fwd(const rsm_feat& left, const rsm_feat& right, void* out, int64_t N, const CorrGeom& g_in,
                       cudaStream_t st, const char* where) {
+  CorrGeom g = g_in;
   const int64_t bx = N * g.gblocks * g.H * g.xtiles;
   const int64_t by = ceil_div(g.D, g.dchp);
   if (!grid_ok(bx) || by > 65535) return RSM_ERR_INVALID_SHAPE;
-  const size_t smem = (size_t)(CKMAX * TX + CKMAX * (TX + g.dchp)) * sizeof(float);
+  auto pair_ok = [&](const rsm_feat& f) {
+    return f.stride_w == 1 && f.stride_n % 2 == 0 && f.stride_c % 2 == 0 && f.stride_h % 2 == 0 && aligned_to(f.data, 4);
+  };
+  g.pairs = sizeof(Tin) == 2 && g.W % 2 == 0 && pair_ok(left) && pair_ok(right);
+  const size_t smem = (size_t)(CKMAX * TX + CKMAX * (TX + g.dchp)) * sizeof(float) +
+                      (g.pairs ? (size_t)CKMAX * (2 * TX + g.dchp) * 2 : 0);
   // vector stores need the run length to divide evenly and the base pointer aligned to the vector
   const int vec = (LAYOUT == LAYOUT_NDHW) ? (g.W % 4 == 0 && aligned_to(out, 4 * sizeof(Tout)))
                                           : (g.D % 8 == 0 && aligned_to(out, 8 * sizeof(Tout)));

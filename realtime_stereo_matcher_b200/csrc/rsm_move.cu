@@ -1,6 +1,8 @@
 // Data-movement volumes: concatenate, interweave, difference (forward + adjoint).
 // All three are HBM-write bound: the kernels stage the tiny inputs on chip and
 // emit coalesced 128-bit stores of the output in the reference's own layout.
+#include <stdlib.h>
+
 #include "rsm_common.cuh"
 
 namespace rsm {
@@ -41,7 +43,28 @@ concat_fwd_kernel(FeatView L, FeatView R, T* __restrict__ out, int C, int H, int
   const T zero = zero_of<T>();
   for (; v < nvec; v += kThreads) {
     const int d0 = dq * VEC;
-    if constexpr (VEC * sizeof(T) == 16) {
+    if constexpr (VEC * sizeof(T) == 32) {
+      // fp32, eight disparities per thread: one 256-bit streaming store (STG.E.ENL2.256)
+      static_assert(sizeof(T) == 4, "256-bit path is fp32 only");
+      float o[8];
+      if (d0 + 7 <= x) {
+        if (!right) {
+          const float v0 = srow[x];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = v0;
+        } else {
+          const float* p = srow + (W - 1 - x + d0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = p[j];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (d0 + j <= x) ? srow[right ? W - 1 - x + d0 + j : x] : 0.f;
+      }
+      asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(orow + (int64_t)v * 8), "f"(o[0]),
+                   "f"(o[1]), "f"(o[2]), "f"(o[3]), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7])
+                   : "memory");
+    } else if constexpr (VEC * sizeof(T) == 16) {
       Vec16<T> o;
       if (d0 + VEC - 1 <= x) {
         // interior vector (~all of them): no per-element range checks
@@ -232,6 +255,16 @@ extern "C" int rsm_concat_fwd(rsm_feat left, rsm_feat right, void* out, int64_t 
     const size_t smem = (size_t)W * sizeof(T) + 16;   // + one spare vector: the 16-bit path reads a fifth word
     if (smem > 200 * 1024) return (int)RSM_ERR_UNSUPPORTED_CONFIG;
     const dim3 grid((unsigned)(N * 2 * C * H));
+    if constexpr (sizeof(T) == 4) {
+      const char* v8 = getenv("RSM_CONCAT_V8");
+      // measured on B200: 256-bit stores win 1-5 % up to D = 96 and lose ~3 % at D = 192
+      if (D % 8 == 0 && D <= 128 && aligned_to(out, 32) && !(v8 && v8[0] == '0')) {
+        auto k = concat_fwd_kernel<T, 8>;      // fp32: 256-bit stores
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k<<<grid, kThreads, smem, st>>>(view_of(left), view_of(right), (T*)out, (int)C, (int)H, (int)W, (int)D);
+        return finish_launch("rsm_concat_fwd");
+      }
+    }
     if (D % VEC == 0 && aligned_to(out, 16)) {
       auto k = concat_fwd_kernel<T, VEC>;
       if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -74,14 +74,31 @@ corr_bwd_tiled_kernel(const Tout* __restrict__ gout, FeatView L, FeatView R, Tin
       if constexpr (LAYOUT == LAYOUT_NDHW) { dl = e / GW; xx = e - dl * GW; }      // x fastest: coalesced rows
       else { xx = e / BW_DCH; dl = e - xx * BW_DCH; }                              // d fastest: contiguous runs
       const int d = dc0 + dl, x = gx0 + xx;
-      sG[dl * GW + xx] = (d < g.D && x < g.W) ? gv.at(d, x) : 0.f;
+      const bool valid = d < g.D && x < g.W;
+      if constexpr (sizeof(Tout) == 4) {   // fp32 gradient: LDGSTS with zero-fill, all loads of the tile in flight
+        const Tout* src = valid ? gv.base + d * gv.sd + x * gv.sx : gv.base;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(sG + dl * GW + xx)),
+                     "l"(src), "r"(valid ? 4 : 0)
+                     : "memory");
+      } else {
+        sG[dl * GW + xx] = valid ? gv.at(d, x) : 0.f;
+      }
     }
     const int fx0 = SIDE == SIDE_LEFT ? x0 - dc0 - BW_DCH : x0 + dc0;
     for (int e = threadIdx.x; e < ncb * FW; e += blockDim.x) {
       const int c = e / FW, j = e - c * FW;
       const int x = fx0 + j;
-      sF[c * FW + j] = (x >= 0 && x < g.W) ? to_f(__ldg(pf + (int64_t)c * F.sc + (int64_t)x * F.sw)) : 0.f;
+      const bool valid = x >= 0 && x < g.W;
+      if constexpr (sizeof(Tin) == 4) {
+        const Tin* src = valid ? pf + (int64_t)c * F.sc + (int64_t)x * F.sw : pf;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(sF + c * FW + j)),
+                     "l"(src), "r"(valid ? 4 : 0)
+                     : "memory");
+      } else {
+        sF[c * FW + j] = valid ? to_f(__ldg(pf + (int64_t)c * F.sc + (int64_t)x * F.sw)) : 0.f;
+      }
     }
+    if constexpr (sizeof(Tin) == 4 || sizeof(Tout) == 4) asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
     if (4 * tc >= ncb) continue;
     // ---- accumulate: disparities four at a time (d = dc0 + 4q + r)

@@ -1,6 +1,10 @@
-// Inner-product / correlation on the 5th-gen tensor cores (tcgen05) for 16-bit features: the
-// (N,D,H,W) volume (EPI_VOLUME) or, fused, the soft-argmax / argmin / argmax of it without ever
-// writing the volume (EPI_REGRESS).
+// Inner-product / correlation on the 5th-gen tensor cores (tcgen05): the (N,D,H,W) volume (EPI_VOLUME)
+// or, fused, the soft-argmax / argmin / argmax of it without ever writing the volume (EPI_REGRESS).
+// fp16 / bf16 features use kind::f16; fp32 features use kind::tf32 three times per k-step on an exact
+// hi/lo split of the operands (x = hi + lo, hi = top 11 significand bits): hi*hi + hi*lo + lo*hi with
+// fp32 accumulation drops only the lo*lo term (~2^-22 relative), i.e. fp32-grade results ("3xTF32";
+// opt-in, RSM_TC_FP32=1).  Non-finite fp32 inputs yield non-finite outputs at the same positions as the
+// reference, but +-inf may come out as NaN (inf * lo with lo = 0).
 //
 // Per epipolar row the correlation is the band  0 <= x - x' < D  of the W x W product
 // P[x, x'] = sum_c L[c, x] * R[c, x']  (the reference's own einsum hint, cost_volume/inner_product.py:33-34).
@@ -32,7 +36,8 @@
 namespace rsm {
 
 constexpr int TC_TM = 128;        // UMMA M: left pixels per tile
-constexpr int TC_KC = 64;         // channels per shared-memory stage
+constexpr int TC_KC = 64;         // channels per shared-memory stage (16-bit features)
+constexpr int TC_KC32 = 16;       // channels per stage for fp32 features (hi + lo copies: same stage bytes)
 constexpr int TC_NSTAGE = 4;      // upper bound on operand stages (g.nstage = 2..4, whatever fits in shared memory)
 constexpr int TC_EPI_WARPS = 8;    // warps 0-7: epilogue (two per TMEM lane quadrant)
 constexpr int TC_THREADS = 32 * TC_EPI_WARPS + 128 + 32;   // + warps 8-11: loaders, warp 12: UMMA issuer
@@ -40,7 +45,7 @@ enum { EPI_VOLUME = 0, EPI_REGRESS = 1 };
 
 struct TcGeom {
   int C, H, W, D;
-  int dch;        // disparities per tile chunk (multiple of 16, <= 128)
+  int dch;        // disparities per tile chunk (multiple of 16, fp32: 32; <= 128)
   int ncol;       // UMMA N = TC_TM + dch
   int ncw;        // TMEM columns an epilogue warp pulls: >= dch/2 + 32, multiple of 16
   int pitch;      // floats per lane row of the skew buffer
@@ -48,7 +53,7 @@ struct TcGeom {
   int xtiles;     // ceil(W / TC_TM)
   int dchunks;    // ceil(D / dch)
   int mean, pow2;
-  int fmt;        // 0 = fp16, 1 = bf16 (UMMA a/b format)
+  int fmt;        // 0 = fp16, 1 = bf16, 2 = tf32 (UMMA a/b format)
   int tmem_buf;   // TMEM columns per accumulator buffer (128 or 256)
   int stage_bytes;
   int d_fastest;  // tile order: disparity chunk fastest (fused regress keeps per-pixel state across chunks)
@@ -69,11 +74,12 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 // shared-memory matrix descriptor, SWIZZLE_NONE, version 1 (cute::UMMA::SmemDescriptor bit layout).
 // MN-major operands: SBO = stride between 8-element groups along M/N, LBO = stride between 8-row groups
 // along K (verified on B200 against the oracle; the swapped assignment produces garbage).
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 0) {
   uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout_type << 61;   // 0 = SWIZZLE_NONE, 1 = SWIZZLE_128B_BASE32B
   return d;
 }
 
@@ -81,6 +87,13 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -119,30 +132,32 @@ __device__ __forceinline__ bool mbar_wait(uint32_t mbar, uint32_t parity) {
 
 template <typename Tin>
 __device__ __forceinline__ uint4 load_chunk_slow(const Tin* __restrict__ src, int x, int W, int64_t sw) {
-  union { uint4 u; Tin e[8]; } tmp;
+  constexpr int EPC = 16 / (int)sizeof(Tin);
+  union { uint4 u; Tin e[EPC]; } tmp;
   tmp.u = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < EPC; ++i)
     if (x + i >= 0 && x + i < W) tmp.e[i] = __ldg(src + (int64_t)(x + i) * sw);
   return tmp.u;
 }
 
 // ---- stage nch channels of one operand with the 128 loader threads (lt = 0..127): xs = first x of the
-// tile, nxg = x-groups of 8.  thread -> (channel inside its K-group: 8 lanes write 128 contiguous bytes,
+// tile, nxg = x-groups of 16 bytes (8 or 4 elements).  thread -> (channel inside its K-group: 8 lanes write 128 contiguous bytes,
 // x-group lane).  Chunks inside the image go global -> shared with 16-byte cp.async (LDGSTS: no register
 // staging, every load of the stage in flight at once), chunks outside are zero-filled by the same
 // instruction (src-size 0); ragged / unaligned chunks take the synchronous element-wise path.
 template <typename Tin>
 __device__ __forceinline__ void stage_operand(const FeatView& F, int64_t n, int y, int c0, int nch, int xs, int nxg, int W,
                                               unsigned char* dst, bool fast, int lt) {
+  constexpr int EPC = 16 / (int)sizeof(Tin);
   const int cl = lt & 7, xl = lt >> 3, nxl = 16;
   const int ncg = nch >> 3;
   const Tin* __restrict__ base =
       reinterpret_cast<const Tin*>(F.data) + n * F.sn + (int64_t)y * F.sh + (int64_t)(c0 + cl) * F.sc;
   for (int xg = xl; xg < nxg; xg += nxl) {
-    const int x = xs + 8 * xg;
-    const bool inside = fast && x >= 0 && x + 8 <= W;
-    const bool empty = x + 8 <= 0 || x >= W;
+    const int x = xs + EPC * xg;
+    const bool inside = fast && x >= 0 && x + EPC <= W;
+    const bool empty = x + EPC <= 0 || x >= W;
     unsigned char* d0 = dst + ((size_t)xg * 8 + cl) * 16;
     if (inside || empty) {
       const Tin* src = inside ? base + x : base;
@@ -157,6 +172,69 @@ __device__ __forceinline__ void stage_operand(const FeatView& F, int64_t n, int 
         *reinterpret_cast<uint4*>(d0 + (size_t)cg * nxg * 128) =
             load_chunk_slow<Tin>(base + (int64_t)(8 * cg) * F.sc, x, W, F.sw);
     }
+  }
+}
+
+// ---- fp32 operands (kind::tf32).  MN-major 32-bit operands exist only in the SWIZZLE_128B_BASE32B layout:
+// an atom = 4 channels (K rows, 128 B apart) x 32 pixels (128 contiguous bytes), whose 32-byte chunks are
+// XOR-ed with the row number (address bits [5,7) ^= bits [7,9)); atoms of one 4-channel group follow each
+// other along x (LBO = 512 B), groups follow each other at SBO = (T/32) * 512 B.  A warp stages one atom
+// per step: lane -> (row = channel, 16-byte chunk), i.e. 4 x 128 contiguous global bytes and 512
+// contiguous (permuted) shared bytes.  Returns through dst the same bytes the split pass revisits.
+struct Atom32 {
+  int kg, xa;   // 4-channel group, 32-pixel atom along x
+  __device__ __forceinline__ void step(int nxa) {
+    xa += 4;
+    while (xa >= nxa) { xa -= nxa; ++kg; }
+  }
+};
+__device__ __forceinline__ uint32_t atom32_off(int kg, int xa, int nxa, int cl, int q) {
+  return (uint32_t)((kg * nxa + xa) * 512 + cl * 128 + ((((q >> 1) ^ cl) & 3) << 5) + ((q & 1) << 4));
+}
+__device__ __forceinline__ void stage_operand32(const FeatView& F, int64_t n, int y, int c0, int nch, int xs, int nxa, int W,
+                                                unsigned char* dst, bool fast, int lt) {
+  const int q = lt & 7, cl = (lt >> 3) & 3;
+  const float* __restrict__ base =
+      reinterpret_cast<const float*>(F.data) + n * F.sn + (int64_t)y * F.sh + (int64_t)(c0 + cl) * F.sc;
+  const int nkg = nch >> 2;
+  Atom32 a{0, lt >> 5};
+  while (a.xa >= nxa) { a.xa -= nxa; ++a.kg; }
+  for (; a.kg < nkg; a.step(nxa)) {
+    const int x = xs + 32 * a.xa + 4 * q;
+    const bool inside = fast && x >= 0 && x + 4 <= W;
+    const bool empty = x + 4 <= 0 || x >= W;
+    unsigned char* d = dst + atom32_off(a.kg, a.xa, nxa, cl, q);
+    const float* src = base + (int64_t)(4 * a.kg) * F.sc;
+    if (inside || empty)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(d)), "l"(inside ? src + x : src),
+                   "r"(inside ? 16 : 0)
+                   : "memory");
+    else
+      *reinterpret_cast<uint4*>(d) = load_chunk_slow<float>(src, x, W, F.sw);
+  }
+}
+// split the chunks this thread staged into hi (in place) and lo (at +lo_off, a multiple of 1024 B: same
+// swizzle phase).  hi keeps the top 11 significand bits, so it is exact in TF32 and lo = x - hi is exact in
+// fp32; non-finite values keep hi = x (NaN canonicalised), lo = 0.
+__device__ __forceinline__ void split_operand32(unsigned char* dst, int nch, int nxa, int lo_off, int lt) {
+  const int q = lt & 7, cl = (lt >> 3) & 3;
+  const int nkg = nch >> 2;
+  Atom32 a{0, lt >> 5};
+  while (a.xa >= nxa) { a.xa -= nxa; ++a.kg; }
+  for (; a.kg < nkg; a.step(nxa)) {
+    unsigned char* p = dst + atom32_off(a.kg, a.xa, nxa, cl, q);
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float f = __uint_as_float(w[i]);
+      hi[i] = w[i] & 0xffffe000u;
+      lo[i] = __float_as_uint(f - __uint_as_float(hi[i]));
+      if (!(fabsf(f) < INFINITY)) { hi[i] = f != f ? 0x7fc00000u : w[i]; lo[i] = 0u; }
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(p + lo_off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
 }
 
@@ -214,7 +292,10 @@ template <typename Tin, typename Tout, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, TcGeom g, int fast) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  unsigned char* stage0 = smem_raw;                                   // NSTAGE x { A: KC*128*2 | B: KC*ncol*2 }
+  constexpr bool F32 = sizeof(Tin) == 4;
+  constexpr int ES = (int)sizeof(Tin), EPC = 16 / ES;       // element bytes, elements per 16-byte chunk
+  constexpr int KC = F32 ? TC_KC32 : TC_KC;                 // channels per stage
+  unsigned char* stage0 = smem_raw;   // NSTAGE x { A: KC*128*ES | B: KC*ncol*ES } (fp32: hi copies, then lo copies)
   float* skew = reinterpret_cast<float*>(smem_raw + g.nstage * (size_t)g.stage_bytes);   // epilogue scratch
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(skew) + g.epi_bytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_NSTAGE + 4);
@@ -243,7 +324,8 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
-  const int nk = (g.C + TC_KC - 1) / TC_KC;
+  const int nk = (g.C + KC - 1) / KC;
+  const int lo_off = KC * (TC_TM + g.ncol) * ES;            // fp32 only: hi -> lo distance inside a stage
   // contiguous tile range of this CTA (neighbouring x tiles share most of their right window in L2)
   int64_t per = (g.tiles + gridDim.x - 1) / gridDim.x;
   if (g.d_fastest) per = (per + g.dchunks - 1) / g.dchunks * g.dchunks;   // never split the chunks of one pixel tile
@@ -254,7 +336,7 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | ((uint32_t)g.fmt << 7) | ((uint32_t)g.fmt << 10) | (1u << 15) | (1u << 16) |
                              ((uint32_t)(g.ncol >> 3) << 17) | ((uint32_t)(TC_TM >> 4) << 24);
-      const uint32_t sbo = 128, lboA = (TC_TM / 8) * 128, lboB = (uint32_t)(g.ncol / 8) * 128;
+      const uint32_t sbo = 128, lboA = (TC_TM / EPC) * 128, lboB = (uint32_t)(g.ncol / EPC) * 128;
       const uint32_t nst = (uint32_t)g.nstage;
       uint32_t it = 0, use = 0;
       for (int64_t t = t_beg; t < t_end; ++t, ++use) {
@@ -262,14 +344,27 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
         mbar_wait(tmem_empty + 8 * buf, ((use >> 1) & 1) ^ 1);            // epilogue drained this accumulator
         for (int kc = 0; kc < nk; ++kc, ++it) {
           const uint32_t s = it % nst;
-          const uint32_t sA = smem_u32(stage0 + (size_t)s * g.stage_bytes), sB = sA + TC_KC * TC_TM * 2;
-          const int nch = min(TC_KC, g.C - kc * TC_KC);
+          const uint32_t sA = smem_u32(stage0 + (size_t)s * g.stage_bytes), sB = sA + KC * TC_TM * ES;
+          const int nch = min(KC, g.C - kc * KC);
           mbar_wait(smem_full + 8 * s, (it / nst) & 1);                   // operands of this k-chunk have landed
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          for (int ks = 0; ks < nch / 16; ++ks) {
-            const uint64_t adesc = umma_desc(sA + ks * 2 * lboA, lboA, sbo);
-            const uint64_t bdesc = umma_desc(sB + ks * 2 * lboB, lboB, sbo);
-            umma_f16(tmem_base + buf * g.tmem_buf, adesc, bdesc, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+          const uint32_t td = tmem_base + buf * g.tmem_buf;
+          if constexpr (F32) {
+            // SWIZZLE_128B_BASE32B: LBO = next 32-pixel atom (512 B), SBO = next 4-channel group
+            const uint32_t sboA32 = (TC_TM / 32) * 512, sboB32 = (uint32_t)(g.ncol / 32) * 512;
+            for (int ks = 0; ks < nch / 8; ++ks) {                        // K = 8 per UMMA: two 4-channel groups
+              const uint64_t ahi = umma_desc(sA + ks * 2 * sboA32, 512, sboA32, 1), alo = umma_desc(sA + lo_off + ks * 2 * sboA32, 512, sboA32, 1);
+              const uint64_t bhi = umma_desc(sB + ks * 2 * sboB32, 512, sboB32, 1), blo = umma_desc(sB + lo_off + ks * 2 * sboB32, 512, sboB32, 1);
+              umma_tf32(td, alo, bhi, idesc, (kc > 0 || ks > 0) ? 1u : 0u);   // small terms first
+              umma_tf32(td, ahi, blo, idesc, 1u);
+              umma_tf32(td, ahi, bhi, idesc, 1u);
+            }
+          } else {
+            for (int ks = 0; ks < nch / 16; ++ks) {                       // K = 16 per UMMA: two K-groups
+              const uint64_t adesc = umma_desc(sA + ks * 2 * lboA, lboA, sbo);
+              const uint64_t bdesc = umma_desc(sB + ks * 2 * lboB, lboB, sbo);
+              umma_f16(td, adesc, bdesc, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+            }
           }
           umma_commit(smem_empty + 8 * s);                                // stage reusable once these complete
           if (kc == nk - 1) umma_commit(tmem_full + 8 * buf);             // accumulator ready for the epilogue
@@ -290,6 +385,12 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
         case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
         default: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
       }
+      if constexpr (F32) {
+        unsigned char* sA = stage0 + (size_t)(job % nst) * g.stage_bytes;
+        const int kc = (int)(job % (uint32_t)nk), nch = min(KC, g.C - kc * KC);
+        split_operand32(sA, nch, TC_TM / 32, lo_off, lt);
+        split_operand32(sA + KC * TC_TM * ES, nch, g.ncol / 32, lo_off, lt);
+      }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (UMMA)
       mbar_arrive(smem_full + 8 * (job % nst));
     };
@@ -300,11 +401,16 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
       for (int kc = 0; kc < nk; ++kc, ++it) {
         const uint32_t s = it % nst;
         unsigned char* sA = stage0 + (size_t)s * g.stage_bytes;
-        unsigned char* sB = sA + TC_KC * TC_TM * 2;
-        const int c0 = kc * TC_KC, nch = min(TC_KC, g.C - c0);
+        unsigned char* sB = sA + KC * TC_TM * ES;
+        const int c0 = kc * KC, nch = min(KC, g.C - c0);
         mbar_wait(smem_empty + 8 * s, ((it / nst) & 1) ^ 1);       // UMMAs that read this stage have completed
-        stage_operand<Tin>(L, tc.n, tc.y, c0, nch, tc.x0, TC_TM / 8, g.W, sA, fast, lt);
-        stage_operand<Tin>(R, tc.n, tc.y, c0, nch, xr0, g.ncol / 8, g.W, sB, fast, lt);
+        if constexpr (F32) {
+          stage_operand32(L, tc.n, tc.y, c0, nch, tc.x0, TC_TM / 32, g.W, sA, fast, lt);
+          stage_operand32(R, tc.n, tc.y, c0, nch, xr0, g.ncol / 32, g.W, sB, fast, lt);
+        } else {
+          stage_operand<Tin>(L, tc.n, tc.y, c0, nch, tc.x0, TC_TM / EPC, g.W, sA, fast, lt);
+          stage_operand<Tin>(R, tc.n, tc.y, c0, nch, xr0, g.ncol / EPC, g.W, sB, fast, lt);
+        }
         asm volatile("cp.async.commit_group;" ::: "memory");
         if (it + 1 - done == nst) {             // keep at most nstage-1 newer groups behind the oldest
           landed(done, (int)nst - 1);
@@ -456,7 +562,8 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
 
 static int tc_geom(int64_t N, int64_t C, int64_t H, int64_t W, int64_t D, int mean, int fmt, TcGeom& g) {
   g.C = (int)C; g.H = (int)H; g.W = (int)W; g.D = (int)D;
-  const int d16 = (int)((D + 15) / 16 * 16);
+  const int dq = fmt == 2 ? 32 : 16;      // fp32 operands come in 32-pixel atoms
+  const int d16 = (int)((D + dq - 1) / dq * dq);
   g.dch = d16 < 128 ? d16 : 128;
   g.ncol = TC_TM + g.dch;
   g.ncw = (g.dch / 2 + 32 + 15) / 16 * 16;
@@ -469,7 +576,7 @@ static int tc_geom(int64_t N, int64_t C, int64_t H, int64_t W, int64_t D, int me
   g.pow2 = (C & (C - 1)) == 0;
   g.fmt = fmt;
   g.tmem_buf = g.ncol <= 128 ? 128 : 256;
-  g.stage_bytes = TC_KC * TC_TM * 2 + TC_KC * g.ncol * 2;
+  g.stage_bytes = fmt == 2 ? 2 * TC_KC32 * (TC_TM + g.ncol) * 4 : TC_KC * (TC_TM + g.ncol) * 2;
   g.d_fastest = 0;
   g.rows = N * H;
   g.tiles = g.rows * g.xtiles * g.dchunks;
@@ -477,8 +584,9 @@ static int tc_geom(int64_t N, int64_t C, int64_t H, int64_t W, int64_t D, int me
   return RSM_OK;
 }
 
-static bool feat_vec8(const rsm_feat& f) {
-  return f.stride_w == 1 && f.stride_n % 8 == 0 && f.stride_c % 8 == 0 && f.stride_h % 8 == 0 && aligned_to(f.data, 16);
+// rows start on 16-byte boundaries: strides are multiples of epc = 16 / sizeof(element) elements
+static bool feat_vec16(const rsm_feat& f, int epc) {
+  return f.stride_w == 1 && f.stride_n % epc == 0 && f.stride_c % epc == 0 && f.stride_h % epc == 0 && aligned_to(f.data, 16);
 }
 
 template <typename Tin, typename Tout, int EPI>
@@ -492,20 +600,35 @@ static int launch_tc(const rsm_feat& left, const rsm_feat& right, void* out, Reg
   auto k = inner_tc_kernel<Tin, Tout, EPI>;
   if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return finish_launch(where);
-  const int fast = feat_vec8(left) && feat_vec8(right);   // 16-byte chunks start at multiples of 8 elements
+  const int epc = 16 / (int)sizeof(Tin);
+  const int fast = feat_vec16(left, epc) && feat_vec16(right, epc);   // 16-byte chunks start at multiples of epc elements
   const unsigned grid = (unsigned)(g.tiles < kNumSMs ? g.tiles : kNumSMs);   // persistent: one CTA per SM
   k<<<grid, TC_THREADS, smem, st>>>(view_of(left), view_of(right), (Tout*)out, rp, g, fast);
   return finish_launch(where);
 }
 
+static int tc_fmt(int in_dtype) { return in_dtype == RSM_F16 ? 0 : in_dtype == RSM_BF16 ? 1 : 2; }
+// 16-bit: whole UMMAs of K = 16.  fp32 (3xTF32, K = 8) is opt-in with RSM_TC_FP32=1: parity-checked, but its
+// operand pipeline (half the bytes in flight per stage, split pass in the loader warps) is still slower than
+// the SIMT fp32 kernel -- see DESIGN.md section 4b.  The environment is read per call so tests can toggle it.
+static bool tc_applies(int in_dtype, int64_t C, int64_t D) {
+  if (C <= 0 || D <= 0) return false;
+  if (in_dtype == RSM_F32) {
+    const char* e = getenv("RSM_TC_FP32");
+    return e && e[0] == '1' && C % 8 == 0;
+  }
+  return C % 16 == 0;
+}
+
 // returns RSM_ERR_UNSUPPORTED_CONFIG when the tensor-core path does not apply (caller falls back to SIMT)
 int launch_inner_tc(const rsm_feat& left, const rsm_feat& right, void* out, int64_t N, int64_t C, int64_t H, int64_t W,
                     int64_t D, int mean, int in_dtype, int out_dtype, cudaStream_t st) {
-  if (in_dtype == RSM_F32 || C % 16 != 0 || C <= 0 || D <= 0) return RSM_ERR_UNSUPPORTED_CONFIG;
+  if (!tc_applies(in_dtype, C, D) || (in_dtype == RSM_F32 && out_dtype != RSM_F32)) return RSM_ERR_UNSUPPORTED_CONFIG;
   TcGeom g;
-  if (int rc = tc_geom(N, C, H, W, D, mean, in_dtype == RSM_F16 ? 0 : 1, g)) return rc;
+  if (int rc = tc_geom(N, C, H, W, D, mean, tc_fmt(in_dtype), g)) return rc;
   const RegressPtrs none{nullptr, nullptr, nullptr, nullptr};
   const char* where = "rsm_inner_fwd(tcgen05)";
+  if (in_dtype == RSM_F32) return launch_tc<float, float, EPI_VOLUME>(left, right, out, none, g, st, where);
   if (in_dtype == RSM_F16) {
     if (out_dtype == RSM_F32) return launch_tc<__half, float, EPI_VOLUME>(left, right, out, none, g, st, where);
     return launch_tc<__half, __half, EPI_VOLUME>(left, right, out, none, g, st, where);
@@ -516,12 +639,13 @@ int launch_inner_tc(const rsm_feat& left, const rsm_feat& right, void* out, int6
 
 int launch_inner_regress_tc(const rsm_feat& left, const rsm_feat& right, int64_t N, int64_t C, int64_t H, int64_t W,
                             int64_t D, int mean, int in_dtype, const rsm_regress_out& out, cudaStream_t st) {
-  if (in_dtype == RSM_F32 || C % 16 != 0 || C <= 0 || D <= 0) return RSM_ERR_UNSUPPORTED_CONFIG;
+  if (!tc_applies(in_dtype, C, D)) return RSM_ERR_UNSUPPORTED_CONFIG;
   TcGeom g;
-  if (int rc = tc_geom(N, C, H, W, D, mean, in_dtype == RSM_F16 ? 0 : 1, g)) return rc;
+  if (int rc = tc_geom(N, C, H, W, D, mean, tc_fmt(in_dtype), g)) return rc;
   g.d_fastest = 1;   // the softmax state of a pixel lives in the epilogue's registers across its disparity chunks
   const RegressPtrs rp{(float*)out.soft, out.argmin, out.argmax, out.lse};
   const char* where = "rsm_inner_regress_fwd(tcgen05)";
+  if (in_dtype == RSM_F32) return launch_tc<float, float, EPI_REGRESS>(left, right, nullptr, rp, g, st, where);
   if (in_dtype == RSM_F16) return launch_tc<__half, float, EPI_REGRESS>(left, right, nullptr, rp, g, st, where);
   return launch_tc<__nv_bfloat16, float, EPI_REGRESS>(left, right, nullptr, rp, g, st, where);
 }

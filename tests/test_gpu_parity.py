@@ -446,3 +446,32 @@ def test_tcgen05_fused_regress(rsm, shape):
     equal(amin, oracle.hard_argmin(vol))
     equal(amax, oracle.hard_argmax(vol))
     equal(rsm.inner_product_volume(dev(l, "bf16"), dev(r, "bf16"), d, out_dtype=torch.float32), vol)
+
+
+@pytest.mark.parametrize("shape", [(1, 8, 2, 128, 16), (2, 64, 4, 240, 48), (1, 24, 3, 312, 48), (1, 128, 2, 480, 192),
+                                   (1, 16, 2, 68, 19), (1, 40, 3, 67, 33)])
+def test_tcgen05_fp32_3xtf32_opt_in(rsm, shape, monkeypatch):
+    """fp32 features on the tensor cores (RSM_TC_FP32=1: kind::tf32 on an exact hi/lo operand split, three
+    UMMAs per k-step).  Within the fp32 tolerance of the float64 result, bit-exact on dyadic inputs, and the
+    fused regression agrees with the oracle on the volume."""
+    n, c, h, w, d = shape
+    rng = np.random.default_rng(51)
+    l = rng.standard_normal((n, c, h, w)).astype(np.float32)
+    r = rng.standard_normal((n, c, h, w)).astype(np.float32)
+    ref = oracle.inner_product_volume(l, r, d, acc_dtype=np.float64, out_dtype=np.float64)
+    monkeypatch.setenv("RSM_TC_FP32", "1")
+    tc = rsm.inner_product_volume(dev(l), dev(r), d)
+    soft, amin, amax = rsm.inner_product_regress(dev(l * 0.5), dev(r * 0.5), d)
+    monkeypatch.delenv("RSM_TC_FP32")
+    simt = rsm.inner_product_volume(dev(l), dev(r), d)
+    atol = corr_atol_fp32(c, np.abs(l).max(), np.abs(r).max())
+    close(tc, ref.astype(np.float32), atol)
+    close(simt, ref.astype(np.float32), atol)
+    vol = oracle.inner_product_volume(l * 0.5, r * 0.5, d)
+    close(soft, oracle.soft_argmax(vol), soft_argmax_atol(d) * 4)
+    assert (amin.cpu().numpy() != oracle.hard_argmin(vol)).mean() < 1e-3
+    assert (amax.cpu().numpy() != oracle.hard_argmax(vol)).mean() < 1e-3
+    l = (rng.integers(-8, 9, (n, c, h, w)) / 8.0).astype(np.float32)
+    r = (rng.integers(-8, 9, (n, c, h, w)) / 8.0).astype(np.float32)
+    monkeypatch.setenv("RSM_TC_FP32", "1")
+    equal(rsm.inner_product_volume(dev(l), dev(r), d), oracle.inner_product_volume(l, r, d))

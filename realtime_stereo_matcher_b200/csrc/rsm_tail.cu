@@ -44,27 +44,34 @@ struct TailGeom {
   int fast4;         // D == 4 * Dc
   int fastx;         // W == 4 * Wc
   int fasty;         // H == 4 * Hc
+  int all4;          // x4 along all three axes with the full 4 x 10 coarse footprint: specialised staging + stabiliser
   float sd, sh, sw;  // in/out scale per axis
 };
 
 // shared memory: [ rows Dc*FH*32 | raw Dc*FH*FW | w1tab D | dstart Dc+1 | i0tab D ]  (tables: generic ratio)
+//            or  [ rows Dc*4*32  | raw Dc*40 (+pad) | part 8*128 | rowmax 128 ]      (all-x4 path)
 struct TailSmem {
   float* rows;
   float* raw;
   float* w1tab;
   int* dstart;
   int* i0tab;
+  float* part;     // all4: per-warp column maxima [8][128], then minima [8][128], of rows
+  float* rowmax;   // all4: max over k of rows[k][fy][tx] [128], then the min [128]
   __device__ __forceinline__ TailSmem(float* base, const TailGeom& g) {
     rows = base;
     raw = rows + g.Dc * g.FH * kTX;
     w1tab = raw + g.Dc * g.FH * g.FW;
     dstart = reinterpret_cast<int*>(w1tab + g.D);
     i0tab = dstart + g.Dc + 1;
+    part = raw + ((g.Dc * g.FH * g.FW + 3) & ~3);
+    rowmax = part + 2 * 8 * 4 * kTX;
   }
 };
 static size_t tail_smem_bytes(const TailGeom& g) {
   size_t n = (size_t)g.Dc * g.FH * (kTX + g.FW);
-  if (!g.fast4) n += (size_t)g.D + g.Dc + 1 + g.D;
+  if (g.all4) n = ((n + 3) & ~(size_t)3) + 2 * 9 * 4 * kTX;
+  else if (!g.fast4) n += (size_t)g.D + g.Dc + 1 + g.D;
   return n * sizeof(float);
 }
 
@@ -139,6 +146,72 @@ __device__ __forceinline__ void stage_tile(const T* __restrict__ cost_b, const T
   __syncthreads();
 }
 
+// Steps 1 + 2 for the x4 x4 x4 head (footprint exactly 4 x 10 coarse pixels per slice): division-free
+// staging with every load of a batch in flight, and, on the way, rowmax[fy][tx] = max_k rows[k][fy][tx].
+// A fine value is a convex combination of two rows entries, so max(rowmax[fy0], rowmax[fy1]) bounds every
+// fine value of the pixel from above: the softmax stabiliser without a pass over the 48 slices.
+template <typename T>
+__device__ __forceinline__ void stage_tile_all4(const T* __restrict__ cost_b, const TailSmem& sm, const TailGeom& g,
+                                                int cy0, int cx0) {
+  constexpr int FW = 10;
+  const int n = g.Dc * 4 * FW;
+  const int plane = g.Hc * g.Wc;           // Dc * Hc * Wc < 2^31 (host check): 32-bit offsets inside a batch item
+  // ---- 1. raw[(k*4 + fy)*10 + fx]
+  for (int e0 = threadIdx.x; e0 < n; e0 += 4 * kNT) {
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * kNT;
+      const int p = e / FW, fx = e - p * FW;
+      const int cy = min(cy0 + (p & 3), g.Hc - 1), cx = min(cx0 + fx, g.Wc - 1);
+      v[u] = e < n ? to_f(__ldg(cost_b + ((p >> 2) * plane + cy * g.Wc + cx))) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (e0 + u * kNT < n) sm.raw[e0 + u * kNT] = v[u];
+  }
+  __syncthreads();
+  // ---- 2. x-interpolation (constant weights, see stage_tile) + running column maxima
+  const int q = threadIdx.x & 7, p0 = threadIdx.x >> 3;     // p0 = 4 * warp + fy
+  const int j = (blockIdx.x * kTX) / 4 + q;
+  const int jm = min(max(j - 1, 0), g.Wc - 1), jc = min(j, g.Wc - 1), jp = min(j + 1, g.Wc - 1);
+  const int am = min(jm - cx0, FW - 1), ac = min(jc - cx0, FW - 1), ap = min(jp - cx0, FW - 1);
+  const int npair = g.Dc * 4;
+  float4 mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  float4 mn = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+  const float* rr = sm.raw + p0 * FW;
+  float* ro = sm.rows + p0 * kTX + 4 * q;
+#pragma unroll 2
+  for (int p = p0; p < npair; p += kNT / 8, rr += (kNT / 8) * FW, ro += (kNT / 8) * kTX) {
+    const float vm = rr[am], vc = rr[ac], vp = rr[ap];
+    float4 o;
+    o.x = 0.375f * vm + 0.625f * vc;
+    o.y = 0.125f * vm + 0.875f * vc;
+    o.z = 0.875f * vc + 0.125f * vp;
+    o.w = 0.625f * vc + 0.375f * vp;
+    *reinterpret_cast<float4*>(ro) = o;
+    mx.x = fmaxf(mx.x, o.x); mx.y = fmaxf(mx.y, o.y); mx.z = fmaxf(mx.z, o.z); mx.w = fmaxf(mx.w, o.w);
+    mn.x = fminf(mn.x, o.x); mn.y = fminf(mn.y, o.y); mn.z = fminf(mn.z, o.z); mn.w = fminf(mn.w, o.w);
+  }
+  // (fmaxf / fminf skip NaNs: a NaN column keeps a finite range, and the NaN then propagates through pass 2)
+  {
+    float* pp = sm.part + (p0 >> 2) * (4 * kTX) + (p0 & 3) * kTX + 4 * q;
+    *reinterpret_cast<float4*>(pp) = mx;
+    *reinterpret_cast<float4*>(pp + 8 * 4 * kTX) = mn;
+  }
+  __syncthreads();
+  {   // threads 0-127: column maxima, threads 128-255: column minima
+    const int c = threadIdx.x & (4 * kTX - 1);
+    const bool lo = threadIdx.x >= 4 * kTX;
+    const float* pp = sm.part + (lo ? 8 * 4 * kTX : 0) + c;
+    float m = pp[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = lo ? fminf(m, pp[w * (4 * kTX)]) : fmaxf(m, pp[w * (4 * kTX)]);
+    sm.rowmax[threadIdx.x] = m;
+  }
+  __syncthreads();
+}
+
 // Step 3: the y-lerp of one output pixel; slice k is at base + k * stride
 struct SliceY {
   const float* p0;   // rows + (y0 - cy0) * 32 + tx
@@ -154,6 +227,20 @@ struct SliceY {
     stride = g.FH * kTX;
   }
   __device__ __forceinline__ float get(int k) const { return wy0 * p0[k * stride] + wy1 * p1[k * stride]; }
+  // all4: compile-time slice stride (4 rows x 32 columns) -> LDS with immediate offsets
+  __device__ __forceinline__ float get4(int k) const { return wy0 * p0[k * (4 * kTX)] + wy1 * p1[k * (4 * kTX)]; }
+  // c_k * log2(e) - M * log2(e)
+  template <bool ALL4>
+  __device__ __forceinline__ float scaled(int k, float neg_ml) const {
+    if constexpr (ALL4) return fmaf(wy0 * kLog2e, p0[k * (4 * kTX)], fmaf(wy1 * kLog2e, p1[k * (4 * kTX)], neg_ml));
+    else return fmaf(get(k), kLog2e, neg_ml);
+  }
+  __device__ __forceinline__ float bound(const TailSmem& sm) const {   // all4: upper bound of every fine value
+    return fmaxf(sm.rowmax[p0 - sm.rows], sm.rowmax[p1 - sm.rows]);
+  }
+  __device__ __forceinline__ float lower_bound(const TailSmem& sm) const {
+    return fminf(sm.rowmax[4 * kTX + (p0 - sm.rows)], sm.rowmax[4 * kTX + (p1 - sm.rows)]);
+  }
 };
 
 struct NoTrack {
@@ -161,7 +248,81 @@ struct NoTrack {
 };
 
 // ===================================================================================== forward
-template <typename T, bool FAST4, bool WANT_ARG>
+// Pass 2 of the x4 head: intervals in ascending d.  Slices are pre-scaled, cs = c*log2(e) - M*log2(e), so
+// exp(f - M) = ex2(lerp(cs0, cs1)); the four fine values of an interval are equally spaced
+// (f_j = cs0 + (2j+1)/8 * dl), so their exponentials form a geometric progression: two ex2 (MUFU is the
+// scarcest pipe here) + three multiplies instead of four ex2.
+//   ROBUST = false: ascending progression from e_0 with ratio 2^(dl/4).  Only valid when no f_j can flush,
+//                   i.e. the caller has bounded the pixel's whole value range below 120 binary orders.
+//   ROBUST = true : anchored at the LARGER end value, descending with ratio r <= 1, so an underflow can only
+//                   ever drop terms that are negligible against the anchor (anchoring at f_0 would lose
+//                   the whole interval when a steep ascending slope flushes e_0); two more instructions.
+// The arg-extrema are tracked on the (monotone) scaled values.
+template <bool ALL4, bool ROBUST, typename Track>
+__device__ __forceinline__ void pass2_x4(const SliceY& sl, float neg_ml, int Dc, int D, float& s, float& ws, Track& trk) {
+  float cs0 = sl.template scaled<ALL4>(0, neg_ml);
+  {   // d' = 0, 1 sit on slice 0
+    const float e = fast_exp2(cs0);
+    s = e + e; ws = e;
+    trk.update(cs0, 0);
+  }
+  float base = ROBUST ? 3.5f : 2.f;   // first fine index of the interval, 4k + 2 (ROBUST: + 1.5)
+  for (int k = 0; k + 1 < Dc; ++k) {
+    const float cs1 = sl.template scaled<ALL4>(k + 1, neg_ml);
+    const float dl = cs1 - cs0;
+    if constexpr (ROBUST) {
+      const float fs = fmaf(0.375f, fabsf(dl), fmaf(0.5f, dl, cs0));        // max(f_0, f_3)
+      const float g0 = fast_exp2(fs), r = fast_exp2(-0.25f * fabsf(dl));
+      const float g1 = g0 * r, g2 = g1 * r, g3 = g2 * r;
+      const float S = (g0 + g1) + (g2 + g3);
+      const float Tn = fmaf(3.f, g3, fmaf(2.f, g2, g1));                    // sum_i i * g_i
+      // ascending slope (dl >= 0): e_j = g_{3-j}, sum_j (b+j) e_j = (b+3) S - Tn;  descending: b S + Tn
+      const float sg = __uint_as_float(0xBF800000u ^ (__float_as_uint(dl) & 0x80000000u));   // -1 : +1
+      s += S;
+      ws = fmaf(fmaf(-1.5f, sg, base), S, ws);
+      ws = fmaf(sg, Tn, ws);
+    } else {
+      const float e0 = fast_exp2(fmaf(0.125f, dl, cs0)), q = fast_exp2(0.25f * dl);
+      const float e1 = e0 * q, e2 = e1 * q, e3 = e2 * q;
+      const float S = (e0 + e1) + (e2 + e3);
+      const float Tm = fmaf(3.f, e3, fmaf(2.f, e2, e1));                    // sum_j j * e_j
+      s += S;
+      ws = fmaf(base, S, ws) + Tm;
+    }
+    const int d0 = 4 * k + 2;
+    trk.update(fmaf(0.125f, dl, cs0), d0); trk.update(fmaf(0.375f, dl, cs0), d0 + 1);
+    trk.update(fmaf(0.625f, dl, cs0), d0 + 2); trk.update(fmaf(0.875f, dl, cs0), d0 + 3);
+    base += 4.f;
+    cs0 = cs1;
+  }
+  {   // d' = D-2, D-1 sit on the last slice
+    const float e = fast_exp2(cs0);
+    s += e + e;
+    ws = fmaf((float)(2 * D - 3), e, ws);
+    trk.update(cs0, D - 2);
+  }
+}
+
+// exact maximum over the FINE values of a pixel (linear inside an interval: attained at an interval end)
+template <bool FAST4, bool ALL4>
+__device__ __forceinline__ float fine_max(const SliceY& sl, const TailSmem& sm, const TailGeom& g) {
+  float c0 = ALL4 ? sl.get4(0) : sl.get(0);
+  float M = c0;                                    // d' = 0 sits on slice 0 (and the last ones on slice Dc-1)
+  for (int k = 0; k + 1 < g.Dc; ++k) {
+    const float c1 = ALL4 ? sl.get4(k + 1) : sl.get(k + 1);
+    if constexpr (FAST4) {
+      M = fmaxf(M, fmaf(0.375f, fabsf(c1 - c0), 0.5f * (c0 + c1)));
+    } else {
+      const float dl = c1 - c0;
+      const int dend = sm.dstart[k + 1];
+      for (int d = sm.dstart[k]; d < dend; ++d) M = fmaxf(M, fmaf(sm.w1tab[d], dl, c0));
+    }
+    c0 = c1;
+  }
+  return fmaxf(M, c0);
+}
+
+template <typename T, bool FAST4, bool ALL4, bool WANT_ARG>
 __global__ void __launch_bounds__(kNT)
 upsample_regress_fwd_kernel(const T* __restrict__ cost, T* __restrict__ soft, int64_t* __restrict__ amin,
                             int64_t* __restrict__ amax, float* __restrict__ lse, TailGeom g) {
@@ -171,56 +332,35 @@ upsample_regress_fwd_kernel(const T* __restrict__ cost, T* __restrict__ soft, in
   const int x = blockIdx.x * kTX + (threadIdx.x & (kTX - 1)), y = blockIdx.y * kTY + threadIdx.x / kTX;
   const int cy0 = lin_index(blockIdx.y * kTY, g.sh, g.Hc).i0;
   const int cx0 = lin_index(blockIdx.x * kTX, g.sw, g.Wc).i0;
-  stage_tile(cost + (int64_t)b * g.Dc * g.Hc * g.Wc, sm, g, cy0, cx0);
+  if constexpr (ALL4) stage_tile_all4(cost + (int64_t)b * g.Dc * g.Hc * g.Wc, sm, g, cy0, cx0);
+  else stage_tile(cost + (int64_t)b * g.Dc * g.Hc * g.Wc, sm, g, cy0, cx0);
   if (x >= g.W || y >= g.H) return;
 
   const SliceY sl(sm, g, y, cy0);
-  // pass 1: stabiliser.  Every fine value is a convex combination of slice values, so their max
-  // bounds it (and is attained within |c_{k+1}-c_k|/8 for the x4 head).
-  float M = -INFINITY;
-  for (int k = 0; k < g.Dc; ++k) M = fmaxf(M, sl.get(k));
-  const float Ml = M * kLog2e;
-
-  // pass 2: intervals in ascending d.  Slices are pre-scaled: cs = c*log2(e) - M*log2(e), so
-  // exp(f - M) = ex2(lerp(cs0, cs1)).  The arg-extrema are tracked on the (monotone) scaled values.
-  float s = 0.f, ws = 0.f;
+  // pass 1: the softmax stabiliser M.  The general paths take the exact maximum of the pixel's fine values.
+  // The all-x4 path takes the bound of stage_tile_all4 (no pass over the slices) whenever the pixel's whole
+  // value range is below 120 binary orders -- every ordinary cost volume -- so that nothing can flush and
+  // the short progression is safe; wider ranges (or NaNs) take the exact maximum and the robust progression.
+  float s, ws;
   typename std::conditional<WANT_ARG, ArgTrack, NoTrack>::type trk;
-  float cs0 = fmaf(sl.get(0), kLog2e, -Ml);
+  float M;
   if constexpr (FAST4) {
-    {   // d' = 0, 1 sit on slice 0
-      const float e = fast_exp2(cs0);
-      s = e + e; ws = e;
-      trk.update(cs0, 0);
+    bool robust = true;
+    if constexpr (ALL4) {
+      M = sl.bound(sm);
+      robust = !((M - sl.lower_bound(sm)) * kLog2e < 120.f);
     }
-    float base = 2.f;   // first fine index of the interval, 4k + 2
-    for (int k = 0; k + 1 < g.Dc; ++k) {
-      const float cs1 = fmaf(sl.get(k + 1), kLog2e, -Ml);
-      const float dl = cs1 - cs0;
-      // the four fine values are equally spaced (f_j = f0 + j * dl/4), so their exponentials form a
-      // geometric progression: two ex2 (MUFU is the scarcest pipe here) + three multiplies instead of
-      // four ex2.  All f_j <= 0 (M is the max), so e_j <= 1; q is clamped so a flushed e0 never meets inf.
-      const float f0 = fmaf(0.125f, dl, cs0);
-      const float e0 = fast_exp2(f0), q = fast_exp2(fminf(0.25f * dl, 126.f));
-      const float e1 = e0 * q, e2 = e1 * q, e3 = e2 * q;
-      [[maybe_unused]] const float f1 = fmaf(0.375f, dl, cs0), f2 = fmaf(0.625f, dl, cs0), f3 = fmaf(0.875f, dl, cs0);
-      const float S = (e0 + e1) + (e2 + e3);
-      const float Tm = fmaf(3.f, e3, fmaf(2.f, e2, e1));   // sum_j j * e_j
-      s += S;
-      ws = fmaf(base, S, ws) + Tm;
-      if constexpr (WANT_ARG) {
-        const int d0 = 4 * k + 2;
-        trk.update(f0, d0); trk.update(f1, d0 + 1); trk.update(f2, d0 + 2); trk.update(f3, d0 + 3);
-      }
-      base += 4.f;
-      cs0 = cs1;
-    }
-    {   // d' = D-2, D-1 sit on the last slice
-      const float e = fast_exp2(cs0);
-      s += e + e;
-      ws = fmaf((float)(2 * g.D - 3), e, ws);
-      trk.update(cs0, g.D - 2);
+    if (robust) {
+      M = fine_max<true, ALL4>(sl, sm, g);
+      pass2_x4<ALL4, true>(sl, -M * kLog2e, g.Dc, g.D, s, ws, trk);
+    } else {
+      pass2_x4<ALL4, false>(sl, -M * kLog2e, g.Dc, g.D, s, ws, trk);
     }
   } else {
+    M = fine_max<false, false>(sl, sm, g);
+    const float Ml = M * kLog2e;
+    s = 0.f; ws = 0.f;
+    float cs0 = fmaf(sl.get(0), kLog2e, -Ml);
     for (int k = 0; k < g.Dc; ++k) {
       const float cs1 = (k + 1 < g.Dc) ? fmaf(sl.get(k + 1), kLog2e, -Ml) : cs0;
       const float dl = cs1 - cs0;
@@ -386,6 +526,11 @@ static int make_geom(int64_t Dc, int64_t Hc, int64_t Wc, int64_t D, int64_t H, i
   g.fast4 = (D == 4 * Dc) ? 1 : 0;
   g.fastx = (W == 4 * Wc) ? 1 : 0;
   g.fasty = (H == 4 * Hc) ? 1 : 0;
+  {
+    const char* e = getenv("RSM_TAIL_GENERIC");   // A/B switch: keep the all-x4 specialisation off
+    g.all4 = g.fast4 && g.fastx && g.fasty && g.FH == 4 && g.FW == 10 && Dc * Hc * Wc < 2147483647LL &&
+             !(e && e[0] == '1');
+  }
   smem = tail_smem_bytes(g);
   if (smem > 200 * 1024) return RSM_ERR_UNSUPPORTED_CONFIG;
   return RSM_OK;
@@ -401,10 +546,10 @@ using namespace rsm;
   if (!guard.ok) { set_cuda_error(cudaGetLastError(), __func__); return RSM_ERR_CUDA; } \
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
-template <typename T, bool FAST4, bool WANT_ARG>
+template <typename T, bool FAST4, bool ALL4, bool WANT_ARG>
 static int launch_tail_fwd(const void* cost, const rsm_regress_out& out, const TailGeom& g, size_t smem, dim3 grid,
                            cudaStream_t st) {
-  auto k = upsample_regress_fwd_kernel<T, FAST4, WANT_ARG>;
+  auto k = upsample_regress_fwd_kernel<T, FAST4, ALL4, WANT_ARG>;
   if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k<<<grid, kNT, smem, st>>>((const T*)cost, (T*)out.soft, out.argmin, out.argmax, out.lse, g);
   return finish_launch("rsm_upsample_regress_fwd");
@@ -425,10 +570,12 @@ extern "C" int rsm_upsample_regress_fwd(const void* cost, int64_t B, int64_t Dc,
   if (grid.y > 65535) return RSM_ERR_INVALID_SHAPE;
   const bool want_arg = out.argmin || out.argmax;
   return RSM_DISPATCH_DTYPE(dtype, T, [&]() -> int {
-    if (g.fast4) return want_arg ? launch_tail_fwd<T, true, true>(cost, out, g, smem, grid, st)
-                                 : launch_tail_fwd<T, true, false>(cost, out, g, smem, grid, st);
-    return want_arg ? launch_tail_fwd<T, false, true>(cost, out, g, smem, grid, st)
-                    : launch_tail_fwd<T, false, false>(cost, out, g, smem, grid, st);
+    if (g.all4) return want_arg ? launch_tail_fwd<T, true, true, true>(cost, out, g, smem, grid, st)
+                                : launch_tail_fwd<T, true, true, false>(cost, out, g, smem, grid, st);
+    if (g.fast4) return want_arg ? launch_tail_fwd<T, true, false, true>(cost, out, g, smem, grid, st)
+                                 : launch_tail_fwd<T, true, false, false>(cost, out, g, smem, grid, st);
+    return want_arg ? launch_tail_fwd<T, false, false, true>(cost, out, g, smem, grid, st)
+                    : launch_tail_fwd<T, false, false, false>(cost, out, g, smem, grid, st);
   });
 }
 

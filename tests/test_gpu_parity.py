@@ -475,3 +475,29 @@ def test_tcgen05_fp32_3xtf32_opt_in(rsm, shape, monkeypatch):
     r = (rng.integers(-8, 9, (n, c, h, w)) / 8.0).astype(np.float32)
     monkeypatch.setenv("RSM_TC_FP32", "1")
     equal(rsm.inner_product_volume(dev(l), dev(r), d), oracle.inner_product_volume(l, r, d))
+
+
+@pytest.mark.parametrize("scale", [3.0, 60.0, 400.0])
+def test_v4_tail_all_x4_stabiliser(rsm, scale, monkeypatch):
+    """x4 along all three axes takes the specialised staging whose softmax stabiliser is an upper BOUND
+    (max of the two source rows) with an exact-maximum fallback when the bound is too loose: costs whose
+    neighbouring columns differ by hundreds must still match the oracle, the generic path
+    (RSM_TAIL_GENERIC=1) and interpolate+softmax on the device; lse and the arg-extrema too."""
+    rng = np.random.default_rng(61)
+    b, dc, hc, wc = 2, 48, 10, 23
+    d, h, w = 4 * dc, 4 * hc, 4 * wc
+    cost = (rng.standard_normal((b, dc, hc, wc)) * scale).astype(np.float32)
+    cost[0, :, 3, :] = -scale * 5          # a whole coarse row far below its neighbours
+    cost[0, 7, 4, ::2] = scale * 5         # isolated peaks: the bound of the rows next to them is loose
+    c = dev(cost)
+    pred, amin, amax = rsm.upsample_regress(c, d, h, w, argmin=True, argmax=True)
+    monkeypatch.setenv("RSM_TAIL_GENERIC", "1")
+    pred_g, amin_g, amax_g = rsm.upsample_regress(c, d, h, w, argmin=True, argmax=True)
+    monkeypatch.delenv("RSM_TAIL_GENERIC")
+    assert torch.isfinite(pred).all()
+    close(pred, oracle.v4_tail(cost, d, h, w), V4_TAIL_ATOL * max(1.0, scale / 3))
+    torch.testing.assert_close(pred, pred_g, atol=V4_TAIL_ATOL * max(1.0, scale / 3), rtol=0)
+    assert (amin != amin_g).float().mean() < 1e-3 and (amax != amax_g).float().mean() < 1e-3
+    fine = torch.nn.functional.interpolate(c.unsqueeze(1), [d, h, w], mode="trilinear").squeeze(1)
+    assert (amax != fine.argmax(1)).float().mean() < 1e-3
+    assert (amin != fine.argmin(1)).float().mean() < 1e-3

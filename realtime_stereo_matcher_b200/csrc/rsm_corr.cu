@@ -505,21 +505,18 @@ static int launch_bwd(const void* gout, const rsm_feat& left, const rsm_feat& ri
   for (int c = BW_CB; c >= 4; c -= 4)
     if (g.cpg % c == 0) { cbs = c; break; }
   const char* naive = getenv("RSM_BWD_NAIVE");
-  // D-innermost gradients of tiny groups are staging-bound in the tiled kernel (transposing 16 KB per 4
-  // channels); the per-element gather kernel is as fast there, so keep it for cpg < 16
-  const bool tiled_pays = LAYOUT == LAYOUT_NDHW || g.cpg >= 16;
-  if (cbs > 0 && g.D > 0 && tiled_pays && !(naive && naive[0] == '1')) {
+  if (cbs > 0 && g.D > 0 && !(naive && naive[0] == '1')) {
     const int cblocks = g.C / cbs;
     const int64_t bx = N * g.H * (int64_t)cblocks * g.xtiles;
     if (!grid_ok(bx)) return RSM_ERR_INVALID_SHAPE;
     if (gl) {
-      const size_t smem = (size_t)(BW_DCH * BW_TX + BW_CB * (BW_TX + BW_DCH)) * sizeof(float);
+      const size_t smem = (size_t)(BW_DCH * (BW_TX + 4) + cbs * (BW_TX + BW_DCH)) * sizeof(float);
       corr_bwd_tiled_kernel<Tin, Tout, LAYOUT, SIDE_LEFT><<<(unsigned)bx, 128, smem, st>>>(
           (const Tout*)gout, view_of(left), view_of(right), (Tin*)gl, g, cblocks, cbs);
       if (int rc = finish_launch(where)) return rc;
     }
     if (gr) {
-      const size_t smem = (size_t)(BW_DCH * (BW_TX + BW_DCH) + BW_CB * (BW_TX + BW_DCH)) * sizeof(float);
+      const size_t smem = (size_t)(BW_DCH * (BW_TX + BW_DCH + 4) + cbs * (BW_TX + BW_DCH)) * sizeof(float);
       auto k = corr_bwd_tiled_kernel<Tin, Tout, LAYOUT, SIDE_RIGHT>;
       if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       k<<<(unsigned)bx, 128, smem, st>>>((const Tout*)gout, view_of(left), view_of(right), (Tin*)gr, g, cblocks, cbs);

@@ -130,6 +130,76 @@ concat_bwd_kernel(const T* __restrict__ gout, T* __restrict__ gl, T* __restrict_
   gr[i] = from_f<T>(sr);
 }
 
+// Row-tiled adjoint: one CTA per (n, channel of the 2C, y) row of the volume, i.e. a contiguous W x D
+// matrix, streamed through shared memory TX pixels at a time with 4-byte LDGSTS (every load of the tile in
+// flight, fully coalesced) into rows of an ODD word pitch, so that both reductions
+//     left  half:  gL[x]  = sum_{d <= x}        M[x][d]        (row sums, masked like the forward fill)
+//     right half:  gR[x'] = sum_{d, x'+d < W}   M[x'+d][d]     (diagonal sums; the tile carries a D-1 pixel halo)
+// read shared memory conflict-free with one pixel per thread.  Sums run in ascending d (deterministic).
+// 16-bit volumes move as 32-bit words holding two disparities (D even).  (A variant with 16-byte copies,
+// a pitch of 4 (mod 8) words and LDS.128 row sums measured 20% slower on B200: the reductions, not the
+// copies, set the pace.)
+template <typename T>
+__device__ __forceinline__ float word_elem(uint32_t w, int d) {
+  if constexpr (sizeof(T) == 4) return __uint_as_float(w);
+  else {
+    const unsigned short h = (d & 1) ? (unsigned short)(w >> 16) : (unsigned short)(w & 0xffffu);
+    return to_f(*reinterpret_cast<const T*>(&h));
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+concat_bwd_row_kernel(const T* __restrict__ gout, T* __restrict__ gl, T* __restrict__ gr, int C, int H, int W,
+                      int D, int TX, int P) {
+  extern __shared__ __align__(16) uint32_t tile[];
+  constexpr int EPW = 4 / (int)sizeof(T);          // elements per 32-bit word
+  const int DW = D / EPW;                          // words per pixel
+  const int64_t row = blockIdx.x;
+  const int y = (int)(row % H);
+  const int ch = (int)((row / H) % (2 * C));
+  const int64_t n = row / ((int64_t)H * 2 * C);
+  const bool right = ch >= C;
+  const uint32_t* __restrict__ src = reinterpret_cast<const uint32_t*>(gout + row * (int64_t)W * D);
+  T* __restrict__ dst = (right ? gr : gl) + ((n * C + (right ? ch - C : ch)) * H + y) * (int64_t)W;
+  // word w of a tile -> pixel w / DW, word w % DW of it; a thread's words are kThreads apart, so both the
+  // shared-memory address and the wrap test advance by constants (no division in the loop)
+  const int stepk = kThreads % DW;
+  const uint32_t dstep = 4u * ((kThreads / DW) * P + stepk), wrapfix = 4u * (P - DW);
+  const int px0 = threadIdx.x / DW, kk0 = threadIdx.x - px0 * DW;
+  const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
+  for (int x0 = 0; x0 < W; x0 += TX) {
+    const int npx = min(TX + (right ? D - 1 : 0), W - x0);
+    __syncthreads();
+    {
+      int kk = kk0;
+      uint32_t sdst = tile_s + 4u * (px0 * P + kk0);
+      const uint32_t* g = src + (int64_t)x0 * DW + threadIdx.x;
+      const int nword = npx * DW;
+      for (int w = threadIdx.x; w < nword; w += kThreads) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst), "l"(g) : "memory");
+        g += kThreads; sdst += dstep; kk += stepk;
+        if (kk >= DW) { kk -= DW; sdst += wrapfix; }
+      }
+      asm volatile("cp.async.wait_all;" ::: "memory");
+    }
+    __syncthreads();
+    for (int xi = threadIdx.x; xi < min(TX, W - x0); xi += kThreads) {
+      const int x = x0 + xi;
+      float acc = 0.f;
+      const uint32_t* r = tile + xi * P;
+      if (!right) {
+        const int nd = min(x, D - 1) + 1;
+        for (int d = 0; d < nd; ++d) acc += word_elem<T>(r[d / EPW], d);
+      } else {
+        const int nd = min(D, W - x);
+        for (int d = 0; d < nd; ++d) acc += word_elem<T>(r[d * P + d / EPW], d);
+      }
+      dst[x] = from_f<T>(acc);
+    }
+  }
+}
+
 // ============================================================================= interweave
 template <typename T, int VEC>
 __global__ void __launch_bounds__(kThreads)
@@ -287,6 +357,25 @@ extern "C" int rsm_concat_bwd(const void* gout, void* gleft, void* gright, int64
   RSM_COMMON_CHECKS(dtype)
   if (!grid_ok(ceil_div(total, kThreads))) return RSM_ERR_INVALID_SHAPE;
   return RSM_DISPATCH_DTYPE(dtype, T, [&]() -> int {
+    // row-tiled kernel: whole words per pixel, word-aligned rows, at most 1024 disparities; RSM_BWD_NAIVE=1
+    // keeps the per-element gather (A/B runs)
+    constexpr int EPW = 4 / (int)sizeof(T);
+    const char* naive = getenv("RSM_BWD_NAIVE");
+    if (D > 0 && D <= 1024 && D % EPW == 0 && aligned_to(gout, 4) && grid_ok(N * 2 * C * H) && !(naive && naive[0] == '1')) {
+      const int DW = (int)D / EPW;
+      const int P = DW | 1;                                          // odd word pitch
+      int64_t tx = (96 * 1024) / (4 * (int64_t)P) - (D - 1);         // pixels per tile within 96 KB, halo included
+      tx = tx < 32 ? 32 : tx;
+      if (tx > W) tx = W;
+      const size_t smem = (size_t)(tx + D - 1) * P * 4;
+      if (smem <= 200 * 1024) {
+        auto k = concat_bwd_row_kernel<T>;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k<<<(unsigned)(N * 2 * C * H), kThreads, smem, st>>>((const T*)gout, (T*)gleft, (T*)gright, (int)C, (int)H,
+                                                             (int)W, (int)D, (int)tx, P);
+        return finish_launch("rsm_concat_bwd");
+      }
+    }
     concat_bwd_kernel<T><<<(unsigned)ceil_div(total, kThreads), kThreads, 0, st>>>(
         (const T*)gout, (T*)gleft, (T*)gright, total, (int)C, (int)H, (int)W, (int)D);
     return finish_launch("rsm_concat_bwd");

@@ -505,6 +505,37 @@ static int launch_bwd(const void* gout, const rsm_feat& left, const rsm_feat& ri
   for (int c = BW_CB; c >= 4; c -= 4)
     if (g.cpg % c == 0) { cbs = c; break; }
   const char* naive = getenv("RSM_BWD_NAIVE");
+  // narrow groups of a D-innermost volume: one CTA per (n, group, y) row stages the gradient row once and
+  // produces both gradients from it (groupwise_bwd_row_kernel)
+  if (LAYOUT == LAYOUT_NGHWD && (g.cpg == 4 || g.cpg == 8) && g.D > 0 && gl && gr && !(naive && naive[0] == '1')) {
+    GroupRowGeom rg;
+    rg.nq = (g.D + 3) / 4;
+    const int D4 = 4 * rg.nq;
+    // parts of <= 160 pixels (one register tile per thread), balanced over the row
+    rg.nparts = (g.W + 159) / 160;
+    rg.XP = ((g.W + rg.nparts - 1) / rg.nparts + 3) / 4 * 4;
+    rg.nparts = (g.W + rg.XP - 1) / rg.XP;
+    int P = rg.XP + D4 + 8;
+    if (P % 8 == 0) P += 4;
+    rg.P = P;
+    rg.DPAD = D4 + 4;
+    rg.FP = rg.DPAD + rg.XP + D4 + 8;
+    const int xqn = rg.XP / 4;
+    rg.dsplit = GR_THREADS / (2 * xqn);
+    if (rg.dsplit > rg.nq) rg.dsplit = rg.nq;
+    if (rg.dsplit < 1) rg.dsplit = 1;
+    const size_t tile = (size_t)D4 * rg.P, parts = (size_t)2 * g.cpg * rg.dsplit * rg.XP;
+    const size_t smem = ((tile > parts ? tile : parts) + 2 * (size_t)g.cpg * rg.FP) * sizeof(float);
+    const int64_t bx = N * g.G * (int64_t)g.H * rg.nparts;
+    if (smem <= 100 * 1024 && 2 * xqn * rg.dsplit <= GR_THREADS && grid_ok(bx)) {
+      auto launch = [&](auto kern) -> int {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<(unsigned)bx, GR_THREADS, smem, st>>>((const Tout*)gout, view_of(left), view_of(right), (Tin*)gl, (Tin*)gr, g, rg);
+        return finish_launch(where);
+      };
+      return g.cpg == 4 ? launch(groupwise_bwd_row_kernel<Tin, Tout, 4>) : launch(groupwise_bwd_row_kernel<Tin, Tout, 8>);
+    }
+  }
   if (cbs > 0 && g.D > 0 && !(naive && naive[0] == '1')) {
     const int cblocks = g.C / cbs;
     const int64_t bx = N * g.H * (int64_t)cblocks * g.xtiles;

@@ -501,3 +501,27 @@ def test_v4_tail_all_x4_stabiliser(rsm, scale, monkeypatch):
     fine = torch.nn.functional.interpolate(c.unsqueeze(1), [d, h, w], mode="trilinear").squeeze(1)
     assert (amax != fine.argmax(1)).float().mean() < 1e-3
     assert (amin != fine.argmin(1)).float().mean() < 1e-3
+
+
+@pytest.mark.parametrize("shape", [(1, 32, 3, 330, 40, 4), (2, 16, 2, 50, 24, 2), (1, 8, 2, 161, 33, 2), (1, 24, 2, 312, 48, 6)])
+@pytest.mark.parametrize("dn", ["fp32", "bf16"])
+def test_groupwise_bwd_row_parts(rsm, shape, dn, monkeypatch):
+    """Narrow groups (4 or 8 channels) take the row-part adjoint kernel: several parts per row, ragged
+    last part, D not a multiple of 8, 8-channel groups, 16-bit tensors -- against the oracle and against
+    the per-element gather kernel (RSM_BWD_NAIVE=1)."""
+    n, c, h, w, d, ng = shape
+    rng = np.random.default_rng(71)
+    l = round_to(rng.standard_normal((n, c, h, w)).astype(np.float32), dn)
+    r = round_to(rng.standard_normal((n, c, h, w)).astype(np.float32), dn)
+    gout = round_to(rng.standard_normal((n, ng, h, w, d)).astype(np.float32), dn)
+    gl, gr = oracle.groupwise_volume_bwd(gout, l, r, ng)
+    res = []
+    for naive in ("0", "1"):
+        monkeypatch.setenv("RSM_BWD_NAIVE", naive)
+        L, R = dev(l, dn, grad=True), dev(r, dn, grad=True)
+        rsm.groupwise_volume(L, R, ng, d).backward(dev(gout, dn))
+        res.append((L.grad, R.grad))
+    atol = GRAD_RTOL * np.sqrt(d) * 16 if dn == "fp32" else RTOL_16[dn] * np.sqrt(d) * 4
+    for a, b in res:
+        close(a, gl, atol)
+        close(b, gr, atol)

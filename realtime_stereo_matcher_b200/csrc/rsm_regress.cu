@@ -155,8 +155,28 @@ regress_bwd_kernel(const T* __restrict__ gout, const T* __restrict__ cost, const
   }
   const T* __restrict__ cb = cost + n * D * HW + p;
   T* __restrict__ gb = gcost + n * D * HW + p;
+  int d = 0;
+  if constexpr (VEC * sizeof(T) == 16) {
+    // eight independent 128-bit loads in flight per thread, like the forward pass
+    constexpr int U = 8;
+    for (; d + U <= D; d += U) {
+      Vec16<T> t[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) t[u] = ldcs16(cb + (int64_t)(d + u) * HW);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        Vec16<T> r;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          const float pr = fast_exp2(fmaf(to_f(t[u].v[j]), kLog2e, -l2[j]));
+          r.v[j] = from_f<T>(g[j] * pr * ((float)(d + u) - e[j]));
+        }
+        stcs16(gb + (int64_t)(d + u) * HW, r);
+      }
+    }
+  }
 #pragma unroll 4
-  for (int d = 0; d < D; ++d) {
+  for (; d < D; ++d) {
     if constexpr (VEC * sizeof(T) == 16) {
       Vec16<T> t = ldcs16(cb + (int64_t)d * HW), r;
 #pragma unroll

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RSM_VERSION 100 /* major*10000 + minor*100 + patch */
+#define RSM_VERSION 101 /* major*10000 + minor*100 + patch */
 
 typedef enum rsm_dtype {
   RSM_F32 = 0,
@@ -125,6 +125,19 @@ int rsm_shift_interweave_fwd(rsm_feat left, rsm_feat right, void* out, int64_t N
 /* gleft[n,c,y,x] = sum_{d<=x} gout[d,n,2c,y,x];  gright[n,c,y,x'] = sum_{d, x'+d<W} gout[d,n,2c+1,y,x'+d] */
 int rsm_shift_interweave_bwd(const void* gout, void* gleft, void* gright, int64_t N, int64_t C,
                              int64_t H, int64_t W, int64_t D, int dtype, int device, void* stream);
+
+/* ---- refinement warp: warp_by_flow_map, model/mobile_stereo_net_v2.py:59-96
+ * (= model/mobile_stereo_net_v3.py:60-97, tools/warp.py:5-42; call sites v2 :127, v3 :136).
+ * image (N,C,H,W), flow (N,flow_channels,H,W) with flow_channels 1 or 2, all dense, same dtype.
+ * out[n,c,y,x] = bilinear sample (zero padding) of image[n,c] at ix = (x - flow[n,0,y,x]) * W/(W-1) - 0.5,
+ * iy = (y - flow[n,1,y,x]) * H/(H-1) - 0.5 (flow[n,1] = 0 for one channel) -- the coordinates
+ * F.grid_sample(align_corners=False) sees after the reference's (size-1) normalisation */
+int rsm_warp_fwd(const void* image, const void* flow, void* out, int64_t N, int64_t C, int64_t H, int64_t W,
+                 int flow_channels, int dtype, int device, void* stream);
+/* adjoint: gimage (N,C,H,W) is ALWAYS fp32 (cleared and accumulated with atomics inside the call, like
+ * ATen's grid_sampler backward); gflow (N,flow_channels,H,W) in `dtype`, may be NULL */
+int rsm_warp_bwd(const void* gout, const void* image, const void* flow, float* gimage, void* gflow, int64_t N,
+                 int64_t C, int64_t H, int64_t W, int flow_channels, int dtype, int device, void* stream);
 
 /* ---- disparity regression over a dense (N,D,H,W) cost: softmax(+cost) expectation
  * (model/mobile_stereo_net.py:144-147, mobile_stereo_net_v4.py:10-14 + :517,

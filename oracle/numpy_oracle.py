@@ -18,6 +18,7 @@ from __future__ import annotations
 import numpy as np
 
 __all__ = [
+    "warp_by_flow_map", "warp_by_flow_map_bwd",
     "concat_volume", "concat_volume_bwd",
     "interweave", "interweave_bwd",
     "inner_product_volume", "inner_product_volume_bwd",
@@ -349,3 +350,80 @@ def inner_product_soft_argmax(left, right, max_disparity, mean=False, acc_dtype=
     soft_argmax and hard_argmax/argmin on the fp32 volume (never rounded to the input dtype)."""
     vol = inner_product_volume(left, right, max_disparity, mean, acc_dtype, out_dtype=acc_dtype)
     return soft_argmax(vol, acc_dtype), hard_argmin(vol), hard_argmax(vol)
+
+
+# ------------------------------------------------------------------ refinement warp (SURVEY 8f-2)
+def _warp_source_index(flow, h, w):
+    """fp32 source coordinates exactly as the reference builds them: grid = index - flow, normalised with
+    (size - 1) (model/mobile_stereo_net_v2.py:82-91) but sampled by F.grid_sample(align_corners=False)
+    (:93-95), whose un-normalisation is ((g + 1) * size - 1) / 2 -- so ix = (x - f) * W / (W - 1) - 0.5 and,
+    even for a 1-channel flow, iy = y * H / (H - 1) - 0.5 is NOT an integer row (the reference's quirk, kept)."""
+    f = np.asarray(flow, dtype=np.float32)
+    n = f.shape[0]
+    one, two = np.float32(1), np.float32(2)
+    gx = np.arange(w, dtype=np.float32)[None, None, :] - f[:, 0]
+    gy = (np.arange(h, dtype=np.float32)[None, :, None] - f[:, 1]) if f.shape[1] == 2 else \
+        np.broadcast_to(np.arange(h, dtype=np.float32)[None, :, None], (n, h, w)).astype(np.float32)
+    gxn = two * gx / np.float32(w - 1.0) - one
+    gyn = two * gy / np.float32(h - 1.0) - one
+    ix = ((gxn + one) * np.float32(w) - one) / two
+    iy = ((gyn + one) * np.float32(h) - one) / two
+    return ix.astype(np.float32), iy.astype(np.float32)
+
+
+def _warp_taps(ix, iy, h, w):
+    """the four bilinear taps of grid_sample(padding_mode='zeros'): (yi, xi, weight, inside) per corner"""
+    x0 = np.floor(ix); y0 = np.floor(iy)
+    taps = []
+    for dy in (0, 1):
+        for dx in (0, 1):
+            xi = x0 + dx; yi = y0 + dy
+            wx = (x0 + 1 - ix) if dx == 0 else (ix - x0)
+            wy = (y0 + 1 - iy) if dy == 0 else (iy - y0)
+            inside = (xi >= 0) & (xi <= w - 1) & (yi >= 0) & (yi <= h - 1)
+            taps.append((np.clip(yi, 0, h - 1).astype(np.int64), np.clip(xi, 0, w - 1).astype(np.int64),
+                         (wx * wy).astype(np.float32), inside, dx, dy, wx.astype(np.float32), wy.astype(np.float32)))
+    return taps
+
+
+def warp_by_flow_map(image, flow):
+    """(N,C,H,W), (N,1|2,H,W) -> (N,C,H,W): warp_by_flow_map, model/mobile_stereo_net_v2.py:59-96
+    (= model/mobile_stereo_net_v3.py:60-97, tools/warp.py:5-42)."""
+    img = np.asarray(image)
+    n, c, h, w = img.shape
+    cf = flow.shape[1]
+    assert cf == 1 or cf == 2, f"invalid flow map dimension 1 or 2 ({cf})!"
+    ix, iy = _warp_source_index(flow, h, w)
+    out = np.zeros((n, c, h, w), dtype=np.float32)
+    bi = np.arange(n)[:, None, None]
+    for yi, xi, wt, inside, *_ in _warp_taps(ix, iy, h, w):
+        v = img[bi, :, yi, xi].astype(np.float32)              # (N,H,W,C)
+        out += np.moveaxis(v * (wt * inside)[..., None], -1, 1)
+    return out.astype(img.dtype)
+
+
+def warp_by_flow_map_bwd(gout, image, flow):
+    """adjoint of :func:`warp_by_flow_map`: (gimage, gflow).  d ix / d f0 = -W / (W - 1), d iy / d f1 = -H / (H - 1)."""
+    img = np.asarray(image, dtype=np.float32)
+    g = np.asarray(gout, dtype=np.float32)
+    n, c, h, w = img.shape
+    cf = flow.shape[1]
+    ix, iy = _warp_source_index(flow, h, w)
+    gimg = np.zeros((n, c, h, w), dtype=np.float64)
+    gix = np.zeros((n, h, w), dtype=np.float64)
+    giy = np.zeros((n, h, w), dtype=np.float64)
+    bi = np.broadcast_to(np.arange(n)[:, None, None], (n, h, w))
+    for yi, xi, wt, inside, dx, dy, wx, wy in _warp_taps(ix, iy, h, w):
+        wgt = (wt * inside).astype(np.float64)
+        for ch in range(c):
+            np.add.at(gimg[:, ch], (bi, yi, xi), g[:, ch] * wgt)
+        v = np.moveaxis(img[bi, :, yi, xi], -1, 1) * inside[:, None]          # (N,C,H,W), zero outside
+        sx = 1.0 if dx == 1 else -1.0
+        sy = 1.0 if dy == 1 else -1.0
+        gix += (g * v).sum(1) * sx * wy
+        giy += (g * v).sum(1) * sy * wx
+    gflow = np.zeros(flow.shape, dtype=np.float64)
+    gflow[:, 0] = -gix * (w / (w - 1.0))
+    if cf == 2:
+        gflow[:, 1] = -giy * (h / (h - 1.0))
+    return gimg.astype(np.asarray(image).dtype), gflow.astype(np.asarray(flow).dtype)

@@ -243,6 +243,50 @@ def shift_interweave_volume(left, right, max_disparity):
     return _ShiftInterweave.apply(left, right, max_disparity)
 
 
+# ----------------------------------------------------------------------- refinement warp
+class _Warp(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda")
+    def forward(ctx, image, flow):
+        if image.dim() != 4 or flow.dim() != 4:
+            raise ValueError(f"expected (N,C,H,W) image and (N,1|2,H,W) flow, got {tuple(image.shape)} and {tuple(flow.shape)}")
+        n, c, h, w = image.shape
+        cf = flow.shape[1]
+        if (flow.shape[0], flow.shape[2], flow.shape[3]) != (n, h, w):
+            raise RuntimeError(f"image {tuple(image.shape)} and flow {tuple(flow.shape)} shapes differ")
+        if image.dtype != flow.dtype:
+            raise TypeError(f"image ({image.dtype}) and flow ({flow.dtype}) dtypes differ")
+        dev = L.require_cuda(image, flow)
+        image, flow = _dense(image), _dense(flow)
+        out = torch.empty_like(image)
+        L.check(L.load().rsm_warp_fwd(image.data_ptr(), flow.data_ptr(), out.data_ptr(), n, c, h, w, cf,
+                                      L.dtype_code(image), dev, L.stream_ptr(dev)), "rsm_warp_fwd")
+        ctx.save_for_backward(image, flow)
+        ctx.dims = (dev, n, c, h, w, cf)
+        return out
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, gout):
+        image, flow = ctx.saved_tensors
+        dev, n, c, h, w, cf = ctx.dims
+        gout = _dense(gout)
+        gimage = torch.empty((n, c, h, w), dtype=torch.float32, device=image.device)   # fp32 atomics accumulate here
+        gflow = torch.empty_like(flow) if ctx.needs_input_grad[1] else None
+        L.check(L.load().rsm_warp_bwd(gout.data_ptr(), image.data_ptr(), flow.data_ptr(), gimage.data_ptr(), L.ptr(gflow),
+                                      n, c, h, w, cf, L.dtype_code(image), dev, L.stream_ptr(dev)), "rsm_warp_bwd")
+        return gimage.to(image.dtype), gflow
+
+
+def warp_by_flow_map(image, flow):
+    """warp_by_flow_map, model/mobile_stereo_net_v2.py:59-96 (= v3 :60-97, tools/warp.py:5-42): bilinear,
+    zero-padded sample of ``image`` (N,C,H,W) at the pixel grid minus ``flow`` (N,1|2,H,W), with the reference's
+    own coordinate convention ((size-1) normalisation seen by grid_sample(align_corners=False))."""
+    cf = flow.shape[1] if flow.dim() == 4 else -1
+    assert cf == 1 or cf == 2, f"invalid flow map dimension 1 or 2 ({cf})!"
+    return _Warp.apply(image, flow)
+
+
 # ---------------------------------------------------------------------------- regression
 def _regress_outputs(shape, dtype, device, soft, argmin, argmax, lse):
     n, h, w = shape

@@ -31,6 +31,12 @@ def shift_interweave_stack(refimg_fea, targetimg_fea, volume_size):
     return F_rsm.shift_interweave_volume(refimg_fea, targetimg_fea, volume_size)
 
 
+def warp_by_flow_map(image, flow):
+    """model/mobile_stereo_net_v2.py:59-96 (= mobile_stereo_net_v3.py:60-97, tools/warp.py:5-42): the
+    refinement warp of RefineNet (call sites v2 :127, v3 :136); same AssertionError on a bad flow shape."""
+    return F_rsm.warp_by_flow_map(image, flow)
+
+
 def disparity_regression_v4(x, maxdisp):
     """model/mobile_stereo_net_v4.py:10-14: x holds PROBABILITIES (already softmax-ed);
     returns sum_d d * x[:, d] as (N,H,W)."""

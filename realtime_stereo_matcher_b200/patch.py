@@ -163,6 +163,9 @@ def patch_reference(fuse: bool = True, model_package: str = "model", cost_volume
     _set(m4, "disparity_regression", mf.disparity_regression_v4)
     done["functions"] += [f"{mc.__name__}.make_correlation_volume", f"{mc.__name__}.disparity_regression",
                           f"{m4.__name__}.interweave_tensors", f"{m4.__name__}.disparity_regression"]
+    for m in (m2, m3):   # refinement warp
+        _set(m, "warp_by_flow_map", mf.warp_by_flow_map)
+        done["functions"].append(f"{m.__name__}.warp_by_flow_map")
     try:
         for sub, cls in (("concatenate", "TorchConcatenateCost"), ("interweave", "TorchInterweaveCost"),
                          ("inner_product", "TorchInnerProductCost"), ("groupwise", "TorchGroupwiseCost")):

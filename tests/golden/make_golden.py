@@ -35,6 +35,8 @@ from cost_volume.interweave import TorchInterweaveCost  # noqa: E402
 import model as ref_model  # noqa: E402
 import model.mobile_disp_net_c as ref_dispc  # noqa: E402
 import model.mobile_stereo_net as ref_v1  # noqa: E402
+import model.mobile_stereo_net_v2 as ref_v2  # noqa: E402
+import model.mobile_stereo_net_v3 as ref_v3  # noqa: E402
 import model.mobile_stereo_net_v4 as ref_v4  # noqa: E402
 
 DT = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}
@@ -239,12 +241,31 @@ def model_callsite_goldens():
          cost3=npy(cls3[0]), final=npy(outs[-1]), **arrays)
 
 
+def warp_goldens():
+    """warp_by_flow_map (refinement warp): v2 / v3 / tools copies are the same function; the
+    flow fields push samples out of the image on both sides; 1- and 2-channel flows."""
+    g = torch.Generator().manual_seed(4321)
+    for tag, n, c, h, w, cf in (("base", 2, 3, 6, 20, 1), ("two", 1, 4, 5, 9, 2), ("feat", 1, 8, 12, 40, 1)):
+        image = torch.randn((n, c, h, w), generator=g).requires_grad_(True)
+        flow = (torch.randn((n, cf, h, w), generator=g) * 3.0 + 2.0).requires_grad_(True)
+        out = ref_v2.warp_by_flow_map(image, flow)
+        assert torch.equal(out, ref_v3.warp_by_flow_map(image, flow))
+        gout = torch.randn(out.shape, generator=g)
+        out.backward(gout)
+        save(f"warp_{tag}", dict(tag=tag, N=n, C=c, H=h, W=w, CF=cf), image=npy(image), flow=npy(flow), out=npy(out),
+             gout=npy(gout), gimage=npy(image.grad), gflow=npy(flow.grad))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
+    if "--only-warp" in sys.argv:
+        warp_goldens()
+        sys.exit(0)
     volume_goldens()
     noncontig_golden()
     regression_goldens()
     tail_goldens()
     model_callsite_goldens()
+    warp_goldens()
     total = sum(os.path.getsize(os.path.join(HERE, f)) for f in os.listdir(HERE) if f.endswith(".npz"))
     print(f"total fixture bytes: {total}")

@@ -149,3 +149,21 @@ def test_v4_head_entry_points_stay_in_bounds(L, geom):
     L.check(lib.rsm_upsample_regress_bwd(gout.data_ptr(), cost.data_ptr(), so.ptr(), ls.ptr(), gc.ptr(), work.ptr(),
                                          b, dc, hc, wc, d, h, w, 0, 0, st), "tail_bwd")
     work.check("rsm_upsample_regress_bwd workspace"), gc.check("rsm_upsample_regress_bwd gcost")
+
+
+@pytest.mark.parametrize("shape", [(2, 5, 7, 33, 1), (1, 3, 4, 9, 2), (1, 1, 2, 2, 1)])
+@pytest.mark.parametrize("dt", DTYPES)
+def test_warp_entry_points_stay_in_bounds(L, shape, dt):
+    n, c, h, w, cf = shape
+    tdt, code = dt
+    lib = L.load()
+    st = L.stream_ptr(0)
+    image = torch.randn((n, c, h, w), device="cuda").to(tdt)
+    flow = (torch.randn((n, cf, h, w), device="cuda") * 5).to(tdt)       # many samples leave the image
+    out = Guarded(n * c * h * w, tdt)
+    L.check(lib.rsm_warp_fwd(image.data_ptr(), flow.data_ptr(), out.ptr(), n, c, h, w, cf, code, 0, st), "warp")
+    out.check("rsm_warp_fwd")
+    gimage, gflow = Guarded(n * c * h * w, torch.float32), Guarded(n * cf * h * w, tdt)
+    L.check(lib.rsm_warp_bwd(out.ptr(), image.data_ptr(), flow.data_ptr(), gimage.ptr(), gflow.ptr(), n, c, h, w, cf,
+                             code, 0, st), "warp_bwd")
+    gimage.check("rsm_warp_bwd gimage"), gflow.check("rsm_warp_bwd gflow")

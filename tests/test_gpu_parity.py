@@ -525,3 +525,56 @@ def test_groupwise_bwd_row_parts(rsm, shape, dn, monkeypatch):
     for a, b in res:
         close(a, gl, atol)
         close(b, gr, atol)
+
+
+# ------------------------------------------------------------ refinement warp
+@pytest.mark.parametrize("name", names("warp_"))
+def test_warp_goldens(rsm, name):
+    """warp_by_flow_map against the reference's own outputs and autograd gradients."""
+    g, m = load(name)
+    image, flow = dev(g["image"], grad=True), dev(g["flow"], grad=True)
+    out = rsm.warp_by_flow_map(image, flow)
+    close(out, g["out"], 2e-5)
+    out.backward(dev(g["gout"]))
+    close(image.grad, g["gimage"], 5e-5)
+    close(flow.grad, g["gflow"], 2e-4)
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 48, 156, 1), (1, 3, 96, 312, 1), (1, 5, 7, 33, 2)])
+@pytest.mark.parametrize("dn", ["fp32", "bf16", "fp16"])
+def test_warp_vs_oracle(rsm, shape, dn):
+    """RefineNet-sized warps (v3: 32-channel features at 1/8 -> 1/4 resolution; v2: RGB) against the oracle
+    and against F.grid_sample fed with the reference's grid on the device."""
+    n, c, h, w, cf = shape
+    rng = np.random.default_rng(81)
+    image = round_to(rng.standard_normal((n, c, h, w)).astype(np.float32), dn)
+    flow = round_to((np.abs(rng.standard_normal((n, cf, h, w))) * 6).astype(np.float32), dn)
+    out = rsm.warp_by_flow_map(dev(image, dn), dev(flow, dn))
+    atol = 2e-5 if dn == "fp32" else RTOL_16[dn] * 4
+    close(out, oracle.warp_by_flow_map(image, flow), atol)
+    if dn == "fp32":
+        im, fl = dev(image, grad=True), dev(flow, grad=True)
+        gout = rng.standard_normal((n, c, h, w)).astype(np.float32)
+        rsm.warp_by_flow_map(im, fl).backward(dev(gout))
+        gi, gf = oracle.warp_by_flow_map_bwd(gout, image, flow)
+        close(im.grad, gi, 1e-4)
+        close(fl.grad, gf, 1e-4 * np.sqrt(c) * 8)
+        # the reference's own op sequence on the device
+        t_im, t_fl = dev(image), dev(flow)
+        gy, gx = torch.meshgrid(torch.arange(h, device="cuda", dtype=torch.float32),
+                                torch.arange(w, device="cuda", dtype=torch.float32), indexing="ij")
+        grid_x = (gx.view(1, 1, h, w) - t_fl[:, 0].view(n, 1, h, w)).permute(0, 2, 3, 1)
+        grid_y = (gy.view(1, 1, h, w) - t_fl[:, 1].view(n, 1, h, w)).permute(0, 2, 3, 1) if cf == 2 else \
+            gy.view(1, h, w, 1).repeat(n, 1, 1, 1)
+        grid = torch.cat((2.0 * grid_x / (w - 1.0) - 1.0, 2.0 * grid_y / (h - 1.0) - 1.0), dim=-1)
+        ref = torch.nn.functional.grid_sample(t_im, grid, mode="bilinear", padding_mode="zeros", align_corners=False)
+        # (ATen's CUDA kernel contracts the un-normalisation into FMAs: coordinates differ by an ulp at x ~ 150)
+        torch.testing.assert_close(out, ref, atol=2e-4, rtol=0)
+
+
+def test_warp_errors(rsm):
+    x = torch.zeros((1, 3, 4, 8), device="cuda")
+    with pytest.raises(AssertionError, match="invalid flow map dimension"):    # mobile_stereo_net_v2.py:72
+        rsm.warp_by_flow_map(x, torch.zeros((1, 3, 4, 8), device="cuda"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        rsm.warp_by_flow_map(x.cpu(), torch.zeros((1, 1, 4, 8)))

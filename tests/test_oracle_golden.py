@@ -122,3 +122,19 @@ def test_groupwise_assert():
     l = np.zeros((1, 6, 2, 3), np.float32)
     with pytest.raises(AssertionError):
         oracle.groupwise_volume(l, l, 4, 2)
+
+
+@pytest.mark.parametrize("name", names("warp_"))
+def test_warp_goldens(name):
+    """warp_by_flow_map, model/mobile_stereo_net_v2.py:59-96 (= v3 :60-97): output and autograd gradients of
+    the reference itself (1- and 2-channel flows, samples leaving the image on both sides)."""
+    g, m = load(name)
+    _close(oracle.warp_by_flow_map(g["image"], g["flow"]), g["out"], 2e-5)
+    gi, gf = oracle.warp_by_flow_map_bwd(g["gout"], g["image"], g["flow"])
+    _close(gi, g["gimage"], 2e-5)
+    _close(gf, g["gflow"], 1e-4)
+
+
+def test_warp_assert():
+    with pytest.raises(AssertionError, match="invalid flow map dimension"):
+        oracle.warp_by_flow_map(np.zeros((1, 2, 3, 4), np.float32), np.zeros((1, 3, 3, 4), np.float32))

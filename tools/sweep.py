@@ -148,6 +148,34 @@ def sweep_tail(cfg, b, dc, hc, wc, iters):
            nb + 2 * b * dc * h * w * 4)
 
 
+def sweep_warp(cfg, n, c, h, w, iters):
+    """refinement warp (8f-2) with a smooth disparity field (what RefineNet feeds it) and with white-noise flow"""
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    image = torch.randn((n, c, h, w), device="cuda", generator=g)
+    yy, xx = torch.meshgrid(torch.arange(h, device="cuda", dtype=torch.float32),
+                            torch.arange(w, device="cuda", dtype=torch.float32), indexing="ij")
+    smooth = (20 + 12 * torch.sin(xx / 37.0) * torch.cos(yy / 23.0)).expand(n, 1, h, w).contiguous()
+    noise = torch.rand((n, 1, h, w), device="cuda", generator=g) * 40
+    shp = dict(N=n, C=c, H=h, W=w)
+    nb = (2 * n * c * h * w + n * h * w) * 4
+    for tag, flow in (("smooth", smooth), ("noise", noise)):
+        with torch.no_grad():
+            report(cfg, f"warp_fwd({tag} flow)", "f32", shp, timed(lambda: rsm.warp_by_flow_map(image, flow), iters), nb)
+        im, fl = image.clone().requires_grad_(True), flow.clone().requires_grad_(True)
+        out = rsm.warp_by_flow_map(im, fl)
+        go = torch.randn_like(out)
+        report(cfg, f"warp_bwd({tag} flow)", "f32", shp,
+               timed(lambda: torch.autograd.grad(out, (im, fl), go, retain_graph=True), iters),
+               (4 * n * c * h * w + 2 * n * h * w) * 4)
+    def ref():
+        grid_x = (xx.view(1, 1, h, w) - smooth[:, 0].view(n, 1, h, w)).permute(0, 2, 3, 1)
+        grid_y = yy.view(1, h, w, 1).repeat(n, 1, 1, 1)
+        grid = torch.cat((2.0 * grid_x / (w - 1.0) - 1.0, 2.0 * grid_y / (h - 1.0) - 1.0), dim=-1)
+        return torch.nn.functional.grid_sample(image, grid, mode="bilinear", padding_mode="zeros", align_corners=False)
+    with torch.no_grad():
+        report(cfg, "warp_fwd_torch(reference op sequence on GPU, smooth flow)", "f32", shp, timed(ref, iters), nb)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=10)
@@ -164,6 +192,8 @@ def main():
     if want("cfg3"):
         sweep_volumes("cfg3", 8, 32, 96, 312, 48, 8, ["f32", "bf16"], a.iters, {"concat", "groupwise", "interweave", "bwd"})
         sweep_tail("cfg3", 8, 48, 96, 312, a.iters)
+        sweep_warp("cfg3", 8, 32, 96, 312, a.iters)      # v3 RefineNet: 32-channel features at 1/4 resolution
+        sweep_warp("cfg3", 8, 3, 192, 624, a.iters)      # v2 RefineNet: RGB at 1/2 resolution
         sweep_regress("cfg3", 8, 192, 384, 1248, ["f32"], a.iters)
     if want("cfg4"):
         for c, g, d in ((32, 8, 48), (64, 16, 96), (128, 32, 192)):

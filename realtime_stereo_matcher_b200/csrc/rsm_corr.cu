@@ -290,6 +290,109 @@ corr_fwd_kernel(FeatView L, FeatView R, Tout* __restrict__ out, CorrGeom g, int 
   }
 }
 
+// ============================================ inner product, fp32 features: 8(x) x 16(d) register tiles
+// The 4x8 tile above needs 4 LDS.128 per 32 FMA: with four warps issuing FMAs the shared-memory pipe (one
+// 128-byte wavefront per clock) saturates at about half the FMA rate.  For the (N,D,H,W) inner product on
+// fp32 features -- the reference's training dtype, too wide for one tensor-core pass -- this kernel doubles
+// the arithmetic per byte read from shared memory: CTA = 128 pixels x <= 64 disparities of one (n, y),
+// thread tile 8(x) x 16(d) = 128 accumulators fed by 2 + 6 LDS.128 per channel (16 FMA per LDS.128).
+// Threads of a warp read 32-byte segments 32 bytes apart; the 16-byte chunks of every staged row are
+// XOR-swizzled (chunk ^= (chunk >> 3) & 1) so that the two halves of a quarter-warp land in different banks.
+// Staging: 16-byte LDGSTS with zero-fill (rows and windows start on 16-byte boundaries: fast path only).
+// The disparity extent of a thread tile is a template parameter (8, 12 or 16) chosen so that 16 * ntd threads
+// fill whole warps for the usual D (48 = 4 x 12, 64 = 4 x 16, 24 = 2 x 12, 16 = 2 x 8).
+constexpr int BG_TX = 128, BG_XT = 8, BG_NTX = BG_TX / BG_XT, BG_CK = 32, BG_MAXNTD = 4;
+
+__device__ __forceinline__ int bg_swz(int chunk) { return chunk ^ ((chunk >> 3) & 1); }
+
+template <typename Tout, int BG_DT>
+__global__ void __launch_bounds__(BG_NTX * BG_MAXNTD)
+inner_fwd_big_kernel(FeatView L, FeatView R, Tout* __restrict__ out, CorrGeom g, int dchp, int xtiles, int vec8) {
+  extern __shared__ __align__(16) float smem[];
+  const int rw = BG_TX + dchp;                     // right window width (multiple of 16 floats)
+  float* sL = smem;                                // [BG_CK][BG_TX]
+  float* sR = smem + BG_CK * BG_TX;                // [BG_CK][rw]
+  int64_t bid = blockIdx.x;
+  const int xt = (int)(bid % xtiles); bid /= xtiles;
+  const int y = (int)(bid % g.H);
+  const int64_t n = bid / g.H;
+  const int x0 = xt * BG_TX, dc0 = blockIdx.y * dchp;
+  const int tx = threadIdx.x % BG_NTX, td = threadIdx.x / BG_NTX;
+  const int rbase = x0 - dc0 - dchp;               // first pixel of the right window
+  const int wchunk = (dchp + BG_XT * tx - BG_DT * td - BG_DT) >> 2;   // window chunk of this thread: w[k], k = DT + i - j
+  const float* __restrict__ pl = reinterpret_cast<const float*>(L.data) + n * L.sn + (int64_t)y * L.sh;
+  const float* __restrict__ pr = reinterpret_cast<const float*>(R.data) + n * R.sn + (int64_t)y * R.sh;
+
+  float acc[BG_XT][BG_DT];
+#pragma unroll
+  for (int i = 0; i < BG_XT; ++i)
+#pragma unroll
+    for (int j = 0; j < BG_DT; ++j) acc[i][j] = 0.f;
+
+  const int lch = BG_TX / 4, rch = rw / 4;          // chunks per row
+  for (int c0 = 0; c0 < g.C; c0 += BG_CK) {
+    const int nch = min(BG_CK, g.C - c0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < lch + rch; e += blockDim.x) {
+      const bool left = e < lch;
+      const int ch = left ? e : e - lch;
+      const int x = left ? x0 + 4 * ch : rbase + 4 * ch;
+      const bool valid = x >= 0 && x < g.W;          // W % 4 == 0 and x % 4 == 0: whole chunks
+      const float* src = valid ? (left ? pl : pr) + (int64_t)c0 * (left ? L.sc : R.sc) + x : pl;
+      const int64_t step = valid ? (left ? L.sc : R.sc) : 0;
+      const uint32_t sdst = (uint32_t)__cvta_generic_to_shared((left ? sL : sR) + 4 * bg_swz(ch));
+      const uint32_t pitch = (uint32_t)(left ? BG_TX : rw) * 4u;
+      const int nbytes = valid ? 16 : 0;
+      for (int c = 0; c < nch; ++c)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sdst + c * pitch), "l"(src + c * step), "r"(nbytes)
+                     : "memory");
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    const float* ql = sL;
+    const float* qr = sR;
+#pragma unroll 2
+    for (int c = 0; c < nch; ++c, ql += BG_TX, qr += rw) {
+      const float4 l0 = *reinterpret_cast<const float4*>(ql + 4 * bg_swz(2 * tx));
+      const float4 l1 = *reinterpret_cast<const float4*>(ql + 4 * bg_swz(2 * tx + 1));
+      constexpr int NW = (BG_DT + BG_XT) / 4;     // chunks covering k = 1 .. DT + 7
+      float w[4 * NW];
+#pragma unroll
+      for (int k = 0; k < NW; ++k) {
+        const float4 t = *reinterpret_cast<const float4*>(qr + 4 * bg_swz(wchunk + k));
+        w[4 * k] = t.x; w[4 * k + 1] = t.y; w[4 * k + 2] = t.z; w[4 * k + 3] = t.w;
+      }
+      const float l[BG_XT] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+#pragma unroll
+      for (int i = 0; i < BG_XT; ++i)
+#pragma unroll
+        for (int j = 0; j < BG_DT; ++j) acc[i][j] = fmaf(l[i], w[BG_DT + i - j], acc[i][j]);
+    }
+  }
+  // ---- scale, zero the x < d triangle, store: 8 consecutive pixels per disparity
+  const int xb = x0 + BG_XT * tx, db = dc0 + BG_DT * td;
+  if (xb >= g.W) return;
+  const float inv = 1.f / (float)g.cpg, cnt = (float)g.cpg;
+#pragma unroll
+  for (int j = 0; j < BG_DT; ++j) {
+    const int d = db + j;
+    if (d >= g.D) break;
+    float v[BG_XT];
+#pragma unroll
+    for (int i = 0; i < BG_XT; ++i) {
+      float a = acc[i][j];
+      if (g.mean) a = g.pow2 ? a * inv : a / cnt;
+      v[i] = xb + i < d ? 0.f : a;
+    }
+    Tout* p = out + (((int64_t)n * g.D + d) * g.H + y) * g.W + xb;
+    if (vec8) store8(p, v);
+    else {                                             // W % 4 == 0 and xb % 8 == 0: whole quads
+      store4(p, v);
+      if (xb + 4 < g.W) store4(p + 4, v + 4);
+    }
+  }
+}
+
 // ======================================================================= volume adjoint
 // One thread per (n,c,y,x); atomic-free gather over d (SURVEY.md 8a backward contracts):
 //   gL[c,x]  = s * sum_{d<=min(x,D-1)}       gV[g(c),d,x]    * R[c,x-d]
@@ -599,6 +702,43 @@ extern "C" int rsm_inner_fwd(rsm_feat left, rsm_feat right, void* out, int64_t N
   if (!(no_tc && no_tc[0] == '1')) {
     const int rc = launch_inner_tc(left, right, out, N, C, H, W, D, reduce == RSM_REDUCE_MEAN, in_dtype, out_dtype, st);
     if (rc != RSM_ERR_UNSUPPORTED_CONFIG) return rc;
+  }
+  // fp32 features: 8x16 register tiles when rows and windows start on 16-byte boundaries
+  // (RSM_INNER_SMALL_TILE=1 keeps the 4x8 kernel: A/B runs)
+  {
+    const char* small = getenv("RSM_INNER_SMALL_TILE");
+    auto v4 = [&](const rsm_feat& f) {
+      return f.stride_w == 1 && f.stride_n % 4 == 0 && f.stride_c % 4 == 0 && f.stride_h % 4 == 0 && aligned_to(f.data, 16);
+    };
+    if (in_dtype == RSM_F32 && out_dtype == RSM_F32 && C >= 16 && D >= 16 && W % 4 == 0 && v4(left) && v4(right) &&
+        aligned_to(out, 16) && !(small && small[0] == '1')) {
+      // (DT, ntd) with an even ntd (whole warps): the smallest chunk DT * ntd covering min(D, 64)
+      static const int kDT[5] = {8, 12, 8, 12, 16}, kNTD[5] = {2, 2, 4, 4, 4};   // chunks 16, 24, 32, 48, 64
+      int pick = 4;
+      for (int k = 0; k < 5; ++k)
+        if (kDT[k] * kNTD[k] >= (D < 64 ? D : 64)) { pick = k; break; }
+      // several chunks: prefer the split with the least padding (e.g. D = 96 -> 2 x 48, not 64 + 32 of 64)
+      if (D > 64) {
+        int64_t best = -1;
+        for (int k = 2; k < 5; ++k) {
+          const int64_t ch = kDT[k] * kNTD[k], padded = ceil_div(D, ch) * ch;
+          if (best < 0 || padded <= best) { best = padded; pick = k; }   // ties: the wider tile
+        }
+      }
+      const int dt = kDT[pick], dchp = dt * kNTD[pick];
+      const int xtiles = (int)ceil_div(W, BG_TX);
+      const int64_t bx = N * H * xtiles, by = ceil_div(D, dchp);
+      if (grid_ok(bx) && by <= 65535) {
+        const size_t smem = (size_t)BG_CK * (2 * BG_TX + dchp) * sizeof(float);
+        const int vec8 = W % 8 == 0 && aligned_to(out, 32);
+        const dim3 grid((unsigned)bx, (unsigned)by);
+        const unsigned nt = BG_NTX * kNTD[pick];
+        if (dt == 8) inner_fwd_big_kernel<float, 8><<<grid, nt, smem, st>>>(view_of(left), view_of(right), (float*)out, g, dchp, xtiles, vec8);
+        else if (dt == 12) inner_fwd_big_kernel<float, 12><<<grid, nt, smem, st>>>(view_of(left), view_of(right), (float*)out, g, dchp, xtiles, vec8);
+        else inner_fwd_big_kernel<float, 16><<<grid, nt, smem, st>>>(view_of(left), view_of(right), (float*)out, g, dchp, xtiles, vec8);
+        return finish_launch("rsm_inner_fwd(8xDT)");
+      }
+    }
   }
   return RSM_DISPATCH_IO(in_dtype, out_dtype, Tin, Tout, [&]() -> int {
     return launch_fwd<Tin, Tout, LAYOUT_NDHW>(left, right, out, N, g, st, "rsm_inner_fwd");

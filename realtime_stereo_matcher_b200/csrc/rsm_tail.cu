@@ -389,7 +389,7 @@ upsample_regress_fwd_kernel(const T* __restrict__ cost, T* __restrict__ soft, in
 //   p(d') = exp(f(d') - lse);  gf = g * p * (d' - E);  gc[i0] += (1-w) gf;  gc[i1] += w gf.
 // Deterministic (no atomics): intervals are visited in order, so slice k is complete once
 // interval k has been processed.
-template <typename T>
+template <typename T, bool ALL4>
 __global__ void __launch_bounds__(kNT)
 upsample_regress_bwd_cols_kernel(const T* __restrict__ gout, const T* __restrict__ cost,
                                  const T* __restrict__ soft, const float* __restrict__ lse,
@@ -400,7 +400,8 @@ upsample_regress_bwd_cols_kernel(const T* __restrict__ gout, const T* __restrict
   const int x = blockIdx.x * kTX + (threadIdx.x & (kTX - 1)), y = blockIdx.y * kTY + threadIdx.x / kTX;
   const int cy0 = lin_index(blockIdx.y * kTY, g.sh, g.Hc).i0;
   const int cx0 = lin_index(blockIdx.x * kTX, g.sw, g.Wc).i0;
-  stage_tile(cost + (int64_t)b * g.Dc * g.Hc * g.Wc, sm, g, cy0, cx0);
+  if constexpr (ALL4) stage_tile_all4(cost + (int64_t)b * g.Dc * g.Hc * g.Wc, sm, g, cy0, cx0);
+  else stage_tile(cost + (int64_t)b * g.Dc * g.Hc * g.Wc, sm, g, cy0, cx0);
   if (x >= g.W || y >= g.H) return;
 
   const SliceY sl(sm, g, y, cy0);
@@ -409,16 +410,16 @@ upsample_regress_bwd_cols_kernel(const T* __restrict__ gout, const T* __restrict
   const int64_t plane = (int64_t)g.H * g.W;
   float* __restrict__ col = wsp + (int64_t)b * g.Dc * plane + (int64_t)y * g.W + x;
 
-  float cs0 = fmaf(sl.get(0), kLog2e, -l2);
+  float cs0 = sl.template scaled<ALL4>(0, -l2);
   float acc0 = 0.f;   // gradient of slice k accumulated so far
-  if (g.fast4) {
+  if (ALL4 || g.fast4) {
     {
       const float p = fast_exp2(cs0);
       acc0 = go * p * ((0.f - E) + (1.f - E));
     }
     float base = 2.f;
     for (int k = 0; k + 1 < g.Dc; ++k) {
-      const float cs1 = fmaf(sl.get(k + 1), kLog2e, -l2);
+      const float cs1 = sl.template scaled<ALL4>(k + 1, -l2);
       const float dl = cs1 - cs0;
       float acc1 = 0.f;
 #pragma unroll
@@ -597,7 +598,7 @@ extern "C" int rsm_upsample_regress_bwd(const void* gout, const void* cost, cons
   if (B > 65535) return RSM_ERR_INVALID_SHAPE;
   RSM_COMMON_CHECKS(dtype)
   return RSM_DISPATCH_DTYPE(dtype, T, [&]() -> int {
-    auto k = upsample_regress_bwd_cols_kernel<T>;
+    auto k = g.all4 ? upsample_regress_bwd_cols_kernel<T, true> : upsample_regress_bwd_cols_kernel<T, false>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const dim3 grid((unsigned)ceil_div(W, kTX), (unsigned)ceil_div(H, kTY), (unsigned)B);
     if (grid.y > 65535) return (int)RSM_ERR_INVALID_SHAPE;

@@ -639,6 +639,36 @@ static int launch_bwd(const void* gout, const rsm_feat& left, const rsm_feat& ri
       return g.cpg == 4 ? launch(groupwise_bwd_row_kernel<Tin, Tout, 4>) : launch(groupwise_bwd_row_kernel<Tin, Tout, 8>);
     }
   }
+  // fp32 inner product: 8x8 register tiles when every row and window starts on a 16-byte boundary
+  // (RSM_BWD_SMALL_TILE=1 keeps the 4x4 kernel: A/B runs)
+  if constexpr (LAYOUT == LAYOUT_NDHW && sizeof(Tin) == 4 && sizeof(Tout) == 4) {
+    const char* small = getenv("RSM_BWD_SMALL_TILE");
+    auto v4 = [&](const rsm_feat& f) {
+      return f.stride_w == 1 && f.stride_n % 4 == 0 && f.stride_c % 4 == 0 && f.stride_h % 4 == 0 && aligned_to(f.data, 16);
+    };
+    if (g.G == 1 && g.C >= 16 && g.D > 0 && g.W % 4 == 0 && v4(left) && v4(right) && aligned_to(gout, 16) &&
+        (!gl || aligned_to(gl, 16)) && (!gr || aligned_to(gr, 16)) && !(naive && naive[0] == '1') &&
+        !(small && small[0] == '1')) {
+      const int xtiles = (int)ceil_div(g.W, BB_TX), cblocks = (int)ceil_div(g.C, BB_CB);
+      const int64_t bx = N * g.H * (int64_t)cblocks * xtiles;
+      if (grid_ok(bx)) {
+        const size_t smem = (size_t)(BB_DCH * BB_TX + BB_CB * BB_FW) * sizeof(float);
+        if (gl) {
+          auto k = inner_bwd_big_kernel<SIDE_LEFT>;
+          cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          k<<<(unsigned)bx, BB_THREADS, smem, st>>>((const float*)gout, view_of(left), view_of(right), (float*)gl, g, xtiles, cblocks);
+          if (int rc = finish_launch(where)) return rc;
+        }
+        if (gr) {
+          auto k = inner_bwd_big_kernel<SIDE_RIGHT>;
+          cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          k<<<(unsigned)bx, BB_THREADS, smem, st>>>((const float*)gout, view_of(left), view_of(right), (float*)gr, g, xtiles, cblocks);
+          if (int rc = finish_launch(where)) return rc;
+        }
+        return RSM_OK;
+      }
+    }
+  }
   if (cbs > 0 && g.D > 0 && !(naive && naive[0] == '1')) {
     const int cblocks = g.C / cbs;
     const int64_t bx = N * g.H * (int64_t)cblocks * g.xtiles;

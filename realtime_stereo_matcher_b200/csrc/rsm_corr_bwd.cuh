@@ -197,6 +197,130 @@ corr_bwd_tiled_kernel(const Tout* __restrict__ gout, FeatView L, FeatView R, Tin
   }
 }
 
+// ================================================== inner product (N,D,H,W), fp32: 8(x) x 8(c) tiles
+// Same contraction as corr_bwd_tiled_kernel with twice the arithmetic per shared-memory byte: CTA = 128
+// pixels x 32 channels of one (n, y), 64 threads, thread tile 8(x) x 8(c), disparities eight at a time:
+//     16 LDS.128 for the gradient block g[8 d][8 x] + 4 LDS.128 per channel for its 16-wide feature window
+//     -> 512 FMA per 48 LDS.128 (10.7 per load; the 4x4 tile gets 5.3).
+// For the right gradient the gradient tile is staged SKEWED, sG[d][x'] = gV[d][x' + d], which turns
+// gR[c,x'] = sum_d gV[d][x'+d] L[c][x'+d] into the same Toeplitz form as the left one (window ascending
+// instead of descending).  Rows are XOR-swizzled by 16-byte chunk (chunk ^= (chunk >> 3) & 1): lanes read
+// 32-byte segments 32 bytes apart.  Staging: 16-byte LDGSTS with zero-fill wherever the source is
+// chunk-aligned (everything except the skewed tile, which moves 4 bytes at a time).
+constexpr int BB_TX = 128, BB_CB = 32, BB_DCH = 64, BB_FW = BB_TX + BB_DCH, BB_THREADS = 64;
+
+__device__ __forceinline__ int bb_swz(int chunk) { return chunk ^ ((chunk >> 3) & 1); }
+
+template <int SIDE>
+__global__ void __launch_bounds__(BB_THREADS)
+inner_bwd_big_kernel(const float* __restrict__ gout, FeatView L, FeatView R, float* __restrict__ gdst, CorrGeom g,
+                     int xtiles, int cblocks) {
+  extern __shared__ __align__(16) float smem[];
+  float* sG = smem;                       // [BB_DCH][BB_TX]
+  float* sF = smem + BB_DCH * BB_TX;      // [BB_CB][BB_FW]
+  int64_t bid = blockIdx.x;
+  const int xt = (int)(bid % xtiles); bid /= xtiles;
+  const int cb = (int)(bid % cblocks); bid /= cblocks;
+  const int y = (int)(bid % g.H);
+  const int64_t n = bid / g.H;
+  const int x0 = xt * BB_TX, c0 = cb * BB_CB;
+  const int ncb = min(BB_CB, g.C - c0);
+  const int tx = threadIdx.x & 15, tc = threadIdx.x >> 4;
+  const float* __restrict__ gbase = gout + ((int64_t)n * g.D * g.H + y) * g.W;     // + d * H * W + x
+  const int64_t gsd = (int64_t)g.H * g.W;
+  const FeatView& F = SIDE == SIDE_LEFT ? R : L;
+  const float* __restrict__ pf = reinterpret_cast<const float*>(F.data) + n * F.sn + (int64_t)y * F.sh + (int64_t)c0 * F.sc;
+
+  float acc[8][8];   // [channel j][pixel i]
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[j][i] = 0.f;
+
+  for (int dc0 = 0; dc0 < g.D; dc0 += BB_DCH) {
+    __syncthreads();
+    // ---- gradient tile
+    if constexpr (SIDE == SIDE_LEFT) {
+      for (int e = threadIdx.x; e < BB_DCH * (BB_TX / 4); e += BB_THREADS) {
+        const int dl = e >> 5, ch = e & 31;
+        const int d = dc0 + dl, x = x0 + 4 * ch;
+        const bool valid = d < g.D && x < g.W;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(sG + dl * BB_TX + 4 * bb_swz(ch))),
+                     "l"(valid ? gbase + d * gsd + x : gbase), "r"(valid ? 16 : 0)
+                     : "memory");
+      }
+    } else {
+      for (int e = threadIdx.x; e < BB_DCH * BB_TX; e += BB_THREADS) {
+        const int dl = e >> 7, xx = e & 127;
+        const int d = dc0 + dl, x = x0 + xx + d;             // skew: column x' holds gV[d][x' + d]
+        const bool valid = d < g.D && x < g.W;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(sG + dl * BB_TX + 4 * bb_swz(xx >> 2) + (xx & 3))),
+                     "l"(valid ? gbase + d * gsd + x : gbase), "r"(valid ? 4 : 0)
+                     : "memory");
+      }
+    }
+    // ---- feature windows: left side R[c][x0 - dc0 - 64 + j], right side L[c][x0 + dc0 + j]
+    const int fx0 = SIDE == SIDE_LEFT ? x0 - dc0 - BB_DCH : x0 + dc0;
+    for (int e = threadIdx.x; e < (BB_FW / 4); e += BB_THREADS) {
+      const int x = fx0 + 4 * e;
+      const bool valid = x >= 0 && x < g.W;
+      const float* src = valid ? pf + x : pf;
+      const int64_t step = valid ? F.sc : 0;
+      const uint32_t sdst = (uint32_t)__cvta_generic_to_shared(sF + 4 * bb_swz(e));
+      for (int c = 0; c < ncb; ++c)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sdst + (uint32_t)(c * BB_FW * 4)), "l"(src + c * step),
+                     "r"(valid ? 16 : 0)
+                     : "memory");
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    if (8 * tc >= ncb) continue;
+    for (int d0 = 0; d0 < BB_DCH; d0 += 8) {
+      if (dc0 + d0 >= g.D) break;
+      float gq[8][8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const float* row = sG + (d0 + r) * BB_TX;
+        const float4 a = *reinterpret_cast<const float4*>(row + 4 * bb_swz(2 * tx));
+        const float4 b = *reinterpret_cast<const float4*>(row + 4 * bb_swz(2 * tx + 1));
+        gq[r][0] = a.x; gq[r][1] = a.y; gq[r][2] = a.z; gq[r][3] = a.w;
+        gq[r][4] = b.x; gq[r][5] = b.y; gq[r][6] = b.z; gq[r][7] = b.w;
+      }
+      // window chunk: left  w[k] = R[x + i - d], k = 8 + i - r  (window starts at 64 + 8 tx - d0 - 8)
+      //               right w[k] = L[x' + i + d], k = i + r      (window starts at 8 tx + d0)
+      const int wch = SIDE == SIDE_LEFT ? (BB_DCH + 8 * tx - d0 - 8) >> 2 : (8 * tx + d0) >> 2;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (8 * tc + j >= ncb) break;
+        const float* frow = sF + (8 * tc + j) * BB_FW;
+        float w[16];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float4 t = *reinterpret_cast<const float4*>(frow + 4 * bb_swz(wch + k));
+          w[4 * k] = t.x; w[4 * k + 1] = t.y; w[4 * k + 2] = t.z; w[4 * k + 3] = t.w;
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            acc[j][i] = fmaf(gq[r][i], SIDE == SIDE_LEFT ? w[8 + i - r] : w[i + r], acc[j][i]);
+      }
+    }
+  }
+  // ---- scale and store (x contiguous)
+  const float cnt = g.mean ? (float)g.cpg : 1.f;
+  const int xb = x0 + 8 * tx;
+  if (xb >= g.W) return;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (8 * tc + j >= ncb) break;
+    float* o = gdst + (((int64_t)n * g.C + c0 + 8 * tc + j) * g.H + y) * g.W + xb;
+    __stcs(reinterpret_cast<float4*>(o), make_float4(acc[j][0] / cnt, acc[j][1] / cnt, acc[j][2] / cnt, acc[j][3] / cnt));
+    if (xb + 4 < g.W)
+      __stcs(reinterpret_cast<float4*>(o + 4), make_float4(acc[j][4] / cnt, acc[j][5] / cnt, acc[j][6] / cnt, acc[j][7] / cnt));
+  }
+}
+
 // ===================================================================== group-wise rows (D innermost)
 // Adjoint of the (N,G,H,W,D) group-wise volume for narrow groups (cpg = 4 or 8 channels): one CTA per
 // (n, group, y) row PART of XP pixels.  The gradient of the part plus a D-pixel halo -- a contiguous

@@ -170,6 +170,7 @@ SHAPES = [  # N, C, H, W, D, G
     (1, 12, 5, 67, 19, 3),       # nothing divisible by 4
     (1, 20, 3, 130, 70, 5),      # D > 64: two disparity chunks
     (3, 5, 4, 9, 13, 5),         # D > W
+    (1, 40, 3, 132, 70, 5),      # 16-byte aligned rows, two disparity chunks, ragged channel block (8x8 / 8xDT tiles)
 ]
 
 

@@ -279,7 +279,7 @@ extern "C" int rsm_regress_fwd(const void* cost, int64_t N, int64_t D, int64_t H
       kern<<<blocks, 256, 0, st>>>((const T*)cost, (T*)out.soft, out.argmin, out.argmax, out.lse, pv, total, (int)D, HW);
     };
     if (vec) {
-      if (want_soft && want_arg) launch(regress_fwd_kernel<T, 4, 4, true, true>);
+      if (want_soft && want_arg) launch(regress_fwd_kernel<T, 4, 8, true, true>);
       else if (want_soft) launch(regress_fwd_kernel<T, 4, 8, true, false>);
       else launch(regress_fwd_kernel<T, 4, 8, false, true>);
     } else {

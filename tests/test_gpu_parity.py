@@ -579,3 +579,25 @@ def test_warp_errors(rsm):
         rsm.warp_by_flow_map(x, torch.zeros((1, 3, 4, 8), device="cuda"))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         rsm.warp_by_flow_map(x.cpu(), torch.zeros((1, 1, 4, 8)))
+
+
+def test_empty_and_degenerate_inputs(rsm):
+    """Empty batch / zero-width inputs and D = 0 go through every op without touching memory (SURVEY 8c:
+    'empty and ragged inputs'); shapes follow the reference's."""
+    z = torch.zeros((0, 8, 4, 16), device="cuda")
+    assert rsm.concat_volume(z, z, 3).shape == (0, 16, 4, 16, 3)
+    assert rsm.interweave(z, z).shape == (0, 16, 4, 16)
+    assert rsm.inner_product_volume(z, z, 3).shape == (0, 3, 4, 16)
+    assert rsm.groupwise_volume(z, z, 4, 3).shape == (0, 4, 4, 16, 3)
+    assert rsm.difference_volume(z, z, 3).shape == (0, 8, 3, 4, 16)
+    assert rsm.soft_argmax(torch.zeros((0, 5, 4, 16), device="cuda")).shape == (0, 4, 16)
+    assert rsm.upsample_regress(torch.zeros((0, 3, 2, 4), device="cuda"), 12, 8, 16).shape == (0, 8, 16)
+    assert rsm.warp_by_flow_map(z, torch.zeros((0, 1, 4, 16), device="cuda")).shape == (0, 8, 4, 16)
+    x = torch.randn((1, 8, 4, 16), device="cuda", requires_grad=True)
+    v = rsm.concat_volume(x, x, 0)                      # no disparities: empty last axis, gradient is zero
+    assert v.shape == (1, 16, 4, 16, 0)
+    v.sum().backward()
+    assert torch.equal(x.grad, torch.zeros_like(x))
+    w0 = torch.zeros((2, 8, 4, 0), device="cuda")       # zero-width feature maps
+    assert rsm.inner_product_volume(w0, w0, 3).shape == (2, 3, 4, 0)
+    assert rsm.difference_volume(w0, w0, 3).shape == (2, 8, 3, 4, 0)

@@ -15,7 +15,13 @@
 // pixel x0 + r sits at column j = r + DCH - dl: a diagonal band.
 //
 // Persistent, warp-specialised CTA (416 threads, one per SM); each CTA owns a contiguous range of tiles:
-//   warps 8-11 loaders: stage the operand slab (<= 64 channels) of a k-chunk into one of 2-4 shared-memory
+//   warp 8     TMA producer (16-bit features whose strides TMA accepts -- the normal case): ONE lane arms
+//              smem_full[s] with the stage's byte count and issues 5-6 cp.async.bulk.tensor box loads
+//              (64 pixels x <= 64 channels each, SWIZZLE_128B: exactly the MN-major UMMA atoms, out-of-range
+//              pixels zero-filled by the TMA unit); measured: the LSU path below tops out at ~2.9 TB/s of
+//              L2 -> shared traffic on B200 whatever its pipeline depth, the TMA path does not
+//   warps 8-11 loaders (fp32 / TMA-incompatible views): stage the operand slab (<= 64 channels) of a k-chunk
+//              into one of 2-4 shared-memory
 //              stages with 16-byte cp.async (features may be strided views; the right window is
 //              zero-filled on both sides by the same instruction), writing the canonical no-swizzle
 //              MN-major core-matrix layout directly:
@@ -31,6 +37,8 @@
 // Two TMEM accumulator buffers decouple the UMMAs of tile t+1 from the epilogue of tile t.
 // mbarriers: smem_full[s] (128 loader arrivals), smem_empty[s] (UMMA commit), tmem_full[b] (UMMA commit),
 // tmem_empty[b] (256 epilogue arrivals).  All waits are bounded (a protocol bug yields NaNs, not a hang).
+#include <cuda.h>   // CUtensorMap (types only; the encoder is looked up at run time, no libcuda link dependency)
+
 #include "rsm_common.cuh"
 
 namespace rsm {
@@ -57,6 +65,9 @@ struct TcGeom {
   int tmem_buf;   // TMEM columns per accumulator buffer (128 or 256)
   int stage_bytes;
   int d_fastest;  // tile order: disparity chunk fastest (fused regress keeps per-pixel state across chunks)
+  int tma;        // operands arrive by TMA (SWIZZLE_128B atoms) instead of the cp.async loaders (no-swizzle atoms)
+  int boxc;       // TMA: channels per box / per k-chunk (<= 64, multiple of 16)
+  int nbb;        // TMA: 64-pixel boxes of the right window = ceil(ncol / 64)
   int nstage;     // operand stages in use: the loaders run up to nstage-1 k-chunks ahead of the UMMAs
   int64_t rows;   // N * H
   int64_t tiles;  // rows * xtiles * dchunks
@@ -96,6 +107,16 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// ---- TMA: one box of a (W, H, C, N) tensor map -> shared memory, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap* map, uint32_t mbar, int x, int y, int c, int n) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_dst), "l"(map), "r"(mbar), "r"(x), "r"(y), "r"(c), "r"(n)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t mbar) {   // implies tcgen05.fence::before_thread_sync
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
@@ -290,8 +311,11 @@ __device__ __forceinline__ void TileCoord::advance(const TcGeom& g) {
 
 template <typename Tin, typename Tout, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, TcGeom g, int fast) {
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
+inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, TcGeom g, int fast,
+                const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUtensorMap tmR) {
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  // swizzled atoms (TMA destinations, UMMA descriptors with base_offset 0) need 1024-byte alignment: 1 KB of slack
+  unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   constexpr bool F32 = sizeof(Tin) == 4;
   constexpr int ES = (int)sizeof(Tin), EPC = 16 / ES;       // element bytes, elements per 16-byte chunk
   constexpr int KC = F32 ? TC_KC32 : TC_KC;                 // channels per stage
@@ -312,7 +336,7 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
   if (threadIdx.x == 0) {
     for (int i = 0; i < TC_NSTAGE; ++i) {
       mbar_init(smem_empty + 8 * i, 1);        // one UMMA commit
-      mbar_init(smem_full + 8 * i, 128);       // every loader thread, after its copies landed
+      mbar_init(smem_full + 8 * i, g.tma ? 1 : 128);   // TMA: the producer's expect_tx; else every loader thread
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tmem_full + 8 * i, 1);
@@ -324,7 +348,7 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
-  const int nk = (g.C + KC - 1) / KC;
+  const int nk = g.tma ? (g.C + g.boxc - 1) / g.boxc : (g.C + KC - 1) / KC;
   const int lo_off = KC * (TC_TM + g.ncol) * ES;            // fp32 only: hi -> lo distance inside a stage
   // contiguous tile range of this CTA (neighbouring x tiles share most of their right window in L2)
   int64_t per = (g.tiles + gridDim.x - 1) / gridDim.x;
@@ -359,6 +383,15 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
               umma_tf32(td, ahi, blo, idesc, 1u);
               umma_tf32(td, ahi, bhi, idesc, 1u);
             }
+          } else if (g.tma) {
+            // SWIZZLE_128B atoms as written by TMA: 8 channels x 64 pixels (1 KB); next 8 channels +1 KB (SBO),
+            // next 64 pixels one box further (LBO); a K = 16 UMMA advances two channel groups
+            const uint32_t boxb = (uint32_t)g.boxc * 128u, sBt = sA + 2 * boxb;
+            for (int ks = 0; ks < g.boxc / 16; ++ks) {
+              const uint64_t adesc = umma_desc(sA + ks * 2048, boxb, 1024, 2);
+              const uint64_t bdesc = umma_desc(sBt + ks * 2048, boxb, 1024, 2);
+              umma_f16(td, adesc, bdesc, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+            }
           } else {
             for (int ks = 0; ks < nch / 16; ++ks) {                       // K = 16 per UMMA: two K-groups
               const uint64_t adesc = umma_desc(sA + ks * 2 * lboA, lboA, sbo);
@@ -368,6 +401,28 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
           }
           umma_commit(smem_empty + 8 * s);                                // stage reusable once these complete
           if (kc == nk - 1) umma_commit(tmem_full + 8 * buf);             // accumulator ready for the epilogue
+        }
+      }
+    }
+  } else if (warp >= TC_EPI_WARPS && g.tma) {
+    // ============================================================================== TMA producer
+    if (warp == TC_EPI_WARPS && lane == 0) {
+      const uint32_t nst = (uint32_t)g.nstage;
+      const uint32_t boxb = (uint32_t)g.boxc * 128u, bytes = (2u + (uint32_t)g.nbb) * boxb;
+      uint32_t it = 0;
+      TileCoord tc = tile_coord(t_beg, g);
+      for (int64_t t = t_beg; t < t_end; ++t, tc.advance(g)) {
+        const int xr0 = tc.x0 - tc.dc0 - g.dch;
+        for (int kc = 0; kc < nk; ++kc, ++it) {
+          const uint32_t s = it % nst;
+          const uint32_t sA = smem_u32(stage0 + (size_t)s * g.stage_bytes), bar = smem_full + 8 * s;
+          mbar_wait(smem_empty + 8 * s, ((it / nst) & 1) ^ 1);       // UMMAs that read this stage have completed
+          mbar_expect_tx(bar, bytes);
+          const int c0 = kc * g.boxc;
+          tma_load_4d(sA, &tmL, bar, tc.x0, tc.y, c0, (int)tc.n);
+          tma_load_4d(sA + boxb, &tmL, bar, tc.x0 + 64, tc.y, c0, (int)tc.n);
+          for (int m = 0; m < g.nbb; ++m)
+            tma_load_4d(sA + (2 + m) * boxb, &tmR, bar, xr0 + 64 * m, tc.y, c0, (int)tc.n);
         }
       }
     }
@@ -589,21 +644,68 @@ static bool feat_vec16(const rsm_feat& f, int epc) {
   return f.stride_w == 1 && f.stride_n % epc == 0 && f.stride_c % epc == 0 && f.stride_h % epc == 0 && aligned_to(f.data, 16);
 }
 
+// ---- tensor maps: (W, H, C, N) view of a feature tensor, box = 64 pixels x 1 row x boxc channels, SWIZZLE_128B
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TmapEncodeFn tmap_encoder() {
+  static const TmapEncodeFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<TmapEncodeFn>(p);
+  }();
+  return fn;
+}
+static bool make_tmap(CUtensorMap* m, const rsm_feat& f, int fmt, const TcGeom& g, int64_t N) {
+  const TmapEncodeFn enc = tmap_encoder();
+  if (!enc || f.stride_w != 1 || !aligned_to(f.data, 16)) return false;
+  const int64_t st[3] = {f.stride_h * 2, f.stride_c * 2, f.stride_n * 2};      // bytes
+  const int64_t ext[3] = {g.H, g.C, N};
+  cuuint64_t gstr[3];
+  for (int i = 0; i < 3; ++i) {
+    int64_t v = st[i];
+    if (ext[i] == 1 && (v % 16 != 0 || v <= 0)) v = 16;                        // never stepped: any legal value
+    if (v <= 0 || v % 16 != 0 || v >= (1LL << 40)) return false;
+    gstr[i] = (cuuint64_t)v;
+  }
+  const cuuint64_t gdim[4] = {(cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.C, (cuuint64_t)N};
+  const cuuint32_t box[4] = {64, 1, (cuuint32_t)g.boxc, 1}, estr[4] = {1, 1, 1, 1};
+  return enc(m, fmt == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(f.data),
+             gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <typename Tin, typename Tout, int EPI>
 static int launch_tc(const rsm_feat& left, const rsm_feat& right, void* out, RegressPtrs rp, const TcGeom& g_in,
                      cudaStream_t st, const char* where) {
   TcGeom g = g_in;
   g.epi_bytes = 32 * TC_EPI_WARPS * g.pitch * 4 + (EPI == EPI_REGRESS ? 2 * 128 * 8 * 4 : 0);   // rows (+ partials)
+  // 16-bit operands by TMA when the views qualify (RSM_TC_TMA=0 keeps the cp.async loaders: A/B runs)
+  alignas(64) CUtensorMap tmL, tmR;
+  memset(&tmL, 0, sizeof(tmL)); memset(&tmR, 0, sizeof(tmR));
+  g.tma = 0; g.boxc = 0; g.nbb = 0;
+  if (sizeof(Tin) == 2) {
+    const char* e = getenv("RSM_TC_TMA");
+    g.boxc = g.C < TC_KC ? g.C : TC_KC;
+    g.nbb = (g.ncol + 63) / 64;
+    if (!(e && e[0] == '0') && make_tmap(&tmL, left, g.fmt, g, g.rows / g.H) && make_tmap(&tmR, right, g.fmt, g, g.rows / g.H)) {
+      g.tma = 1;
+      g.stage_bytes = (2 + g.nbb) * g.boxc * 128;
+    }
+  }
   g.nstage = TC_NSTAGE;
-  while (g.nstage > 2 && g.nstage * (size_t)g.stage_bytes + (size_t)g.epi_bytes + 160 > 220 * 1024) --g.nstage;
-  const size_t smem = g.nstage * (size_t)g.stage_bytes + (size_t)g.epi_bytes + 160;
+  while (g.nstage > 2 && g.nstage * (size_t)g.stage_bytes + (size_t)g.epi_bytes + 160 + 1024 > 220 * 1024) --g.nstage;
+  const size_t smem = g.nstage * (size_t)g.stage_bytes + (size_t)g.epi_bytes + 160 + 1024;
   auto k = inner_tc_kernel<Tin, Tout, EPI>;
   if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return finish_launch(where);
   const int epc = 16 / (int)sizeof(Tin);
   const int fast = feat_vec16(left, epc) && feat_vec16(right, epc);   // 16-byte chunks start at multiples of epc elements
   const unsigned grid = (unsigned)(g.tiles < kNumSMs ? g.tiles : kNumSMs);   // persistent: one CTA per SM
-  k<<<grid, TC_THREADS, smem, st>>>(view_of(left), view_of(right), (Tout*)out, rp, g, fast);
+  k<<<grid, TC_THREADS, smem, st>>>(view_of(left), view_of(right), (Tout*)out, rp, g, fast, tmL, tmR);
   return finish_launch(where);
 }
 

@@ -23,3 +23,12 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _deterministic_inputs():
+    """Every test starts from the same torch seed (CPU and CUDA generators): a failure must be reproducible."""
+    import torch
+
+    torch.manual_seed(1234)
+    yield

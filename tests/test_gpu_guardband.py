@@ -10,8 +10,15 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-SENT = -12345.5          # representable in fp32 / fp16 / bf16
+SENT = -61440.0          # exactly representable in fp32 / fp16 / bf16 and > 10 sigma away from anything an op
+                         # can legitimately produce here (a sentinel inside the output range makes 'never written'
+                         # fire at random: -12345.5 rounds to -12352 in bf16, which sum_d d*cost[d] hits ~3 % of the time)
 GUARD = 1024             # elements on each side
+
+
+@pytest.fixture(autouse=True)
+def _seed():
+    torch.manual_seed(20240917)     # deterministic inputs: a guard-band failure must be reproducible
 
 
 @pytest.fixture(scope="module")

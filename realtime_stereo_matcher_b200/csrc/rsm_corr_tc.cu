@@ -46,7 +46,8 @@ namespace rsm {
 constexpr int TC_TM = 128;        // UMMA M: left pixels per tile
 constexpr int TC_KC = 64;         // channels per shared-memory stage (16-bit features)
 constexpr int TC_KC32 = 16;       // channels per stage for fp32 features (hi + lo copies: same stage bytes)
-constexpr int TC_NSTAGE = 4;      // upper bound on operand stages (g.nstage = 2..4, whatever fits in shared memory)
+constexpr int TC_NSTAGE = 6;      // upper bound on operand stages (g.nstage = 2..6, whatever fits in shared memory)
+constexpr int TC_BAR_BYTES = 256; // mbarriers (3 per stage + 4 TMEM + 2 lo-slot) and the TMEM address slot
 constexpr int TC_EPI_WARPS = 8;    // warps 0-7: epilogue (two per TMEM lane quadrant)
 constexpr int TC_THREADS = 32 * TC_EPI_WARPS + 128 + 32;   // + warps 8-11: loaders, warp 12: UMMA issuer
 enum { EPI_VOLUME = 0, EPI_REGRESS = 1 };
@@ -65,6 +66,8 @@ struct TcGeom {
   int tmem_buf;   // TMEM columns per accumulator buffer (128 or 256)
   int stage_bytes;
   int d_fastest;  // tile order: disparity chunk fastest (fused regress keeps per-pixel state across chunks)
+  int tma32;      // fp32 operands arrive by TMA into a deep raw/hi ring; splitter warps write hi in place and lo
+                  // into one of two lo slots (stage_bytes = one hi stage; the lo slots follow the ring)
   int tma;        // operands arrive by TMA (SWIZZLE_128B atoms) instead of the cp.async loaders (no-swizzle atoms)
   int boxc;       // TMA: channels per box / per k-chunk (<= 64, multiple of 16)
   int nbb;        // TMA: 64-pixel boxes of the right window = ceil(ncol / 64)
@@ -320,11 +323,12 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
   constexpr int ES = (int)sizeof(Tin), EPC = 16 / ES;       // element bytes, elements per 16-byte chunk
   constexpr int KC = F32 ? TC_KC32 : TC_KC;                 // channels per stage
   unsigned char* stage0 = smem_raw;   // NSTAGE x { A: KC*128*ES | B: KC*ncol*ES } (fp32: hi copies, then lo copies)
-  float* skew = reinterpret_cast<float*>(smem_raw + g.nstage * (size_t)g.stage_bytes);   // epilogue scratch
+  float* skew = reinterpret_cast<float*>(smem_raw + (g.nstage + (g.tma32 ? 2 : 0)) * (size_t)g.stage_bytes);   // epilogue scratch
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(skew) + g.epi_bytes);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_NSTAGE + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * TC_NSTAGE + 6);
   const uint32_t smem_empty = smem_u32(bars), smem_full = smem_u32(bars + TC_NSTAGE),
-                 tmem_full = smem_u32(bars + 2 * TC_NSTAGE), tmem_empty = smem_u32(bars + 2 * TC_NSTAGE + 2);
+                 tmem_full = smem_u32(bars + 2 * TC_NSTAGE), tmem_empty = smem_u32(bars + 2 * TC_NSTAGE + 2),
+                 raw_full = smem_u32(bars + 2 * TC_NSTAGE + 4), lo_empty = smem_u32(bars + 3 * TC_NSTAGE + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0) {
@@ -341,7 +345,9 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
     for (int i = 0; i < 2; ++i) {
       mbar_init(tmem_full + 8 * i, 1);
       mbar_init(tmem_empty + 8 * i, 32 * TC_EPI_WARPS);
+      mbar_init(lo_empty + 8 * i, 1);          // one UMMA commit
     }
+    for (int i = 0; i < TC_NSTAGE; ++i) mbar_init(raw_full + 8 * i, 1);   // fp32 TMA: producer's expect_tx
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -373,7 +379,21 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
           mbar_wait(smem_full + 8 * s, (it / nst) & 1);                   // operands of this k-chunk have landed
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t td = tmem_base + buf * g.tmem_buf;
-          if constexpr (F32) {
+          if (F32 && g.tma32) {
+            // boxes of 32 pixels x 16 channels as written by TMA (SWIZZLE_128B_ATOM_32B = the UMMA BASE32B
+            // atoms): next 4 channels +512 B (SBO), next 32 pixels one 2 KB box further (LBO); hi operands in
+            // ring stage s, lo operands in slot it & 1
+            const uint32_t lo = smem_u32(stage0 + (size_t)nst * g.stage_bytes + (size_t)(it & 1) * g.stage_bytes);
+            const uint32_t bofs = KC * TC_TM * ES;
+            for (int ks = 0; ks < KC / 8; ++ks) {
+              const uint64_t ahi = umma_desc(sA + ks * 1024, 2048, 512, 1), alo = umma_desc(lo + ks * 1024, 2048, 512, 1);
+              const uint64_t bhi = umma_desc(sA + bofs + ks * 1024, 2048, 512, 1), blo = umma_desc(lo + bofs + ks * 1024, 2048, 512, 1);
+              umma_tf32(td, alo, bhi, idesc, (kc > 0 || ks > 0) ? 1u : 0u);   // small terms first
+              umma_tf32(td, ahi, blo, idesc, 1u);
+              umma_tf32(td, ahi, bhi, idesc, 1u);
+            }
+            umma_commit(lo_empty + 8 * (it & 1));                         // lo slot reusable once these complete
+          } else if constexpr (F32) {
             // SWIZZLE_128B_BASE32B: LBO = next 32-pixel atom (512 B), SBO = next 4-channel group
             const uint32_t sboA32 = (TC_TM / 32) * 512, sboB32 = (uint32_t)(g.ncol / 32) * 512;
             for (int ks = 0; ks < nch / 8; ++ks) {                        // K = 8 per UMMA: two 4-channel groups
@@ -403,6 +423,55 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
           if (kc == nk - 1) umma_commit(tmem_full + 8 * buf);             // accumulator ready for the epilogue
         }
       }
+    }
+  } else if (F32 && warp >= TC_EPI_WARPS && g.tma32) {
+    // ===================================================== fp32: TMA producer + hi/lo splitter warps
+    // Thread 0 of the four splitter warps keeps nstage-1 raw k-chunks in flight (10 box loads of 32 pixels x
+    // 16 channels each).  All 128 threads then split a landed chunk 16 bytes at a time -- hi in place, lo
+    // into slot job & 1 (free once the UMMAs of job-2 have completed) -- and hand it to the issuer.
+    const int lt = threadIdx.x - 32 * TC_EPI_WARPS;
+    const uint32_t nst = (uint32_t)g.nstage;
+    const uint32_t hb = (uint32_t)g.stage_bytes;
+    const uint32_t njobs = (uint32_t)((t_end - t_beg) * nk);
+    unsigned char* lo_base = stage0 + (size_t)nst * hb;
+    uint32_t issued = 0;
+    TileCoord tcp = tile_coord(t_beg, g);        // coordinates of the next job to issue (producer only)
+    int kcp = 0;
+    for (uint32_t it = 0; it < njobs; ++it) {
+      if (lt == 0) {
+        while (issued < njobs && issued < it + nst - 1 + 1) {
+          const uint32_t s = issued % nst, bar = raw_full + 8 * s;
+          mbar_wait(smem_empty + 8 * s, ((issued / nst) & 1) ^ 1);       // UMMAs that read this hi stage are done
+          mbar_expect_tx(bar, hb);
+          const uint32_t dstA = smem_u32(stage0 + (size_t)s * hb), dstB = dstA + KC * TC_TM * ES;
+          const int c0 = kcp * KC, xr0 = tcp.x0 - tcp.dc0 - g.dch;
+          for (int m = 0; m < TC_TM / 32; ++m) tma_load_4d(dstA + m * 2048, &tmL, bar, tcp.x0 + 32 * m, tcp.y, c0, (int)tcp.n);
+          for (int m = 0; m < g.ncol / 32; ++m) tma_load_4d(dstB + m * 2048, &tmR, bar, xr0 + 32 * m, tcp.y, c0, (int)tcp.n);
+          ++issued;
+          if (++kcp == nk) { kcp = 0; tcp.advance(g); }
+        }
+      }
+      const uint32_t s = it % nst;
+      unsigned char* hi = stage0 + (size_t)s * hb;
+      unsigned char* lo = lo_base + (size_t)(it & 1) * hb;
+      mbar_wait(raw_full + 8 * s, (it / nst) & 1);                       // the raw chunk has landed
+      mbar_wait(lo_empty + 8 * (it & 1), ((it >> 1) & 1) ^ 1);           // UMMAs of job it-2 released the lo slot
+      for (uint32_t o = 16u * lt; o < hb; o += 16u * 128u) {
+        const uint4 v = *reinterpret_cast<const uint4*>(hi + o);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float f = __uint_as_float(w[i]);
+          h[i] = w[i] & 0xffffe000u;
+          l[i] = __float_as_uint(f - __uint_as_float(h[i]));
+          if (!(fabsf(f) < INFINITY)) { h[i] = f != f ? 0x7fc00000u : w[i]; l[i] = 0u; }
+        }
+        *reinterpret_cast<uint4*>(hi + o) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(lo + o) = make_uint4(l[0], l[1], l[2], l[3]);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy writes -> async proxy (UMMA)
+      mbar_arrive(smem_full + 8 * s);
     }
   } else if (warp >= TC_EPI_WARPS && g.tma) {
     // ============================================================================== TMA producer
@@ -662,7 +731,8 @@ static TmapEncodeFn tmap_encoder() {
 static bool make_tmap(CUtensorMap* m, const rsm_feat& f, int fmt, const TcGeom& g, int64_t N) {
   const TmapEncodeFn enc = tmap_encoder();
   if (!enc || f.stride_w != 1 || !aligned_to(f.data, 16)) return false;
-  const int64_t st[3] = {f.stride_h * 2, f.stride_c * 2, f.stride_n * 2};      // bytes
+  const int es = fmt == 2 ? 4 : 2;
+  const int64_t st[3] = {f.stride_h * es, f.stride_c * es, f.stride_n * es};   // bytes
   const int64_t ext[3] = {g.H, g.C, N};
   cuuint64_t gstr[3];
   for (int i = 0; i < 3; ++i) {
@@ -672,7 +742,14 @@ static bool make_tmap(CUtensorMap* m, const rsm_feat& f, int fmt, const TcGeom& 
     gstr[i] = (cuuint64_t)v;
   }
   const cuuint64_t gdim[4] = {(cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.C, (cuuint64_t)N};
-  const cuuint32_t box[4] = {64, 1, (cuuint32_t)g.boxc, 1}, estr[4] = {1, 1, 1, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  if (fmt == 2) {   // fp32: 32 pixels x 16 channels, 32-byte swizzle atoms (the UMMA SWIZZLE_128B_BASE32B layout)
+    const cuuint32_t box[4] = {32, 1, (cuuint32_t)TC_KC32, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(f.data), gdim, gstr, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  }
+  const cuuint32_t box[4] = {64, 1, (cuuint32_t)g.boxc, 1};
   return enc(m, fmt == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(f.data),
              gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -686,7 +763,14 @@ static int launch_tc(const rsm_feat& left, const rsm_feat& right, void* out, Reg
   // 16-bit operands by TMA when the views qualify (RSM_TC_TMA=0 keeps the cp.async loaders: A/B runs)
   alignas(64) CUtensorMap tmL, tmR;
   memset(&tmL, 0, sizeof(tmL)); memset(&tmR, 0, sizeof(tmR));
-  g.tma = 0; g.boxc = 0; g.nbb = 0;
+  g.tma = 0; g.boxc = 0; g.nbb = 0; g.tma32 = 0;
+  if (sizeof(Tin) == 4) {
+    const char* e = getenv("RSM_TC_TMA");
+    if (!(e && e[0] == '0') && make_tmap(&tmL, left, 2, g, g.rows / g.H) && make_tmap(&tmR, right, 2, g, g.rows / g.H)) {
+      g.tma32 = 1;
+      g.stage_bytes = TC_KC32 * (TC_TM + g.ncol) * 4;     // one raw/hi stage; two lo slots of the same size follow the ring
+    }
+  }
   if (sizeof(Tin) == 2) {
     const char* e = getenv("RSM_TC_TMA");
     g.boxc = g.C < TC_KC ? g.C : TC_KC;
@@ -697,8 +781,9 @@ static int launch_tc(const rsm_feat& left, const rsm_feat& right, void* out, Reg
     }
   }
   g.nstage = TC_NSTAGE;
-  while (g.nstage > 2 && g.nstage * (size_t)g.stage_bytes + (size_t)g.epi_bytes + 160 + 1024 > 220 * 1024) --g.nstage;
-  const size_t smem = g.nstage * (size_t)g.stage_bytes + (size_t)g.epi_bytes + 160 + 1024;
+  const int extra = g.tma32 ? 2 : 0;   // lo slots
+  while (g.nstage > 2 && (g.nstage + extra) * (size_t)g.stage_bytes + (size_t)g.epi_bytes + TC_BAR_BYTES + 1024 > 220 * 1024) --g.nstage;
+  const size_t smem = (g.nstage + extra) * (size_t)g.stage_bytes + (size_t)g.epi_bytes + TC_BAR_BYTES + 1024;
   auto k = inner_tc_kernel<Tin, Tout, EPI>;
   if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return finish_launch(where);

@@ -14,29 +14,32 @@
 // memory, fp32 accumulators in TMEM, issued by one thread).  The value for disparity dc0 + dl of
 // pixel x0 + r sits at column j = r + DCH - dl: a diagonal band.
 //
-// Persistent, warp-specialised CTA (416 threads, one per SM); each CTA owns a contiguous range of tiles:
-//   warp 8     TMA producer (16-bit features whose strides TMA accepts -- the normal case): ONE lane arms
-//              smem_full[s] with the stage's byte count and issues 5-6 cp.async.bulk.tensor box loads
-//              (64 pixels x <= 64 channels each, SWIZZLE_128B: exactly the MN-major UMMA atoms, out-of-range
-//              pixels zero-filled by the TMA unit); measured: the LSU path below tops out at ~2.9 TB/s of
-//              L2 -> shared traffic on B200 whatever its pipeline depth, the TMA path does not
-//   warps 8-11 loaders (fp32 / TMA-incompatible views): stage the operand slab (<= 64 channels) of a k-chunk
-//              into one of 2-4 shared-memory
-//              stages with 16-byte cp.async (features may be strided views; the right window is
-//              zero-filled on both sides by the same instruction), writing the canonical no-swizzle
-//              MN-major core-matrix layout directly:
+// Persistent, warp-specialised CTA (448 threads, one per SM); each CTA owns a contiguous range of tiles:
+//   warp 13    TMA producer (16-bit features whose strides TMA accepts -- the normal case -- and the opt-in fp32
+//              path): ONE lane arms smem_full[s] / raw_full[s] with the stage's byte count and issues the
+//              cp.async.bulk.tensor box loads of a k-chunk (16-bit: 5-6 boxes of 64 pixels x <= 64 channels,
+//              SWIZZLE_128B; fp32: 10 boxes of 32 pixels x 16 channels, SWIZZLE_128B_ATOM_32B): exactly the
+//              MN-major UMMA atoms, out-of-range pixels zero-filled by the TMA unit.  Measured: the LSU path below
+//              tops out at ~2.9 TB/s of L2 -> shared traffic on B200 whatever its pipeline depth.
+//   warps 8-11 cp.async loaders (views TMA cannot address): stage the operand slab (<= 64 channels) of a k-chunk
+//              into one of 2-6 shared-memory stages with 16-byte cp.async (features may be strided views; the
+//              right window is zero-filled on both sides by the same instruction), writing the canonical
+//              no-swizzle MN-major core-matrix layout directly:
 //                  addr(x, c) = ((c/8) * (T/8) + x/8) * 128 + (c%8) * 16 + (x%8) * 2;
-//              up to nstage-1 newer cp.async groups stay in flight behind the one being waited for;
+//              up to nstage-1 newer cp.async groups stay in flight behind the one being waited for.
+//              fp32 TMA path: the same warps split every landed raw chunk into hi (in place) and lo (one of two
+//              rotating slots).  16-bit TMA volume path: they are a third epilogue group (disparity thirds).
 //   warp 12    UMMA issuer (one lane): waits smem_full / tmem_empty, issues the tcgen05.mma chain of the
 //              k-chunk, commits it to smem_empty (stage reusable) and tmem_full (accumulator ready);
-//   warps 0-7  epilogue, two warps per TMEM lane quadrant (each takes half of the disparities):
+//   warps 0-7  epilogue, two (three) warps per TMEM lane quadrant, each taking a part of the disparities:
 //              tcgen05.ld the columns covering its lanes, park them in a padded shared-memory row per
 //              lane, read them back skewed so that for every disparity 32 lanes hold 32 consecutive x, then
 //              either store the (N,D,H,W) volume (EPI_VOLUME) or run the chunked online softmax +
 //              arg-extrema over them (EPI_REGRESS; the two halves of a quadrant merge through smem).
 // Two TMEM accumulator buffers decouple the UMMAs of tile t+1 from the epilogue of tile t.
-// mbarriers: smem_full[s] (128 loader arrivals), smem_empty[s] (UMMA commit), tmem_full[b] (UMMA commit),
-// tmem_empty[b] (256 epilogue arrivals).  All waits are bounded (a protocol bug yields NaNs, not a hang).
+// mbarriers: smem_full[s] (TMA bytes or 128 loader / splitter arrivals), smem_empty[s] (UMMA commit), raw_full[s]
+// (fp32 TMA bytes), lo_empty[2] (UMMA commit), tmem_full[b] (UMMA commit), tmem_empty[b] (epilogue arrivals).
+// All waits are bounded (a protocol bug yields NaNs, not a hang).
 #include <cuda.h>   // CUtensorMap (types only; the encoder is looked up at run time, no libcuda link dependency)
 
 #include "rsm_common.cuh"
@@ -49,14 +52,14 @@ constexpr int TC_KC32 = 16;       // channels per stage for fp32 features (hi + 
 constexpr int TC_NSTAGE = 6;      // upper bound on operand stages (g.nstage = 2..6, whatever fits in shared memory)
 constexpr int TC_BAR_BYTES = 256; // mbarriers (3 per stage + 4 TMEM + 2 lo-slot) and the TMEM address slot
 constexpr int TC_EPI_WARPS = 8;    // warps 0-7: epilogue (two per TMEM lane quadrant)
-constexpr int TC_THREADS = 32 * TC_EPI_WARPS + 128 + 32;   // + warps 8-11: loaders, warp 12: UMMA issuer
+constexpr int TC_THREADS = 32 * TC_EPI_WARPS + 128 + 64;   // + warps 8-11: loaders / splitters / third epilogue group,
+                                                          //   warp 12: UMMA issuer, warp 13: TMA producer
 enum { EPI_VOLUME = 0, EPI_REGRESS = 1 };
 
 struct TcGeom {
   int C, H, W, D;
   int dch;        // disparities per tile chunk (multiple of 16, fp32: 32; <= 128)
   int ncol;       // UMMA N = TC_TM + dch
-  int ncw;        // TMEM columns an epilogue warp pulls: >= dch/2 + 32, multiple of 16
   int pitch;      // floats per lane row of the skew buffer
   int epi_bytes;  // epilogue scratch: skew rows (volume) or partial softmax states (regress)
   int xtiles;     // ceil(W / TC_TM)
@@ -66,6 +69,8 @@ struct TcGeom {
   int tmem_buf;   // TMEM columns per accumulator buffer (128 or 256)
   int stage_bytes;
   int d_fastest;  // tile order: disparity chunk fastest (fused regress keeps per-pixel state across chunks)
+  int nsplit;     // epilogue warps per TMEM lane quadrant (2, or 3 when warps 8-11 are free: 16-bit TMA volume path)
+  int eb[4];      // disparity bounds of the epilogue parts inside a chunk: part p covers [eb[p], eb[p+1])
   int tma32;      // fp32 operands arrive by TMA into a deep raw/hi ring; splitter warps write hi in place and lo
                   // into one of two lo slots (stage_bytes = one hi stage; the lo slots follow the ring)
   int tma;        // operands arrive by TMA (SWIZZLE_128B atoms) instead of the cp.async loaders (no-swizzle atoms)
@@ -344,7 +349,7 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tmem_full + 8 * i, 1);
-      mbar_init(tmem_empty + 8 * i, 32 * TC_EPI_WARPS);
+      mbar_init(tmem_empty + 8 * i, 32 * 4 * g.nsplit);
       mbar_init(lo_empty + 8 * i, 1);          // one UMMA commit
     }
     for (int i = 0; i < TC_NSTAGE; ++i) mbar_init(raw_full + 8 * i, 1);   // fp32 TMA: producer's expect_tx
@@ -424,33 +429,56 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
         }
       }
     }
+  } else if (warp == TC_EPI_WARPS + 5) {
+    // ============================================================================== TMA producer
+    // One lane keeps every free stage loading: the stage-free barrier (UMMA commit) is the only throttle.
+    if (lane == 0 && g.tma) {
+      const uint32_t nst = (uint32_t)g.nstage;
+      const uint32_t boxb = (uint32_t)g.boxc * 128u, bytes = (2u + (uint32_t)g.nbb) * boxb;
+      uint32_t it = 0;
+      TileCoord tc = tile_coord(t_beg, g);
+      for (int64_t t = t_beg; t < t_end; ++t, tc.advance(g)) {
+        const int xr0 = tc.x0 - tc.dc0 - g.dch;
+        for (int kc = 0; kc < nk; ++kc, ++it) {
+          const uint32_t s = it % nst;
+          const uint32_t sA = smem_u32(stage0 + (size_t)s * g.stage_bytes), bar = smem_full + 8 * s;
+          mbar_wait(smem_empty + 8 * s, ((it / nst) & 1) ^ 1);       // UMMAs that read this stage have completed
+          mbar_expect_tx(bar, bytes);
+          const int c0 = kc * g.boxc;
+          tma_load_4d(sA, &tmL, bar, tc.x0, tc.y, c0, (int)tc.n);
+          tma_load_4d(sA + boxb, &tmL, bar, tc.x0 + 64, tc.y, c0, (int)tc.n);
+          for (int m = 0; m < g.nbb; ++m)
+            tma_load_4d(sA + (2 + m) * boxb, &tmR, bar, xr0 + 64 * m, tc.y, c0, (int)tc.n);
+        }
+      }
+    } else if (lane == 0 && g.tma32) {
+      // fp32: raw k-chunks (10 box loads of 32 pixels x 16 channels) into the hi ring
+      const uint32_t nst = (uint32_t)g.nstage, hb = (uint32_t)g.stage_bytes;
+      uint32_t it = 0;
+      TileCoord tc = tile_coord(t_beg, g);
+      for (int64_t t = t_beg; t < t_end; ++t, tc.advance(g)) {
+        const int xr0 = tc.x0 - tc.dc0 - g.dch;
+        for (int kc = 0; kc < nk; ++kc, ++it) {
+          const uint32_t s = it % nst, bar = raw_full + 8 * s;
+          mbar_wait(smem_empty + 8 * s, ((it / nst) & 1) ^ 1);       // UMMAs that read this hi stage are done
+          mbar_expect_tx(bar, hb);
+          const uint32_t dstA = smem_u32(stage0 + (size_t)s * hb), dstB = dstA + KC * TC_TM * ES;
+          const int c0 = kc * KC;
+          for (int m = 0; m < TC_TM / 32; ++m) tma_load_4d(dstA + m * 2048, &tmL, bar, tc.x0 + 32 * m, tc.y, c0, (int)tc.n);
+          for (int m = 0; m < g.ncol / 32; ++m) tma_load_4d(dstB + m * 2048, &tmR, bar, xr0 + 32 * m, tc.y, c0, (int)tc.n);
+        }
+      }
+    }
   } else if (F32 && warp >= TC_EPI_WARPS && g.tma32) {
-    // ===================================================== fp32: TMA producer + hi/lo splitter warps
-    // Thread 0 of the four splitter warps keeps nstage-1 raw k-chunks in flight (10 box loads of 32 pixels x
-    // 16 channels each).  All 128 threads then split a landed chunk 16 bytes at a time -- hi in place, lo
-    // into slot job & 1 (free once the UMMAs of job-2 have completed) -- and hand it to the issuer.
+    // =============================================================== fp32: hi/lo splitter warps
+    // All 128 threads split a landed raw chunk 16 bytes at a time -- hi in place, lo into slot job & 1 (free
+    // once the UMMAs of job-2 have completed) -- and hand it to the issuer.
     const int lt = threadIdx.x - 32 * TC_EPI_WARPS;
     const uint32_t nst = (uint32_t)g.nstage;
     const uint32_t hb = (uint32_t)g.stage_bytes;
     const uint32_t njobs = (uint32_t)((t_end - t_beg) * nk);
     unsigned char* lo_base = stage0 + (size_t)nst * hb;
-    uint32_t issued = 0;
-    TileCoord tcp = tile_coord(t_beg, g);        // coordinates of the next job to issue (producer only)
-    int kcp = 0;
     for (uint32_t it = 0; it < njobs; ++it) {
-      if (lt == 0) {
-        while (issued < njobs && issued < it + nst - 1 + 1) {
-          const uint32_t s = issued % nst, bar = raw_full + 8 * s;
-          mbar_wait(smem_empty + 8 * s, ((issued / nst) & 1) ^ 1);       // UMMAs that read this hi stage are done
-          mbar_expect_tx(bar, hb);
-          const uint32_t dstA = smem_u32(stage0 + (size_t)s * hb), dstB = dstA + KC * TC_TM * ES;
-          const int c0 = kcp * KC, xr0 = tcp.x0 - tcp.dc0 - g.dch;
-          for (int m = 0; m < TC_TM / 32; ++m) tma_load_4d(dstA + m * 2048, &tmL, bar, tcp.x0 + 32 * m, tcp.y, c0, (int)tcp.n);
-          for (int m = 0; m < g.ncol / 32; ++m) tma_load_4d(dstB + m * 2048, &tmR, bar, xr0 + 32 * m, tcp.y, c0, (int)tcp.n);
-          ++issued;
-          if (++kcp == nk) { kcp = 0; tcp.advance(g); }
-        }
-      }
       const uint32_t s = it % nst;
       unsigned char* hi = stage0 + (size_t)s * hb;
       unsigned char* lo = lo_base + (size_t)(it & 1) * hb;
@@ -473,29 +501,9 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy writes -> async proxy (UMMA)
       mbar_arrive(smem_full + 8 * s);
     }
-  } else if (warp >= TC_EPI_WARPS && g.tma) {
-    // ============================================================================== TMA producer
-    if (warp == TC_EPI_WARPS && lane == 0) {
-      const uint32_t nst = (uint32_t)g.nstage;
-      const uint32_t boxb = (uint32_t)g.boxc * 128u, bytes = (2u + (uint32_t)g.nbb) * boxb;
-      uint32_t it = 0;
-      TileCoord tc = tile_coord(t_beg, g);
-      for (int64_t t = t_beg; t < t_end; ++t, tc.advance(g)) {
-        const int xr0 = tc.x0 - tc.dc0 - g.dch;
-        for (int kc = 0; kc < nk; ++kc, ++it) {
-          const uint32_t s = it % nst;
-          const uint32_t sA = smem_u32(stage0 + (size_t)s * g.stage_bytes), bar = smem_full + 8 * s;
-          mbar_wait(smem_empty + 8 * s, ((it / nst) & 1) ^ 1);       // UMMAs that read this stage have completed
-          mbar_expect_tx(bar, bytes);
-          const int c0 = kc * g.boxc;
-          tma_load_4d(sA, &tmL, bar, tc.x0, tc.y, c0, (int)tc.n);
-          tma_load_4d(sA + boxb, &tmL, bar, tc.x0 + 64, tc.y, c0, (int)tc.n);
-          for (int m = 0; m < g.nbb; ++m)
-            tma_load_4d(sA + (2 + m) * boxb, &tmR, bar, xr0 + 64 * m, tc.y, c0, (int)tc.n);
-        }
-      }
-    }
-  } else if (warp >= TC_EPI_WARPS) {
+  } else if (warp >= TC_EPI_WARPS && (g.tma32 || (g.tma && g.nsplit == 2))) {
+    // warps 8-11 have nothing to do (16-bit TMA path with the two-way epilogue)
+  } else if (warp >= TC_EPI_WARPS && !g.tma) {
     // ================================================================================== loaders
     // One cp.async group per k-chunk job; up to nstage-1 newer groups stay in flight while the loaders
     // wait for the oldest one to land, fence it for the async proxy and signal smem_full.  The loaders
@@ -545,11 +553,14 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
     for (; done < it; ++done) landed(done, (int)(it - done - 1));   // drain
   } else {
     // ================================================================================= epilogue
-    // warp -> (TMEM lane quadrant q, disparity half hh): lanes 32q.., disparities [hh*dh, (hh+1)*dh).
-    // Disparity dl of lane t sits at column 32q + t + dch - dl; this warp's window starts at
-    // 32q + cs with cs = dch - (hh+1)*dh and is ncw columns wide (>= dh + 32, multiple of 16).
+    // warp -> (TMEM lane quadrant q, disparity part hh): lanes 32q.., disparities [eb[hh], eb[hh+1]) of the chunk
+    // (halves; thirds when warps 8-11 join in: 16-bit TMA volume path).  Disparity dl of lane t sits at column
+    // 32q + t + dch - dl; this warp's window starts at 32q + cs with cs = dch - eb[hh+1] and is ncw columns wide
+    // (>= part width + 32, multiple of 16).
     const int q = warp & 3, hh = warp >> 2;
-    const int dh = g.dch / 2, cs = g.dch - (hh + 1) * dh, ncw = g.ncw;
+    const int plo = hh == 0 ? g.eb[0] : hh == 1 ? g.eb[1] : g.eb[2];     // (static indices: no local copy of g)
+    const int phi = hh == 0 ? g.eb[1] : hh == 1 ? g.eb[2] : g.eb[3];
+    const int cs = g.dch - phi, ncw = (phi - plo + 32 + 15) / 16 * 16;
     const float inv = 1.f / (float)g.C, cnt = (float)g.C;
     const float nanv = __int_as_float(0x7fc00000);
     uint32_t use = 0;
@@ -566,7 +577,7 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
       const uint32_t taddr = tmem_base + buf * g.tmem_buf + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * q + cs);
       const int x = tc.x0 + 32 * q + lane;
       const int dmax = min(g.dch, g.D - tc.dc0);
-      const int dlo = hh * dh, dhi = min((hh + 1) * dh, dmax);
+      const int dlo = plo, dhi = min(phi, dmax);
 
       // ---- TMEM -> one padded shared-memory row per lane (up to four 16-column loads in flight per wait)
       float* row = skew + (size_t)(32 * warp + lane) * g.pitch;
@@ -588,7 +599,7 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
       mbar_arrive(tmem_empty + 8 * buf);                   // this thread is done with the TMEM buffer
       __syncwarp();
       // ---- skewed read-back: value(dl) = rp0[-dl]; zeros where x < d, i.e. for dl >= dz
-      const float* rp0 = row + lane + (hh + 1) * dh;
+      const float* rp0 = row + lane + phi;
       const float mul = !ok ? nanv : (g.mean ? (g.pow2 ? inv : 1.f) : 1.f);   // NaN marks a pipeline fault
       const bool divide = g.mean && !g.pow2;
       const int dz = max(dlo, min(dhi, x - tc.dc0 + 1));    // [dlo, dz): values, [dz, dhi): fill
@@ -690,10 +701,6 @@ static int tc_geom(int64_t N, int64_t C, int64_t H, int64_t W, int64_t D, int me
   const int d16 = (int)((D + dq - 1) / dq * dq);
   g.dch = d16 < 128 ? d16 : 128;
   g.ncol = TC_TM + g.dch;
-  g.ncw = (g.dch / 2 + 32 + 15) / 16 * 16;
-  int p = g.ncw;                         // pitch: >= ncw, multiple of 4 with an odd quotient (conflict-free
-  if ((p / 4) % 2 == 0) p += 4;          // 128-bit row writes and conflict-free skewed 32-bit reads)
-  g.pitch = p;
   g.xtiles = (int)ceil_div(W, TC_TM);
   g.dchunks = (int)ceil_div(D, g.dch);
   g.mean = mean;
@@ -759,7 +766,6 @@ template <typename Tin, typename Tout, int EPI>
 static int launch_tc(const rsm_feat& left, const rsm_feat& right, void* out, RegressPtrs rp, const TcGeom& g_in,
                      cudaStream_t st, const char* where) {
   TcGeom g = g_in;
-  g.epi_bytes = 32 * TC_EPI_WARPS * g.pitch * 4 + (EPI == EPI_REGRESS ? 2 * 128 * 8 * 4 : 0);   // rows (+ partials)
   // 16-bit operands by TMA when the views qualify (RSM_TC_TMA=0 keeps the cp.async loaders: A/B runs)
   alignas(64) CUtensorMap tmL, tmR;
   memset(&tmL, 0, sizeof(tmL)); memset(&tmR, 0, sizeof(tmR));
@@ -780,6 +786,25 @@ static int launch_tc(const rsm_feat& left, const rsm_feat& right, void* out, Reg
       g.stage_bytes = (2 + g.nbb) * g.boxc * 128;
     }
   }
+  // epilogue parts: halves of the chunk, or thirds (bounds on multiples of 8) when warps 8-11 are free
+  g.nsplit = (EPI == EPI_VOLUME && g.tma) ? 3 : 2;
+  {
+    const char* e = getenv("RSM_TC_NSPLIT");
+    if (e && e[0] == '2') g.nsplit = 2;
+    auto r8 = [&](int v) { v = (v + 7) / 8 * 8; return v < g.dch ? v : g.dch; };
+    g.eb[0] = 0;
+    if (g.nsplit == 2) { g.eb[1] = g.dch / 2; g.eb[2] = g.dch; g.eb[3] = g.dch; }
+    else { g.eb[1] = r8(g.dch / 3); g.eb[2] = r8(2 * g.dch / 3); g.eb[3] = g.dch; }
+    int ncw = 0;                           // TMEM columns the widest part pulls: >= width + 32, multiple of 16
+    for (int k = 0; k < g.nsplit; ++k) {
+      const int c = (g.eb[k + 1] - g.eb[k] + 32 + 15) / 16 * 16;
+      ncw = c > ncw ? c : ncw;
+    }
+    int p = ncw;                           // pitch: >= ncw, multiple of 4 with an odd quotient (conflict-free
+    if ((p / 4) % 2 == 0) p += 4;          // 128-bit row writes and conflict-free skewed 32-bit reads)
+    g.pitch = p;
+  }
+  g.epi_bytes = 32 * 4 * g.nsplit * g.pitch * 4 + (EPI == EPI_REGRESS ? 2 * 128 * 8 * 4 : 0);   // rows (+ partials)
   g.nstage = TC_NSTAGE;
   const int extra = g.tma32 ? 2 : 0;   // lo slots
   while (g.nstage > 2 && (g.nstage + extra) * (size_t)g.stage_bytes + (size_t)g.epi_bytes + TC_BAR_BYTES + 1024 > 220 * 1024) --g.nstage;

@@ -13,6 +13,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "rsm_common.cuh"
 
 namespace rsm {
@@ -639,14 +641,16 @@ static int launch_bwd(const void* gout, const rsm_feat& left, const rsm_feat& ri
       return g.cpg == 4 ? launch(groupwise_bwd_row_kernel<Tin, Tout, 4>) : launch(groupwise_bwd_row_kernel<Tin, Tout, 8>);
     }
   }
-  // fp32 inner product: 8x8 register tiles when every row and window starts on a 16-byte boundary
-  // (RSM_BWD_SMALL_TILE=1 keeps the 4x4 kernel: A/B runs)
-  if constexpr (LAYOUT == LAYOUT_NDHW && sizeof(Tin) == 4 && sizeof(Tout) == 4) {
+  // inner product: 8x8 register tiles when every row and window starts on a 16-byte boundary (fp32: W % 4,
+  // 16-bit: W % 8) and all three tensors share one dtype (RSM_BWD_SMALL_TILE=1 keeps the 4x4 kernel: A/B runs)
+  if constexpr (LAYOUT == LAYOUT_NDHW && std::is_same<Tin, Tout>::value) {
     const char* small = getenv("RSM_BWD_SMALL_TILE");
-    auto v4 = [&](const rsm_feat& f) {
-      return f.stride_w == 1 && f.stride_n % 4 == 0 && f.stride_c % 4 == 0 && f.stride_h % 4 == 0 && aligned_to(f.data, 16);
+    constexpr int EPV = 16 / (int)sizeof(Tin);
+    auto v16 = [&](const rsm_feat& f) {
+      return f.stride_w == 1 && f.stride_n % EPV == 0 && f.stride_c % EPV == 0 && f.stride_h % EPV == 0 && aligned_to(f.data, 16);
     };
-    if (g.G == 1 && g.C >= 16 && g.D > 0 && g.W % 4 == 0 && v4(left) && v4(right) && aligned_to(gout, 16) &&
+    // (16-bit tensors are widened synchronously while staging: only worth it from 32 channels up, measured)
+    if (g.G == 1 && g.C >= (sizeof(Tin) == 4 ? 16 : 32) && g.D > 0 && g.W % EPV == 0 && v16(left) && v16(right) && aligned_to(gout, 16) &&
         (!gl || aligned_to(gl, 16)) && (!gr || aligned_to(gr, 16)) && !(naive && naive[0] == '1') &&
         !(small && small[0] == '1')) {
       const int xtiles = (int)ceil_div(g.W, BB_TX), cblocks = (int)ceil_div(g.C, BB_CB);
@@ -654,15 +658,15 @@ static int launch_bwd(const void* gout, const rsm_feat& left, const rsm_feat& ri
       if (grid_ok(bx)) {
         const size_t smem = (size_t)(BB_DCH * BB_TX + BB_CB * BB_FW) * sizeof(float);
         if (gl) {
-          auto k = inner_bwd_big_kernel<SIDE_LEFT>;
+          auto k = inner_bwd_big_kernel<Tin, SIDE_LEFT>;
           cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-          k<<<(unsigned)bx, BB_THREADS, smem, st>>>((const float*)gout, view_of(left), view_of(right), (float*)gl, g, xtiles, cblocks);
+          k<<<(unsigned)bx, BB_THREADS, smem, st>>>((const Tin*)gout, view_of(left), view_of(right), (Tin*)gl, g, xtiles, cblocks);
           if (int rc = finish_launch(where)) return rc;
         }
         if (gr) {
-          auto k = inner_bwd_big_kernel<SIDE_RIGHT>;
+          auto k = inner_bwd_big_kernel<Tin, SIDE_RIGHT>;
           cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-          k<<<(unsigned)bx, BB_THREADS, smem, st>>>((const float*)gout, view_of(left), view_of(right), (float*)gr, g, xtiles, cblocks);
+          k<<<(unsigned)bx, BB_THREADS, smem, st>>>((const Tin*)gout, view_of(left), view_of(right), (Tin*)gr, g, xtiles, cblocks);
           if (int rc = finish_launch(where)) return rc;
         }
         return RSM_OK;

@@ -211,9 +211,23 @@ constexpr int BB_TX = 128, BB_CB = 32, BB_DCH = 64, BB_FW = BB_TX + BB_DCH, BB_T
 
 __device__ __forceinline__ int bb_swz(int chunk) { return chunk ^ ((chunk >> 3) & 1); }
 
-template <int SIDE>
+// 8 consecutive 16-bit elements (one 16-byte load) widened to fp32 and stored as two swizzled 16-byte chunks
+template <typename T>
+__device__ __forceinline__ void bb_stage8(float* row, int ch2, const T* src, bool valid) {
+  Vec16<T> v;
+  if (valid) v = ldg16(src);
+  float f[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] = valid ? to_f(v.v[i]) : 0.f;
+  *reinterpret_cast<float4*>(row + 4 * bb_swz(2 * ch2)) = make_float4(f[0], f[1], f[2], f[3]);
+  *reinterpret_cast<float4*>(row + 4 * bb_swz(2 * ch2 + 1)) = make_float4(f[4], f[5], f[6], f[7]);
+}
+
+// T = element type of the features, the gradient of the volume and the feature gradients (all equal here);
+// fp32 moves by LDGSTS, 16-bit tensors by 16-byte loads widened on the way into shared memory.
+template <typename T, int SIDE>
 __global__ void __launch_bounds__(BB_THREADS)
-inner_bwd_big_kernel(const float* __restrict__ gout, FeatView L, FeatView R, float* __restrict__ gdst, CorrGeom g,
+inner_bwd_big_kernel(const T* __restrict__ gout, FeatView L, FeatView R, T* __restrict__ gdst, CorrGeom g,
                      int xtiles, int cblocks) {
   extern __shared__ __align__(16) float smem[];
   float* sG = smem;                       // [BB_DCH][BB_TX]
@@ -226,10 +240,10 @@ inner_bwd_big_kernel(const float* __restrict__ gout, FeatView L, FeatView R, flo
   const int x0 = xt * BB_TX, c0 = cb * BB_CB;
   const int ncb = min(BB_CB, g.C - c0);
   const int tx = threadIdx.x & 15, tc = threadIdx.x >> 4;
-  const float* __restrict__ gbase = gout + ((int64_t)n * g.D * g.H + y) * g.W;     // + d * H * W + x
+  const T* __restrict__ gbase = gout + ((int64_t)n * g.D * g.H + y) * g.W;         // + d * H * W + x
   const int64_t gsd = (int64_t)g.H * g.W;
   const FeatView& F = SIDE == SIDE_LEFT ? R : L;
-  const float* __restrict__ pf = reinterpret_cast<const float*>(F.data) + n * F.sn + (int64_t)y * F.sh + (int64_t)c0 * F.sc;
+  const T* __restrict__ pf = reinterpret_cast<const T*>(F.data) + n * F.sn + (int64_t)y * F.sh + (int64_t)c0 * F.sc;
 
   float acc[8][8];   // [channel j][pixel i]
 #pragma unroll
@@ -240,7 +254,7 @@ inner_bwd_big_kernel(const float* __restrict__ gout, FeatView L, FeatView R, flo
   for (int dc0 = 0; dc0 < g.D; dc0 += BB_DCH) {
     __syncthreads();
     // ---- gradient tile
-    if constexpr (SIDE == SIDE_LEFT) {
+    if constexpr (SIDE == SIDE_LEFT && sizeof(T) == 4) {
       for (int e = threadIdx.x; e < BB_DCH * (BB_TX / 4); e += BB_THREADS) {
         const int dl = e >> 5, ch = e & 31;
         const int d = dc0 + dl, x = x0 + 4 * ch;
@@ -249,28 +263,47 @@ inner_bwd_big_kernel(const float* __restrict__ gout, FeatView L, FeatView R, flo
                      "l"(valid ? gbase + d * gsd + x : gbase), "r"(valid ? 16 : 0)
                      : "memory");
       }
+    } else if constexpr (SIDE == SIDE_LEFT) {
+      for (int e = threadIdx.x; e < BB_DCH * (BB_TX / 8); e += BB_THREADS) {
+        const int dl = e >> 4, ch2 = e & 15;
+        const int d = dc0 + dl, x = x0 + 8 * ch2;
+        bb_stage8<T>(sG + dl * BB_TX, ch2, gbase + d * gsd + x, d < g.D && x < g.W);   // W % 8 == 0: whole octets
+      }
     } else {
       for (int e = threadIdx.x; e < BB_DCH * BB_TX; e += BB_THREADS) {
         const int dl = e >> 7, xx = e & 127;
         const int d = dc0 + dl, x = x0 + xx + d;             // skew: column x' holds gV[d][x' + d]
         const bool valid = d < g.D && x < g.W;
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(sG + dl * BB_TX + 4 * bb_swz(xx >> 2) + (xx & 3))),
-                     "l"(valid ? gbase + d * gsd + x : gbase), "r"(valid ? 4 : 0)
-                     : "memory");
+        float* dst = sG + dl * BB_TX + 4 * bb_swz(xx >> 2) + (xx & 3);
+        if constexpr (sizeof(T) == 4) {
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)),
+                       "l"(valid ? gbase + d * gsd + x : gbase), "r"(valid ? 4 : 0)
+                       : "memory");
+        } else {
+          *dst = valid ? to_f(__ldg(gbase + d * gsd + x)) : 0.f;
+        }
       }
     }
     // ---- feature windows: left side R[c][x0 - dc0 - 64 + j], right side L[c][x0 + dc0 + j]
     const int fx0 = SIDE == SIDE_LEFT ? x0 - dc0 - BB_DCH : x0 + dc0;
-    for (int e = threadIdx.x; e < (BB_FW / 4); e += BB_THREADS) {
-      const int x = fx0 + 4 * e;
-      const bool valid = x >= 0 && x < g.W;
-      const float* src = valid ? pf + x : pf;
-      const int64_t step = valid ? F.sc : 0;
-      const uint32_t sdst = (uint32_t)__cvta_generic_to_shared(sF + 4 * bb_swz(e));
-      for (int c = 0; c < ncb; ++c)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sdst + (uint32_t)(c * BB_FW * 4)), "l"(src + c * step),
-                     "r"(valid ? 16 : 0)
-                     : "memory");
+    if constexpr (sizeof(T) == 4) {
+      for (int e = threadIdx.x; e < (BB_FW / 4); e += BB_THREADS) {
+        const int x = fx0 + 4 * e;
+        const bool valid = x >= 0 && x < g.W;
+        const T* src = valid ? pf + x : pf;
+        const int64_t step = valid ? F.sc : 0;
+        const uint32_t sdst = (uint32_t)__cvta_generic_to_shared(sF + 4 * bb_swz(e));
+        for (int c = 0; c < ncb; ++c)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sdst + (uint32_t)(c * BB_FW * 4)), "l"(src + c * step),
+                       "r"(valid ? 16 : 0)
+                       : "memory");
+      }
+    } else {
+      for (int e = threadIdx.x; e < ncb * (BB_FW / 8); e += BB_THREADS) {
+        const int c = e / (BB_FW / 8), ch2 = e - c * (BB_FW / 8);
+        const int x = fx0 + 8 * ch2;                          // fx0 % 8 == 0 and W % 8 == 0: whole octets
+        bb_stage8<T>(sF + c * BB_FW, ch2, pf + (int64_t)c * F.sc + x, x >= 0 && x < g.W);
+      }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
@@ -314,10 +347,17 @@ inner_bwd_big_kernel(const float* __restrict__ gout, FeatView L, FeatView R, flo
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     if (8 * tc + j >= ncb) break;
-    float* o = gdst + (((int64_t)n * g.C + c0 + 8 * tc + j) * g.H + y) * g.W + xb;
-    __stcs(reinterpret_cast<float4*>(o), make_float4(acc[j][0] / cnt, acc[j][1] / cnt, acc[j][2] / cnt, acc[j][3] / cnt));
-    if (xb + 4 < g.W)
-      __stcs(reinterpret_cast<float4*>(o + 4), make_float4(acc[j][4] / cnt, acc[j][5] / cnt, acc[j][6] / cnt, acc[j][7] / cnt));
+    T* o = gdst + (((int64_t)n * g.C + c0 + 8 * tc + j) * g.H + y) * g.W + xb;
+    if constexpr (sizeof(T) == 4) {
+      __stcs(reinterpret_cast<float4*>(o), make_float4(acc[j][0] / cnt, acc[j][1] / cnt, acc[j][2] / cnt, acc[j][3] / cnt));
+      if (xb + 4 < g.W)
+        __stcs(reinterpret_cast<float4*>(o + 4), make_float4(acc[j][4] / cnt, acc[j][5] / cnt, acc[j][6] / cnt, acc[j][7] / cnt));
+    } else {
+      Vec16<T> v;                                             // W % 8 == 0: the whole octet is inside the row
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v.v[i] = from_f<T>(acc[j][i] / cnt);
+      stcs16(o, v);
+    }
   }
 }
 

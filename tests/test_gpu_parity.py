@@ -601,3 +601,24 @@ def test_empty_and_degenerate_inputs(rsm):
     w0 = torch.zeros((2, 8, 4, 0), device="cuda")       # zero-width feature maps
     assert rsm.inner_product_volume(w0, w0, 3).shape == (2, 3, 4, 0)
     assert rsm.difference_volume(w0, w0, 3).shape == (2, 8, 3, 4, 0)
+
+
+@pytest.mark.parametrize("shape", [(1, 64, 3, 240, 48), (2, 40, 2, 136, 70), (1, 32, 2, 128, 24)])
+@pytest.mark.parametrize("dn", ["bf16", "fp16"])
+@pytest.mark.parametrize("mean", [False, True])
+def test_inner_bwd_16bit_big_tiles(rsm, shape, dn, mean, monkeypatch):
+    """16-bit tensors through the 8x8-tile inner-product adjoint (rows on 16-byte boundaries: W % 8 == 0),
+    against the fp32 oracle on the same rounded inputs and against the per-element gather kernel."""
+    n, c, h, w, d = shape
+    rng = np.random.default_rng(91)
+    l = round_to(rng.standard_normal((n, c, h, w)).astype(np.float32), dn)
+    r = round_to(rng.standard_normal((n, c, h, w)).astype(np.float32), dn)
+    gout = round_to(rng.standard_normal((n, d, h, w)).astype(np.float32), dn)
+    gl, gr = oracle.inner_product_volume_bwd(gout, l, r, mean=mean)
+    atol = RTOL_16[dn] * np.sqrt(d) * 4 / (c if mean else 1)
+    for naive in ("0", "1"):
+        monkeypatch.setenv("RSM_BWD_NAIVE", naive)
+        L, R = dev(l, dn, grad=True), dev(r, dn, grad=True)
+        rsm.inner_product_volume(L, R, d, mean=mean).backward(dev(gout, dn))
+        close(L.grad, gl, atol, RTOL_16[dn])
+        close(R.grad, gr, atol, RTOL_16[dn])

@@ -656,30 +656,34 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
           }
           m = mn;
         }
-        // after the last chunk, combine the two warps of a quadrant: hh = 1 parks its state, hh = 0 merges
-        // and stores (equal values: the smaller index wins, as torch does)
+        // after the last chunk, combine the warps of a quadrant: parts 1.. park their state, part 0 merges them
+        // in ascending disparity order and stores (equal values: the smaller index wins, as torch does)
         if (tc.dc0 + g.dch < g.D) { __syncwarp(); continue; }
-        float* part = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(skew) + g.epi_bytes - 2 * 128 * 8 * 4) +
-                      ((size_t)(combines++ & 1) * 128 + 32 * q + lane) * 8;
-        if (hh == 1) {
+        float* pbase = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(skew) + g.epi_bytes - 2 * 2 * 128 * 8 * 4) +
+                       (size_t)(combines++ & 1) * (2 * 128 * 8);
+        if (hh >= 1) {
+          float* part = pbase + ((size_t)(hh - 1) * 128 + 32 * q + lane) * 8;
           part[0] = m; part[1] = s; part[2] = ws; part[3] = minv; part[4] = maxv;
           part[5] = __int_as_float(mini); part[6] = __int_as_float(maxi); part[7] = __int_as_float(nani);
         }
-        asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+        asm volatile("bar.sync %0, %1;" ::"r"(2 + q), "r"(32 * g.nsplit) : "memory");
         if (hh == 0 && x < g.W) {
-          const float m2 = part[0], s2 = part[1], w2 = part[2], minv2 = part[3], maxv2 = part[4];
-          const int mini2 = __float_as_int(part[5]), maxi2 = __float_as_int(part[6]), nani2 = __float_as_int(part[7]);
-          const float M = fmaxf(m, m2);
-          const float a1 = (m == -INFINITY) ? 0.f : fast_exp2((m - M) * kLog2e);
-          const float a2 = (m2 == -INFINITY) ? 0.f : fast_exp2((m2 - M) * kLog2e);
-          const float S = s * a1 + s2 * a2, WS = ws * a1 + w2 * a2;
-          if (minv2 < minv || (minv2 == minv && mini2 < mini)) mini = mini2;
-          if (maxv2 > maxv || (maxv2 == maxv && maxi2 < maxi)) maxi = maxi2;
-          nani = min(nani, nani2);
+          for (int k = 0; k + 1 < g.nsplit; ++k) {
+            const float* part = pbase + ((size_t)k * 128 + 32 * q + lane) * 8;
+            const float m2 = part[0], s2 = part[1], w2 = part[2], minv2 = part[3], maxv2 = part[4];
+            const int mini2 = __float_as_int(part[5]), maxi2 = __float_as_int(part[6]), nani2 = __float_as_int(part[7]);
+            const float M = fmaxf(m, m2);
+            const float a1 = (m == -INFINITY) ? 0.f : fast_exp2((m - M) * kLog2e);
+            const float a2 = (m2 == -INFINITY) ? 0.f : fast_exp2((m2 - M) * kLog2e);
+            s = s * a1 + s2 * a2; ws = ws * a1 + w2 * a2; m = M;
+            if (minv2 < minv || (minv2 == minv && mini2 < mini)) { minv = minv2; mini = mini2; }
+            if (maxv2 > maxv || (maxv2 == maxv && maxi2 < maxi)) { maxv = maxv2; maxi = maxi2; }
+            nani = min(nani, nani2);
+          }
           if (nani != 0x7fffffff) { mini = nani; maxi = nani; }
           const int64_t o = ((int64_t)tc.n * g.H + tc.y) * g.W + x;
-          if (rp.soft) rp.soft[o] = WS / S;
-          if (rp.lse) rp.lse[o] = M + __logf(S);
+          if (rp.soft) rp.soft[o] = ws / s;
+          if (rp.lse) rp.lse[o] = m + __logf(s);
           if (rp.amin) rp.amin[o] = mini;
           if (rp.amax) rp.amax[o] = maxi;
         }
@@ -786,25 +790,29 @@ static int launch_tc(const rsm_feat& left, const rsm_feat& right, void* out, Reg
       g.stage_bytes = (2 + g.nbb) * g.boxc * 128;
     }
   }
-  // epilogue parts: halves of the chunk, or thirds (bounds on multiples of 8) when warps 8-11 are free
-  g.nsplit = (EPI == EPI_VOLUME && g.tma) ? 3 : 2;
-  {
-    const char* e = getenv("RSM_TC_NSPLIT");
-    if (e && e[0] == '2') g.nsplit = 2;
+  // epilogue parts: halves of the chunk, or thirds (bounds on multiples of 8) when warps 8-11 are free and the
+  // wider scratch still leaves room for two operand stages
+  auto epilogue_parts = [&](int nsplit) {
+    g.nsplit = nsplit;
     auto r8 = [&](int v) { v = (v + 7) / 8 * 8; return v < g.dch ? v : g.dch; };
     g.eb[0] = 0;
-    if (g.nsplit == 2) { g.eb[1] = g.dch / 2; g.eb[2] = g.dch; g.eb[3] = g.dch; }
+    if (nsplit == 2) { g.eb[1] = g.dch / 2; g.eb[2] = g.dch; g.eb[3] = g.dch; }
     else { g.eb[1] = r8(g.dch / 3); g.eb[2] = r8(2 * g.dch / 3); g.eb[3] = g.dch; }
     int ncw = 0;                           // TMEM columns the widest part pulls: >= width + 32, multiple of 16
-    for (int k = 0; k < g.nsplit; ++k) {
+    for (int k = 0; k < nsplit; ++k) {
       const int c = (g.eb[k + 1] - g.eb[k] + 32 + 15) / 16 * 16;
       ncw = c > ncw ? c : ncw;
     }
     int p = ncw;                           // pitch: >= ncw, multiple of 4 with an odd quotient (conflict-free
     if ((p / 4) % 2 == 0) p += 4;          // 128-bit row writes and conflict-free skewed 32-bit reads)
     g.pitch = p;
+    g.epi_bytes = 32 * 4 * nsplit * g.pitch * 4 + (EPI == EPI_REGRESS ? 2 * 2 * 128 * 8 * 4 : 0);   // rows (+ partials)
+  };
+  {
+    const char* e = getenv("RSM_TC_NSPLIT");
+    epilogue_parts(g.tma && !(e && e[0] == '2') ? 3 : 2);
+    if (g.nsplit == 3 && 2 * (size_t)g.stage_bytes + (size_t)g.epi_bytes + TC_BAR_BYTES + 1024 > 220 * 1024) epilogue_parts(2);
   }
-  g.epi_bytes = 32 * 4 * g.nsplit * g.pitch * 4 + (EPI == EPI_REGRESS ? 2 * 128 * 8 * 4 : 0);   // rows (+ partials)
   g.nstage = TC_NSTAGE;
   const int extra = g.tma32 ? 2 : 0;   // lo slots
   while (g.nstage > 2 && (g.nstage + extra) * (size_t)g.stage_bytes + (size_t)g.epi_bytes + TC_BAR_BYTES + 1024 > 220 * 1024) --g.nstage;

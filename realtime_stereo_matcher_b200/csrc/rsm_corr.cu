@@ -307,9 +307,17 @@ constexpr int BG_TX = 128, BG_XT = 8, BG_NTX = BG_TX / BG_XT, BG_CK = 32, BG_MAX
 
 __device__ __forceinline__ int bg_swz(int chunk) { return chunk ^ ((chunk >> 3) & 1); }
 
-template <typename Tout, int BG_DT>
+struct RegressOutPtrs {   // FUSED: the tile goes to the soft-argmax / arg-extrema scan instead of global memory
+  float* soft;
+  int64_t* amin;
+  int64_t* amax;
+  float* lse;
+};
+
+template <typename Tout, int BG_DT, bool FUSED>
 __global__ void __launch_bounds__(BG_NTX * BG_MAXNTD)
-inner_fwd_big_kernel(FeatView L, FeatView R, Tout* __restrict__ out, CorrGeom g, int dchp, int xtiles, int vec8) {
+inner_fwd_big_kernel(FeatView L, FeatView R, Tout* __restrict__ out, CorrGeom g, int dchp, int xtiles, int vec8,
+                     RegressOutPtrs ro) {
   extern __shared__ __align__(16) float smem[];
   const int rw = BG_TX + dchp;                     // right window width (multiple of 16 floats)
   float* sL = smem;                                // [BG_CK][BG_TX]
@@ -371,10 +379,69 @@ inner_fwd_big_kernel(FeatView L, FeatView R, Tout* __restrict__ out, CorrGeom g,
         for (int j = 0; j < BG_DT; ++j) acc[i][j] = fmaf(l[i], w[BG_DT + i - j], acc[i][j]);
     }
   }
-  // ---- scale, zero the x < d triangle, store: 8 consecutive pixels per disparity
   const int xb = x0 + BG_XT * tx, db = dc0 + BG_DT * td;
-  if (xb >= g.W) return;
   const float inv = 1.f / (float)g.cpg, cnt = (float)g.cpg;
+  if constexpr (FUSED) {
+    // ---- the whole disparity range is in this CTA (D <= dchp): park the scaled tile over the dead operand slabs,
+    // sV[x][d] with an odd pitch, then one thread per pixel walks its D values in ascending order: chunked online
+    // softmax (one rescale exp per 8 values), strict compares so the first index wins ties, NaNs win through a
+    // flag -- torch.argmin / argmax semantics (same scan as inner_regress_fwd_kernel)
+    const int dp = dchp + 1;
+    float* sV = smem;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < BG_XT; ++i)
+#pragma unroll
+      for (int j = 0; j < BG_DT; ++j) {
+        float a = acc[i][j];
+        if (g.mean) a = g.pow2 ? a * inv : a / cnt;
+        sV[(BG_XT * tx + i) * dp + BG_DT * td + j] = xb + i < db + j ? 0.f : a;
+      }
+    __syncthreads();
+    for (int xx = threadIdx.x; xx < BG_TX; xx += blockDim.x) {
+      const int x = x0 + xx;
+      if (x >= g.W) continue;
+      const float* col = sV + xx * dp;
+      float m = -INFINITY, s = 0.f, ws = 0.f, minv = INFINITY, maxv = -INFINITY;
+      int mini = 0, maxi = 0, nani = -1;
+      for (int d0 = 0; d0 < g.D; d0 += 8) {
+        float v[8];
+        float gm = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int d = d0 + k;
+          float f = -INFINITY;
+          if (d < g.D) {
+            f = col[d];
+            if (f < minv) { minv = f; mini = d; }
+            if (f > maxv) { maxv = f; maxi = d; }
+            if (f != f && nani < 0) nani = d;
+          }
+          v[k] = f;
+          gm = fmaxf(gm, f);
+        }
+        const float mn = fmaxf(m, gm), mnl = mn * kLog2e;
+        const float a = (m == -INFINITY) ? 0.f : fast_exp2(fmaf(m, kLog2e, -mnl));
+        s *= a; ws *= a;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float e = fast_exp2(fmaf(v[k], kLog2e, -mnl));     // past the end: exp2(-inf) = 0
+          s += e;
+          ws = fmaf((float)(d0 + k), e, ws);
+        }
+        m = mn;
+      }
+      if (nani >= 0) { mini = nani; maxi = nani; }
+      const int64_t o = ((int64_t)n * g.H + y) * g.W + x;
+      if (ro.soft) ro.soft[o] = ws / s;
+      if (ro.lse) ro.lse[o] = m + __logf(s);
+      if (ro.amin) ro.amin[o] = mini;
+      if (ro.amax) ro.amax[o] = maxi;
+    }
+    return;
+  }
+  // ---- scale, zero the x < d triangle, store: 8 consecutive pixels per disparity
+  if (xb >= g.W) return;
 #pragma unroll
   for (int j = 0; j < BG_DT; ++j) {
     const int d = db + j;
@@ -767,9 +834,10 @@ extern "C" int rsm_inner_fwd(rsm_feat left, rsm_feat right, void* out, int64_t N
         const int vec8 = W % 8 == 0 && aligned_to(out, 32);
         const dim3 grid((unsigned)bx, (unsigned)by);
         const unsigned nt = BG_NTX * kNTD[pick];
-        if (dt == 8) inner_fwd_big_kernel<float, 8><<<grid, nt, smem, st>>>(view_of(left), view_of(right), (float*)out, g, dchp, xtiles, vec8);
-        else if (dt == 12) inner_fwd_big_kernel<float, 12><<<grid, nt, smem, st>>>(view_of(left), view_of(right), (float*)out, g, dchp, xtiles, vec8);
-        else inner_fwd_big_kernel<float, 16><<<grid, nt, smem, st>>>(view_of(left), view_of(right), (float*)out, g, dchp, xtiles, vec8);
+        const RegressOutPtrs none{nullptr, nullptr, nullptr, nullptr};
+        if (dt == 8) inner_fwd_big_kernel<float, 8, false><<<grid, nt, smem, st>>>(view_of(left), view_of(right), (float*)out, g, dchp, xtiles, vec8, none);
+        else if (dt == 12) inner_fwd_big_kernel<float, 12, false><<<grid, nt, smem, st>>>(view_of(left), view_of(right), (float*)out, g, dchp, xtiles, vec8, none);
+        else inner_fwd_big_kernel<float, 16, false><<<grid, nt, smem, st>>>(view_of(left), view_of(right), (float*)out, g, dchp, xtiles, vec8, none);
         return finish_launch("rsm_inner_fwd(8xDT)");
       }
     }
@@ -839,6 +907,33 @@ extern "C" int rsm_inner_regress_fwd(rsm_feat left, rsm_feat right, int64_t N, i
     if (!(no_tc && no_tc[0] == '1')) {   // 16-bit features, D <= 128: tcgen05 tiles reduced straight out of TMEM
       const int rc = launch_inner_regress_tc(left, right, N, C, H, W, D, reduce == RSM_REDUCE_MEAN, in_dtype, out, st);
       if (rc != RSM_ERR_UNSUPPORTED_CONFIG) return rc;
+    }
+  }
+  // fp32 features, all disparities in one 64-wide chunk, rows on 16-byte boundaries: the 8xDT-tile kernel with
+  // the regression scan as its epilogue (RSM_INNER_SMALL_TILE=1 keeps the 4x8 kernel: A/B runs)
+  {
+    const char* small = getenv("RSM_INNER_SMALL_TILE");
+    auto v4 = [&](const rsm_feat& f) {
+      return f.stride_w == 1 && f.stride_n % 4 == 0 && f.stride_c % 4 == 0 && f.stride_h % 4 == 0 && aligned_to(f.data, 16);
+    };
+    if (in_dtype == RSM_F32 && C >= 16 && D >= 16 && D <= 16 * BG_MAXNTD && W % 4 == 0 && v4(left) && v4(right) &&
+        !(small && small[0] == '1')) {
+      static const int kDT[5] = {8, 12, 8, 12, 16}, kNTD[5] = {2, 2, 4, 4, 4};   // chunks 16, 24, 32, 48, 64
+      int pick = 4;
+      for (int k = 0; k < 5; ++k)
+        if (kDT[k] * kNTD[k] >= D) { pick = k; break; }
+      const int dt = kDT[pick], dchp = dt * kNTD[pick];
+      const int xtiles = (int)ceil_div(W, BG_TX);
+      const int64_t bxb = N * H * xtiles;
+      if (grid_ok(bxb)) {
+        const size_t smemb = (size_t)BG_CK * (2 * BG_TX + dchp) * sizeof(float);   // >= BG_TX * (dchp + 1) floats
+        const RegressOutPtrs ro{(float*)out.soft, out.argmin, out.argmax, out.lse};
+        const unsigned nt = BG_NTX * kNTD[pick];
+        if (dt == 8) inner_fwd_big_kernel<float, 8, true><<<(unsigned)bxb, nt, smemb, st>>>(view_of(left), view_of(right), nullptr, g, dchp, xtiles, 0, ro);
+        else if (dt == 12) inner_fwd_big_kernel<float, 12, true><<<(unsigned)bxb, nt, smemb, st>>>(view_of(left), view_of(right), nullptr, g, dchp, xtiles, 0, ro);
+        else inner_fwd_big_kernel<float, 16, true><<<(unsigned)bxb, nt, smemb, st>>>(view_of(left), view_of(right), nullptr, g, dchp, xtiles, 0, ro);
+        return finish_launch("rsm_inner_regress_fwd(8xDT)");
+      }
     }
   }
   const int64_t bx = N * g.H * g.xtiles;

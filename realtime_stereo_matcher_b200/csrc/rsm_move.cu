@@ -274,6 +274,68 @@ difference_fwd_kernel(FeatView L, FeatView R, T* __restrict__ out, int64_t total
   }
 }
 
+// Row-block version of the difference volume: one CTA per (n, c, block of YB image rows).  The YB rows of both
+// features are staged in shared memory once and every disparity plane's YB x W block -- contiguous in the
+// (N,C,D,H,W) volume -- is written with 16-byte streaming stores, one warp per disparity.  No divisions on the
+// store path, each input element is read from HBM once instead of D times through L1/L2.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+difference_fwd_rows_kernel(FeatView L, FeatView R, T* __restrict__ out, int C, int H, int W, int D, float fill, int YB,
+                           int yblocks) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int VEC = 16 / (int)sizeof(T);
+  T* sL = reinterpret_cast<T*>(smem_raw);
+  const int padR = (D + 2 * VEC - 1) / VEC * VEC;           // front margin: x - d < 0 stays inside the buffer
+  T* sR = sL + (size_t)YB * W + padR;
+  int64_t bid = blockIdx.x;
+  const int yb = (int)(bid % yblocks); bid /= yblocks;
+  const int c = (int)(bid % C);
+  const int64_t n = bid / C;
+  const int y0 = yb * YB, ny = min(YB, H - y0);
+  const T* __restrict__ pl = reinterpret_cast<const T*>(L.data) + n * L.sn + (int64_t)c * L.sc + (int64_t)y0 * L.sh;
+  const T* __restrict__ pr = reinterpret_cast<const T*>(R.data) + n * R.sn + (int64_t)c * R.sc + (int64_t)y0 * R.sh;
+  for (int yy = threadIdx.x >> 5; yy < ny; yy += kThreads / 32)
+    for (int x = threadIdx.x & 31; x < W; x += 32) {
+      sL[yy * W + x] = __ldg(pl + (int64_t)yy * L.sh + (int64_t)x * L.sw);
+      sR[yy * W + x] = __ldg(pr + (int64_t)yy * R.sh + (int64_t)x * R.sw);
+    }
+  __syncthreads();
+  const int WV = W / VEC, nvec = ny * WV;
+  const T fillv = from_f<T>(fill);
+  const int lane = threadIdx.x & 31;
+  for (int d = threadIdx.x >> 5; d < D; d += kThreads / 32) {
+    T* __restrict__ o = out + ((((int64_t)n * C + c) * D + d) * H + y0) * (int64_t)W;
+    int yy = lane / WV, xv = lane - yy * WV;                 // one division per disparity row, then incremental
+    const int sh = (VEC - d % VEC) % VEC;                     // (x - d) mod VEC for x % VEC == 0: warp-uniform
+    for (int v = lane; v < nvec; v += 32) {
+      const T* rl = sL + yy * W + xv * VEC;
+      const Vec16<T> l = *reinterpret_cast<const Vec16<T>*>(rl);
+      Vec16<T> r;
+      if constexpr (sizeof(T) == 4) {
+        // right row shifted by d: two aligned 16-byte loads + a warp-uniform rotation instead of four strided
+        // scalar loads (each of which would be a 4-way bank conflict)
+        const T* ra = sR + yy * W + xv * VEC - d - sh;        // aligned quad holding x - d - sh .. (sh = 0: exact)
+        const Vec16<T> a = *reinterpret_cast<const Vec16<T>*>(ra);
+        const Vec16<T> b = *reinterpret_cast<const Vec16<T>*>(ra + VEC);
+        float w[8] = {a.v[0], a.v[1], a.v[2], a.v[3], b.v[0], b.v[1], b.v[2], b.v[3]};
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          const float rv = sh == 0 ? w[j] : sh == 1 ? w[j + 1] : sh == 2 ? w[j + 2] : w[j + 3];
+          r.v[j] = (xv * VEC + j >= d) ? l.v[j] - rv : fillv;
+        }
+      } else {
+        const T* rr = sR + yy * W + xv * VEC - d;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j)
+          r.v[j] = (xv * VEC + j >= d) ? from_f<T>(to_f(l.v[j]) - to_f(rr[j])) : fillv;
+      }
+      stcs16(o + (int64_t)v * VEC, r);
+      xv += 32;
+      while (xv >= WV) { xv -= WV; ++yy; }
+    }
+  }
+}
+
 // gL[c,x] = sum_{d<=x} gV[c,d,x];  gR[c,x'] = -sum_{d, x'+d<W} gV[c,d,x'+d]
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
@@ -439,6 +501,20 @@ extern "C" int rsm_difference_fwd(rsm_feat left, rsm_feat right, void* out, int6
   return RSM_DISPATCH_DTYPE(dtype, T, [&]() -> int {
     constexpr int VEC = 16 / sizeof(T);
     const bool vec = W % VEC == 0 && aligned_to(out, 16);
+    // row-block kernel: 8 image rows per CTA (RSM_DIFF_ELEMENTWISE=1 keeps the per-vector kernel: A/B runs)
+    {
+      const char* e = getenv("RSM_DIFF_ELEMENTWISE");
+      const int YB = 8;
+      const int64_t yblocks = ceil_div(H, YB), bx = N * C * yblocks;
+      const size_t smem = ((size_t)2 * YB * W + (D + 2 * VEC - 1) / VEC * VEC + VEC) * sizeof(T);
+      if (vec && smem <= 96 * 1024 && grid_ok(bx) && H * W % VEC == 0 && !(e && e[0] == '1')) {
+        auto k = difference_fwd_rows_kernel<T>;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k<<<(unsigned)bx, kThreads, smem, st>>>(view_of(left), view_of(right), (T*)out, (int)C, (int)H, (int)W, (int)D, fill,
+                                                YB, (int)yblocks);
+        return finish_launch("rsm_difference_fwd");
+      }
+    }
     const int64_t total = N * C * D * H * (vec ? W / VEC : W);
     if (!grid_ok(ceil_div(total, kThreads))) return (int)RSM_ERR_INVALID_SHAPE;
     const unsigned blocks = (unsigned)ceil_div(total, kThreads);

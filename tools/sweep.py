@@ -185,6 +185,7 @@ def main():
     rsm.load_library()
     if want("cfg1"):
         sweep_volumes("cfg1", 1, 32, 48, 156, 24, 8, ["f32"], a.iters, {"difference", "bwd"})
+        sweep_volumes("cfg1", 8, 32, 48, 156, 24, 8, ["f32", "bf16"], a.iters, {"difference", "bwd"})   # training batch of 8
         sweep_regress("cfg1", 1, 24, 48, 156, ["f32"], a.iters)
     if want("cfg2"):
         for c in (16, 64):

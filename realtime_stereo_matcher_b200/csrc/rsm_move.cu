@@ -222,6 +222,55 @@ interweave_fwd_kernel(FeatView L, FeatView R, T* __restrict__ out, int64_t total
   }
 }
 
+// 3-D grid version: blockIdx.y = output channel, blockIdx.z = batch item, blockIdx.x over the 16-byte vectors of one
+// (H, W) plane, several per thread -- no 64-bit index arithmetic; planes of W-contiguous rows (also width-cropped
+// views: one 32-bit division per vector for the row index)
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kThreads)
+interweave_fwd_plane_kernel(FeatView L, FeatView R, T* __restrict__ out, int C, int H, int W, int dense) {
+  const int ch = blockIdx.y;
+  const int64_t n = blockIdx.z;
+  const FeatView& F = (ch & 1) ? R : L;
+  const T* __restrict__ src = reinterpret_cast<const T*>(F.data) + n * F.sn + (int64_t)(ch >> 1) * F.sc;
+  T* __restrict__ dst = out + (n * 2 * C + ch) * (int64_t)H * W;
+  const int WV = W / VEC, nvec = H * WV;
+  constexpr int U = 4;
+  const int v0 = (blockIdx.x * U) * kThreads + threadIdx.x;
+  Vec16<T> t[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int v = v0 + u * kThreads;
+    if (v < nvec) {
+      if (dense) t[u] = ldcs16(src + (int64_t)v * VEC);
+      else { const int y = v / WV, xv = v - y * WV; t[u] = ldcs16(src + (int64_t)y * F.sh + xv * VEC); }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int v = v0 + u * kThreads;
+    if (v < nvec) stcs16(dst + (int64_t)v * VEC, t[u]);
+  }
+}
+
+// adjoint with the same grid: plane (n, ch) of the gradient goes to gl (even ch) or gr (odd ch)
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kThreads)
+interweave_bwd_plane_kernel(const T* __restrict__ gout, T* __restrict__ gl, T* __restrict__ gr, int C, int nvec) {
+  const int ch = blockIdx.y;
+  const int64_t n = blockIdx.z;
+  const T* __restrict__ src = gout + (n * 2 * C + ch) * (int64_t)nvec * VEC;
+  T* __restrict__ dst = ((ch & 1) ? gr : gl) + (n * C + (ch >> 1)) * (int64_t)nvec * VEC;
+  constexpr int U = 4;
+  const int v0 = (blockIdx.x * U) * kThreads + threadIdx.x;
+  Vec16<T> t[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    if (v0 + u * kThreads < nvec) t[u] = ldcs16(src + (int64_t)(v0 + u * kThreads) * VEC);
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    if (v0 + u * kThreads < nvec) stcs16(dst + (int64_t)(v0 + u * kThreads) * VEC, t[u]);
+}
+
 template <typename T, int VEC>
 __global__ void __launch_bounds__(kThreads)
 interweave_bwd_kernel(const T* __restrict__ gout, T* __restrict__ gl, T* __restrict__ gr,
@@ -454,6 +503,14 @@ extern "C" int rsm_interweave_fwd(rsm_feat left, rsm_feat right, void* out, int6
     constexpr int VEC = 16 / sizeof(T);
     const bool vec = W % VEC == 0 && feat_vec_ok(left, VEC, sizeof(T)) && feat_vec_ok(right, VEC, sizeof(T)) &&
                      aligned_to(out, 16);
+    if (vec && 2 * C <= 65535 && N <= 65535 && H * (W / VEC) < (1LL << 30)) {
+      const int nvec = (int)(H * (W / VEC));
+      const dim3 grid((unsigned)ceil_div(nvec, 4 * kThreads), (unsigned)(2 * C), (unsigned)N);
+      const int dense = left.stride_h == W && right.stride_h == W;
+      interweave_fwd_plane_kernel<T, VEC><<<grid, kThreads, 0, st>>>(view_of(left), view_of(right), (T*)out, (int)C, (int)H,
+                                                                   (int)W, dense);
+      return finish_launch("rsm_interweave_fwd");
+    }
     const int64_t total = N * 2 * C * H * (vec ? W / VEC : W);
     if (!grid_ok(ceil_div(total, kThreads))) return (int)RSM_ERR_INVALID_SHAPE;
     const unsigned blocks = (unsigned)ceil_div(total, kThreads);
@@ -478,6 +535,11 @@ extern "C" int rsm_interweave_bwd(const void* gout, void* gleft, void* gright, i
     const int64_t plane = H * W;
     const bool vec = plane % VEC == 0 && aligned_to(gout, 16) && aligned_to(gleft, 16) && aligned_to(gright, 16);
     const int64_t plane_vec = vec ? plane / VEC : plane;
+    if (vec && 2 * C <= 65535 && N <= 65535 && plane_vec < (1LL << 30)) {
+      const dim3 grid((unsigned)ceil_div(plane_vec, 4 * kThreads), (unsigned)(2 * C), (unsigned)N);
+      interweave_bwd_plane_kernel<T, VEC><<<grid, kThreads, 0, st>>>((const T*)gout, (T*)gleft, (T*)gright, (int)C, (int)plane_vec);
+      return finish_launch("rsm_interweave_bwd");
+    }
     const int64_t total = N * 2 * C * plane_vec;
     if (!grid_ok(ceil_div(total, kThreads))) return (int)RSM_ERR_INVALID_SHAPE;
     const unsigned blocks = (unsigned)ceil_div(total, kThreads);

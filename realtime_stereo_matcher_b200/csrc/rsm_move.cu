@@ -327,15 +327,23 @@ difference_fwd_kernel(FeatView L, FeatView R, T* __restrict__ out, int64_t total
 // features are staged in shared memory once and every disparity plane's YB x W block -- contiguous in the
 // (N,C,D,H,W) volume -- is written with 16-byte streaming stores, one warp per disparity.  No divisions on the
 // store path, each input element is read from HBM once instead of D times through L1/L2.
-template <typename T>
+// VEC consecutive pixels per store: 16 / 8 / 4 / 2 bytes, the widest one the row length and alignment allow
+template <int BYTES> struct StoreWord;
+template <> struct StoreWord<16> { using type = uint4; };
+template <> struct StoreWord<8> { using type = uint2; };
+template <> struct StoreWord<4> { using type = uint32_t; };
+template <> struct StoreWord<2> { using type = unsigned short; };
+
+template <typename T, int VEC>
 __global__ void __launch_bounds__(kThreads)
 difference_fwd_rows_kernel(FeatView L, FeatView R, T* __restrict__ out, int C, int H, int W, int D, float fill, int YB,
                            int yblocks) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int VEC = 16 / (int)sizeof(T);
+  using Word = typename StoreWord<VEC * (int)sizeof(T)>::type;
   T* sL = reinterpret_cast<T*>(smem_raw);
-  const int padR = (D + 2 * VEC - 1) / VEC * VEC;           // front margin: x - d < 0 stays inside the buffer
-  T* sR = sL + (size_t)YB * W + padR;
+  constexpr int AL = 16 / (int)sizeof(T);
+  const int padR = (D + 2 * AL - 1) / AL * AL;              // front margin: x - d < 0 stays inside the buffer
+  T* sR = sL + ((size_t)YB * W + AL - 1) / AL * AL + padR;
   int64_t bid = blockIdx.x;
   const int yb = (int)(bid % yblocks); bid /= yblocks;
   const int c = (int)(bid % C);
@@ -355,14 +363,14 @@ difference_fwd_rows_kernel(FeatView L, FeatView R, T* __restrict__ out, int C, i
   for (int d = threadIdx.x >> 5; d < D; d += kThreads / 32) {
     T* __restrict__ o = out + ((((int64_t)n * C + c) * D + d) * H + y0) * (int64_t)W;
     int yy = lane / WV, xv = lane - yy * WV;                 // one division per disparity row, then incremental
-    const int sh = (VEC - d % VEC) % VEC;                     // (x - d) mod VEC for x % VEC == 0: warp-uniform
+    [[maybe_unused]] const int sh = (VEC - d % VEC) % VEC;    // (x - d) mod VEC for x % VEC == 0: warp-uniform
     for (int v = lane; v < nvec; v += 32) {
       const T* rl = sL + yy * W + xv * VEC;
-      const Vec16<T> l = *reinterpret_cast<const Vec16<T>*>(rl);
-      Vec16<T> r;
-      if constexpr (sizeof(T) == 4) {
+      union { Word raw; T v[VEC]; } r;
+      if constexpr (sizeof(T) == 4 && VEC == 4) {
         // right row shifted by d: two aligned 16-byte loads + a warp-uniform rotation instead of four strided
         // scalar loads (each of which would be a 4-way bank conflict)
+        const Vec16<T> l = *reinterpret_cast<const Vec16<T>*>(rl);
         const T* ra = sR + yy * W + xv * VEC - d - sh;        // aligned quad holding x - d - sh .. (sh = 0: exact)
         const Vec16<T> a = *reinterpret_cast<const Vec16<T>*>(ra);
         const Vec16<T> b = *reinterpret_cast<const Vec16<T>*>(ra + VEC);
@@ -376,9 +384,9 @@ difference_fwd_rows_kernel(FeatView L, FeatView R, T* __restrict__ out, int C, i
         const T* rr = sR + yy * W + xv * VEC - d;
 #pragma unroll
         for (int j = 0; j < VEC; ++j)
-          r.v[j] = (xv * VEC + j >= d) ? from_f<T>(to_f(l.v[j]) - to_f(rr[j])) : fillv;
+          r.v[j] = (xv * VEC + j >= d) ? from_f<T>(to_f(rl[j]) - to_f(rr[j])) : fillv;
       }
-      stcs16(o + (int64_t)v * VEC, r);
+      __stcs(reinterpret_cast<Word*>(o + (int64_t)v * VEC), r.raw);
       xv += 32;
       while (xv >= WV) { xv -= WV; ++yy; }
     }
@@ -563,18 +571,26 @@ extern "C" int rsm_difference_fwd(rsm_feat left, rsm_feat right, void* out, int6
   return RSM_DISPATCH_DTYPE(dtype, T, [&]() -> int {
     constexpr int VEC = 16 / sizeof(T);
     const bool vec = W % VEC == 0 && aligned_to(out, 16);
-    // row-block kernel: 8 image rows per CTA (RSM_DIFF_ELEMENTWISE=1 keeps the per-vector kernel: A/B runs)
+    // row-block kernel: 8 image rows per CTA, the widest store the row length and the output alignment allow
+    // (RSM_DIFF_ELEMENTWISE=1 keeps the per-vector kernel: A/B runs)
     {
       const char* e = getenv("RSM_DIFF_ELEMENTWISE");
       const int YB = 8;
+      constexpr int AL = 16 / (int)sizeof(T);
       const int64_t yblocks = ceil_div(H, YB), bx = N * C * yblocks;
-      const size_t smem = ((size_t)2 * YB * W + (D + 2 * VEC - 1) / VEC * VEC + VEC) * sizeof(T);
-      if (vec && smem <= 96 * 1024 && grid_ok(bx) && H * W % VEC == 0 && !(e && e[0] == '1')) {
-        auto k = difference_fwd_rows_kernel<T>;
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k<<<(unsigned)bx, kThreads, smem, st>>>(view_of(left), view_of(right), (T*)out, (int)C, (int)H, (int)W, (int)D, fill,
-                                                YB, (int)yblocks);
-        return finish_launch("rsm_difference_fwd");
+      const size_t smem = ((size_t)2 * (YB * W + AL) + (D + 2 * AL - 1) / AL * AL + AL) * sizeof(T);
+      if (smem <= 96 * 1024 && grid_ok(bx) && !(e && e[0] == '1')) {
+        auto launch = [&](auto k) -> int {
+          if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          k<<<(unsigned)bx, kThreads, smem, st>>>(view_of(left), view_of(right), (T*)out, (int)C, (int)H, (int)W, (int)D, fill,
+                                                  YB, (int)yblocks);
+          return finish_launch("rsm_difference_fwd");
+        };
+        auto fits = [&](int v) { return W % v == 0 && aligned_to(out, (size_t)v * sizeof(T)); };
+        if (fits(AL)) return launch(difference_fwd_rows_kernel<T, AL>);
+        if (AL >= 4 && fits(AL / 2)) return launch(difference_fwd_rows_kernel<T, AL / 2>);
+        if (AL >= 8 && fits(AL / 4)) return launch(difference_fwd_rows_kernel<T, AL / 4>);
+        return launch(difference_fwd_rows_kernel<T, 1>);
       }
     }
     const int64_t total = N * C * D * H * (vec ? W / VEC : W);

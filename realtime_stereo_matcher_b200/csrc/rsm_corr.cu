@@ -196,11 +196,13 @@ __device__ __forceinline__ void store_tile(float (&acc)[XT][DT], Tout* __restric
         for (int j = 0; j < DT; ++j) acc[i][j] = acc[i][j] / cnt;
     }
   }
+  if (xb < db + DT - 1) {                      // only tiles touching the x < d triangle pay for the masking
 #pragma unroll
-  for (int i = 0; i < XT; ++i)
+    for (int i = 0; i < XT; ++i)
 #pragma unroll
-    for (int j = 0; j < DT; ++j)
-      if (xb + i < db + j) acc[i][j] = 0.f;   // the reference leaves zeros where x < d
+      for (int j = 0; j < DT; ++j)
+        if (xb + i < db + j) acc[i][j] = 0.f;   // the reference leaves zeros where x < d
+  }
 
   if constexpr (LAYOUT == LAYOUT_NDHW) {
     if (xb >= g.W) return;

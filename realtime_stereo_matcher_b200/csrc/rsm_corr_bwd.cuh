@@ -433,6 +433,37 @@ groupwise_bwd_row_kernel(const Tout* __restrict__ gout, FeatView L, FeatView R, 
       }
       r = noct;
     }
+    if constexpr (sizeof(Tout) == 2) {
+      // 16-bit gradient, even D, word-aligned rows: a warp takes 4 pixels x 16 disparities as 32-bit pairs (32-byte
+      // runs), a quad at a time with four independent loads in flight per thread, widened on the way into sG
+      if (g.D % 2 == 0 && (reinterpret_cast<uintptr_t>(grow) & 3) == 0) {
+        const int D16 = (D4 + 15) >> 4, dp = lane >> 2;
+        const int nitem = nxg * D16;
+        const uint32_t* __restrict__ gw = reinterpret_cast<const uint32_t*>(grow);
+        const int DW = g.D >> 1;
+        for (int it0 = threadIdx.x >> 5; it0 < nitem; it0 += 4 * (GR_THREADS / 32)) {
+          uint32_t w[4];
+          int jj[4], dd[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int it = it0 + u * (GR_THREADS / 32);
+            const int xq = it / D16, d16 = it - xq * D16;
+            jj[u] = 4 * xq + xl; dd[u] = 16 * d16 + 2 * dp;
+            const bool valid = it < nitem && jj[u] < wleft && dd[u] < g.D;
+            w[u] = valid ? __ldg(gw + (int64_t)jj[u] * DW + (dd[u] >> 1)) : 0u;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (it0 + u * (GR_THREADS / 32) < nitem && dd[u] < D4) {
+              const float2 f = unpack2<Tout>(w[u]);
+              sG[dd[u] * rg.P + jj[u]] = f.x;
+              sG[(dd[u] + 1) * rg.P + jj[u]] = f.y;
+            }
+          }
+        }
+        r = noct;
+      }
+    }
     for (; r < noct; r += GR_THREADS / 32) {
       const int j = 4 * xg + xl, d = 8 * dg + dl;
       const bool valid = j < wleft && d < g.D;

@@ -145,14 +145,17 @@ __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
 }
-// wait for completion of the phase with the given parity; bounded so a protocol bug cannot hang the GPU
+// wait for completion of the phase with the given parity; bounded so a protocol bug cannot hang the GPU.
+// try_wait carries a suspend-time hint: the waiting thread sleeps in hardware until the phase completes (or the
+// hint expires) instead of spinning -- a spinning issuer / producer lane was taking half the issue slots of its
+// scheduler away from the epilogue warps that share it (measured: those warps ran 2x slower).
 __device__ __forceinline__ bool mbar_wait(uint32_t mbar, uint32_t parity) {
-  for (int it = 0; it < (1 << 22); ++it) {
+  for (int it = 0; it < (1 << 16); ++it) {
     uint32_t ok;
     asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(mbar), "r"(parity)
+        : "r"(mbar), "r"(parity), "r"(0x989680u)
         : "memory");
     if (ok) return true;
   }
@@ -608,19 +611,23 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
         if (x < g.W) {
           const int64_t dstride = (int64_t)g.H * g.W;
           Tout* __restrict__ o = out + (((int64_t)tc.n * g.D + tc.dc0 + dlo) * g.H + tc.y) * g.W + x;
+          // one uniform loop over the warp's disparities: the x < d fill is a select, not a second loop with a
+          // per-lane trip count (on the first tile of a row the divergent version made three warps of the CTA 2-3x
+          // slower than the rest, and the slowest epilogue warp sets the tile period -- measured with clock64)
           int dl = dlo;
-          if (!divide) {
-            for (; dl + 4 <= dz; dl += 4) {                  // 4 independent LDS -> STG chains
-              const float v0 = rp0[-dl], v1 = rp0[-dl - 1], v2 = rp0[-dl - 2], v3 = rp0[-dl - 3];
-              __stcs(o, from_f<Tout>(v0 * mul)); o += dstride;
-              __stcs(o, from_f<Tout>(v1 * mul)); o += dstride;
-              __stcs(o, from_f<Tout>(v2 * mul)); o += dstride;
-              __stcs(o, from_f<Tout>(v3 * mul)); o += dstride;
-            }
+          for (; dl + 4 <= dhi; dl += 4) {                   // 4 independent LDS -> STG chains
+            float v0 = rp0[-dl], v1 = rp0[-dl - 1], v2 = rp0[-dl - 2], v3 = rp0[-dl - 3];
+            if (divide) { v0 = v0 * mul / cnt; v1 = v1 * mul / cnt; v2 = v2 * mul / cnt; v3 = v3 * mul / cnt; }
+            else { v0 *= mul; v1 *= mul; v2 *= mul; v3 *= mul; }
+            __stcs(o, from_f<Tout>(dl < dz ? v0 : 0.f)); o += dstride;
+            __stcs(o, from_f<Tout>(dl + 1 < dz ? v1 : 0.f)); o += dstride;
+            __stcs(o, from_f<Tout>(dl + 2 < dz ? v2 : 0.f)); o += dstride;
+            __stcs(o, from_f<Tout>(dl + 3 < dz ? v3 : 0.f)); o += dstride;
           }
-          for (; dl < dz; ++dl, o += dstride) __stcs(o, from_f<Tout>(divide ? rp0[-dl] * mul / cnt : rp0[-dl] * mul));
-          const Tout zero = from_f<Tout>(0.f);
-          for (; dl < dhi; ++dl, o += dstride) __stcs(o, zero);
+          for (; dl < dhi; ++dl, o += dstride) {
+            const float v = divide ? rp0[-dl] * mul / cnt : rp0[-dl] * mul;
+            __stcs(o, from_f<Tout>(dl < dz ? v : 0.f));
+          }
         }
       } else {
         // ---- fused regression over this warp's disparities in ascending order (first index wins ties)

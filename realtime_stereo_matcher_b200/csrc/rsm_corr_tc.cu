@@ -635,7 +635,52 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
           m = -INFINITY; s = 0.f; ws = 0.f; minv = INFINITY; maxv = -INFINITY;
           mini = 0x7fffffff; maxi = 0x7fffffff; nani = 0x7fffffff;
         }
-        for (int d0 = dlo; d0 < dhi; d0 += 8) {
+        int d0 = dlo;
+        // full chunks of 8, lean form (the epilogue warps are issue-bound: three share a scheduler).  Extrema by
+        // FMNMX trees, their first index by equality selects, one running-extremum update per chunk; the exponent
+        // weights are compile-time k on top of a per-chunk float base (no I2F); NaNs are looked for only when the
+        // chunk's sum of exponentials is NaN.  torch semantics as below: first index wins ties, NaN wins.
+        for (; d0 + 8 <= dhi; d0 += 8) {
+          float v[8];
+          const bool allin = __all_sync(0xffffffffu, dz >= d0 + 8);        // no x < d fill in this chunk (usual)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            float f = divide ? rp0[-(d0 + k)] * mul / cnt : rp0[-(d0 + k)] * mul;
+            if (!allin) f = d0 + k < dz ? f : 0.f;                          // fill takes part (F8)
+            v[k] = f;
+          }
+          const float lo01 = fminf(v[0], v[1]), lo23 = fminf(v[2], v[3]), lo45 = fminf(v[4], v[5]), lo67 = fminf(v[6], v[7]);
+          const float hi01 = fmaxf(v[0], v[1]), hi23 = fmaxf(v[2], v[3]), hi45 = fmaxf(v[4], v[5]), hi67 = fmaxf(v[6], v[7]);
+          const float cmin = fminf(fminf(lo01, lo23), fminf(lo45, lo67));
+          const float cmax = fmaxf(fmaxf(hi01, hi23), fmaxf(hi45, hi67));
+          int imin = 7, imax = 7;
+#pragma unroll
+          for (int k = 6; k >= 0; --k) {                                     // first k attaining the extremum
+            imin = v[k] == cmin ? k : imin;
+            imax = v[k] == cmax ? k : imax;
+          }
+          if (cmin < minv) { minv = cmin; mini = tc.dc0 + d0 + imin; }
+          if (cmax > maxv) { maxv = cmax; maxi = tc.dc0 + d0 + imax; }
+          const float mn = fmaxf(m, cmax);
+          const float mnl = mn * kLog2e;
+          const float a = (m == -INFINITY) ? 0.f : fast_exp2(fmaf(m, kLog2e, -mnl));
+          float e[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) e[k] = fast_exp2(fmaf(v[k], kLog2e, -mnl));
+          const float S = ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+          const float T = (fmaf(2.f, e[2], e[1]) + fmaf(3.f, e[3], 4.f * e[4])) +
+                          (fmaf(5.f, e[5], 6.f * e[6]) + 7.f * e[7]);                   // sum_k k * e_k
+          const float fb = (float)(tc.dc0 + d0);
+          s = fmaf(s, a, S);
+          ws = fmaf(ws, a, fmaf(fb, S, T));
+          m = mn;
+          if (S != S) {                                                      // a NaN in the chunk (rare): first one
+#pragma unroll
+            for (int k = 7; k >= 0; --k)
+              if (v[k] != v[k]) nani = min(nani, tc.dc0 + d0 + k);
+          }
+        }
+        for (; d0 < dhi; d0 += 8) {                                          // ragged tail: element-wise form
           float v[8];
           float gm = -INFINITY;
 #pragma unroll

@@ -44,6 +44,48 @@ struct RegressState {
       minv[j] = INFINITY; maxv[j] = -INFINITY; mini[j] = 0; maxi[j] = 0; nan[j] = false;
     }
   }
+  // a full chunk of 8 disparities d0 .. d0+7, lean form (the combined soft + arg kernel is issue-bound): extrema
+  // by FMNMX trees, their first index by equality selects, ONE running-extremum update per chunk, compile-time
+  // exponent weights on top of a per-chunk float base.  The NaN flag is conservative (sum of exponentials, or sum
+  // of the values for the arg-only kernel, is NaN): the rescan at the end decides.  Same torch semantics.
+  __device__ __forceinline__ void consume_full8(const float (&v)[8][VEC], int d0) {
+    const float fb = (float)d0;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const float cmax = fmaxf(fmaxf(fmaxf(v[0][j], v[1][j]), fmaxf(v[2][j], v[3][j])),
+                               fmaxf(fmaxf(v[4][j], v[5][j]), fmaxf(v[6][j], v[7][j])));
+      if constexpr (SOFT) {
+        const float mn = fmaxf(m[j], cmax);
+        const float mnl = mn * kLog2e;
+        const float a = (m[j] == -INFINITY) ? 0.f : fast_exp2(fmaf(m[j], kLog2e, -mnl));
+        float e[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) e[k] = fast_exp2(fmaf(v[k][j], kLog2e, -mnl));
+        const float S = ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+        const float T = (fmaf(2.f, e[2], e[1]) + fmaf(3.f, e[3], 4.f * e[4])) + (fmaf(5.f, e[5], 6.f * e[6]) + 7.f * e[7]);
+        s[j] = fmaf(s[j], a, S);
+        ws[j] = fmaf(ws[j], a, fmaf(fb, S, T));
+        m[j] = mn;
+        if constexpr (ARG) nan[j] |= (S != S);
+      }
+      if constexpr (ARG) {
+        const float cmin = fminf(fminf(fminf(v[0][j], v[1][j]), fminf(v[2][j], v[3][j])),
+                                 fminf(fminf(v[4][j], v[5][j]), fminf(v[6][j], v[7][j])));
+        int imin = 7, imax = 7;
+#pragma unroll
+        for (int k = 6; k >= 0; --k) {
+          imin = v[k][j] == cmin ? k : imin;
+          imax = v[k][j] == cmax ? k : imax;
+        }
+        if (cmin < minv[j]) { minv[j] = cmin; mini[j] = d0 + imin; }
+        if (cmax > maxv[j]) { maxv[j] = cmax; maxi[j] = d0 + imax; }
+        if constexpr (!SOFT) {
+          const float vs = ((v[0][j] + v[1][j]) + (v[2][j] + v[3][j])) + ((v[4][j] + v[5][j]) + (v[6][j] + v[7][j]));
+          nan[j] |= (vs != vs);
+        }
+      }
+    }
+  }
   // consume disparities d0 .. d0+CNT-1 held in v[k][j]
   template <int DCH>
   __device__ __forceinline__ void consume(const float (&v)[DCH][VEC], int d0, int cnt) {
@@ -99,7 +141,8 @@ regress_fwd_kernel(const T* __restrict__ cost, T* __restrict__ soft, int64_t* __
     float v[DCH][VEC];
 #pragma unroll
     for (int k = 0; k < DCH; ++k) load_vec<T, VEC>(base + (int64_t)(d0 + k) * HW, v[k]);
-    st.template consume<DCH>(v, d0, DCH);
+    if constexpr (DCH == 8) st.consume_full8(v, d0);
+    else st.template consume<DCH>(v, d0, DCH);
   }
   if (d0 < D) {                            // ragged tail
     float v[DCH][VEC];

@@ -121,6 +121,69 @@ struct ArgTrack {
   }
 };
 
+// Per-pixel running soft-argmax / arg-extrema state, fed 8 disparities at a time in ascending order (torch
+// semantics: first index wins ties; NaN wins, first one).  Lean form for issue-bound epilogues: extrema by FMNMX
+// trees, their first index by equality selects, one running-extremum update per chunk, compile-time exponent
+// weights on top of a per-chunk float base, NaNs looked for only when the chunk's sum of exponentials is NaN.
+struct ScanState {
+  float m = -INFINITY, s = 0.f, ws = 0.f, minv = INFINITY, maxv = -INFINITY;
+  int mini = 0, maxi = 0, nani = 0x7fffffff;
+  __device__ __forceinline__ void chunk8(const float (&v)[8], int d0) {
+    const float cmin = fminf(fminf(fminf(v[0], v[1]), fminf(v[2], v[3])), fminf(fminf(v[4], v[5]), fminf(v[6], v[7])));
+    const float cmax = fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
+    int imin = 7, imax = 7;
+#pragma unroll
+    for (int k = 6; k >= 0; --k) {
+      imin = v[k] == cmin ? k : imin;
+      imax = v[k] == cmax ? k : imax;
+    }
+    if (cmin < minv) { minv = cmin; mini = d0 + imin; }
+    if (cmax > maxv) { maxv = cmax; maxi = d0 + imax; }
+    const float mn = fmaxf(m, cmax), mnl = mn * kLog2e;
+    const float a = (m == -INFINITY) ? 0.f : fast_exp2(fmaf(m, kLog2e, -mnl));
+    float e[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) e[k] = fast_exp2(fmaf(v[k], kLog2e, -mnl));
+    const float S = ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+    const float T = (fmaf(2.f, e[2], e[1]) + fmaf(3.f, e[3], 4.f * e[4])) + (fmaf(5.f, e[5], 6.f * e[6]) + 7.f * e[7]);
+    s = fmaf(s, a, S);
+    ws = fmaf(ws, a, fmaf((float)d0, S, T));
+    m = mn;
+    if (S != S) {
+#pragma unroll
+      for (int k = 7; k >= 0; --k)
+        if (v[k] != v[k]) nani = min(nani, d0 + k);
+    }
+  }
+  // ragged tail: cnt < 8 values
+  __device__ __forceinline__ void tail(const float (&v)[8], int d0, int cnt) {
+    float gm = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (k < cnt) {
+        const float f = v[k];
+        if (f < minv) { minv = f; mini = d0 + k; }
+        if (f > maxv) { maxv = f; maxi = d0 + k; }
+        if (f != f) nani = min(nani, d0 + k);
+        gm = fmaxf(gm, f);
+      }
+    const float mn = fmaxf(m, gm), mnl = mn * kLog2e;
+    const float a = (m == -INFINITY) ? 0.f : fast_exp2(fmaf(m, kLog2e, -mnl));
+    s *= a; ws *= a;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (k < cnt) {
+        const float e = fast_exp2(fmaf(v[k], kLog2e, -mnl));
+        s += e;
+        ws = fmaf((float)(d0 + k), e, ws);
+      }
+    m = mn;
+  }
+  __device__ __forceinline__ void finish() {
+    if (nani != 0x7fffffff) { mini = nani; maxi = nani; }
+  }
+};
+
 struct FeatView {  // device-side copy of rsm_feat
   const void* data;
   int64_t sn, sc, sh, sw;

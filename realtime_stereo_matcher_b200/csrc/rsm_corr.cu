@@ -404,41 +404,26 @@ inner_fwd_big_kernel(FeatView L, FeatView R, Tout* __restrict__ out, CorrGeom g,
       const int x = x0 + xx;
       if (x >= g.W) continue;
       const float* col = sV + xx * dp;
-      float m = -INFINITY, s = 0.f, ws = 0.f, minv = INFINITY, maxv = -INFINITY;
-      int mini = 0, maxi = 0, nani = -1;
-      for (int d0 = 0; d0 < g.D; d0 += 8) {
+      ScanState sc;
+      int d0 = 0;
+      for (; d0 + 8 <= g.D; d0 += 8) {
         float v[8];
-        float gm = -INFINITY;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int d = d0 + k;
-          float f = -INFINITY;
-          if (d < g.D) {
-            f = col[d];
-            if (f < minv) { minv = f; mini = d; }
-            if (f > maxv) { maxv = f; maxi = d; }
-            if (f != f && nani < 0) nani = d;
-          }
-          v[k] = f;
-          gm = fmaxf(gm, f);
-        }
-        const float mn = fmaxf(m, gm), mnl = mn * kLog2e;
-        const float a = (m == -INFINITY) ? 0.f : fast_exp2(fmaf(m, kLog2e, -mnl));
-        s *= a; ws *= a;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float e = fast_exp2(fmaf(v[k], kLog2e, -mnl));     // past the end: exp2(-inf) = 0
-          s += e;
-          ws = fmaf((float)(d0 + k), e, ws);
-        }
-        m = mn;
+        for (int k = 0; k < 8; ++k) v[k] = col[d0 + k];
+        sc.chunk8(v, d0);
       }
-      if (nani >= 0) { mini = nani; maxi = nani; }
+      if (d0 < g.D) {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = d0 + k < g.D ? col[d0 + k] : 0.f;
+        sc.tail(v, d0, g.D - d0);
+      }
+      sc.finish();
       const int64_t o = ((int64_t)n * g.H + y) * g.W + x;
-      if (ro.soft) ro.soft[o] = ws / s;
-      if (ro.lse) ro.lse[o] = m + __logf(s);
-      if (ro.amin) ro.amin[o] = mini;
-      if (ro.amax) ro.amax[o] = maxi;
+      if (ro.soft) ro.soft[o] = sc.ws / sc.s;
+      if (ro.lse) ro.lse[o] = sc.m + __logf(sc.s);
+      if (ro.amin) ro.amin[o] = sc.mini;
+      if (ro.amax) ro.amax[o] = sc.maxi;
     }
     return;
   }
@@ -587,41 +572,26 @@ inner_regress_fwd_kernel(FeatView L, FeatView R, float* __restrict__ soft, int64
     const int x = x0 + xx;
     if (x >= g.W) continue;
     const float* col = sV + xx * dp;
-    float m = -INFINITY, s = 0.f, ws = 0.f, minv = INFINITY, maxv = -INFINITY;
-    int mini = 0, maxi = 0, nani = -1;
-    for (int d0 = 0; d0 < g.D; d0 += 8) {
+    ScanState sc;
+    int d0 = 0;
+    for (; d0 + 8 <= g.D; d0 += 8) {
       float v[8];
-      float gm = -INFINITY;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int d = d0 + k;
-        float f = -INFINITY;
-        if (d < g.D) {
-          f = col[d];
-          if (f < minv) { minv = f; mini = d; }
-          if (f > maxv) { maxv = f; maxi = d; }
-          if (f != f && nani < 0) nani = d;
-        }
-        v[k] = f;
-        gm = fmaxf(gm, f);
-      }
-      const float mn = fmaxf(m, gm), mnl = mn * kLog2e;
-      const float a = (m == -INFINITY) ? 0.f : fast_exp2(fmaf(m, kLog2e, -mnl));
-      s *= a; ws *= a;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float e = fast_exp2(fmaf(v[k], kLog2e, -mnl));     // past the end: exp2(-inf) = 0
-        s += e;
-        ws = fmaf((float)(d0 + k), e, ws);
-      }
-      m = mn;
+      for (int k = 0; k < 8; ++k) v[k] = col[d0 + k];
+      sc.chunk8(v, d0);
     }
-    if (nani >= 0) { mini = nani; maxi = nani; }
+    if (d0 < g.D) {
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = d0 + k < g.D ? col[d0 + k] : 0.f;
+      sc.tail(v, d0, g.D - d0);
+    }
+    sc.finish();
     const int64_t o = ((int64_t)n * g.H + y) * g.W + x;
-    if (soft) soft[o] = ws / s;
-    if (lse) lse[o] = m + __logf(s);
-    if (amin) amin[o] = mini;
-    if (amax) amax[o] = maxi;
+    if (soft) soft[o] = sc.ws / sc.s;
+    if (lse) lse[o] = sc.m + __logf(sc.s);
+    if (amin) amin[o] = sc.mini;
+    if (amax) amax[o] = sc.maxi;
   }
 }
 

@@ -688,8 +688,8 @@ static int launch_bwd(const void* gout, const rsm_feat& left, const rsm_feat& ri
     auto v16 = [&](const rsm_feat& f) {
       return f.stride_w == 1 && f.stride_n % EPV == 0 && f.stride_c % EPV == 0 && f.stride_h % EPV == 0 && aligned_to(f.data, 16);
     };
-    // (16-bit tensors are widened synchronously while staging: only worth it from 32 channels up, measured)
-    if (g.G == 1 && g.C >= (sizeof(Tin) == 4 ? 16 : 32) && g.D > 0 && g.W % EPV == 0 && v16(left) && v16(right) && aligned_to(gout, 16) &&
+    // (16-bit tensors are widened synchronously while staging, a few loads in flight per thread)
+    if (g.G == 1 && g.C >= 16 && g.D > 0 && g.W % EPV == 0 && v16(left) && v16(right) && aligned_to(gout, 16) &&
         (!gl || aligned_to(gl, 16)) && (!gr || aligned_to(gr, 16)) && !(naive && naive[0] == '1') &&
         !(small && small[0] == '1')) {
       const int xtiles = (int)ceil_div(g.W, BB_TX), cblocks = (int)ceil_div(g.C, BB_CB);

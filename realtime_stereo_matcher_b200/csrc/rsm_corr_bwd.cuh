@@ -206,16 +206,23 @@ corr_bwd_tiled_kernel(const Tout* __restrict__ gout, FeatView L, FeatView R, Tin
 // gR[c,x'] = sum_d gV[d][x'+d] L[c][x'+d] into the same Toeplitz form as the left one (window ascending
 // instead of descending).  Rows are XOR-swizzled by 16-byte chunk (chunk ^= (chunk >> 3) & 1): lanes read
 // 32-byte segments 32 bytes apart.  Staging: 16-byte LDGSTS with zero-fill wherever the source is
-// chunk-aligned (everything except the skewed tile, which moves 4 bytes at a time).
+// chunk-aligned (everything except the fp32 skewed tile, which moves 4 bytes at a time).  16-bit tensors are
+// widened on the way in: 16-byte loads (four in flight per thread) for the aligned tiles; the skewed tile a row
+// per warp, eight rows in flight -- each lane takes the two aligned 8-byte quads around its four columns and
+// funnel-shifts them by the row's misalignment (ncu: 750 -> 477 us for the right gradient at cfg2 C=64 against
+// element-wise moves, which were latency-bound with one or two loads in flight).
 constexpr int BB_TX = 128, BB_CB = 32, BB_DCH = 64, BB_FW = BB_TX + BB_DCH, BB_THREADS = 64;
 
 __device__ __forceinline__ int bb_swz(int chunk) { return chunk ^ ((chunk >> 3) & 1); }
 
 // 8 consecutive 16-bit elements (one 16-byte load) widened to fp32 and stored as two swizzled 16-byte chunks
+template <typename T> __device__ __forceinline__ float bits_to_f(uint32_t lo16);
+template <> __device__ __forceinline__ float bits_to_f<__half>(uint32_t lo16) { return __half2float(__ushort_as_half((unsigned short)lo16)); }
+template <> __device__ __forceinline__ float bits_to_f<__nv_bfloat16>(uint32_t lo16) { return __uint_as_float(lo16 << 16); }
+template <> __device__ __forceinline__ float bits_to_f<float>(uint32_t) { return 0.f; }   // never used: fp32 moves by LDGSTS
+
 template <typename T>
-__device__ __forceinline__ void bb_stage8(float* row, int ch2, const T* src, bool valid) {
-  Vec16<T> v;
-  if (valid) v = ldg16(src);
+__device__ __forceinline__ void bb_store8(float* row, int ch2, const Vec16<T>& v, bool valid) {
   float f[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) f[i] = valid ? to_f(v.v[i]) : 0.f;
@@ -253,7 +260,8 @@ inner_bwd_big_kernel(const T* __restrict__ gout, FeatView L, FeatView R, T* __re
 
   for (int dc0 = 0; dc0 < g.D; dc0 += BB_DCH) {
     __syncthreads();
-    // ---- gradient tile
+    // ---- gradient tile (the sum below reads whole groups of eight rows)
+    const int nrows = min(BB_DCH, (g.D - dc0 + 7) & ~7);
     if constexpr (SIDE == SIDE_LEFT && sizeof(T) == 4) {
       for (int e = threadIdx.x; e < BB_DCH * (BB_TX / 4); e += BB_THREADS) {
         const int dl = e >> 5, ch = e & 31;
@@ -264,23 +272,66 @@ inner_bwd_big_kernel(const T* __restrict__ gout, FeatView L, FeatView R, T* __re
                      : "memory");
       }
     } else if constexpr (SIDE == SIDE_LEFT) {
-      for (int e = threadIdx.x; e < BB_DCH * (BB_TX / 8); e += BB_THREADS) {
-        const int dl = e >> 4, ch2 = e & 15;
-        const int d = dc0 + dl, x = x0 + 8 * ch2;
-        bb_stage8<T>(sG + dl * BB_TX, ch2, gbase + d * gsd + x, d < g.D && x < g.W);   // W % 8 == 0: whole octets
+      // W % 8 == 0: whole octets; four 16-byte loads in flight per thread before anything is widened
+      for (int e0 = threadIdx.x; e0 < nrows * (BB_TX / 8); e0 += 4 * BB_THREADS) {
+        Vec16<T> v[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = e0 + u * BB_THREADS;
+          const int d = dc0 + (e >> 4), x = x0 + 8 * (e & 15);
+          ok[u] = d < g.D && x < g.W;
+          if (ok[u]) v[u] = ldg16(gbase + d * gsd + x);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = e0 + u * BB_THREADS;
+          if ((e >> 4) < nrows) bb_store8<T>(sG + (e >> 4) * BB_TX, e & 15, v[u], ok[u]);
+        }
       }
     } else {
-      for (int e = threadIdx.x; e < BB_DCH * BB_TX; e += BB_THREADS) {
-        const int dl = e >> 7, xx = e & 127;
-        const int d = dc0 + dl, x = x0 + xx + d;             // skew: column x' holds gV[d][x' + d]
-        const bool valid = d < g.D && x < g.W;
-        float* dst = sG + dl * BB_TX + 4 * bb_swz(xx >> 2) + (xx & 3);
-        if constexpr (sizeof(T) == 4) {
+      if constexpr (sizeof(T) == 4) {
+        for (int e = threadIdx.x; e < BB_DCH * BB_TX; e += BB_THREADS) {
+          const int dl = e >> 7, xx = e & 127;
+          const int d = dc0 + dl, x = x0 + xx + d;             // skew: column x' holds gV[d][x' + d]
+          const bool valid = d < g.D && x < g.W;
+          float* dst = sG + dl * BB_TX + 4 * bb_swz(xx >> 2) + (xx & 3);
           asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)),
                        "l"(valid ? gbase + d * gsd + x : gbase), "r"(valid ? 4 : 0)
                        : "memory");
-        } else {
-          *dst = valid ? to_f(__ldg(gbase + d * gsd + x)) : 0.f;
+        }
+      } else {
+        // 16-bit: a warp moves one row at a time.  Lane l needs gV[d][x0 + d + 4l .. + 3]: the two aligned
+        // quads around it, funnel-shifted by the row's misalignment (warp-uniform), widened, one 16-byte store
+        // (eight rows = sixteen 8-byte loads in flight per lane: the staging is synchronous and latency-bound)
+        const int lane = threadIdx.x & 31;
+        constexpr int NW = BB_THREADS / 32, RB = 8;
+        for (int dl0 = threadIdx.x >> 5; dl0 < nrows; dl0 += NW * RB) {
+          uint2 lo[RB], hi[RB];
+#pragma unroll
+          for (int u = 0; u < RB; ++u) {
+            const int d = dc0 + dl0 + NW * u;
+            const int xa = ((x0 + d) & ~3) + 4 * lane;
+            lo[u] = make_uint2(0u, 0u);
+            hi[u] = make_uint2(0u, 0u);
+            if (d < g.D) {
+              const T* src = gbase + d * gsd;
+              if (xa < g.W) lo[u] = __ldg(reinterpret_cast<const uint2*>(src + xa));          // W % 4 == 0: whole quads
+              if (xa + 4 < g.W) hi[u] = __ldg(reinterpret_cast<const uint2*>(src + xa + 4));
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < RB; ++u) {
+            const int dl = dl0 + NW * u;
+            if (dl >= nrows) break;
+            const int s = (x0 + dc0 + dl) & 3;
+            const bool wo = (s >> 1) != 0;
+            const uint32_t w0 = wo ? lo[u].y : lo[u].x, w1 = wo ? hi[u].x : lo[u].y, w2 = wo ? hi[u].y : hi[u].x;
+            const int bs = 16 * (s & 1);
+            const uint32_t o0 = __funnelshift_r(w0, w1, bs), o1 = __funnelshift_r(w1, w2, bs);
+            *reinterpret_cast<float4*>(sG + dl * BB_TX + 4 * bb_swz(lane)) =
+                make_float4(bits_to_f<T>(o0 & 0xffffu), bits_to_f<T>(o0 >> 16), bits_to_f<T>(o1 & 0xffffu), bits_to_f<T>(o1 >> 16));
+          }
         }
       }
     }
@@ -299,10 +350,24 @@ inner_bwd_big_kernel(const T* __restrict__ gout, FeatView L, FeatView R, T* __re
                        : "memory");
       }
     } else {
-      for (int e = threadIdx.x; e < ncb * (BB_FW / 8); e += BB_THREADS) {
-        const int c = e / (BB_FW / 8), ch2 = e - c * (BB_FW / 8);
-        const int x = fx0 + 8 * ch2;                          // fx0 % 8 == 0 and W % 8 == 0: whole octets
-        bb_stage8<T>(sF + c * BB_FW, ch2, pf + (int64_t)c * F.sc + x, x >= 0 && x < g.W);
+      // fx0 % 8 == 0 and W % 8 == 0: whole octets, four loads in flight (deeper batches measured slower)
+      const int total = ncb * (BB_FW / 8);
+      for (int e0 = threadIdx.x; e0 < total; e0 += 4 * BB_THREADS) {
+        Vec16<T> v[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = e0 + u * BB_THREADS;
+          const int c = e / (BB_FW / 8), x = fx0 + 8 * (e - c * (BB_FW / 8));
+          ok[u] = e < total && x >= 0 && x < g.W;
+          if (ok[u]) v[u] = ldg16(pf + (int64_t)c * F.sc + x);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = e0 + u * BB_THREADS;
+          const int c = e / (BB_FW / 8);
+          if (e < total) bb_store8<T>(sF + c * BB_FW, e - c * (BB_FW / 8), v[u], ok[u]);
+        }
       }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RSM_VERSION 101 /* major*10000 + minor*100 + patch */
+#define RSM_VERSION 102 /* major*10000 + minor*100 + patch */
 
 typedef enum rsm_dtype {
   RSM_F32 = 0,
@@ -138,6 +138,26 @@ int rsm_warp_fwd(const void* image, const void* flow, void* out, int64_t N, int6
  * ATen's grid_sampler backward); gflow (N,flow_channels,H,W) in `dtype`, may be NULL */
 int rsm_warp_bwd(const void* gout, const void* image, const void* flow, float* gimage, void* gflow, int64_t N,
                  int64_t C, int64_t H, int64_t W, int flow_channels, int dtype, int device, void* stream);
+
+/* ---- pre / post steps either side of the path.  `planes` = N*C images of one size.
+ * prepare: model/mobile_stereo_net.py:121-130 (= _v2.py:194-203, _v3.py:296-305, mobile_disp_net_c.py:339-351;
+ * _v4.py:433-434 with Hp = H, Wp = W): out (planes,Hp,Wp) = 2 * (img / 255) - 1 for y < H, x < W and 0 in the
+ * right / bottom pad (F.pad after the normalisation), each op rounded as the reference's tensor ops */
+int rsm_prepare_fwd(const void* img, void* out, int64_t planes, int64_t H, int64_t W, int64_t Hp, int64_t Wp,
+                    int dtype, int device, void* stream);
+/* gimg (planes,H,W) = (gout[:, :H, :W] * 2) / 255 */
+int rsm_prepare_bwd(const void* gout, void* gimg, int64_t planes, int64_t H, int64_t W, int64_t Hp, int64_t Wp,
+                    int dtype, int device, void* stream);
+/* finalize: model/mobile_stereo_net.py:154-159 (= _v2.py:227-232; mode 0 = F.interpolate's default 'nearest') and
+ * disparity_interpolate + crop + negate, model/mobile_disp_net_c.py:223-234 + :408-411 (mode 1 = bilinear,
+ * align_corners=False): out (planes,h,w) = -resize(disp * vscale, (Hp,Wp))[:h, :w], disp (planes,hs,ws);
+ * the reference passes vscale = Wp / ws.  ATen's index rules: scale = (float)in/out; nearest
+ * min((int)floorf(dst*scale), in-1); linear max(scale*(dst+0.5)-0.5, 0) */
+int rsm_finalize_fwd(const void* disp, void* out, int64_t planes, int64_t hs, int64_t ws, int64_t Hp, int64_t Wp,
+                     int64_t h, int64_t w, float vscale, int mode, int dtype, int device, void* stream);
+/* adjoint: gdisp (planes,hs,ws) gathered per source pixel from gout (planes,h,w); deterministic */
+int rsm_finalize_bwd(const void* gout, void* gdisp, int64_t planes, int64_t hs, int64_t ws, int64_t Hp, int64_t Wp,
+                     int64_t h, int64_t w, float vscale, int mode, int dtype, int device, void* stream);
 
 /* ---- disparity regression over a dense (N,D,H,W) cost: softmax(+cost) expectation
  * (model/mobile_stereo_net.py:144-147, mobile_stereo_net_v4.py:10-14 + :517,

@@ -19,6 +19,7 @@ import numpy as np
 
 __all__ = [
     "warp_by_flow_map", "warp_by_flow_map_bwd",
+    "prepare_input", "prepare_input_bwd", "finalize_disparity", "finalize_disparity_bwd",
     "concat_volume", "concat_volume_bwd",
     "interweave", "interweave_bwd",
     "inner_product_volume", "inner_product_volume_bwd",
@@ -427,3 +428,84 @@ def warp_by_flow_map_bwd(gout, image, flow):
     if cf == 2:
         gflow[:, 1] = -giy * (h / (h - 1.0))
     return gimg.astype(np.asarray(image).dtype), gflow.astype(np.asarray(flow).dtype)
+
+
+# ------------------------------------------------------------------ pre / post steps
+def prepare_input(img, align=1):
+    """(N,C,H,W) -> (N,C,Hp,Wp): model/mobile_stereo_net.py:121-130 (= _v2.py:194-203, _v3.py:296-305,
+    mobile_disp_net_c.py:339-351): 2 * (img / 255) - 1 in the tensor's dtype, then zero padding on the right /
+    bottom to a multiple of ``align``."""
+    img = np.asarray(img)
+    dt = img.dtype.type
+    x = dt(2.0) * (img / dt(255.0)) - dt(1.0)
+    h, w = img.shape[2:]
+    h_pad = (align - (h % align)) % align
+    w_pad = (align - (w % align)) % align
+    return np.pad(x, ((0, 0), (0, 0), (0, h_pad), (0, w_pad)))
+
+
+def prepare_input_bwd(gout, size):
+    """adjoint of prepare_input: (gout[:, :, :H, :W] * 2) / 255."""
+    gout = np.asarray(gout)
+    dt = gout.dtype.type
+    h, w = size
+    return (gout[:, :, :h, :w] * dt(2.0)) / dt(255.0)
+
+
+def _resize_taps(out_size, in_size, mode):
+    """ATen's source indices / weights for one axis (UpSample.h): scale = float(in) / out;
+    nearest: min(int(floorf(dst * scale)), in - 1); linear (align_corners=False): src = max(scale * (dst + 0.5) - 0.5, 0),
+    i0 = int(src), i1 = i0 + (i0 < in - 1), l1 = src - i0."""
+    f32 = np.float32
+    scale = f32(in_size) / f32(out_size)
+    dst = np.arange(out_size, dtype=np.float32)
+    if mode == "nearest":
+        i0 = np.minimum(np.floor(dst * scale).astype(np.int64), in_size - 1)
+        return i0, i0, np.ones(out_size, f32), np.zeros(out_size, f32)
+    src = np.maximum(scale * (dst + f32(0.5)) - f32(0.5), f32(0.0)).astype(f32)
+    i0 = np.minimum(src.astype(np.int64), in_size - 1)
+    i1 = i0 + (i0 < in_size - 1)
+    l1 = np.clip(src - i0.astype(f32), 0.0, 1.0).astype(f32)
+    return i0, i1, (f32(1.0) - l1).astype(f32), l1
+
+
+def _final_scale(disp_shape, padded_size, mode):
+    hs, ws = disp_shape[2:]
+    if mode == "bilinear" and (hs, ws) == tuple(padded_size):
+        return np.float32(1.0)          # disparity_interpolate: same-size maps pass through (mobile_disp_net_c.py:228)
+    return np.float32(float(padded_size[1]) / ws)
+
+
+def finalize_disparity(disp, padded_size, size=None, mode="nearest"):
+    """(N,C,hs,ws) -> (N,C,h,w): -1.0 * F.interpolate(disp * scale, padded_size)[:, :, :h, :w], scale = Wp / ws --
+    model/mobile_stereo_net.py:154-159 (= _v2.py:227-232, nearest) and model/mobile_disp_net_c.py:223-234 + :408-411
+    (bilinear, align_corners=False)."""
+    disp = np.asarray(disp)
+    hp, wp = padded_size
+    h, w = (hp, wp) if size is None else size
+    hs, ws = disp.shape[2:]
+    v = (disp.astype(np.float32) * _final_scale(disp.shape, padded_size, mode)).astype(disp.dtype).astype(np.float32)
+    y0, y1, ly0, ly1 = (a[:h] for a in _resize_taps(hp, hs, mode))
+    x0, x1, lx0, lx1 = (a[:w] for a in _resize_taps(wp, ws, mode))
+    if mode == "nearest":
+        out = v[:, :, y0][:, :, :, x0]
+    else:
+        top = lx0 * v[:, :, y0][:, :, :, x0] + lx1 * v[:, :, y0][:, :, :, x1]
+        bot = lx0 * v[:, :, y1][:, :, :, x0] + lx1 * v[:, :, y1][:, :, :, x1]
+        out = ly0[:, None] * top + ly1[:, None] * bot
+    return (-out).astype(disp.dtype)
+
+
+def finalize_disparity_bwd(gout, disp_shape, padded_size, mode="nearest"):
+    """adjoint of finalize_disparity with respect to disp (float64 accumulation)."""
+    gout = np.asarray(gout)
+    n, c, h, w = gout.shape
+    hs, ws = disp_shape[2:]
+    hp, wp = padded_size
+    y0, y1, ly0, ly1 = (a[:h] for a in _resize_taps(hp, hs, mode))
+    x0, x1, lx0, lx1 = (a[:w] for a in _resize_taps(wp, ws, mode))
+    my = np.zeros((h, hs)); mx = np.zeros((w, ws))
+    np.add.at(my, (np.arange(h), y0), ly0); np.add.at(my, (np.arange(h), y1), ly1)
+    np.add.at(mx, (np.arange(w), x0), lx0); np.add.at(mx, (np.arange(w), x1), lx1)
+    g = np.einsum("ys,ncyx,xt->ncst", my, gout.astype(np.float64), mx)
+    return (-float(_final_scale(disp_shape, padded_size, mode)) * g).astype(gout.dtype)

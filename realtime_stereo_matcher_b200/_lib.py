@@ -47,6 +47,10 @@ SIGNATURES = {
     "rsm_shift_interweave_bwd": [vp, vp, vp, i64, i64, i64, i64, i64, ci, ci, vp],
     "rsm_warp_fwd": [vp, vp, vp, i64, i64, i64, i64, ci, ci, ci, vp],
     "rsm_warp_bwd": [vp, vp, vp, vp, vp, i64, i64, i64, i64, ci, ci, ci, vp],
+    "rsm_prepare_fwd": [vp, vp, i64, i64, i64, i64, i64, ci, ci, vp],
+    "rsm_prepare_bwd": [vp, vp, i64, i64, i64, i64, i64, ci, ci, vp],
+    "rsm_finalize_fwd": [vp, vp, i64, i64, i64, i64, i64, i64, i64, cf, ci, ci, ci, vp],
+    "rsm_finalize_bwd": [vp, vp, i64, i64, i64, i64, i64, i64, i64, cf, ci, ci, ci, vp],
     "rsm_regress_fwd": [vp, i64, i64, i64, i64, ci, RsmRegressOut, ci, vp],
     "rsm_regress_bwd": [vp, vp, vp, vp, vp, i64, i64, i64, i64, ci, ci, vp],
     "rsm_expect_fwd": [vp, vp, i64, i64, i64, i64, ci, ci, vp],

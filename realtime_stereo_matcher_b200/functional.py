@@ -287,6 +287,95 @@ def warp_by_flow_map(image, flow):
     return _Warp.apply(image, flow)
 
 
+# ---------------------------------------------------------------------------- pre / post steps
+class _Prepare(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda")
+    def forward(ctx, img, hp, wp):
+        dev = L.require_cuda(img)
+        img = _dense(img)
+        n, c, h, w = img.shape
+        out = torch.empty((n, c, hp, wp), dtype=img.dtype, device=img.device)
+        L.check(L.load().rsm_prepare_fwd(img.data_ptr(), out.data_ptr(), n * c, h, w, hp, wp, L.dtype_code(img), dev,
+                                         L.stream_ptr(dev)), "rsm_prepare_fwd")
+        ctx.dims = (dev, n, c, h, w, hp, wp)
+        return out
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, gout):
+        dev, n, c, h, w, hp, wp = ctx.dims
+        gout = _dense(gout)
+        gimg = torch.empty((n, c, h, w), dtype=gout.dtype, device=gout.device)
+        L.check(L.load().rsm_prepare_bwd(gout.data_ptr(), gimg.data_ptr(), n * c, h, w, hp, wp, L.dtype_code(gout), dev,
+                                         L.stream_ptr(dev)), "rsm_prepare_bwd")
+        return gimg, None, None
+
+
+def prepare_input(img, align=1):
+    """The models' first lines, model/mobile_stereo_net.py:121-130 (= _v2.py:194-203, _v3.py:296-305,
+    mobile_disp_net_c.py:339-351; _v4.py:433-434 with ``align=1``): ``2 * (img / 255) - 1`` then zero padding on the
+    right / bottom up to a multiple of ``align``.  (N,C,H,W) -> (N,C,Hp,Wp)."""
+    if img.dim() != 4:
+        raise ValueError(f"expected a (N,C,H,W) image, got {tuple(img.shape)}")
+    if int(align) < 1:
+        raise ValueError(f"align must be >= 1, got {align}")
+    h, w = img.shape[2:]
+    hp = h + (align - (h % align)) % align
+    wp = w + (align - (w % align)) % align
+    return _Prepare.apply(img, int(hp), int(wp))
+
+
+_RESIZE_MODES = {"nearest": 0, "bilinear": 1}
+
+
+class _Finalize(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda")
+    def forward(ctx, disp, hp, wp, h, w, vscale, mode):
+        dev = L.require_cuda(disp)
+        disp = _dense(disp)
+        n, c, hs, ws = disp.shape
+        out = torch.empty((n, c, h, w), dtype=disp.dtype, device=disp.device)
+        L.check(L.load().rsm_finalize_fwd(disp.data_ptr(), out.data_ptr(), n * c, hs, ws, hp, wp, h, w, vscale, mode,
+                                          L.dtype_code(disp), dev, L.stream_ptr(dev)), "rsm_finalize_fwd")
+        ctx.dims = (dev, n, c, hs, ws, hp, wp, h, w, vscale, mode)
+        return out
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, gout):
+        dev, n, c, hs, ws, hp, wp, h, w, vscale, mode = ctx.dims
+        gout = _dense(gout)
+        gdisp = torch.empty((n, c, hs, ws), dtype=gout.dtype, device=gout.device)
+        L.check(L.load().rsm_finalize_bwd(gout.data_ptr(), gdisp.data_ptr(), n * c, hs, ws, hp, wp, h, w, vscale, mode,
+                                          L.dtype_code(gout), dev, L.stream_ptr(dev)), "rsm_finalize_bwd")
+        return gdisp, None, None, None, None, None, None
+
+
+def finalize_disparity(disp, padded_size, size=None, mode="nearest", negate=True):
+    """The models' last lines: ``-1.0 * F.interpolate(disp * scale, padded_size)[:, :, :h, :w]`` with
+    ``scale = padded_W / disp_W`` -- model/mobile_stereo_net.py:154-159 (= _v2.py:227-232; ``mode="nearest"``, the
+    F.interpolate default) and ``disparity_interpolate`` + crop + negate, model/mobile_disp_net_c.py:223-234 +
+    :408-411 (``mode="bilinear"``, align_corners=False; a same-size map is only cropped and negated there).
+    (N,C,hs,ws) -> (N,C,h,w); ``size`` defaults to ``padded_size``; ``negate=False`` keeps the sign (the resize
+    alone, e.g. as a drop-in for ``disparity_interpolate``)."""
+    if disp.dim() != 4:
+        raise ValueError(f"expected a (N,C,h,w) disparity map, got {tuple(disp.shape)}")
+    if mode not in _RESIZE_MODES:
+        raise ValueError(f"mode must be 'nearest' or 'bilinear', got {mode!r}")
+    hp, wp = (int(v) for v in padded_size)
+    h, w = (hp, wp) if size is None else (int(v) for v in size)
+    if not (0 <= h <= hp and 0 <= w <= wp):
+        raise ValueError(f"crop size {(h, w)} exceeds the resized map {(hp, wp)}")
+    hs, ws = disp.shape[2:]
+    vscale = float(wp) / ws if ws > 0 else 1.0
+    if mode == "bilinear" and (hs, ws) == (hp, wp):
+        vscale = 1.0      # disparity_interpolate leaves a same-size map untouched (mobile_disp_net_c.py:228)
+    # every rounding in the kernel is sign-symmetric, so "do not negate" is exactly a negated value scale
+    return _Finalize.apply(disp, hp, wp, h, w, vscale if negate else -vscale, _RESIZE_MODES[mode])
+
+
 # ---------------------------------------------------------------------------- regression
 def _regress_outputs(shape, dtype, device, soft, argmin, argmax, lse):
     n, h, w = shape

@@ -37,6 +37,26 @@ def warp_by_flow_map(image, flow):
     return F_rsm.warp_by_flow_map(image, flow)
 
 
+def prepare_input(img, align=1):
+    """model/mobile_stereo_net.py:121-130 (= _v2.py:194-203, _v3.py:296-305, mobile_disp_net_c.py:339-351,
+    _v4.py:433-434 with align=1): 2 * (img / 255) - 1, zero-padded right / bottom to a multiple of ``align``."""
+    return F_rsm.prepare_input(img, align)
+
+
+def finalize_disparity(x, padded_size, size):
+    """model/mobile_stereo_net.py:156 + :159 (= _v2.py:229 + :232, _v3.py): -1.0 * F.interpolate(x * scale,
+    padded_size)[:, :, :h, :w] with scale = padded_W / x_W."""
+    return F_rsm.finalize_disparity(x, padded_size, size, mode="nearest")
+
+
+def disparity_interpolate(disp, shape):
+    """model/mobile_disp_net_c.py:223-234: bilinear (align_corners=False) resize of ``disp * (dst_w / src_w)``;
+    a map already at ``shape`` is returned untouched."""
+    if tuple(disp.shape[2:]) == tuple(shape):
+        return disp
+    return F_rsm.finalize_disparity(disp, shape, None, mode="bilinear", negate=False)
+
+
 def disparity_regression_v4(x, maxdisp):
     """model/mobile_stereo_net_v4.py:10-14: x holds PROBABILITIES (already softmax-ed);
     returns sum_d d * x[:, d] as (N,H,W)."""

@@ -20,8 +20,6 @@ from __future__ import annotations
 import importlib
 from typing import Dict, List, Tuple
 
-import torch.nn.functional as F
-
 from . import cost_volume as cv_mirror
 from . import model_functions as mf
 
@@ -36,11 +34,8 @@ def _set(obj, name, value):
 # ------------------------------------------------------------------ fused forward glue
 def _normalise_and_pad(self, l_img, r_img):
     # mobile_stereo_net.py:121-130 (same in v2 :194-203, v3 :296-305)
-    l_img = (2.0 * (l_img / 255.0) - 1.0).contiguous()
-    r_img = (2.0 * (r_img / 255.0) - 1.0).contiguous()
     h, w = l_img.shape[2:]
-    pad = (0, (self.align - w % self.align) % self.align, 0, (self.align - h % self.align) % self.align)
-    return F.pad(l_img, pad), F.pad(r_img, pad), h, w
+    return mf.prepare_input(l_img, self.align), mf.prepare_input(r_img, self.align), h, w
 
 
 def _refine_outputs(x, steps, l_img, h, w):
@@ -48,8 +43,8 @@ def _refine_outputs(x, steps, l_img, h, w):
     outs = []
     for step in steps:
         x = step(x)
-        outs.append(F.interpolate(x * (l_img.size(3) / x.size(3)), l_img.shape[2:])[:, :, :h, :w])
-    return [-1.0 * o for o in outs]
+        outs.append(mf.finalize_disparity(x, l_img.shape[2:], (h, w)))
+    return outs
 
 
 def forward_v1(self, left_img, right_img):
@@ -114,8 +109,7 @@ def v4_volume_batched(self, featL, featR, chunk=None):
 def forward_v4(self, L, R):
     """MobileStereoNetV4.forward (mobile_stereo_net_v4.py:432-524) with interweave and the
     trilinear -> softmax -> expectation head on the fused kernels."""
-    L = (2.0 * (L / 255.0) - 1.0).contiguous()
-    R = (2.0 * (R / 255.0) - 1.0).contiguous()
+    L, R = mf.prepare_input(L), mf.prepare_input(R)          # :433-434 (v4 does not pad)
     featL = self.preconv11(self.feature_extraction(L))
     featR = self.preconv11(self.feature_extraction(R))
     B, C, H, W = featL.shape
@@ -159,9 +153,11 @@ def patch_reference(fuse: bool = True, model_package: str = "model", cost_volume
         done["functions"].append(f"{m.__name__}.make_cost_volume")
     _set(mc, "make_correlation_volume", mf.make_correlation_volume)
     _set(mc, "disparity_regression", mf.disparity_regression_dispnetc)
+    _set(mc, "disparity_interpolate", mf.disparity_interpolate)
     _set(m4, "interweave_tensors", mf.interweave_tensors)
     _set(m4, "disparity_regression", mf.disparity_regression_v4)
     done["functions"] += [f"{mc.__name__}.make_correlation_volume", f"{mc.__name__}.disparity_regression",
+                          f"{mc.__name__}.disparity_interpolate",
                           f"{m4.__name__}.interweave_tensors", f"{m4.__name__}.disparity_regression"]
     for m in (m2, m3):   # refinement warp
         _set(m, "warp_by_flow_map", mf.warp_by_flow_map)

@@ -256,8 +256,52 @@ def warp_goldens():
              gout=npy(gout), gimage=npy(image.grad), gflow=npy(flow.grad))
 
 
+def prepost_goldens():
+    """Pre / post steps exactly as the reference models execute them.  v1: the normalised + padded
+    images are what `feature_extractor` receives (mobile_stereo_net.py:121-130), the post step maps each RefineNet
+    output to the returned full-resolution map (:154-159); gradients by autograd through the model's own graph.
+    DispNetC: `disparity_interpolate` (mobile_disp_net_c.py:223-234) followed by the crop + negate of :408-411."""
+    cfgdir = os.path.join(REF, "configure")
+    torch.manual_seed(99)
+    g = torch.Generator().manual_seed(99)
+    cfg = json.load(open(os.path.join(cfgdir, "stereo_net_config.json")))
+    net = ref_model.build_model(cfg["model"]).eval()
+    limg = (torch.rand((1, 3, 52, 90), generator=g) * 255.0).requires_grad_(True)
+    rimg = torch.roll(limg.detach(), shifts=-3, dims=3)
+    prepared, refined = [], []
+    hooks = [net.feature_extractor.register_forward_pre_hook(lambda m, i: prepared.append(i[0]))]
+    hooks += [r.register_forward_hook(lambda m, i, o: refined.append(o)) for r in net.refine_layer]
+    outs = net(limg, rimg)
+    for hk in hooks:
+        hk.remove()
+    gprep = torch.randn(prepared[0].shape, generator=g)
+    (glimg,) = torch.autograd.grad(prepared[0], limg, gprep, retain_graph=True)
+    arrays = dict(limg=npy(limg), rimg=npy(rimg), prep_l=npy(prepared[0]), prep_r=npy(prepared[1]), gprep=npy(gprep),
+                  glimg=npy(glimg))
+    for k, (x, o) in enumerate(zip(refined, outs)):
+        go = torch.randn(o.shape, generator=g)
+        (gx,) = torch.autograd.grad(o, x, go, retain_graph=True)
+        arrays[f"refined{k}"], arrays[f"final{k}"], arrays[f"gfinal{k}"], arrays[f"grefined{k}"] = npy(x), npy(o), npy(go), npy(gx)
+    save("prepost_v1", dict(align=int(net.align), H=52, W=90, n_out=len(outs), mode="nearest"), **arrays)
+
+    # DispNetC: six scales of one 52 x 90 frame padded to 64 x 128 (align 2**6), the last already at full size
+    hp, wp, h, w = 64, 128, 52, 90
+    arrays = {}
+    shapes = [(1, 2), (2, 4), (4, 8), (8, 16), (32, 64), (64, 128)]
+    for k, (hs, ws) in enumerate(shapes):
+        disp = (torch.randn((2, 1, hs, ws), generator=g) * 4.0).requires_grad_(True)
+        out = -1.0 * ref_dispc.disparity_interpolate(disp, (hp, wp))[:, :, :h, :w]
+        go = torch.randn(out.shape, generator=g)
+        out.backward(go)
+        arrays[f"disp{k}"], arrays[f"out{k}"], arrays[f"gout{k}"], arrays[f"gdisp{k}"] = npy(disp), npy(out), npy(go), npy(disp.grad)
+    save("prepost_dispnetc", dict(Hp=hp, Wp=wp, H=h, W=w, n=len(shapes), mode="bilinear"), **arrays)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
+    if "--only-prepost" in sys.argv:
+        prepost_goldens()
+        sys.exit(0)
     if "--only-warp" in sys.argv:
         warp_goldens()
         sys.exit(0)
@@ -267,5 +311,6 @@ if __name__ == "__main__":
     tail_goldens()
     model_callsite_goldens()
     warp_goldens()
+    prepost_goldens()
     total = sum(os.path.getsize(os.path.join(HERE, f)) for f in os.listdir(HERE) if f.endswith(".npz"))
     print(f"total fixture bytes: {total}")

@@ -174,3 +174,36 @@ def test_warp_entry_points_stay_in_bounds(L, shape, dt):
     L.check(lib.rsm_warp_bwd(out.ptr(), image.data_ptr(), flow.data_ptr(), gimage.ptr(), gflow.ptr(), n, c, h, w, cf,
                              code, 0, st), "warp_bwd")
     gimage.check("rsm_warp_bwd gimage"), gflow.check("rsm_warp_bwd gflow")
+
+
+@pytest.mark.parametrize("case", [(3, 13, 22, 16, 24), (2, 8, 16, 8, 16), (1, 5, 7, 8, 8)])
+@pytest.mark.parametrize("dt", DTYPES)
+def test_prepare_entry_points_stay_in_bounds(L, case, dt):
+    planes, h, w, hp, wp = case
+    tdt, code = dt
+    lib = L.load()
+    st = L.stream_ptr(0)
+    img = (torch.rand((planes, h, w), device="cuda") * 255).to(tdt)
+    out = Guarded(planes * hp * wp, tdt)
+    L.check(lib.rsm_prepare_fwd(img.data_ptr(), out.ptr(), planes, h, w, hp, wp, code, 0, st), "prepare")
+    out.check("rsm_prepare_fwd")
+    gimg = Guarded(planes * h * w, tdt)
+    L.check(lib.rsm_prepare_bwd(out.ptr(), gimg.ptr(), planes, h, w, hp, wp, code, 0, st), "prepare_bwd")
+    gimg.check("rsm_prepare_bwd")
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("case", [(2, 5, 7, 40, 56, 37, 50), (1, 33, 50, 20, 30, 20, 29), (3, 1, 1, 9, 5, 9, 5), (1, 6, 9, 6, 9, 5, 9)])
+@pytest.mark.parametrize("dt", DTYPES)
+def test_finalize_entry_points_stay_in_bounds(L, case, mode, dt):
+    planes, hs, ws, hp, wp, h, w = case
+    tdt, code = dt
+    lib = L.load()
+    st = L.stream_ptr(0)
+    disp = torch.randn((planes, hs, ws), device="cuda").to(tdt)
+    out = Guarded(planes * h * w, tdt)
+    L.check(lib.rsm_finalize_fwd(disp.data_ptr(), out.ptr(), planes, hs, ws, hp, wp, h, w, wp / ws, mode, code, 0, st), "finalize")
+    out.check("rsm_finalize_fwd")
+    gdisp = Guarded(planes * hs * ws, tdt)
+    L.check(lib.rsm_finalize_bwd(out.ptr(), gdisp.ptr(), planes, hs, ws, hp, wp, h, w, wp / ws, mode, code, 0, st), "finalize_bwd")
+    gdisp.check("rsm_finalize_bwd")

@@ -581,6 +581,113 @@ def test_warp_errors(rsm):
         rsm.warp_by_flow_map(x.cpu(), torch.zeros((1, 1, 4, 8)))
 
 
+# ------------------------------------------------------------ pre / post steps
+def test_prepost_v1_goldens(rsm):
+    """prepare_input / finalize_disparity against what the reference model itself computes
+    (mobile_stereo_net.py:121-130, :154-159): bit-exact forward, gradients within fp32 summation order."""
+    g, m = load("prepost_v1")
+    limg = dev(g["limg"], grad=True)
+    prep = rsm.prepare_input(limg, m["align"])
+    assert torch.equal(prep.cpu(), torch.from_numpy(g["prep_l"]))
+    assert torch.equal(rsm.prepare_input(dev(g["rimg"]), m["align"]).cpu(), torch.from_numpy(g["prep_r"]))
+    prep.backward(dev(g["gprep"]))
+    assert torch.equal(limg.grad.cpu(), torch.from_numpy(g["glimg"]))
+    padded = g["prep_l"].shape[2:]
+    for k in range(m["n_out"]):
+        x = dev(g[f"refined{k}"], grad=True)
+        out = rsm.finalize_disparity(x, padded, (m["H"], m["W"]))
+        assert torch.equal(out.cpu(), torch.from_numpy(g[f"final{k}"]))
+        out.backward(dev(g[f"gfinal{k}"]))
+        close(x.grad, g[f"grefined{k}"], 1e-4, 3e-4)
+
+
+def test_prepost_dispnetc_goldens(rsm):
+    """disparity_interpolate + crop + negate (mobile_disp_net_c.py:223-234, :408-411), six scales incl. same-size."""
+    g, m = load("prepost_dispnetc")
+    for k in range(m["n"]):
+        x = dev(g[f"disp{k}"], grad=True)
+        out = rsm.finalize_disparity(x, (m["Hp"], m["Wp"]), (m["H"], m["W"]), mode="bilinear")
+        close(out, g[f"out{k}"], 1e-5, 1e-5)
+        out.backward(dev(g[f"gout{k}"]))
+        close(x.grad, g[f"gdisp{k}"], 1e-4, 3e-4)     # fp32 sums of up to 64 x 64 terms
+
+
+@pytest.mark.parametrize("dn", ["fp32", "bf16", "fp16"])
+@pytest.mark.parametrize("case", [(2, 3, 384, 1248, 8), (1, 3, 375, 1242, 64), (3, 1, 17, 33, 16), (1, 3, 64, 128, 1)])
+def test_prepare_vs_oracle(rsm, case, dn):
+    """KITTI-sized frames (aligned: vector path; 375 x 1242 -> 384 x 1280: scalar path) and odd shapes; all dtypes
+    bit-exact (16-bit tensors round after each op, as torch does)."""
+    n, c, h, w, align = case
+    rng = np.random.default_rng(5)
+    img = round_to((rng.random((n, c, h, w)) * 255).astype(np.float32), dn)
+    x = dev(img, dn)
+    out = rsm.prepare_input(x, align)
+    t = x.cpu()
+    ref = torch.nn.functional.pad((2.0 * (t / 255.0) - 1.0), (0, (align - w % align) % align, 0, (align - h % align) % align))
+    assert out.shape == ref.shape and torch.equal(out.cpu(), ref)
+    if dn == "fp32":
+        assert np.array_equal(out.cpu().numpy(), oracle.prepare_input(img, align))
+        gout = rng.standard_normal(tuple(out.shape)).astype(np.float32)
+        xg = dev(img, grad=True)
+        rsm.prepare_input(xg, align).backward(dev(gout))
+        assert np.array_equal(xg.grad.cpu().numpy(), oracle.prepare_input_bwd(gout, (h, w)))
+
+
+@pytest.mark.parametrize("mode", ["nearest", "bilinear"])
+@pytest.mark.parametrize("case", [(2, 48, 156, 384, 1248, 384, 1248), (1, 96, 320, 384, 1280, 375, 1242), (2, 5, 7, 40, 56, 37, 50),
+                                   (1, 6, 9, 16, 24, 13, 22), (1, 33, 50, 20, 30, 20, 29), (1, 16, 24, 16, 24, 13, 22)])
+def test_finalize_vs_oracle(rsm, case, mode):
+    """Up- and down-sampling ratios, integer and fractional, cropped and not, against the oracle; the nearest map is
+    bit-exact, the bilinear one and the gradients agree to fp32 rounding.  Also against F.interpolate on the device."""
+    n, hs, ws, hp, wp, h, w = case
+    rng = np.random.default_rng(17)
+    disp = (rng.standard_normal((n, 1, hs, ws)) * 5).astype(np.float32)
+    x = dev(disp, grad=True)
+    out = rsm.finalize_disparity(x, (hp, wp), (h, w), mode=mode)
+    ref = oracle.finalize_disparity(disp, (hp, wp), (h, w), mode)
+    if mode == "nearest":
+        assert np.array_equal(out.detach().cpu().numpy(), ref)
+    else:
+        close(out, ref, 1e-5, 1e-5)
+    gout = rng.standard_normal((n, 1, h, w)).astype(np.float32)
+    out.backward(dev(gout))
+    close(x.grad, oracle.finalize_disparity_bwd(gout, disp.shape, (hp, wp), mode), 1e-4, 3e-4)
+    t = dev(disp)
+    if mode == "nearest":
+        tref = -1.0 * torch.nn.functional.interpolate(t * (float(wp) / ws), (hp, wp))[:, :, :h, :w]
+        assert torch.equal(out.detach(), tref)
+    elif (hs, ws) != (hp, wp):
+        tref = -1.0 * torch.nn.functional.interpolate(t * (float(wp) / ws), (hp, wp), mode="bilinear", align_corners=False)[:, :, :h, :w]
+        torch.testing.assert_close(out.detach(), tref, atol=1e-4, rtol=1e-5)
+
+
+@pytest.mark.parametrize("dn", ["bf16", "fp16"])
+def test_finalize_16bit(rsm, dn):
+    rng = np.random.default_rng(3)
+    disp = round_to((rng.standard_normal((2, 1, 12, 20)) * 5).astype(np.float32), dn)
+    x = dev(disp, dn)
+    out = rsm.finalize_disparity(x, (96, 160), (90, 155))
+    ref = -1.0 * torch.nn.functional.interpolate(x * (160.0 / 20), (96, 160))[:, :, :90, :155]
+    assert torch.equal(out, ref)
+    outb = rsm.finalize_disparity(x, (96, 160), (90, 155), mode="bilinear")
+    refb = -1.0 * torch.nn.functional.interpolate(x * (160.0 / 20), (96, 160), mode="bilinear", align_corners=False)[:, :, :90, :155]
+    torch.testing.assert_close(outb.float(), refb.float(), atol=RTOL_16[dn] * 64, rtol=RTOL_16[dn] * 2)
+
+
+def test_prepost_errors(rsm):
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        rsm.prepare_input(torch.zeros((1, 3, 4, 8)), 8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        rsm.finalize_disparity(torch.zeros((1, 1, 4, 8)), (8, 16))
+    x = torch.zeros((1, 1, 4, 8), device="cuda")
+    with pytest.raises(ValueError, match="mode must be"):
+        rsm.finalize_disparity(x, (8, 16), mode="bicubic")
+    with pytest.raises(ValueError, match="exceeds"):
+        rsm.finalize_disparity(x, (8, 16), (9, 16))
+    assert rsm.prepare_input(torch.zeros((0, 3, 5, 7), device="cuda"), 8).shape == (0, 3, 8, 8)
+    assert rsm.finalize_disparity(torch.zeros((0, 1, 4, 8), device="cuda"), (8, 16), (7, 15)).shape == (0, 1, 7, 15)
+
+
 def test_empty_and_degenerate_inputs(rsm):
     """Empty batch / zero-width inputs and D = 0 go through every op without touching memory (SURVEY 8c:
     'empty and ragged inputs'); shapes follow the reference's."""

@@ -138,3 +138,30 @@ def test_warp_goldens(name):
 def test_warp_assert():
     with pytest.raises(AssertionError, match="invalid flow map dimension"):
         oracle.warp_by_flow_map(np.zeros((1, 2, 3, 4), np.float32), np.zeros((1, 3, 3, 4), np.float32))
+
+
+# ------------------------------------------------------------ pre / post steps
+def test_prepost_v1_goldens():
+    """The reference model's own prepared images (input of feature_extractor) and the mapping from each RefineNet
+    output to the returned map, mobile_stereo_net.py:121-130 / :154-159, with autograd gradients."""
+    g, m = load("prepost_v1")
+    for img, prep in ((g["limg"], g["prep_l"]), (g["rimg"], g["prep_r"])):
+        out = oracle.prepare_input(img, m["align"])
+        assert out.shape == prep.shape and np.array_equal(out, prep)          # bit-exact: same fp32 op sequence
+    assert np.array_equal(oracle.prepare_input_bwd(g["gprep"], (m["H"], m["W"])), g["glimg"])
+    padded = g["prep_l"].shape[2:]
+    for k in range(m["n_out"]):
+        out = oracle.finalize_disparity(g[f"refined{k}"], padded, (m["H"], m["W"]), "nearest")
+        assert np.array_equal(out, g[f"final{k}"])                              # a gather: bit-exact
+        _close(oracle.finalize_disparity_bwd(g[f"gfinal{k}"], g[f"refined{k}"].shape, padded, "nearest"),
+               g[f"grefined{k}"], 1e-4, 3e-4)
+
+
+def test_prepost_dispnetc_goldens():
+    """disparity_interpolate + crop + negate, mobile_disp_net_c.py:223-234 + :408-411, six scales."""
+    g, m = load("prepost_dispnetc")
+    for k in range(m["n"]):
+        out = oracle.finalize_disparity(g[f"disp{k}"], (m["Hp"], m["Wp"]), (m["H"], m["W"]), "bilinear")
+        _close(out, g[f"out{k}"], 1e-5, 1e-5)
+        _close(oracle.finalize_disparity_bwd(g[f"gout{k}"], g[f"disp{k}"].shape, (m["Hp"], m["Wp"]), "bilinear"),
+               g[f"gdisp{k}"], 1e-4, 3e-4)     # fp32 sums of up to 64 x 64 terms

@@ -37,6 +37,10 @@ def oracle_backed(monkeypatch):
     monkeypatch.setattr(F_rsm, "expectation",
                         lambda p: _t((_np(p) * np.arange(p.shape[1], dtype=np.float32).reshape(1, -1, 1, 1)).sum(1), p))
     monkeypatch.setattr(F_rsm, "upsample_regress", lambda c, d, h, w, argmin=False, argmax=False: _t(oracle.v4_tail(_np(c), d, h, w), c))
+    monkeypatch.setattr(F_rsm, "prepare_input", lambda img, align=1: _t(oracle.prepare_input(_np(img), align), img))
+    monkeypatch.setattr(F_rsm, "finalize_disparity",
+                        lambda d, padded, size=None, mode="nearest", negate=True:
+                        _t((1.0 if negate else -1.0) * oracle.finalize_disparity(_np(d), tuple(padded), None if size is None else tuple(size), mode), d))
     monkeypatch.setattr(F_rsm, "warp_by_flow_map", lambda im, fl: _t(oracle.warp_by_flow_map(_np(im), _np(fl)), im))
     monkeypatch.setattr(F_rsm, "shift_interweave_volume", lambda l, r, d: _t(oracle.shift_interweave_volume(_np(l), _np(r), d), l))
     sys.path.insert(0, REF)
@@ -77,7 +81,7 @@ def test_patched_forward_matches_reference(oracle_backed, cfg_name, size, fuse):
 def test_patch_lists_everything(oracle_backed):
     from realtime_stereo_matcher_b200 import patch_reference
     done = patch_reference(fuse=True)
-    assert len(done["functions"]) == 9 and len(done["classes"]) == 4 and len(done["forwards"]) == 4
+    assert len(done["functions"]) == 10 and len(done["classes"]) == 4 and len(done["forwards"]) == 4
     import cost_volume.groupwise as cg
     import realtime_stereo_matcher_b200 as rsm
     assert cg.TorchGroupwiseCost is rsm.TorchGroupwiseCost

@@ -176,6 +176,34 @@ def sweep_warp(cfg, n, c, h, w, iters):
         report(cfg, "warp_fwd_torch(reference op sequence on GPU, smooth flow)", "f32", shp, timed(ref, iters), nb)
 
 
+def sweep_prepost(cfg, n, h, w, align, factor, iters):
+    """pre / post steps (8f-3): normalise + pad of an RGB frame; scale + resize + crop + negate of a 1/factor map"""
+    F = torch.nn.functional
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    img = torch.rand((n, 3, h, w), device="cuda", generator=g) * 255
+    hp, wp = h + (align - h % align) % align, w + (align - w % align) % align
+    shp = dict(N=n, H=h, W=w, Hp=hp, Wp=wp)
+    nb = n * 3 * (h * w + hp * wp) * 4
+    with torch.no_grad():
+        report(cfg, "prepare_input", "f32", shp, timed(lambda: rsm.prepare_input(img, align), iters), nb)
+        report(cfg, "prepare_input_torch(reference op sequence on GPU)", "f32", shp,
+               timed(lambda: F.pad((2.0 * (img / 255.0) - 1.0).contiguous(), (0, wp - w, 0, hp - h)), iters), nb)
+    disp = torch.rand((n, 1, hp // factor, wp // factor), device="cuda", generator=g) * 20
+    nb = n * (disp.shape[2] * disp.shape[3] + h * w) * 4
+    for mode in ("nearest", "bilinear"):
+        kw = {} if mode == "nearest" else dict(mode="bilinear", align_corners=False)
+        with torch.no_grad():
+            report(cfg, f"finalize_disparity({mode}, x{factor})", "f32", shp,
+                   timed(lambda: rsm.finalize_disparity(disp, (hp, wp), (h, w), mode=mode), iters), nb)
+            report(cfg, f"finalize_torch({mode}, x{factor}; reference op sequence on GPU)", "f32", shp,
+                   timed(lambda: -1.0 * F.interpolate(disp * (float(wp) / disp.shape[3]), (hp, wp), **kw)[:, :, :h, :w], iters), nb)
+        dg = disp.clone().requires_grad_(True)
+        out = rsm.finalize_disparity(dg, (hp, wp), (h, w), mode=mode)
+        go = torch.randn_like(out)
+        report(cfg, f"finalize_disparity_bwd({mode}, x{factor})", "f32", shp,
+               timed(lambda: torch.autograd.grad(out, dg, go, retain_graph=True), iters), nb)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=10)
@@ -196,6 +224,8 @@ def main():
         sweep_warp("cfg3", 8, 32, 96, 312, a.iters)      # v3 RefineNet: 32-channel features at 1/4 resolution
         sweep_warp("cfg3", 8, 3, 192, 624, a.iters)      # v2 RefineNet: RGB at 1/2 resolution
         sweep_regress("cfg3", 8, 192, 384, 1248, ["f32"], a.iters)
+        sweep_prepost("cfg3", 8, 375, 1242, 64, 4, a.iters)   # raw KITTI frame -> 384 x 1280, 1/4-resolution map back
+        sweep_prepost("cfg3", 8, 384, 1248, 8, 8, a.iters)
     if want("cfg4"):
         for c, g, d in ((32, 8, 48), (64, 16, 96), (128, 32, 192)):
             sweep_volumes("cfg4", 1, c, 270, 480, d, g, ["f32", "bf16"], a.iters, {"concat", "groupwise", "inner", "fused"})

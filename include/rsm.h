@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RSM_VERSION 102 /* major*10000 + minor*100 + patch */
+#define RSM_VERSION 103 /* major*10000 + minor*100 + patch */
 
 typedef enum rsm_dtype {
   RSM_F32 = 0,
@@ -158,6 +158,28 @@ int rsm_finalize_fwd(const void* disp, void* out, int64_t planes, int64_t hs, in
 /* adjoint: gdisp (planes,hs,ws) gathered per source pixel from gout (planes,h,w); deterministic */
 int rsm_finalize_bwd(const void* gout, void* gdisp, int64_t planes, int64_t hs, int64_t ws, int64_t Hp, int64_t Wp,
                      int64_t h, int64_t w, float vscale, int mode, int dtype, int device, void* stream);
+
+/* ---- loss and metrics on the device.  Reductions run in two fixed-shape stages through
+ * `workspace` (>= RSM_REDUCE_WS_DOUBLES doubles, device memory, contents irrelevant) and are deterministic. */
+#define RSM_REDUCE_MAX_BLOCKS 1184
+#define RSM_REDUCE_WS_DOUBLES (RSM_REDUCE_MAX_BLOCKS * 8)
+/* one term of SequenceLoss.forward, loss/loss.py:36-81: pred (N,1,hs,ws) is resized like
+ * F.interpolate(pred * (W / ws), (H, W)) (nearest; identity when the sizes agree, :71-73), compared with gt (N,1,H,W)
+ * by L1 (kind 0) or smooth-L1 with beta 1 (kind 1, the last prediction, :75-78) and averaged over
+ * valid = (flow_valid >= 0.5) & (|gt| < max_flow) (:55-58); flow_valid (N,H,W) is fp32.
+ * result[4] (device, fp64) = {mean, valid count, non-finite predictions seen, infinite valid ground truth} -- the
+ * last two are the asserts of :60,:66-67, left to the caller to test with one read */
+int rsm_seqloss_fwd(const void* pred, const void* gt, const float* valid, double* workspace, double* result, int64_t N,
+                    int64_t hs, int64_t ws, int64_t H, int64_t W, float max_flow, int kind, int dtype, int device,
+                    void* stream);
+/* gpred (N,1,hs,ws) = gmean[0] / count * d mean / d pred; gmean (device, fp32 scalar), result from the forward call */
+int rsm_seqloss_bwd(const float* gmean, const double* result, const void* pred, const void* gt, const float* valid,
+                    void* gpred, int64_t N, int64_t hs, int64_t ws, int64_t H, int64_t W, float max_flow, int kind,
+                    int dtype, int device, void* stream);
+/* get_flow_map_metrics, loss/loss.py:6-22: epe = sqrt(sum_c (pred - gt)^2) over flow_valid >= 0.5;
+ * result[8] (device, fp64) = {epe mean, share < 0.5 px, < 1 px, < 3 px, < 5 px, min pred[0], max pred[0], valid count} */
+int rsm_flow_metrics(const void* gt, const void* pred, const float* valid, double* workspace, double* result, int64_t N,
+                     int64_t C, int64_t H, int64_t W, int dtype, int device, void* stream);
 
 /* ---- disparity regression over a dense (N,D,H,W) cost: softmax(+cost) expectation
  * (model/mobile_stereo_net.py:144-147, mobile_stereo_net_v4.py:10-14 + :517,

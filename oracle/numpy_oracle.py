@@ -20,6 +20,7 @@ import numpy as np
 __all__ = [
     "warp_by_flow_map", "warp_by_flow_map_bwd",
     "prepare_input", "prepare_input_bwd", "finalize_disparity", "finalize_disparity_bwd",
+    "sequence_loss", "sequence_loss_bwd", "flow_map_metrics",
     "concat_volume", "concat_volume_bwd",
     "interweave", "interweave_bwd",
     "inner_product_volume", "inner_product_volume_bwd",
@@ -509,3 +510,69 @@ def finalize_disparity_bwd(gout, disp_shape, padded_size, mode="nearest"):
     np.add.at(mx, (np.arange(w), x0), lx0); np.add.at(mx, (np.arange(w), x1), lx1)
     g = np.einsum("ys,ncyx,xt->ncst", my, gout.astype(np.float64), mx)
     return (-float(_final_scale(disp_shape, padded_size, mode)) * g).astype(gout.dtype)
+
+
+# ------------------------------------------------------------------ loss / metrics
+def _loss_mask(flow_gt, flow_valid, max_flow):
+    """loss/loss.py:55-58: (flow_valid >= 0.5) & (sqrt(sum_c gt^2) < max_flow), shape (N,1,H,W)."""
+    mag = np.sqrt(np.sum(flow_gt.astype(np.float32) ** 2, axis=1, dtype=np.float32))
+    return ((flow_valid >= 0.5) & (mag < max_flow))[:, None]
+
+
+def _loss_resize(pred, size):
+    """loss/loss.py:71-73: F.interpolate(pred * (W / w), size) (nearest) when the shapes differ."""
+    hs, ws = pred.shape[2:]
+    if (hs, ws) == tuple(size):
+        return pred.astype(np.float32), np.float32(1.0), None, None
+    scale = np.float32(float(size[1]) / ws)
+    y0 = _resize_taps(size[0], hs, "nearest")[0]
+    x0 = _resize_taps(size[1], ws, "nearest")[0]
+    return (pred.astype(np.float32) * scale)[:, :, y0][:, :, :, x0], scale, y0, x0
+
+
+def sequence_loss(flow_preds, flow_gt, flow_valid, loss_gamma=0.9, max_flow=700):
+    """SequenceLoss.forward, loss/loss.py:36-81: sum_i gamma^(n-1-i) * mean over the valid pixels of |gt - p_i|
+    (smooth-L1 with beta 1 for the last prediction); float64 accumulation."""
+    mask = _loss_mask(flow_gt, flow_valid, max_flow)
+    n = len(flow_preds)
+    total = 0.0
+    for i, pred in enumerate(flow_preds):
+        p = _loss_resize(np.asarray(pred), flow_gt.shape[2:])[0]
+        d = np.abs(flow_gt.astype(np.float32) - p)
+        el = np.where(d < 1.0, np.float32(0.5) * d * d, d - np.float32(0.5)) if i == n - 1 else d
+        total += loss_gamma ** (n - 1 - i) * el[mask].astype(np.float64).mean()
+    return np.float32(total)
+
+
+def sequence_loss_bwd(flow_preds, flow_gt, flow_valid, loss_gamma=0.9, max_flow=700, gout=1.0):
+    """gradients of sequence_loss with respect to every prediction."""
+    mask = _loss_mask(flow_gt, flow_valid, max_flow)
+    count = float(mask.sum())
+    n = len(flow_preds)
+    grads = []
+    for i, pred in enumerate(flow_preds):
+        pred = np.asarray(pred)
+        p, scale, y0, x0 = _loss_resize(pred, flow_gt.shape[2:])
+        d = flow_gt.astype(np.float32) - p
+        if i == n - 1:
+            g = np.where(np.abs(d) < 1.0, -d, -np.sign(d))
+        else:
+            g = -np.sign(d)
+        g = np.where(mask, g, 0.0).astype(np.float64) * (gout * loss_gamma ** (n - 1 - i) / count)
+        if y0 is None:
+            grads.append(g.astype(pred.dtype))
+            continue
+        hs, ws = pred.shape[2:]
+        acc = np.zeros(pred.shape, np.float64)
+        np.add.at(acc, (slice(None), slice(None), y0[:, None], x0[None, :]), g)
+        grads.append((acc * float(scale)).astype(pred.dtype))
+    return grads
+
+
+def flow_map_metrics(flow_gt, flow_pred, flow_valid):
+    """get_flow_map_metrics, loss/loss.py:6-22."""
+    epe = np.sqrt(np.sum((flow_pred.astype(np.float32) - flow_gt.astype(np.float32)) ** 2, axis=1, dtype=np.float32))
+    epe = epe.reshape(-1)[(flow_valid >= 0.5).reshape(-1)]
+    return {"epe": float(epe.astype(np.float64).mean()), "0.5px": float((epe < 0.5).mean()), "1px": float((epe < 1).mean()),
+            "3px": float((epe < 3).mean()), "5px": float((epe < 5).mean()),
+            "min": float(flow_pred[0].min()), "max": float(flow_pred[0].max())}

@@ -9,10 +9,13 @@ from . import cost_volume, functional, model_functions
 from ._lib import LIB_PATH, load as load_library
 from .cost_volume import (TorchConcatenateCost, TorchGroupwiseCost, TorchInnerProductCost,
                           TorchInterweaveCost)
-from .functional import (concat_volume, difference_volume, expectation, finalize_disparity, groupwise_pointwise,
+from .functional import (concat_volume, difference_volume, expectation, finalize_disparity, flow_map_metrics,
+                         groupwise_pointwise,
                          groupwise_volume, hard_argmax, hard_argmin, inner_product_regress,
-                         inner_product_volume, interweave, prepare_input, regress, shift_interweave_volume,
+                         inner_product_volume, interweave, prepare_input, regress, sequence_loss_term,
+                         shift_interweave_volume,
                          soft_argmax, upsample_regress, warp_by_flow_map)
+from .loss import SequenceLoss, build_loss_function, get_flow_map_metrics
 from .model_functions import (disparity_regression_dispnetc, disparity_regression_v4, interweave_tensors,
                               make_correlation_volume, make_cost_volume, softmax_regression, v4_head)
 from .patch import patch_reference, unpatch_reference

@@ -31,6 +31,8 @@ class RsmRegressOut(C.Structure):
 
 i64, vp, ci, cf = C.c_int64, C.c_void_p, C.c_int, C.c_float
 
+RSM_REDUCE_WS_DOUBLES = 1184 * 8   # include/rsm.h
+
 # name -> argtypes, exactly the prototypes of include/rsm.h (tests/test_abi.py checks the header)
 SIGNATURES = {
     "rsm_concat_fwd": [RsmFeat, RsmFeat, vp, i64, i64, i64, i64, i64, ci, ci, vp],
@@ -47,6 +49,9 @@ SIGNATURES = {
     "rsm_shift_interweave_bwd": [vp, vp, vp, i64, i64, i64, i64, i64, ci, ci, vp],
     "rsm_warp_fwd": [vp, vp, vp, i64, i64, i64, i64, ci, ci, ci, vp],
     "rsm_warp_bwd": [vp, vp, vp, vp, vp, i64, i64, i64, i64, ci, ci, ci, vp],
+    "rsm_seqloss_fwd": [vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, cf, ci, ci, ci, vp],
+    "rsm_seqloss_bwd": [vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, cf, ci, ci, ci, vp],
+    "rsm_flow_metrics": [vp, vp, vp, vp, vp, i64, i64, i64, i64, ci, ci, vp],
     "rsm_prepare_fwd": [vp, vp, i64, i64, i64, i64, i64, ci, ci, vp],
     "rsm_prepare_bwd": [vp, vp, i64, i64, i64, i64, i64, ci, ci, vp],
     "rsm_finalize_fwd": [vp, vp, i64, i64, i64, i64, i64, i64, i64, cf, ci, ci, ci, vp],

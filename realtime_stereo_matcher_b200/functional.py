@@ -376,6 +376,73 @@ def finalize_disparity(disp, padded_size, size=None, mode="nearest", negate=True
     return _Finalize.apply(disp, hp, wp, h, w, vscale if negate else -vscale, _RESIZE_MODES[mode])
 
 
+# ---------------------------------------------------------------------------- loss / metrics
+def _reduce_workspace(device):
+    return torch.empty((L.RSM_REDUCE_WS_DOUBLES,), dtype=torch.float64, device=device)
+
+
+class _SeqLossTerm(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, pred, gt, valid, max_flow, kind):
+        dev = L.require_cuda(pred, gt, valid)
+        pred, gt, valid = _dense(pred), _dense(gt), _dense(valid)
+        n, _, hs, ws = pred.shape
+        h, w = gt.shape[2:]
+        result = torch.empty((4,), dtype=torch.float64, device=pred.device)
+        L.check(L.load().rsm_seqloss_fwd(pred.data_ptr(), gt.data_ptr(), valid.data_ptr(), _reduce_workspace(pred.device).data_ptr(),
+                                         result.data_ptr(), n, hs, ws, h, w, max_flow, kind, L.dtype_code(pred), dev,
+                                         L.stream_ptr(dev)), "rsm_seqloss_fwd")
+        ctx.save_for_backward(pred, gt, valid, result)
+        ctx.dims = (dev, n, hs, ws, h, w, max_flow, kind)
+        ctx.mark_non_differentiable(result)
+        return result[0].to(torch.float32), result
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, gmean, _gresult):
+        pred, gt, valid, result = ctx.saved_tensors
+        dev, n, hs, ws, h, w, max_flow, kind = ctx.dims
+        gmean = gmean.to(torch.float32).contiguous()
+        gpred = torch.empty_like(pred)
+        L.check(L.load().rsm_seqloss_bwd(gmean.data_ptr(), result.data_ptr(), pred.data_ptr(), gt.data_ptr(), valid.data_ptr(),
+                                         gpred.data_ptr(), n, hs, ws, h, w, max_flow, kind, L.dtype_code(pred), dev,
+                                         L.stream_ptr(dev)), "rsm_seqloss_bwd")
+        return gpred, None, None, None, None
+
+
+def sequence_loss_term(pred, flow_gt, flow_valid, max_flow=700.0, smooth=False):
+    """One term of SequenceLoss.forward (loss/loss.py:55-80): the masked mean of |gt - p| (``smooth``: smooth-L1,
+    beta 1) with p = F.interpolate(pred * scale, gt size) when the sizes differ.  Returns ``(mean, stats)``:
+    a differentiable fp32 scalar and the fp64 vector {mean, valid count, non-finite predictions, infinite valid gt}."""
+    if pred.dim() != 4 or flow_gt.dim() != 4 or pred.shape[1] != 1 or flow_gt.shape[1] != 1:
+        raise ValueError(f"expected (N,1,h,w) prediction and (N,1,H,W) ground truth, got {tuple(pred.shape)} and {tuple(flow_gt.shape)}")
+    if flow_valid.shape != (flow_gt.shape[0],) + tuple(flow_gt.shape[2:]) or pred.shape[0] != flow_gt.shape[0]:
+        raise RuntimeError(f"shapes differ: pred {tuple(pred.shape)}, gt {tuple(flow_gt.shape)}, valid {tuple(flow_valid.shape)}")
+    if pred.dtype != flow_gt.dtype:                 # torch's type promotion in `gt - pred`
+        dt = torch.promote_types(pred.dtype, flow_gt.dtype)
+        pred, flow_gt = pred.to(dt), flow_gt.to(dt)
+    return _SeqLossTerm.apply(pred, flow_gt, flow_valid.to(torch.float32), float(max_flow), 1 if smooth else 0)
+
+
+def flow_map_metrics(flow_gt, flow_pred, flow_valid):
+    """get_flow_map_metrics (loss/loss.py:6-22) as ONE pass; returns the device vector (fp64)
+    {epe, 0.5px, 1px, 3px, 5px, min, max, valid count} without synchronising."""
+    if flow_gt.dim() != 4 or flow_gt.shape != flow_pred.shape:
+        raise RuntimeError(f"flow_gt {tuple(flow_gt.shape)} and flow_pred {tuple(flow_pred.shape)} shapes differ")
+    n, c, h, w = flow_gt.shape
+    if tuple(flow_valid.shape) != (n, h, w):
+        raise RuntimeError(f"flow_valid {tuple(flow_valid.shape)} does not match {(n, h, w)}")
+    if flow_gt.dtype != flow_pred.dtype:
+        raise TypeError(f"flow_gt ({flow_gt.dtype}) and flow_pred ({flow_pred.dtype}) dtypes differ")
+    dev = L.require_cuda(flow_gt, flow_pred, flow_valid)
+    gt, pred, valid = _dense(flow_gt.detach()), _dense(flow_pred.detach()), _dense(flow_valid.detach().to(torch.float32))
+    result = torch.empty((8,), dtype=torch.float64, device=gt.device)
+    L.check(L.load().rsm_flow_metrics(gt.data_ptr(), pred.data_ptr(), valid.data_ptr(), _reduce_workspace(gt.device).data_ptr(),
+                                      result.data_ptr(), n, c, h, w, L.dtype_code(gt), dev, L.stream_ptr(dev)), "rsm_flow_metrics")
+    return result
+
+
 # ---------------------------------------------------------------------------- regression
 def _regress_outputs(shape, dtype, device, soft, argmin, argmax, lse):
     n, h, w = shape

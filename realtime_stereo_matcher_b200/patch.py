@@ -138,11 +138,12 @@ def forward_v4(self, L, R):
 
 
 # ---------------------------------------------------------------------------- patching
-def patch_reference(fuse: bool = True, model_package: str = "model", cost_volume_package: str = "cost_volume") -> Dict[str, List[str]]:
+def patch_reference(fuse: bool = True, model_package: str = "model", cost_volume_package: str = "cost_volume",
+                    loss_package: str = "loss") -> Dict[str, List[str]]:
     """Patch an importable reference checkout in place.  Returns what was patched.
 
     Raises ImportError when the reference packages cannot be imported (nothing is patched)."""
-    done: Dict[str, List[str]] = {"functions": [], "classes": [], "forwards": []}
+    done: Dict[str, List[str]] = {"functions": [], "classes": [], "forwards": [], "loss": []}
     m1 = importlib.import_module(f"{model_package}.mobile_stereo_net")
     m2 = importlib.import_module(f"{model_package}.mobile_stereo_net_v2")
     m3 = importlib.import_module(f"{model_package}.mobile_stereo_net_v3")
@@ -170,6 +171,17 @@ def patch_reference(fuse: bool = True, model_package: str = "model", cost_volume
             done["classes"].append(f"{mod.__name__}.{cls}")
     except ImportError:
         pass  # cost_volume/ is imported by nothing in the reference: optional
+    try:   # loss / metrics on the device; scripts that did `from loss.loss import ...` before
+        # this call keep their own binding -- patch first, or use the import swap of INTEGRATION.md
+        from . import loss as loss_mirror
+        lpkg = importlib.import_module(loss_package)
+        lmod = importlib.import_module(f"{loss_package}.loss")
+        _set(lpkg, "SequenceLoss", loss_mirror.SequenceLoss)
+        _set(lmod, "SequenceLoss", loss_mirror.SequenceLoss)
+        _set(lmod, "get_flow_map_metrics", loss_mirror.get_flow_map_metrics)
+        done["loss"] += [f"{lpkg.__name__}.SequenceLoss", f"{lmod.__name__}.SequenceLoss", f"{lmod.__name__}.get_flow_map_metrics"]
+    except ImportError:
+        pass
     if fuse:
         for mod, cls, fwd in ((m1, "MobileStereoNet", forward_v1), (m2, "MobileStereoNetV2", forward_v2),
                               (m3, "MobileStereoNetV3", forward_v3), (m4, "MobileStereoNetV4", forward_v4)):

@@ -297,8 +297,33 @@ def prepost_goldens():
     save("prepost_dispnetc", dict(Hp=hp, Wp=wp, H=h, W=w, n=len(shapes), mode="bilinear"), **arrays)
 
 
+def loss_goldens():
+    """SequenceLoss / get_flow_map_metrics executed from the reference's loss/loss.py: predictions at
+    1/4, 1/2 and full size plus a fractional ratio, a ground truth that exceeds max_flow_magnitude in places and a
+    random validity mask; gradients of the loss with respect to every prediction by autograd."""
+    from loss.loss import SequenceLoss as RefSequenceLoss, get_flow_map_metrics as ref_metrics
+    g = torch.Generator().manual_seed(2024)
+    for tag, (n, h, w), sizes, max_flow in (("pyramid", (2, 24, 40), [(6, 10), (12, 20), (24, 40)], 30.0),
+                                             ("fractional", (1, 20, 30), [(7, 11), (20, 30)], 700.0),
+                                             ("single", (3, 9, 13), [(9, 13)], 5.0)):
+        gt = torch.randn((n, 1, h, w), generator=g) * 20.0
+        valid = (torch.rand((n, h, w), generator=g) > 0.3).float()
+        preds = [(F.interpolate(gt, s) * (s[1] / w) + torch.randn((n, 1) + s, generator=g) * 1.5).requires_grad_(True)
+                 for s in sizes]
+        loss = RefSequenceLoss(loss_gamma=0.9, max_flow_magnitude=max_flow)(preds, gt, valid)
+        loss.backward()
+        metrics = ref_metrics(gt, preds[-1].detach(), valid)
+        arrays = dict(gt=npy(gt), valid=npy(valid), loss=npy(loss))
+        for k, p in enumerate(preds):
+            arrays[f"pred{k}"], arrays[f"gpred{k}"] = npy(p), npy(p.grad)
+        save(f"loss_{tag}", dict(tag=tag, n_preds=len(preds), gamma=0.9, max_flow=max_flow, metrics=metrics), **arrays)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
+    if "--only-loss" in sys.argv:
+        loss_goldens()
+        sys.exit(0)
     if "--only-prepost" in sys.argv:
         prepost_goldens()
         sys.exit(0)
@@ -312,5 +337,6 @@ if __name__ == "__main__":
     model_callsite_goldens()
     warp_goldens()
     prepost_goldens()
+    loss_goldens()
     total = sum(os.path.getsize(os.path.join(HERE, f)) for f in os.listdir(HERE) if f.endswith(".npz"))
     print(f"total fixture bytes: {total}")

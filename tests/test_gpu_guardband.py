@@ -207,3 +207,31 @@ def test_finalize_entry_points_stay_in_bounds(L, case, mode, dt):
     gdisp = Guarded(planes * hs * ws, tdt)
     L.check(lib.rsm_finalize_bwd(out.ptr(), gdisp.ptr(), planes, hs, ws, hp, wp, h, w, wp / ws, mode, code, 0, st), "finalize_bwd")
     gdisp.check("rsm_finalize_bwd")
+
+
+@pytest.mark.parametrize("case", [(2, 6, 10, 24, 40), (1, 7, 11, 20, 30), (3, 9, 13, 9, 13)])
+@pytest.mark.parametrize("dt", DTYPES)
+def test_loss_entry_points_stay_in_bounds(L, case, dt):
+    n, hs, ws, h, w = case
+    tdt, code = dt
+    lib = L.load()
+    st = L.stream_ptr(0)
+    pred = torch.randn((n, 1, hs, ws), device="cuda").to(tdt)
+    gt = (torch.randn((n, 1, h, w), device="cuda") * 3).to(tdt)
+    valid = (torch.rand((n, h, w), device="cuda") > 0.3).float()
+    work = torch.empty((L.RSM_REDUCE_WS_DOUBLES,), dtype=torch.float64, device="cuda")
+    for kind in (0, 1):
+        result = Guarded(4, torch.float64)
+        L.check(lib.rsm_seqloss_fwd(pred.data_ptr(), gt.data_ptr(), valid.data_ptr(), work.data_ptr(), result.ptr(), n, hs, ws,
+                                    h, w, 700.0, kind, code, 0, st), "seqloss")
+        result.check("rsm_seqloss_fwd")
+        gmean = torch.ones((), device="cuda")
+        gpred = Guarded(n * hs * ws, tdt)
+        L.check(lib.rsm_seqloss_bwd(gmean.data_ptr(), result.ptr(), pred.data_ptr(), gt.data_ptr(), valid.data_ptr(), gpred.ptr(),
+                                    n, hs, ws, h, w, 700.0, kind, code, 0, st), "seqloss_bwd")
+        gpred.check("rsm_seqloss_bwd")
+    if (hs, ws) == (h, w):
+        result = Guarded(8, torch.float64)
+        L.check(lib.rsm_flow_metrics(gt.data_ptr(), pred.data_ptr(), valid.data_ptr(), work.data_ptr(), result.ptr(), n, 1, h, w,
+                                     code, 0, st), "metrics")
+        result.check("rsm_flow_metrics")

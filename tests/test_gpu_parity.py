@@ -688,6 +688,79 @@ def test_prepost_errors(rsm):
     assert rsm.finalize_disparity(torch.zeros((0, 1, 4, 8), device="cuda"), (8, 16), (7, 15)).shape == (0, 1, 7, 15)
 
 
+# ------------------------------------------------------------ loss / metrics
+@pytest.mark.parametrize("name", names("loss_"))
+def test_loss_goldens(rsm, name):
+    """SequenceLoss / get_flow_map_metrics mirrors against the reference's own loss value, gradients and metrics."""
+    g, m = load(name)
+    preds = [dev(g[f"pred{k}"], grad=True) for k in range(m["n_preds"])]
+    gt, valid = dev(g["gt"]), dev(g["valid"])
+    loss = rsm.SequenceLoss(loss_gamma=m["gamma"], max_flow_magnitude=m["max_flow"])(preds, gt, valid)
+    close(loss, g["loss"], 0, 2e-6)
+    loss.backward()
+    for k, p in enumerate(preds):
+        close(p.grad, g[f"gpred{k}"], 1e-8, 1e-5)
+    got = rsm.get_flow_map_metrics(gt, preds[-1].detach(), valid)
+    assert list(got) == list(m["metrics"])
+    for key, ref in m["metrics"].items():
+        np.testing.assert_allclose(got[key], ref, atol=1e-7, rtol=2e-6)
+
+
+@pytest.mark.parametrize("case", [(8, 384, 1248, [(96, 312), (192, 624), (384, 1248)]), (2, 375, 1242, [(375, 1242)] * 3),
+                                   (1, 33, 77, [(5, 9), (33, 77)])])
+def test_loss_vs_oracle(rsm, case):
+    """Training-batch sizes (cfg3 frames; DispNetC-style full-size predictions; odd ratios) against the oracle,
+    and against the reference's op sequence on the device."""
+    n, h, w, sizes = case
+    rng = np.random.default_rng(11)
+    gt = (rng.standard_normal((n, 1, h, w)) * 40).astype(np.float32)
+    valid = (rng.random((n, h, w)) > 0.2).astype(np.float32)
+    preds = [(rng.standard_normal((n, 1) + s) * 10).astype(np.float32) for s in sizes]
+    tp = [dev(p, grad=True) for p in preds]
+    tgt, tv = dev(gt), dev(valid)
+    loss = rsm.SequenceLoss(0.9, 60.0)(tp, tgt, tv)
+    close(loss, oracle.sequence_loss(preds, gt, valid, 0.9, 60.0), 0, 2e-6)
+    loss.backward()
+    for p, gp in zip(tp, oracle.sequence_loss_bwd(preds, gt, valid, 0.9, 60.0)):
+        close(p.grad, gp, 1e-9, 1e-5)
+    # the reference's op sequence with torch on the device
+    Fn = torch.nn.functional
+    mask = ((tv >= 0.5) & (torch.sum(tgt ** 2, dim=1).sqrt() < 60.0)).unsqueeze(1)
+    ref = 0.0
+    for i, p in enumerate(tp):
+        q = p.detach()
+        if q.shape != tgt.shape:
+            q = Fn.interpolate(q * (float(w) / q.shape[-1]), (h, w))
+        el = Fn.smooth_l1_loss(tgt, q, reduction="none", beta=1.0) if i == len(tp) - 1 else Fn.l1_loss(tgt, q, reduction="none")
+        ref = ref + 0.9 ** (len(tp) - 1 - i) * el[mask].mean()
+    torch.testing.assert_close(loss.detach(), ref, rtol=2e-5, atol=0)
+    got = rsm.get_flow_map_metrics(tgt, tp[-1].detach(), tv)
+    want = oracle.flow_map_metrics(gt, preds[-1], valid)
+    for key in want:
+        np.testing.assert_allclose(got[key], want[key], atol=1e-7, rtol=2e-6)
+
+
+def test_loss_error_behaviour(rsm):
+    gt = torch.zeros((1, 1, 4, 8), device="cuda")
+    valid = torch.ones((1, 4, 8), device="cuda")
+    loss = rsm.SequenceLoss()
+    with pytest.raises(AssertionError, match="empty flow predictions"):          # loss.py:53
+        loss([], gt, valid)
+    with pytest.raises(AssertionError):                                           # loss.py:59
+        loss([gt], gt, torch.ones((1, 4, 7), device="cuda"))
+    bad = gt.clone()
+    bad[0, 0, 1, 2] = float("nan")
+    with pytest.raises(AssertionError, match="non-finite"):                       # loss.py:66-67
+        loss([bad], gt, valid)
+    assert torch.isnan(rsm.SequenceLoss(check_finite=False)([bad], gt, valid))
+    assert torch.isnan(loss([gt], gt, torch.zeros_like(valid)))                   # empty mask: mean of nothing
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        loss([gt.cpu()], gt.cpu(), valid.cpu())
+    with pytest.raises(NotImplementedError):
+        rsm.build_loss_function({"type": "Other", "parameters": {}})
+    assert isinstance(rsm.build_loss_function({"type": "SequenceLoss", "parameters": {"loss_gamma": 0.8}}), rsm.SequenceLoss)
+
+
 def test_empty_and_degenerate_inputs(rsm):
     """Empty batch / zero-width inputs and D = 0 go through every op without touching memory (SURVEY 8c:
     'empty and ragged inputs'); shapes follow the reference's."""

@@ -165,3 +165,18 @@ def test_prepost_dispnetc_goldens():
         _close(out, g[f"out{k}"], 1e-5, 1e-5)
         _close(oracle.finalize_disparity_bwd(g[f"gout{k}"], g[f"disp{k}"].shape, (m["Hp"], m["Wp"]), "bilinear"),
                g[f"gdisp{k}"], 1e-4, 3e-4)     # fp32 sums of up to 64 x 64 terms
+
+
+# ------------------------------------------------------------ loss / metrics
+@pytest.mark.parametrize("name", names("loss_"))
+def test_loss_goldens(name):
+    """SequenceLoss.forward / get_flow_map_metrics, loss/loss.py:6-81, against the reference's own values and
+    autograd gradients (pyramid of predictions, fractional resize ratio, max-flow and validity masks)."""
+    g, m = load(name)
+    preds = [g[f"pred{k}"] for k in range(m["n_preds"])]
+    _close(oracle.sequence_loss(preds, g["gt"], g["valid"], m["gamma"], m["max_flow"]), g["loss"], 0, 1e-6)
+    for k, gp in enumerate(oracle.sequence_loss_bwd(preds, g["gt"], g["valid"], m["gamma"], m["max_flow"])):
+        _close(gp, g[f"gpred{k}"], 1e-8, 1e-5)
+    got = oracle.flow_map_metrics(g["gt"], preds[-1], g["valid"])
+    for key, ref in m["metrics"].items():
+        _close(got[key], ref, 1e-7, 1e-6)

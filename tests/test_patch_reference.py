@@ -85,3 +85,10 @@ def test_patch_lists_everything(oracle_backed):
     import cost_volume.groupwise as cg
     import realtime_stereo_matcher_b200 as rsm
     assert cg.TorchGroupwiseCost is rsm.TorchGroupwiseCost
+    import loss as ref_loss_pkg
+    import loss.loss as ref_loss
+    assert len(done["loss"]) == 3
+    assert ref_loss.SequenceLoss is rsm.SequenceLoss and ref_loss.get_flow_map_metrics is rsm.get_flow_map_metrics
+    assert isinstance(ref_loss_pkg.build_loss_function({"type": "SequenceLoss", "parameters": {}}), rsm.SequenceLoss)
+    rsm.unpatch_reference()
+    assert ref_loss.SequenceLoss is not rsm.SequenceLoss and ref_loss.SequenceLoss.__module__ == "loss.loss"

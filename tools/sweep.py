@@ -204,6 +204,45 @@ def sweep_prepost(cfg, n, h, w, align, factor, iters):
                timed(lambda: torch.autograd.grad(out, dg, go, retain_graph=True), iters), nb)
 
 
+def sweep_loss(cfg, n, h, w, sizes, iters):
+    """SequenceLoss + metrics (8f-4) for a training batch: forward + backward of the loss, and the metrics, against
+    the reference's op sequence (torch on the same GPU; its .item() / assert synchronisations left out)"""
+    F = torch.nn.functional
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    gt = torch.randn((n, 1, h, w), device="cuda", generator=g) * 40
+    valid = (torch.rand((n, h, w), device="cuda", generator=g) > 0.2).float()
+    preds = [(torch.randn((n, 1) + s, device="cuda", generator=g) * 10).requires_grad_(True) for s in sizes]
+    shp = dict(N=n, H=h, W=w, preds=[list(s) for s in sizes])
+    nb = (sum(p.numel() for p in preds) * 2 + len(preds) * 2 * n * h * w * 2) * 4
+    loss_fn = rsm.SequenceLoss(0.9, 700, check_finite=False)
+
+    def ours():
+        return torch.autograd.grad(loss_fn(preds, gt, valid), preds)
+
+    def ref():
+        mask = ((valid >= 0.5) & (torch.sum(gt ** 2, dim=1).sqrt() < 700)).unsqueeze(1)
+        total = 0.0
+        for i, p in enumerate(preds):
+            q = p
+            if q.shape != gt.shape:
+                q = F.interpolate(q * (float(w) / q.shape[-1]), (h, w))
+            el = F.smooth_l1_loss(gt, q, reduction="none", beta=1.0) if i == len(preds) - 1 else F.l1_loss(gt, q, reduction="none")
+            total = total + 0.9 ** (len(preds) - 1 - i) * el[mask].mean()
+        return torch.autograd.grad(total, preds)
+
+    report(cfg, "sequence_loss fwd+bwd", "f32", shp, timed(ours, iters), nb)
+    report(cfg, "sequence_loss_torch fwd+bwd (reference op sequence on GPU, asserts left out)", "f32", shp, timed(ref, max(3, iters // 3)), nb)
+    last = preds[-1].detach()
+    if last.shape == gt.shape:
+        report(cfg, "flow_map_metrics (device vector, no sync)", "f32", shp, timed(lambda: rsm.flow_map_metrics(gt, last, valid), iters), 3 * n * h * w * 4)
+
+        def ref_metrics():
+            epe = torch.sum((last - gt) ** 2, dim=1).sqrt().view(-1)[(valid >= 0.5).view(-1)]
+            return [epe.mean(), (epe < 0.5).float().mean(), (epe < 1).float().mean(), (epe < 3).float().mean(),
+                    (epe < 5).float().mean(), torch.min(last[0]), torch.max(last[0])]
+        report(cfg, "flow_map_metrics_torch (reference op sequence on GPU, .item() left out)", "f32", shp, timed(ref_metrics, iters), 3 * n * h * w * 4)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=10)
@@ -226,6 +265,8 @@ def main():
         sweep_regress("cfg3", 8, 192, 384, 1248, ["f32"], a.iters)
         sweep_prepost("cfg3", 8, 375, 1242, 64, 4, a.iters)   # raw KITTI frame -> 384 x 1280, 1/4-resolution map back
         sweep_prepost("cfg3", 8, 384, 1248, 8, 8, a.iters)
+        sweep_loss("cfg3", 8, 384, 1248, [(96, 312), (192, 624), (384, 1248)], a.iters)
+        sweep_loss("cfg3", 8, 384, 1248, [(384, 1248)] * 6, a.iters)      # DispNetC: six full-size predictions
     if want("cfg4"):
         for c, g, d in ((32, 8, 48), (64, 16, 96), (128, 32, 192)):
             sweep_volumes("cfg4", 1, c, 270, 480, d, g, ["f32", "bf16"], a.iters, {"concat", "groupwise", "inner", "fused"})

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RSM_VERSION 103 /* major*10000 + minor*100 + patch */
+#define RSM_VERSION 104 /* major*10000 + minor*100 + patch */
 
 typedef enum rsm_dtype {
   RSM_F32 = 0,
@@ -47,7 +47,8 @@ typedef enum rsm_status {
   RSM_ERR_NULL_POINTER = 3,
   RSM_ERR_CUDA = 4,             /* a CUDA runtime call or launch failed */
   RSM_ERR_MISALIGNED = 5,       /* dense output / gradient pointer not aligned to its element */
-  RSM_ERR_UNSUPPORTED_CONFIG = 6
+  RSM_ERR_UNSUPPORTED_CONFIG = 6,
+  RSM_ERR_IO = 7                /* a file could not be opened, read or written (rsm_pfm_*) */
 } rsm_status;
 
 /* how a correlation is normalised over the reduced channels */
@@ -180,6 +181,16 @@ int rsm_seqloss_bwd(const float* gmean, const double* result, const void* pred, 
  * result[8] (device, fp64) = {epe mean, share < 0.5 px, < 1 px, < 3 px, < 5 px, min pred[0], max pred[0], valid count} */
 int rsm_flow_metrics(const void* gt, const void* pred, const float* valid, double* workspace, double* result, int64_t N,
                      int64_t C, int64_t H, int64_t W, int dtype, int device, void* stream);
+
+/* ---- PFM files, tools/pfm_file_io.py:6-77 (writer call site test_stereo.py:133).  HOST pointers; `image` is
+ * H x W x channels fp32 in C order, channels 1 ("Pf") or 3 ("PF"); the scale is written with "%f", negated on a
+ * little-endian host as the reference does; flip_rows != 0 stores / returns the rows bottom-up, which is what the
+ * reference's np.flipud at the call site (write) and inside read_pfm_file (:44) amount to */
+int rsm_pfm_write(const char* path, const float* image, int64_t H, int64_t W, int channels, double scale, int flip_rows);
+/* header only: sizes, channels, the scale as stored (negative = little-endian data), byte offset of the data */
+int rsm_pfm_read_header(const char* path, int64_t* H, int64_t* W, int* channels, double* scale, int64_t* data_offset);
+/* data into a caller-allocated H x W x channels buffer, converted to the host byte order */
+int rsm_pfm_read(const char* path, float* image, int64_t H, int64_t W, int channels, int flip_rows);
 
 /* ---- disparity regression over a dense (N,D,H,W) cost: softmax(+cost) expectation
  * (model/mobile_stereo_net.py:144-147, mobile_stereo_net_v4.py:10-14 + :517,

@@ -19,6 +19,7 @@ from .loss import SequenceLoss, build_loss_function, get_flow_map_metrics
 from .model_functions import (disparity_regression_dispnetc, disparity_regression_v4, interweave_tensors,
                               make_correlation_volume, make_cost_volume, softmax_regression, v4_head)
 from .patch import patch_reference, unpatch_reference
+from .pfm_file_io import read_pfm_file, write_disparity_pfm, write_pfm_file
 from .pipeline import HostPipeline
 from .sharding import all_gather_metrics, shard_range
 

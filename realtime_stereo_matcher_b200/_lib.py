@@ -49,6 +49,9 @@ SIGNATURES = {
     "rsm_shift_interweave_bwd": [vp, vp, vp, i64, i64, i64, i64, i64, ci, ci, vp],
     "rsm_warp_fwd": [vp, vp, vp, i64, i64, i64, i64, ci, ci, ci, vp],
     "rsm_warp_bwd": [vp, vp, vp, vp, vp, i64, i64, i64, i64, ci, ci, ci, vp],
+    "rsm_pfm_write": [C.c_char_p, vp, i64, i64, ci, C.c_double, ci],
+    "rsm_pfm_read_header": [C.c_char_p, vp, vp, vp, vp, vp],
+    "rsm_pfm_read": [C.c_char_p, vp, i64, i64, ci, ci],
     "rsm_seqloss_fwd": [vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, cf, ci, ci, ci, vp],
     "rsm_seqloss_bwd": [vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, cf, ci, ci, ci, vp],
     "rsm_flow_metrics": [vp, vp, vp, vp, vp, i64, i64, i64, i64, ci, ci, vp],

@@ -13,6 +13,12 @@ void set_cuda_error(cudaError_t e, const char* where) {
            cudaGetErrorName(e), cudaGetErrorString(e));
 }
 
+static thread_local char g_io_detail[512] = {0};
+
+void set_io_error(const char* what, const char* path) {
+  snprintf(g_io_detail, sizeof(g_io_detail), "%s: %s", what, path ? path : "(null)");
+}
+
 }  // namespace rsm
 
 extern "C" int rsm_version(void) { return RSM_VERSION; }
@@ -26,6 +32,7 @@ extern "C" const char* rsm_last_error(int code) {
     case RSM_ERR_CUDA: return rsm::g_cuda_detail[0] ? rsm::g_cuda_detail : "CUDA failure";
     case RSM_ERR_MISALIGNED: return "dense tensor pointer is not aligned to its element size";
     case RSM_ERR_UNSUPPORTED_CONFIG: return "unsupported configuration for this kernel";
+    case RSM_ERR_IO: return rsm::g_io_detail[0] ? rsm::g_io_detail : "file input / output failure";
     default: return "unknown rsm status code";
   }
 }

@@ -319,8 +319,34 @@ def loss_goldens():
         save(f"loss_{tag}", dict(tag=tag, n_preds=len(preds), gamma=0.9, max_flow=max_flow, metrics=metrics), **arrays)
 
 
+def pfm_goldens():
+    """PFM files written by the reference's tools/pfm_file_io.py (the bytes themselves) and what its reader returns."""
+    import tempfile
+    from tools.pfm_file_io import read_pfm_file as ref_read, write_pfm_file as ref_write
+    rng = np.random.default_rng(7)
+    arrays, meta = {}, []
+    with tempfile.TemporaryDirectory() as tmp:
+        for k, (shape, scale) in enumerate((((5, 7), 1), ((4, 6, 1), 2.5), ((3, 5, 3), 1.0), ((1, 1), 0.125))):
+            img = (rng.standard_normal(shape) * 50).astype(np.float32)
+            path = os.path.join(tmp, f"g{k}.pfm")
+            ref_write(path, img, scale)
+            data, rscale = ref_read(path)
+            arrays[f"img{k}"], arrays[f"bytes{k}"] = img, np.frombuffer(open(path, "rb").read(), dtype=np.uint8)
+            arrays[f"read{k}"] = np.ascontiguousarray(data)
+            meta.append(dict(scale=scale, read_scale=rscale))
+        # the call test_stereo.py:133 makes
+        disp = (rng.random((6, 9)) * 192).astype(np.float32)
+        path = os.path.join(tmp, "disp.pfm")
+        ref_write(path, np.flipud(disp), 1.0)
+        arrays["disp"], arrays["disp_bytes"] = disp, np.frombuffer(open(path, "rb").read(), dtype=np.uint8)
+    save("pfm_files", dict(cases=meta), **arrays)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
+    if "--only-pfm" in sys.argv:
+        pfm_goldens()
+        sys.exit(0)
     if "--only-loss" in sys.argv:
         loss_goldens()
         sys.exit(0)
@@ -338,5 +364,6 @@ if __name__ == "__main__":
     warp_goldens()
     prepost_goldens()
     loss_goldens()
+    pfm_goldens()
     total = sum(os.path.getsize(os.path.join(HERE, f)) for f in os.listdir(HERE) if f.endswith(".npz"))
     print(f"total fixture bytes: {total}")

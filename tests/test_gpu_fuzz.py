@@ -110,3 +110,53 @@ def test_random_shapes_regression(rsm, seed):
         gout = rng.standard_normal((n, h, w)).astype(np.float32)
         rsm.soft_argmax(c).backward(dev(gout))
         np.testing.assert_allclose(host(c.grad), oracle.soft_argmax_bwd(gout, cost), rtol=0, atol=GRAD_RTOL * d)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_shapes_prepost_and_loss(rsm, seed):
+    """Pre / post steps and the loss on random frame sizes, alignments and resize ratios:
+    aligned and unaligned rows, up- and down-sampling, crops, against the oracle."""
+    rng = np.random.default_rng(5000 + seed)
+    n, c = int(rng.integers(1, 3)), int(rng.choice([1, 3]))
+    h, w = int(rng.integers(3, 40)), int(rng.integers(3, 70))
+    align = int(rng.choice([1, 4, 8, 16, 64]))
+    img = (rng.random((n, c, h, w)) * 255).astype(np.float32)
+    tag = f"n{n} c{c} h{h} w{w} align{align}"
+    x = dev(img, grad=True)
+    out = rsm.prepare_input(x, align)
+    ref = oracle.prepare_input(img, align)
+    np.testing.assert_array_equal(host(out), ref, err_msg=tag)
+    gout = rng.standard_normal(ref.shape).astype(np.float32)
+    out.backward(dev(gout))
+    np.testing.assert_array_equal(host(x.grad), oracle.prepare_input_bwd(gout, (h, w)), err_msg=tag)
+
+    hp, wp = ref.shape[2:]
+    hs, ws = int(rng.integers(1, hp + 6)), int(rng.integers(1, wp + 6))
+    disp = (rng.standard_normal((n, 1, hs, ws)) * 7).astype(np.float32)
+    for mode in ("nearest", "bilinear"):
+        t = dev(disp, grad=True)
+        fin = rsm.finalize_disparity(t, (hp, wp), (h, w), mode=mode)
+        want = oracle.finalize_disparity(disp, (hp, wp), (h, w), mode)
+        if mode == "nearest":
+            np.testing.assert_array_equal(host(fin), want, err_msg=tag)
+        else:
+            np.testing.assert_allclose(host(fin), want, atol=1e-5, rtol=1e-5, err_msg=tag)
+        go = rng.standard_normal((n, 1, h, w)).astype(np.float32)
+        fin.backward(dev(go))
+        np.testing.assert_allclose(host(t.grad), oracle.finalize_disparity_bwd(go, disp.shape, (hp, wp), mode),
+                                   atol=1e-4, rtol=3e-4, err_msg=f"{tag} {mode} {hs}x{ws}")
+
+    gt = (rng.standard_normal((n, 1, h, w)) * 30).astype(np.float32)
+    valid = (rng.random((n, h, w)) > 0.25).astype(np.float32)
+    sizes = [(int(rng.integers(1, h + 3)), int(rng.integers(1, w + 3))), (h, w)]
+    preds = [(rng.standard_normal((n, 1) + s) * 10).astype(np.float32) for s in sizes]
+    tp = [dev(p, grad=True) for p in preds]
+    loss = rsm.SequenceLoss(0.85, 40.0)(tp, dev(gt), dev(valid))
+    np.testing.assert_allclose(host(loss), oracle.sequence_loss(preds, gt, valid, 0.85, 40.0), rtol=3e-6, err_msg=tag)
+    loss.backward()
+    for p, gp in zip(tp, oracle.sequence_loss_bwd(preds, gt, valid, 0.85, 40.0)):
+        np.testing.assert_allclose(host(p.grad), gp, atol=1e-8, rtol=1e-5, err_msg=tag)
+    got = rsm.get_flow_map_metrics(dev(gt), tp[-1].detach(), dev(valid))
+    want = oracle.flow_map_metrics(gt, preds[-1], valid)
+    for key in want:
+        np.testing.assert_allclose(got[key], want[key], atol=1e-7, rtol=3e-6, err_msg=f"{tag} {key}")

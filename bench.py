@@ -153,7 +153,9 @@ def dist_setup(n_gpus):
         backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
             torch.cuda.set_device(local)
-        dist.init_process_group(backend)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local))   # rank -> GPU stated, not guessed
+        else:
+            dist.init_process_group(backend)
     return world, rank, local
 
 
@@ -216,7 +218,10 @@ def run_reference(args, wl):
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    }), file=_RESULT_OUT, flush=True)
+
+
+_RESULT_OUT = sys.stdout   # main() swaps in a private copy of the original stdout
 
 
 # ------------------------------------------------------------------------------ our arm
@@ -336,7 +341,7 @@ def run_b200(args, wl):
         "gpu_launches": len(wl.kernels) * K,
         "clocks": clocks,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=_RESULT_OUT, flush=True)
 
 
 def main():
@@ -348,6 +353,12 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries the ONE JSON line and nothing else: everything written to fd 1 from here on (NCCL's version
+    # banner under NCCL_DEBUG, library chatter) is sent to stderr, the result goes to a private copy of stdout
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     wl = WORKLOADS[args.workload]()
     if args.impl == "reference":
         run_reference(args, wl)

@@ -153,6 +153,10 @@ def dist_setup(n_gpus):
         backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
             torch.cuda.set_device(local)
+            # host side of the end-to-end path: keep each rank (and the pinned buffers it allocates) on the NUMA
+            # node of its own GPU
+            from realtime_stereo_matcher_b200.sharding import bind_host_to_device
+            bind_host_to_device(local)
             dist.init_process_group(backend, device_id=torch.device("cuda", local))   # rank -> GPU stated, not guessed
         else:
             dist.init_process_group(backend)

@@ -21,6 +21,6 @@ from .model_functions import (disparity_regression_dispnetc, disparity_regressio
 from .patch import patch_reference, unpatch_reference
 from .pfm_file_io import read_pfm_file, write_disparity_pfm, write_pfm_file
 from .pipeline import HostPipeline
-from .sharding import all_gather_metrics, shard_range
+from .sharding import all_gather_metrics, bind_host_to_device, shard_range
 
 __version__ = "0.1.0"

@@ -32,3 +32,30 @@ def all_gather_metrics(metrics: Dict[str, float], device=None) -> Dict[str, list
     out = [torch.empty_like(mine) for _ in range(dist.get_world_size())]
     dist.all_gather(out, mine)
     return {k: [float(t[i]) for t in out] for i, k in enumerate(keys)}
+
+
+def bind_host_to_device(device_index: int) -> list:
+    """Pin the calling process to the CPU cores NVML reports as local to GPU ``device_index`` (its NUMA node), so
+    that the pinned host buffers a rank allocates afterwards are first-touched next to the GPU's PCIe root.  With one
+    process per GPU and ~100 MB of host input per step and rank this keeps the ranks off each other's memory
+    controllers.  Returns the CPU list applied ([] when NVML or the affinity call is unavailable: nothing changes)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = device_index
+        if visible:
+            ids = [v.strip() for v in visible.split(",") if v.strip()]
+            if device_index < len(ids) and ids[device_index].isdigit():
+                phys = int(ids[device_index])
+        handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return []

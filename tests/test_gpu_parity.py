@@ -740,6 +740,21 @@ def test_loss_vs_oracle(rsm, case):
         np.testing.assert_allclose(got[key], want[key], atol=1e-7, rtol=2e-6)
 
 
+@pytest.mark.parametrize("c", [1, 2, 3])
+def test_flow_metrics_channels(rsm, c):
+    """get_flow_map_metrics sums the squared error over the channel axis (loss.py:10): optical-flow shaped inputs."""
+    rng = np.random.default_rng(23 + c)
+    gt = (rng.standard_normal((2, c, 19, 31)) * 3).astype(np.float32)
+    pred = gt + rng.standard_normal(gt.shape).astype(np.float32) * 2
+    valid = (rng.random((2, 19, 31)) > 0.4).astype(np.float32)
+    got = rsm.get_flow_map_metrics(dev(gt), dev(pred), dev(valid))
+    want = oracle.flow_map_metrics(gt, pred, valid)
+    for key in want:
+        np.testing.assert_allclose(got[key], want[key], atol=1e-7, rtol=3e-6, err_msg=key)
+    vec = rsm.flow_map_metrics(dev(gt), dev(pred), dev(valid))
+    assert vec.dtype == torch.float64 and vec.shape == (8,) and float(vec[7]) == float(valid.sum())
+
+
 def test_loss_error_behaviour(rsm):
     gt = torch.zeros((1, 1, 4, 8), device="cuda")
     valid = torch.ones((1, 4, 8), device="cuda")

@@ -695,18 +695,20 @@ static int launch_bwd(const void* gout, const rsm_feat& left, const rsm_feat& ri
       const int xtiles = (int)ceil_div(g.W, BB_TX), cblocks = (int)ceil_div(g.C, BB_CB);
       const int64_t bx = N * g.H * (int64_t)cblocks * xtiles;
       if (grid_ok(bx)) {
-        const size_t smem = (size_t)(BB_DCH * BB_TX + BB_CB * BB_FW) * sizeof(float);
-        if (gl) {
-          auto k = inner_bwd_big_kernel<Tin, SIDE_LEFT>;
+        // disparities per pass: 48 unless 64 leaves fewer dead rows in the last pass
+        const int64_t waste48 = ceil_div(g.D, 48) * 48 - g.D, waste64 = ceil_div(g.D, 64) * 64 - g.D;
+        const bool d48 = waste48 <= waste64;
+        const size_t smem = bb_smem_bytes(d48 ? 48 : 64);
+        auto launch = [&](auto k, void* dst) -> int {
           cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-          k<<<(unsigned)bx, BB_THREADS, smem, st>>>((const Tin*)gout, view_of(left), view_of(right), (Tin*)gl, g, xtiles, cblocks);
-          if (int rc = finish_launch(where)) return rc;
+          k<<<(unsigned)bx, BB_THREADS, smem, st>>>((const Tin*)gout, view_of(left), view_of(right), (Tin*)dst, g, xtiles, cblocks);
+          return finish_launch(where);
+        };
+        if (gl) {
+          if (int rc = d48 ? launch(inner_bwd_big_kernel<Tin, SIDE_LEFT, 48>, gl) : launch(inner_bwd_big_kernel<Tin, SIDE_LEFT, 64>, gl)) return rc;
         }
         if (gr) {
-          auto k = inner_bwd_big_kernel<Tin, SIDE_RIGHT>;
-          cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-          k<<<(unsigned)bx, BB_THREADS, smem, st>>>((const Tin*)gout, view_of(left), view_of(right), (Tin*)gr, g, xtiles, cblocks);
-          if (int rc = finish_launch(where)) return rc;
+          if (int rc = d48 ? launch(inner_bwd_big_kernel<Tin, SIDE_RIGHT, 48>, gr) : launch(inner_bwd_big_kernel<Tin, SIDE_RIGHT, 64>, gr)) return rc;
         }
         return RSM_OK;
       }

@@ -211,7 +211,11 @@ corr_bwd_tiled_kernel(const Tout* __restrict__ gout, FeatView L, FeatView R, Tin
 // per warp, eight rows in flight -- each lane takes the two aligned 8-byte quads around its four columns and
 // funnel-shifts them by the row's misalignment (ncu: 750 -> 477 us for the right gradient at cfg2 C=64 against
 // element-wise moves, which were latency-bound with one or two loads in flight).
-constexpr int BB_TX = 128, BB_CB = 32, BB_DCH = 64, BB_FW = BB_TX + BB_DCH, BB_THREADS = 64;
+// DCH = disparities staged per pass, a template parameter: 48 keeps the tiles at 47 KB (four CTAs per SM instead of
+// three at 64 -- the kernel is latency-bound at 6 warps per SM, ncu: 42 % issue slots) and fits D = 48 / 96 / 192
+// without dead rows; 64 where that wastes less.
+constexpr int BB_TX = 128, BB_CB = 32, BB_THREADS = 64;
+constexpr size_t bb_smem_bytes(int dch) { return (size_t)(dch * BB_TX + BB_CB * (BB_TX + dch)) * sizeof(float); }
 
 __device__ __forceinline__ int bb_swz(int chunk) { return chunk ^ ((chunk >> 3) & 1); }
 
@@ -232,13 +236,14 @@ __device__ __forceinline__ void bb_store8(float* row, int ch2, const Vec16<T>& v
 
 // T = element type of the features, the gradient of the volume and the feature gradients (all equal here);
 // fp32 moves by LDGSTS, 16-bit tensors by 16-byte loads widened on the way into shared memory.
-template <typename T, int SIDE>
+template <typename T, int SIDE, int DCH>
 __global__ void __launch_bounds__(BB_THREADS)
 inner_bwd_big_kernel(const T* __restrict__ gout, FeatView L, FeatView R, T* __restrict__ gdst, CorrGeom g,
                      int xtiles, int cblocks) {
+  constexpr int FW = BB_TX + DCH;         // feature window: the tile plus DCH pixels of disparity reach
   extern __shared__ __align__(16) float smem[];
-  float* sG = smem;                       // [BB_DCH][BB_TX]
-  float* sF = smem + BB_DCH * BB_TX;      // [BB_CB][BB_FW]
+  float* sG = smem;                       // [DCH][BB_TX]
+  float* sF = smem + DCH * BB_TX;      // [BB_CB][FW]
   int64_t bid = blockIdx.x;
   const int xt = (int)(bid % xtiles); bid /= xtiles;
   const int cb = (int)(bid % cblocks); bid /= cblocks;
@@ -258,12 +263,12 @@ inner_bwd_big_kernel(const T* __restrict__ gout, FeatView L, FeatView R, T* __re
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[j][i] = 0.f;
 
-  for (int dc0 = 0; dc0 < g.D; dc0 += BB_DCH) {
+  for (int dc0 = 0; dc0 < g.D; dc0 += DCH) {
     __syncthreads();
     // ---- gradient tile (the sum below reads whole groups of eight rows)
-    const int nrows = min(BB_DCH, (g.D - dc0 + 7) & ~7);
+    const int nrows = min(DCH, (g.D - dc0 + 7) & ~7);
     if constexpr (SIDE == SIDE_LEFT && sizeof(T) == 4) {
-      for (int e = threadIdx.x; e < BB_DCH * (BB_TX / 4); e += BB_THREADS) {
+      for (int e = threadIdx.x; e < DCH * (BB_TX / 4); e += BB_THREADS) {
         const int dl = e >> 5, ch = e & 31;
         const int d = dc0 + dl, x = x0 + 4 * ch;
         const bool valid = d < g.D && x < g.W;
@@ -291,7 +296,7 @@ inner_bwd_big_kernel(const T* __restrict__ gout, FeatView L, FeatView R, T* __re
       }
     } else {
       if constexpr (sizeof(T) == 4) {
-        for (int e = threadIdx.x; e < BB_DCH * BB_TX; e += BB_THREADS) {
+        for (int e = threadIdx.x; e < DCH * BB_TX; e += BB_THREADS) {
           const int dl = e >> 7, xx = e & 127;
           const int d = dc0 + dl, x = x0 + xx + d;             // skew: column x' holds gV[d][x' + d]
           const bool valid = d < g.D && x < g.W;
@@ -336,44 +341,44 @@ inner_bwd_big_kernel(const T* __restrict__ gout, FeatView L, FeatView R, T* __re
       }
     }
     // ---- feature windows: left side R[c][x0 - dc0 - 64 + j], right side L[c][x0 + dc0 + j]
-    const int fx0 = SIDE == SIDE_LEFT ? x0 - dc0 - BB_DCH : x0 + dc0;
+    const int fx0 = SIDE == SIDE_LEFT ? x0 - dc0 - DCH : x0 + dc0;
     if constexpr (sizeof(T) == 4) {
-      for (int e = threadIdx.x; e < (BB_FW / 4); e += BB_THREADS) {
+      for (int e = threadIdx.x; e < (FW / 4); e += BB_THREADS) {
         const int x = fx0 + 4 * e;
         const bool valid = x >= 0 && x < g.W;
         const T* src = valid ? pf + x : pf;
         const int64_t step = valid ? F.sc : 0;
         const uint32_t sdst = (uint32_t)__cvta_generic_to_shared(sF + 4 * bb_swz(e));
         for (int c = 0; c < ncb; ++c)
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sdst + (uint32_t)(c * BB_FW * 4)), "l"(src + c * step),
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sdst + (uint32_t)(c * FW * 4)), "l"(src + c * step),
                        "r"(valid ? 16 : 0)
                        : "memory");
       }
     } else {
       // fx0 % 8 == 0 and W % 8 == 0: whole octets, four loads in flight (deeper batches measured slower)
-      const int total = ncb * (BB_FW / 8);
+      const int total = ncb * (FW / 8);
       for (int e0 = threadIdx.x; e0 < total; e0 += 4 * BB_THREADS) {
         Vec16<T> v[4];
         bool ok[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int e = e0 + u * BB_THREADS;
-          const int c = e / (BB_FW / 8), x = fx0 + 8 * (e - c * (BB_FW / 8));
+          const int c = e / (FW / 8), x = fx0 + 8 * (e - c * (FW / 8));
           ok[u] = e < total && x >= 0 && x < g.W;
           if (ok[u]) v[u] = ldg16(pf + (int64_t)c * F.sc + x);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int e = e0 + u * BB_THREADS;
-          const int c = e / (BB_FW / 8);
-          if (e < total) bb_store8<T>(sF + c * BB_FW, e - c * (BB_FW / 8), v[u], ok[u]);
+          const int c = e / (FW / 8);
+          if (e < total) bb_store8<T>(sF + c * FW, e - c * (FW / 8), v[u], ok[u]);
         }
       }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
     if (8 * tc >= ncb) continue;
-    for (int d0 = 0; d0 < BB_DCH; d0 += 8) {
+    for (int d0 = 0; d0 < DCH; d0 += 8) {
       if (dc0 + d0 >= g.D) break;
       float gq[8][8];
 #pragma unroll
@@ -386,11 +391,11 @@ inner_bwd_big_kernel(const T* __restrict__ gout, FeatView L, FeatView R, T* __re
       }
       // window chunk: left  w[k] = R[x + i - d], k = 8 + i - r  (window starts at 64 + 8 tx - d0 - 8)
       //               right w[k] = L[x' + i + d], k = i + r      (window starts at 8 tx + d0)
-      const int wch = SIDE == SIDE_LEFT ? (BB_DCH + 8 * tx - d0 - 8) >> 2 : (8 * tx + d0) >> 2;
+      const int wch = SIDE == SIDE_LEFT ? (DCH + 8 * tx - d0 - 8) >> 2 : (8 * tx + d0) >> 2;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         if (8 * tc + j >= ncb) break;
-        const float* frow = sF + (8 * tc + j) * BB_FW;
+        const float* frow = sF + (8 * tc + j) * FW;
         float w[16];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {

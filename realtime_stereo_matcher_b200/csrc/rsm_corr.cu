@@ -680,7 +680,7 @@ static int launch_bwd(const void* gout, const rsm_feat& left, const rsm_feat& ri
       return g.cpg == 4 ? launch(groupwise_bwd_row_kernel<Tin, Tout, 4>) : launch(groupwise_bwd_row_kernel<Tin, Tout, 8>);
     }
   }
-  // inner product: 8x8 register tiles when every row and window starts on a 16-byte boundary (fp32: W % 4,
+  // inner product: 8(x) x 4(c) register tiles when every row and window starts on a 16-byte boundary (fp32: W % 4,
   // 16-bit: W % 8) and all three tensors share one dtype (RSM_BWD_SMALL_TILE=1 keeps the 4x4 kernel: A/B runs)
   if constexpr (LAYOUT == LAYOUT_NDHW && std::is_same<Tin, Tout>::value) {
     const char* small = getenv("RSM_BWD_SMALL_TILE");

@@ -197,11 +197,11 @@ corr_bwd_tiled_kernel(const Tout* __restrict__ gout, FeatView L, FeatView R, Tin
   }
 }
 
-// ================================================== inner product (N,D,H,W), fp32: 8(x) x 8(c) tiles
-// Same contraction as corr_bwd_tiled_kernel with twice the arithmetic per shared-memory byte: CTA = 128
-// pixels x 32 channels of one (n, y), 64 threads, thread tile 8(x) x 8(c), disparities eight at a time:
+// ================================================== inner product (N,D,H,W): 8(x) x BB_CPT(c) tiles
+// Same contraction as corr_bwd_tiled_kernel with more arithmetic per shared-memory byte: CTA = 128
+// pixels x 32 channels of one (n, y), thread tile 8(x) x BB_CPT(c), disparities eight at a time:
 //     16 LDS.128 for the gradient block g[8 d][8 x] + 4 LDS.128 per channel for its 16-wide feature window
-//     -> 512 FMA per 48 LDS.128 (10.7 per load; the 4x4 tile gets 5.3).
+//     -> 8 x 8 tile: 512 FMA per 48 LDS.128 (10.7 per load); 8 x 4 tile: 256 per 32 (8); the 4x4 tile gets 5.3.
 // For the right gradient the gradient tile is staged SKEWED, sG[d][x'] = gV[d][x' + d], which turns
 // gR[c,x'] = sum_d gV[d][x'+d] L[c][x'+d] into the same Toeplitz form as the left one (window ascending
 // instead of descending).  Rows are XOR-swizzled by 16-byte chunk (chunk ^= (chunk >> 3) & 1): lanes read
@@ -214,7 +214,10 @@ corr_bwd_tiled_kernel(const Tout* __restrict__ gout, FeatView L, FeatView R, Tin
 // DCH = disparities staged per pass, a template parameter: 48 keeps the tiles at 47 KB (four CTAs per SM instead of
 // three at 64 -- the kernel is latency-bound at 6 warps per SM, ncu: 42 % issue slots) and fits D = 48 / 96 / 192
 // without dead rows; 64 where that wastes less.
-constexpr int BB_TX = 128, BB_CB = 32, BB_THREADS = 64;
+// 128 threads = 16 pixel octets x 8 channel quads: the 8(x) x 4(c) thread tile has a worse FMA : LDS ratio than 8 x 8,
+// but the kernel is latency-bound (ncu: 6 warps per SM, 42 % of the issue slots with 64-thread CTAs) and twice the
+// warps won (cfg2 C=64 fp32 791 -> 699 us).
+constexpr int BB_TX = 128, BB_CB = 32, BB_THREADS = 128, BB_CPT = BB_CB / (BB_THREADS / 16);   // channels per thread
 constexpr size_t bb_smem_bytes(int dch) { return (size_t)(dch * BB_TX + BB_CB * (BB_TX + dch)) * sizeof(float); }
 
 __device__ __forceinline__ int bb_swz(int chunk) { return chunk ^ ((chunk >> 3) & 1); }
@@ -237,7 +240,7 @@ __device__ __forceinline__ void bb_store8(float* row, int ch2, const Vec16<T>& v
 // T = element type of the features, the gradient of the volume and the feature gradients (all equal here);
 // fp32 moves by LDGSTS, 16-bit tensors by 16-byte loads widened on the way into shared memory.
 template <typename T, int SIDE, int DCH>
-__global__ void __launch_bounds__(BB_THREADS)
+__global__ void __launch_bounds__(BB_THREADS, 4)
 inner_bwd_big_kernel(const T* __restrict__ gout, FeatView L, FeatView R, T* __restrict__ gdst, CorrGeom g,
                      int xtiles, int cblocks) {
   constexpr int FW = BB_TX + DCH;         // feature window: the tile plus DCH pixels of disparity reach
@@ -257,9 +260,9 @@ inner_bwd_big_kernel(const T* __restrict__ gout, FeatView L, FeatView R, T* __re
   const FeatView& F = SIDE == SIDE_LEFT ? R : L;
   const T* __restrict__ pf = reinterpret_cast<const T*>(F.data) + n * F.sn + (int64_t)y * F.sh + (int64_t)c0 * F.sc;
 
-  float acc[8][8];   // [channel j][pixel i]
+  float acc[BB_CPT][8];   // [channel j][pixel i]
 #pragma unroll
-  for (int j = 0; j < 8; ++j)
+  for (int j = 0; j < BB_CPT; ++j)
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[j][i] = 0.f;
 
@@ -377,7 +380,7 @@ inner_bwd_big_kernel(const T* __restrict__ gout, FeatView L, FeatView R, T* __re
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
-    if (8 * tc >= ncb) continue;
+    if (BB_CPT * tc >= ncb) continue;
     for (int d0 = 0; d0 < DCH; d0 += 8) {
       if (dc0 + d0 >= g.D) break;
       float gq[8][8];
@@ -393,9 +396,9 @@ inner_bwd_big_kernel(const T* __restrict__ gout, FeatView L, FeatView R, T* __re
       //               right w[k] = L[x' + i + d], k = i + r      (window starts at 8 tx + d0)
       const int wch = SIDE == SIDE_LEFT ? (DCH + 8 * tx - d0 - 8) >> 2 : (8 * tx + d0) >> 2;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (8 * tc + j >= ncb) break;
-        const float* frow = sF + (8 * tc + j) * FW;
+      for (int j = 0; j < BB_CPT; ++j) {
+        if (BB_CPT * tc + j >= ncb) break;
+        const float* frow = sF + (BB_CPT * tc + j) * FW;
         float w[16];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -415,9 +418,9 @@ inner_bwd_big_kernel(const T* __restrict__ gout, FeatView L, FeatView R, T* __re
   const int xb = x0 + 8 * tx;
   if (xb >= g.W) return;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    if (8 * tc + j >= ncb) break;
-    T* o = gdst + (((int64_t)n * g.C + c0 + 8 * tc + j) * g.H + y) * g.W + xb;
+  for (int j = 0; j < BB_CPT; ++j) {
+    if (BB_CPT * tc + j >= ncb) break;
+    T* o = gdst + (((int64_t)n * g.C + c0 + BB_CPT * tc + j) * g.H + y) * g.W + xb;
     if constexpr (sizeof(T) == 4) {
       __stcs(reinterpret_cast<float4*>(o), make_float4(acc[j][0] / cnt, acc[j][1] / cnt, acc[j][2] / cnt, acc[j][3] / cnt));
       if (xb + 4 < g.W)

@@ -2,8 +2,9 @@
 """Benchmark of the cost-volume + disparity-regression hot path (BASELINE.json metric:
 stereo pairs/s at 384x1248; cost-volume GB/s vs HBM peak).
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (torch port)
+    python bench.py --gpus N --steps K --warmup W              # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...     # the UNMODIFIED reference's CPU path (baseline/_ref)
+    python bench.py --workload cfg5_train --gpus N ...          # training step (BASELINE config 5): fwd + bwd + DDP
 
 One "step" = one pass of the hot path over one batch of synthetic stereo pairs per GPU.  The
 default workload is BASELINE config 3 as SURVEY.md F3/8d reads it (the configuration the metric
@@ -38,17 +39,18 @@ class Cfg3:
     dtype = "f32"
     kernels = ("corr_fwd_kernel[groupwise]", "concat_fwd_kernel", "upsample_regress_fwd_kernel")
     dominant = 1  # index into kernels: concat is the HBM-write stream
+    l2_note = "4 rotating input sets; each step writes 3.3 GB of volumes (>> 126 MB L2)"
 
-    def host_inputs(self, seed, n=None):
+    def host_inputs(self, seed, n=None, dtype=torch.float32):
         n = n or self.N
         g = torch.Generator().manual_seed(seed)
-        return (torch.randn((n, self.C, self.H4, self.W4), generator=g),
-                torch.randn((n, self.C, self.H4, self.W4), generator=g),
-                torch.randn((n, self.D4, self.H4, self.W4), generator=g) * 3.0)
+        return tuple(t.to(dtype) for t in (torch.randn((n, self.C, self.H4, self.W4), generator=g),
+                                           torch.randn((n, self.C, self.H4, self.W4), generator=g),
+                                           torch.randn((n, self.D4, self.H4, self.W4), generator=g) * 3.0))
 
-    def algorithmic_bytes(self):
+    def algorithmic_bytes(self, e=4):
         """every input element read once, every output element written once."""
-        e, n = 4, self.N
+        n = self.N
         feat = n * self.C * self.H4 * self.W4 * e
         return {
             "groupwise": 2 * feat + n * self.G * self.H4 * self.W4 * self.D4 * e,
@@ -67,7 +69,18 @@ class Cfg3:
         if mark: mark()
         return gw, cat, disp
 
-    def cpu_step(self, tp, inp):
+    def ref_step(self, ref, inp):
+        """The same step through the UNMODIFIED reference (baseline/_ref) on the CPU: cost_volume/groupwise.py:24-56,
+        cost_volume/concatenate.py:11-41, model/mobile_stereo_net_v4.py:511-518."""
+        import torch.nn.functional as F
+        left, right, cost = inp
+        gw = ref.cv_groupwise.TorchGroupwiseCost(self.G, self.D4)(left, right)
+        cat = ref.cv_concatenate.TorchConcatenateCost(self.D4)(left, right)
+        c = F.interpolate(cost.unsqueeze(1), [self.D, self.H, self.W], mode="trilinear").squeeze(1)
+        disp = ref.v4.disparity_regression(F.softmax(c, dim=1), self.D)
+        return gw, cat, disp
+
+    def port_step(self, tp, inp):
         left, right, cost = inp
         tp.groupwise_volume(left, right, self.G, self.D4)
         tp.concat_volume(left, right, self.D4)
@@ -75,6 +88,12 @@ class Cfg3:
 
 
 WORKLOADS = {"cfg3": Cfg3}
+
+
+def config_dict(wl, world):
+    """The SAME dict in both arms (the driver compares it)."""
+    return {"workload": wl.name, "pairs_per_gpu_per_step": wl.pairs_per_step, "l2": wl.l2_note,
+            "parallelism": f"dp{world} (batch sharded, no data-path collective)"}
 
 
 # ------------------------------------------------------------------------------ helpers
@@ -97,7 +116,7 @@ class ClockSampler:
             self.proc = None
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "power_w_max": None}
         if not self.proc:
             return out
         time.sleep(0.15)
@@ -108,7 +127,7 @@ class ClockSampler:
             self.proc.kill()
         rows = [r.split(",") for r in open(self.path).read().strip().splitlines() if r.count(",") >= 7]
         os.unlink(self.path)
-        sm = []
+        sm, pw = [], []
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in rows:
@@ -116,6 +135,7 @@ class ClockSampler:
             try:
                 sm.append(float(r[0]))
                 out["sm_max_mhz"] = float(r[1])
+                pw.append(float(r[2]))
             except ValueError:
                 continue
             for nme, v in zip(names, r[4:8]):
@@ -123,6 +143,8 @@ class ClockSampler:
                     reasons.add(nme)
         if sm:
             out["sm_mhz"] = statistics.median(sm)
+        if pw:
+            out["power_w_max"] = max(pw)
         out["reasons"] = sorted(reasons)
         out["samples"] = len(sm)
         return out
@@ -178,48 +200,65 @@ def max_over_ranks(x, world, device):
     return float(t)
 
 
-def time_cpu_port(wl, sample_pairs, budget_s=15.0, max_reps=5):
-    """The reference's CPU path (torch port) on a bounded sample; returns (pairs/s, info)."""
+def load_reference():
+    """(kind, callable step(wl, inputs)) for the CPU arm: the unmodified reference from baseline/_ref when it is
+    installed (tools/install_ref.py; gpurun ships it), else the torch port of its op sequence."""
+    from oracle import ref_loader
+    if ref_loader.available():
+        ref = ref_loader.load()
+        ref_loader.verify_unmodified()
+        return "reference", (lambda wl, inp: wl.ref_step(ref, inp))
     from oracle import torch_port as tp
+    return "port", (lambda wl, inp: wl.port_step(tp, inp))
+
+
+def time_cpu_reference(wl, budget_s=20.0, max_reps=3):
+    """The reference's CPU path on the full per-GPU batch, best of <= max_reps passes within the budget."""
+    kind, step = load_reference()
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    inp = wl.host_inputs(1234, n=sample_pairs)
+    inp = wl.host_inputs(1234)
     with torch.no_grad():
-        wl.cpu_step(tp, inp)  # warm-up
-        best, spent, reps = float("inf"), 0.0, 0
-        while reps < max_reps and (reps == 0 or spent < budget_s):
+        t0 = time.perf_counter()
+        step(wl, inp)                                 # warm-up (also the first timing if it alone eats the budget)
+        best = time.perf_counter() - t0
+        spent, reps = best, 1
+        while reps < max_reps and spent < budget_s:
             t0 = time.perf_counter()
-            wl.cpu_step(tp, inp)
+            step(wl, inp)
             dt = time.perf_counter() - t0
             best, spent, reps = min(best, dt), spent + dt, reps + 1
-    return sample_pairs / best, {"cores": threads, "reps": reps, "best_s": best}
+    return wl.pairs_per_step / best, {"cores": threads, "reps": reps, "best_s": best, "kind": kind}
 
 
 # -------------------------------------------------------------------------- reference arm
 def run_reference(args, wl):
-    world, rank, _ = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), 0
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # rank 0 alone runs the CPU arm
-    from oracle import torch_port as tp
+    kind, step = load_reference()
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    sample = 1
-    inp = wl.host_inputs(1234, n=sample)
+    inp = wl.host_inputs(1234)
     with torch.no_grad():
         for _ in range(args.warmup):
-            wl.cpu_step(tp, inp)
+            step(wl, inp)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            wl.cpu_step(tp, inp)
+            step(wl, inp)
         dt = time.perf_counter() - t0
-    value = sample * args.steps / dt
-    desc = f"{sample} of {wl.pairs_per_step} pairs per step (same shapes), torch {torch.__version__} CPU, fp32"
+    value = wl.pairs_per_step * args.steps / dt
+    what = ("the UNMODIFIED reference (baseline/_ref: TorchGroupwiseCost, TorchConcatenateCost, v4 "
+            "F.interpolate->softmax->disparity_regression)" if kind == "reference"
+            else "torch CPU port of the reference op sequence (baseline/_ref not installed)")
+    desc = (f"all {wl.pairs_per_step} pairs of the per-GPU batch per step, {what}, torch {torch.__version__} CPU, fp32, "
+            f"{threads} threads")
     print(json.dumps({
         "impl": "reference", "metric": "stereo_pairs_per_sec", "value": value, "unit": "pairs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
-        "config": {"workload": wl.name, "sample": desc},
-        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": desc},
+        "config": config_dict(wl, max(world, args.gpus)),
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": kind, "sample": desc},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }), file=_RESULT_OUT, flush=True)
@@ -229,6 +268,125 @@ _RESULT_OUT = sys.stdout   # main() swaps in a private copy of the original stdo
 
 
 # ------------------------------------------------------------------------------ our arm
+def time_op(fn, reps, flush):
+    """Mean device time of fn() over `reps` launches, L2 flushed before each (CUDA events on the current stream)."""
+    evs = []
+    for _ in range(reps):
+        flush()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    return statistics.mean(a.elapsed_time(b) for a, b in evs)
+
+
+def tensor_core_kernels(rsm, dev, peak):
+    """Driver-timed numbers for the tcgen05 path (not part of `value`): BASELINE config 2 -- MobileDispNetC's mean
+    correlation at (32, 64, 144, 240), D = 48 in bf16 -- as the volume-writing kernel and as the fused
+    build -> regress kernel (no volume)."""
+    n, c, h, w, d = 32, 64, 144, 240, 48
+    g = torch.Generator(device=dev).manual_seed(5)
+    sets = [(torch.randn((n, c, h, w), device=dev, generator=g).to(torch.bfloat16),
+             torch.randn((n, c, h, w), device=dev, generator=g).to(torch.bfloat16)) for _ in range(3)]
+    junk = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)      # 256 MB > L2
+    flush = lambda: junk.zero_()
+    state = {"i": 0}
+
+    def nxt():
+        state["i"] += 1
+        return sets[state["i"] % 3]
+
+    out = {}
+    feat = 2 * n * c * h * w * 2
+    flops = 2.0 * n * c * h * w * d
+    for name, fn, bytes_ in (
+            ("inner_mean_fwd[bf16,cfg2,tcgen05]", lambda: rsm.make_correlation_volume(*nxt(), d), feat + n * d * h * w * 2),
+            ("inner_regress_fused[bf16,cfg2,tcgen05]", lambda: rsm.inner_product_regress(*nxt(), d, mean=True), feat + n * h * w * 20)):
+        for _ in range(3):
+            fn()
+        ms = time_op(fn, 10, flush)
+        out[name] = {"ms": ms, "algorithmic_GBps": bytes_ / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": bytes_ / (ms * 1e-3) / 1e9 / peak,
+                     "useful_TFLOPs": flops / (ms * 1e-3) / 1e12}
+    return out
+
+
+def sustained_concat(rsm, wl, sets, peak, seconds=2.0):
+    """The dominant HBM-bound kernel back to back for >= `seconds` of device time: does the roofline fraction hold
+    under a long load (power / clocks), not only in a 15 ms burst?"""
+    ab = wl.algorithmic_bytes()["concat"]
+    reps = max(50, int(seconds / 0.00047))
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for i in range(reps):
+        left, right, _ = sets[i % len(sets)]
+        out = rsm.concat_volume(left, right, wl.D4)
+        del out
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    gbs = ab / (ms * 1e-3) / 1e9
+    return {"kernel": "concat_fwd_kernel", "launches": reps, "seconds": a.elapsed_time(b) * 1e-3, "avg_launch_ms": ms,
+            "achieved": gbs, "frac": gbs / peak}
+
+
+def h2d_ceiling(dev, nbytes, reps=8):
+    """Plain pinned-memory cudaMemcpyAsync of the same byte count: the box's host->device ceiling for one rank."""
+    h = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    for _ in range(2):
+        d.copy_(h, non_blocking=True)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        d.copy_(h, non_blocking=True)
+    b.record()
+    torch.cuda.synchronize()
+    return nbytes * reps / (a.elapsed_time(b) * 1e-3) / 1e9
+
+
+def run_e2e(rsm, wl, dev, world, rank, K, dtype):
+    """The step through the public streaming API from PINNED HOST buffers: H2D, kernels, D2H inside the region."""
+    host_sets = [tuple(t.pin_memory() for t in wl.host_inputs(99 + 17 * rank + s, dtype=dtype)) for s in range(2)]
+    out_dtype = dtype
+    outs = [torch.empty((wl.N, wl.H, wl.W), dtype=out_dtype).pin_memory() for _ in range(3)]
+    h2d = sum(t.numel() * t.element_size() for t in host_sets[0])
+    d2h = outs[0].numel() * outs[0].element_size()
+
+    # serial form: copy, compute, copy back, wait (what a caller without the pipeline gets)
+    def e2e_serial(i):
+        inp = tuple(t.to(dev, non_blocking=True) for t in host_sets[i % 2])
+        disp = wl.step(rsm, inp)[2]
+        outs[0].copy_(disp, non_blocking=True)
+        torch.cuda.synchronize()
+
+    for i in range(3):
+        e2e_serial(i)
+    barrier(world)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(K):
+        e2e_serial(i)
+    torch.cuda.synchronize()
+    serial_s = max_over_ranks(time.perf_counter() - t0, world, dev)
+
+    pipe = rsm.HostPipeline(lambda l, r, c: wl.step(rsm, (l, r, c))[2], device=dev, depth=2)
+    for _ in pipe.run((host_sets[i % 2] for i in range(4)), outs):
+        pass
+    barrier(world)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    n_done = sum(1 for _ in pipe.run((host_sets[i % 2] for i in range(K)), outs))
+    torch.cuda.synchronize()
+    mine = time.perf_counter() - t0
+    e2e_s = max_over_ranks(mine, world, dev)
+    assert n_done == K
+    return {"seconds": e2e_s, "serial_seconds": serial_s, "h2d": h2d, "d2h": d2h, "h2d_GBps_this_rank": h2d * K / mine / 1e9}
+
+
 def run_b200(args, wl):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
@@ -238,6 +396,7 @@ def run_b200(args, wl):
     world, rank, local = dist_setup(args.gpus)
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    peak, peak_src = measured_peak()
 
     # rotating input sets, resident in HBM before the timed region
     nsets = 4
@@ -269,79 +428,62 @@ def run_b200(args, wl):
         op_ms = [statistics.mean(marks[i][j].elapsed_time(marks[i][j + 1]) for i in range(K))
                  for j in range(len(wl.kernels))]
 
+        # ---- a >= 2 s back-to-back run of the dominant kernel (clocks sampled across it as well)
+        sustained = sustained_concat(rsm, wl, sets, peak) if not args.quick else None
+        barrier(world)
+
         # ---- end to end through the public API with HOST buffers (pinned), copies inside the region
-        host_sets = [tuple(t.pin_memory() for t in wl.host_inputs(99 + 17 * rank + s)) for s in range(2)]
-        host_out = torch.empty((wl.N, wl.H, wl.W), dtype=torch.float32).pin_memory()
-        h2d = sum(t.numel() * t.element_size() for t in host_sets[0])
-        d2h = host_out.numel() * host_out.element_size()
-
-        def e2e_serial(i):
-            inp = tuple(t.to(dev, non_blocking=True) for t in host_sets[i % 2])
-            disp = wl.step(rsm, inp)[2]
-            host_out.copy_(disp, non_blocking=True)
-            torch.cuda.synchronize()      # the caller owns the disparity on the host
-            return disp
-
-        for i in range(3):
-            e2e_serial(i)
+        e32 = run_e2e(rsm, wl, dev, world, rank, K, torch.float32)
+        e16 = run_e2e(rsm, wl, dev, world, rank, K, torch.float16)
         barrier(world)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for i in range(K):
-            e2e_serial(i)
-        torch.cuda.synchronize()
-        e2e_serial_s = max_over_ranks(time.perf_counter() - t0, world, dev)
-
-        # the public streaming API: H2D of batch i+1 overlaps the kernels of batch i (double buffer)
-        pipe = rsm.HostPipeline(lambda l, r, c: wl.step(rsm, (l, r, c))[2], device=dev, depth=2)
-        outs = [host_out, torch.empty_like(host_out).pin_memory()]
-        for _ in pipe.run((host_sets[i % 2] for i in range(3)), outs):
-            pass
+        clocks = sampler.stop() if rank == 0 else None   # sampled across the device-timed, sustained and e2e regions
+        ceiling = h2d_ceiling(dev, e32["h2d"])
+        ceiling_all = max_over_ranks(-ceiling, world, dev)   # min over ranks
+        extra = tensor_core_kernels(rsm, dev, peak) if (rank == 0 and not args.quick) else {}
         barrier(world)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        n_done = sum(1 for _ in pipe.run((host_sets[i % 2] for i in range(K)), outs))
-        torch.cuda.synchronize()
-        e2e_s = max_over_ranks(time.perf_counter() - t0, world, dev)
-        assert n_done == K
-        barrier(world)
-        clocks = sampler.stop() if rank == 0 else None   # sampled across the device-timed and e2e regions
 
     pairs = wl.pairs_per_step * world * K
     value = pairs / (ms_total * 1e-3)
-    e2e_value = pairs / e2e_s
     if rank != 0:
         return
-    # ---- CPU baseline beside it (rank 0, N=1 only): the reference's CPU path on a bounded sample
+    # ---- CPU baseline beside it (rank 0, N=1 only): the reference's CPU path on the same per-GPU batch
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        v, info = time_cpu_port(wl, sample_pairs=1)
-        cpu = {"value": v, "unit": "pairs/s", "cores": info["cores"], "kind": "port",
-               "sample": f"1 of {wl.pairs_per_step} pairs (same shapes), best of {info['reps']} passes "
-                         f"({info['best_s']:.2f} s each), torch CPU port of the reference op sequence"}
+        v, info = time_cpu_reference(wl)
+        cpu = {"value": v, "unit": "pairs/s", "cores": info["cores"], "kind": info["kind"],
+               "sample": f"all {wl.pairs_per_step} pairs of one step, best of {info['reps']} passes "
+                         f"({info['best_s']:.2f} s each), " +
+                         ("the unmodified reference from baseline/_ref" if info["kind"] == "reference"
+                          else "torch CPU port of the reference op sequence")}
     ab = wl.algorithmic_bytes()
     names = list(ab)
     dom = wl.dominant
-    peak, peak_src = measured_peak()
     achieved = ab[names[dom]] / (op_ms[dom] * 1e-3) / 1e9
+    kernels = {n: {"ms": op_ms[j], "algorithmic_GBps": ab[n] / (op_ms[j] * 1e-3) / 1e9,
+                   "frac_of_hbm_peak": ab[n] / (op_ms[j] * 1e-3) / 1e9 / peak} for j, n in enumerate(names)}
+    kernels.update(extra)
     line = {
         "metric": "stereo_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": K,
         "warmup": Wm, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
-        "config": {"workload": wl.name, "pairs_per_gpu_per_step": wl.pairs_per_step,
-                   "l2": "4 rotating input sets; each step writes 3.3 GB of volumes (>> 126 MB L2)",
-                   "parallelism": f"dp{world} (batch sharded, no data-path collective)"},
+        "config": config_dict(wl, world),
         "roofline": {"bound": "hbm", "kernel": wl.kernels[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": ncu_traffic(wl.kernels[dom]), "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": ab[names[dom]], "avg_launch_ms": op_ms[dom]},
-        "kernels": {n: {"ms": op_ms[j], "algorithmic_GBps": ab[n] / (op_ms[j] * 1e-3) / 1e9}
-                    for j, n in enumerate(names)},
+                     "algorithmic_bytes_per_launch": ab[names[dom]], "avg_launch_ms": op_ms[dom],
+                     "sustained": sustained},
+        "kernels": kernels,
         "cpu_baseline": cpu,
-        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "serial_value": pairs / e2e_serial_s,
-                "note": "public API HostPipeline: per step pinned host features+cost -> H2D -> 3 kernels -> D2H of "
-                        "the disparity map, H2D of step i+1 overlapped with the kernels of step i (serial_value: no "
-                        "overlap); the volumes stay in HBM for the aggregation network, as in the model"},
+        "e2e": {"value": pairs / e32["seconds"], "unit": "pairs/s", "h2d_bytes_per_step": e32["h2d"],
+                "d2h_bytes_per_step": e32["d2h"], "serial_value": pairs / e32["serial_seconds"],
+                "h2d_GBps_rank0": e32["h2d_GBps_this_rank"], "h2d_ceiling_GBps_min_rank": -ceiling_all,
+                "f16_features": {"value": pairs / e16["seconds"], "h2d_bytes_per_step": e16["h2d"],
+                                 "d2h_bytes_per_step": e16["d2h"], "h2d_GBps_rank0": e16["h2d_GBps_this_rank"],
+                                 "note": "same step with fp16 host features / cost (what autocast evaluation feeds "
+                                         "the path): half the bytes on the PCIe link, kernels run in fp16"},
+                "note": "public API HostPipeline: per step pinned host features+cost -> H2D (copy-in stream) -> 3 "
+                        "kernels -> D2H of the disparity map (copy-out stream), device buffers allocated once; "
+                        "serial_value: no overlap; h2d_ceiling: a bare pinned cudaMemcpyAsync of the same bytes on "
+                        "this box; the volumes stay in HBM for the aggregation network, as in the model"},
         "gpu_launches": len(wl.kernels) * K,
         "clocks": clocks,
     }
@@ -354,8 +496,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS) + ["cfg5_train"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="skip the sustained loop and the extra tensor-core kernels")
     args = ap.parse_args()
     # stdout carries the ONE JSON line and nothing else: everything written to fd 1 from here on (NCCL's version
     # banner under NCCL_DEBUG, library chatter) is sent to stderr, the result goes to a private copy of stdout
@@ -363,11 +506,18 @@ def main():
     sys.stdout.flush()
     _RESULT_OUT = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
-    wl = WORKLOADS[args.workload]()
-    if args.impl == "reference":
-        run_reference(args, wl)
+    if args.workload == "cfg5_train":
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("rsm_train_bench", os.path.join(ROOT, "tools", "train_bench.py"))
+        train_bench = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(train_bench)
+        train_bench.run(args, _RESULT_OUT)
     else:
-        run_b200(args, wl)
+        wl = WORKLOADS[args.workload]()
+        if args.impl == "reference":
+            run_reference(args, wl)
+        else:
+            run_b200(args, wl)
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         import torch.distributed as dist
         if dist.is_initialized():

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RSM_VERSION 104 /* major*10000 + minor*100 + patch */
+#define RSM_VERSION 105 /* major*10000 + minor*100 + patch */
 
 typedef enum rsm_dtype {
   RSM_F32 = 0,
@@ -69,6 +69,9 @@ typedef struct rsm_regress_out {
   int64_t* argmin;   /* (N,H,W) torch.argmin(cost, 1): first index on ties, NaN wins       */
   int64_t* argmax;   /* (N,H,W) torch.argmax(cost, 1)                                       */
   float* lse;        /* (N,H,W) fp32 log-sum-exp over D, saved for the backward pass        */
+  float* expect;     /* (N,H,W) the expectation again, ALWAYS fp32 (not rounded to a 16-bit cost dtype):
+                      * what the backward pass reads, and what a caller under autocast returns -- the reference's
+                      * F.softmax runs in fp32 there, so its disparity is fp32 (mobile_stereo_net.py:144-147)  */
 } rsm_regress_out;
 
 int rsm_version(void);
@@ -136,7 +139,8 @@ int rsm_shift_interweave_bwd(const void* gout, void* gleft, void* gright, int64_
 int rsm_warp_fwd(const void* image, const void* flow, void* out, int64_t N, int64_t C, int64_t H, int64_t W,
                  int flow_channels, int dtype, int device, void* stream);
 /* adjoint: gimage (N,C,H,W) is ALWAYS fp32 (cleared and accumulated with atomics inside the call, like
- * ATen's grid_sampler backward); gflow (N,flow_channels,H,W) in `dtype`, may be NULL */
+ * ATen's grid_sampler backward); gflow (N,flow_channels,H,W) in `dtype`; either may be NULL (not needed: no
+ * memset, no atomics for a NULL gimage), not both */
 int rsm_warp_bwd(const void* gout, const void* image, const void* flow, float* gimage, void* gflow, int64_t N,
                  int64_t C, int64_t H, int64_t W, int flow_channels, int dtype, int device, void* stream);
 
@@ -198,8 +202,8 @@ int rsm_pfm_read(const char* path, float* image, int64_t H, int64_t W, int chann
  * not in the reference) in ONE pass over the volume */
 int rsm_regress_fwd(const void* cost, int64_t N, int64_t D, int64_t H, int64_t W, int dtype,
                     rsm_regress_out out, int device, void* stream);
-/* gcost[d] = gout * p[d] * (d - soft);  soft/lse from the forward call; gout (N,H,W) in dtype */
-int rsm_regress_bwd(const void* gout, const void* cost, const void* soft, const float* lse,
+/* gcost[d] = gout * p[d] * (d - expect);  expect/lse (fp32) from the forward call; gout (N,H,W) in dtype */
+int rsm_regress_bwd(const void* gout, const void* cost, const float* expect, const float* lse,
                     void* gcost, int64_t N, int64_t D, int64_t H, int64_t W, int dtype,
                     int device, void* stream);
 
@@ -219,7 +223,7 @@ int rsm_upsample_regress_fwd(const void* cost, int64_t B, int64_t Dc, int64_t Hc
                              int device, void* stream);
 /* bytes of scratch the backward needs (a (B,Dc,H,W) fp32 tensor) */
 int64_t rsm_upsample_regress_bwd_workspace(int64_t B, int64_t Dc, int64_t H, int64_t W);
-int rsm_upsample_regress_bwd(const void* gout, const void* cost, const void* soft,
+int rsm_upsample_regress_bwd(const void* gout, const void* cost, const float* expect,
                              const float* lse, void* gcost, void* workspace, int64_t B,
                              int64_t Dc, int64_t Hc, int64_t Wc, int64_t D, int64_t H, int64_t W,
                              int dtype, int device, void* stream);

@@ -26,12 +26,14 @@ class RsmFeat(C.Structure):
 
 
 class RsmRegressOut(C.Structure):
-    _fields_ = [("soft", C.c_void_p), ("argmin", C.c_void_p), ("argmax", C.c_void_p), ("lse", C.c_void_p)]
+    _fields_ = [("soft", C.c_void_p), ("argmin", C.c_void_p), ("argmax", C.c_void_p), ("lse", C.c_void_p),
+                ("expect", C.c_void_p)]
 
 
 i64, vp, ci, cf = C.c_int64, C.c_void_p, C.c_int, C.c_float
 
 RSM_REDUCE_WS_DOUBLES = 1184 * 8   # include/rsm.h
+RSM_VERSION = 105                  # include/rsm.h; the argument layouts below were written for this ABI
 
 # name -> argtypes, exactly the prototypes of include/rsm.h (tests/test_abi.py checks the header)
 SIGNATURES = {
@@ -92,6 +94,12 @@ def load() -> C.CDLL:
     lib.rsm_last_error.restype = C.c_char_p
     lib.rsm_upsample_regress_bwd_workspace.argtypes = [i64, i64, i64, i64]
     lib.rsm_upsample_regress_bwd_workspace.restype = i64
+    got = lib.rsm_version()
+    if got != RSM_VERSION:
+        # the .so is git-ignored and copied between boxes: a stale binary would be called with the wrong layouts
+        raise RuntimeError(
+            f"{LIB_PATH} reports ABI version {got}, this package was written for {RSM_VERSION}: rebuild it with "
+            "`python -m realtime_stereo_matcher_b200.build --force`")
     _lib = lib
     return lib
 

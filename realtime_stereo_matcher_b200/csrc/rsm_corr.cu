@@ -871,6 +871,8 @@ extern "C" int rsm_inner_regress_fwd(rsm_feat left, rsm_feat right, int64_t N, i
                                      int device, void* stream) {
   CorrGeom g;
   if (D <= 0) return RSM_ERR_INVALID_SHAPE;
+  if (out.soft && out.expect && out.soft != (void*)out.expect) return RSM_ERR_UNSUPPORTED_CONFIG;   // both are the fp32 plane here
+  if (!out.soft) out.soft = out.expect;
   if (int rc = make_geom(N, C, H, W, D, 1, reduce == RSM_REDUCE_MEAN, true, g)) return rc;
   if (N * H * W == 0) return RSM_OK;
   if (C > 0 && (!left.data || !right.data)) return RSM_ERR_NULL_POINTER;

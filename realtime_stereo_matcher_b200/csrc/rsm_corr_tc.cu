@@ -39,7 +39,8 @@
 // Two TMEM accumulator buffers decouple the UMMAs of tile t+1 from the epilogue of tile t.
 // mbarriers: smem_full[s] (TMA bytes or 128 loader / splitter arrivals), smem_empty[s] (UMMA commit), raw_full[s]
 // (fp32 TMA bytes), lo_empty[2] (UMMA commit), tmem_full[b] (UMMA commit), tmem_empty[b] (epilogue arrivals).
-// All waits are bounded (a protocol bug yields NaNs, not a hang).
+// All waits are bounded: a wait that expires traps (launch failure -> RSM_ERR_CUDA), never a hang, never a
+// silently wrong result.
 #include <cuda.h>   // CUtensorMap (types only; the encoder is looked up at run time, no libcuda link dependency)
 
 #include "rsm_common.cuh"
@@ -149,17 +150,21 @@ __device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
 // try_wait carries a suspend-time hint: the waiting thread sleeps in hardware until the phase completes (or the
 // hint expires) instead of spinning -- a spinning issuer / producer lane was taking half the issue slots of its
 // scheduler away from the epilogue warps that share it (measured: those warps ran 2x slower).
-__device__ __forceinline__ bool mbar_wait(uint32_t mbar, uint32_t parity) {
-  for (int it = 0; it < (1 << 16); ++it) {
+// A wait that expires (4096 x 10 ms) is a protocol failure: EVERY role stops there -- the kernel traps, the launch
+// fails with a sticky CUDA error and the next rsm_* call on the device returns RSM_ERR_CUDA.  No role ever runs on
+// past a failed wait (it would overwrite a shared-memory stage or a TMEM buffer that is still in use), so the
+// kernel cannot return RSM_OK with a poisoned volume.
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  for (int it = 0; it < (1 << 12); ++it) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(mbar), "r"(parity), "r"(0x989680u)
         : "memory");
-    if (ok) return true;
+    if (ok) return;
   }
-  return false;
+  __trap();
 }
 
 template <typename Tin>
@@ -565,7 +570,6 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
     const int phi = hh == 0 ? g.eb[1] : hh == 1 ? g.eb[2] : g.eb[3];
     const int cs = g.dch - phi, ncw = (phi - plo + 32 + 15) / 16 * 16;
     const float inv = 1.f / (float)g.C, cnt = (float)g.C;
-    const float nanv = __int_as_float(0x7fc00000);
     uint32_t use = 0;
     // EPI_REGRESS: running softmax / arg-extrema state of this lane's pixel, carried across the disparity
     // chunks of a tile (chunks of one pixel tile are consecutive: d-fastest tile order)
@@ -575,7 +579,7 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
     TileCoord tc = tile_coord(t_beg, g);
     for (int64_t t = t_beg; t < t_end; ++t, ++use, tc.advance(g)) {
       const uint32_t buf = use & 1;
-      const bool ok = mbar_wait(tmem_full + 8 * buf, (use >> 1) & 1);
+      mbar_wait(tmem_full + 8 * buf, (use >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + buf * g.tmem_buf + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * q + cs);
       const int x = tc.x0 + 32 * q + lane;
@@ -603,7 +607,7 @@ inner_tc_kernel(FeatView L, FeatView R, Tout* __restrict__ out, RegressPtrs rp, 
       __syncwarp();
       // ---- skewed read-back: value(dl) = rp0[-dl]; zeros where x < d, i.e. for dl >= dz
       const float* rp0 = row + lane + phi;
-      const float mul = !ok ? nanv : (g.mean ? (g.pow2 ? inv : 1.f) : 1.f);   // NaN marks a pipeline fault
+      const float mul = g.mean ? (g.pow2 ? inv : 1.f) : 1.f;
       const bool divide = g.mean && !g.pow2;
       const int dz = max(dlo, min(dhi, x - tc.dc0 + 1));    // [dlo, dz): values, [dz, dhi): fill
 

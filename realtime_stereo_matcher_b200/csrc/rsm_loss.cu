@@ -23,6 +23,13 @@ constexpr int RED_THREADS = 256;
 constexpr int RED_MAX_BLOCKS = RSM_REDUCE_MAX_BLOCKS;   // 8 per SM
 constexpr int RED_SLOTS = 8;                            // doubles per partial
 
+// torch.min / torch.max propagate NaN (loss/loss.py:19-20 logs them as the divergence tell-tale, train_stereo.py:174);
+// fmin / fmax would drop it
+__device__ __forceinline__ double nan_min(double a, double b) { return (a != a || b != b) ? (double)NAN : fmin(a, b); }
+__device__ __forceinline__ double nan_max(double a, double b) { return (a != a || b != b) ? (double)NAN : fmax(a, b); }
+__device__ __forceinline__ float nan_minf(float a, float b) { return (a != a || b != b) ? NAN : fminf(a, b); }
+__device__ __forceinline__ float nan_maxf(float a, float b) { return (a != a || b != b) ? NAN : fmaxf(a, b); }
+
 template <int K>
 __device__ __forceinline__ void block_reduce_store(double (&v)[K], const bool (&is_min)[K], const bool (&is_max)[K],
                                                    double* __restrict__ dst) {
@@ -33,7 +40,7 @@ __device__ __forceinline__ void block_reduce_store(double (&v)[K], const bool (&
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const double other = __shfl_down_sync(0xffffffffu, v[k], o);
-      v[k] = is_min[k] ? fmin(v[k], other) : is_max[k] ? fmax(v[k], other) : v[k] + other;
+      v[k] = is_min[k] ? nan_min(v[k], other) : is_max[k] ? nan_max(v[k], other) : v[k] + other;
     }
     if (lane == 0) sh[warp][k] = v[k];
   }
@@ -43,7 +50,7 @@ __device__ __forceinline__ void block_reduce_store(double (&v)[K], const bool (&
     for (int k = 0; k < K; ++k) {
       double a = sh[0][k];
       for (int w = 1; w < RED_THREADS / 32; ++w)
-        a = is_min[k] ? fmin(a, sh[w][k]) : is_max[k] ? fmax(a, sh[w][k]) : a + sh[w][k];
+        a = is_min[k] ? nan_min(a, sh[w][k]) : is_max[k] ? nan_max(a, sh[w][k]) : a + sh[w][k];
       dst[k] = a;
     }
   }
@@ -180,7 +187,7 @@ metrics_partial_kernel(const T* __restrict__ gt, const T* __restrict__ pred, con
         const float pv = to_f(pred[q]);
         const float d = to_f(from_f<T>(__fsub_rn(pv, to_f(gt[q]))));
         sq = c == 0 ? to_f(from_f<T>(__fmul_rn(d, d))) : to_f(from_f<T>(__fadd_rn(sq, to_f(from_f<T>(__fmul_rn(d, d))))));
-        if (n == 0) { mn = fminf(mn, pv); mx = fmaxf(mx, pv); }
+        if (n == 0) { mn = nan_minf(mn, pv); mx = nan_maxf(mx, pv); }
       }
       if (valid[row * W + x] >= 0.5f) {
         const float e = to_f(from_f<T>(sqrtf(sq)));
@@ -190,7 +197,7 @@ metrics_partial_kernel(const T* __restrict__ gt, const T* __restrict__ pred, con
     }
     acc[0] += (double)esum; acc[1] += (double)cnt; acc[2] += (double)c05; acc[3] += (double)c1;
     acc[4] += (double)c3; acc[5] += (double)c5;
-    acc[6] = fmin(acc[6], (double)mn); acc[7] = fmax(acc[7], (double)mx);
+    acc[6] = nan_min(acc[6], (double)mn); acc[7] = nan_max(acc[7], (double)mx);
   }
   const bool mn[8] = {false, false, false, false, false, false, true, false};
   const bool mx[8] = {false, false, false, false, false, false, false, true};
@@ -205,7 +212,7 @@ metrics_final_kernel(const double* __restrict__ partial, int nblocks, double* __
     const double* s = partial + (int64_t)b * RED_SLOTS;
 #pragma unroll
     for (int k = 0; k < 6; ++k) acc[k] += s[k];
-    acc[6] = fmin(acc[6], s[6]); acc[7] = fmax(acc[7], s[7]);
+    acc[6] = nan_min(acc[6], s[6]); acc[7] = nan_max(acc[7], s[7]);
   }
   const bool mn[8] = {false, false, false, false, false, false, true, false};
   const bool mx[8] = {false, false, false, false, false, false, false, true};

@@ -127,7 +127,7 @@ struct RegressState {
 template <typename T, int VEC, int DCH, bool SOFT, bool ARG>
 __global__ void __launch_bounds__(256)
 regress_fwd_kernel(const T* __restrict__ cost, T* __restrict__ soft, int64_t* __restrict__ amin,
-                   int64_t* __restrict__ amax, float* __restrict__ lse, int64_t pix_vec_per_img,
+                   int64_t* __restrict__ amax, float* __restrict__ lse, float* __restrict__ expect, int64_t pix_vec_per_img,
                    int64_t total_vec, int D, int64_t HW) {
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= total_vec) return;
@@ -160,7 +160,9 @@ regress_fwd_kernel(const T* __restrict__ cost, T* __restrict__ soft, int64_t* __
 #pragma unroll
   for (int j = 0; j < VEC; ++j) {
     if constexpr (SOFT) {
-      if (soft) soft[o + j] = from_f<T>(st.ws[j] / st.s[j]);
+      const float e = st.ws[j] / st.s[j];
+      if (soft) soft[o + j] = from_f<T>(e);
+      if (expect) expect[o + j] = e;
       if (lse) lse[o + j] = st.m[j] + __logf(st.s[j]);
     }
     if constexpr (ARG) {
@@ -181,7 +183,7 @@ regress_fwd_kernel(const T* __restrict__ cost, T* __restrict__ soft, int64_t* __
 // gcost[d] = g * softmax_d * (d - E), with softmax_d = exp(cost[d] - lse)
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256)
-regress_bwd_kernel(const T* __restrict__ gout, const T* __restrict__ cost, const T* __restrict__ soft,
+regress_bwd_kernel(const T* __restrict__ gout, const T* __restrict__ cost, const float* __restrict__ expect,
                    const float* __restrict__ lse, T* __restrict__ gcost, int64_t pix_vec_per_img,
                    int64_t total_vec, int D, int64_t HW) {
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
@@ -193,7 +195,7 @@ regress_bwd_kernel(const T* __restrict__ gout, const T* __restrict__ cost, const
 #pragma unroll
   for (int j = 0; j < VEC; ++j) {
     g[j] = to_f(gout[o + j]);
-    e[j] = to_f(soft[o + j]);
+    e[j] = expect[o + j];
     l2[j] = lse[o + j] * kLog2e;
   }
   const T* __restrict__ cb = cost + n * D * HW + p;
@@ -317,9 +319,9 @@ extern "C" int rsm_regress_fwd(const void* cost, int64_t N, int64_t D, int64_t H
     const int64_t total = N * pv;
     if (!grid_ok(ceil_div(total, 256))) return (int)RSM_ERR_INVALID_SHAPE;
     const unsigned blocks = (unsigned)ceil_div(total, 256);
-    const bool want_soft = out.soft || out.lse, want_arg = out.argmin || out.argmax;
+    const bool want_soft = out.soft || out.lse || out.expect, want_arg = out.argmin || out.argmax;
     auto launch = [&](auto kern) {
-      kern<<<blocks, 256, 0, st>>>((const T*)cost, (T*)out.soft, out.argmin, out.argmax, out.lse, pv, total, (int)D, HW);
+      kern<<<blocks, 256, 0, st>>>((const T*)cost, (T*)out.soft, out.argmin, out.argmax, out.lse, out.expect, pv, total, (int)D, HW);
     };
     if (vec) {
       if (want_soft && want_arg) launch(regress_fwd_kernel<T, 4, 8, true, true>);
@@ -334,12 +336,12 @@ extern "C" int rsm_regress_fwd(const void* cost, int64_t N, int64_t D, int64_t H
   });
 }
 
-extern "C" int rsm_regress_bwd(const void* gout, const void* cost, const void* soft, const float* lse,
+extern "C" int rsm_regress_bwd(const void* gout, const void* cost, const float* expect, const float* lse,
                                void* gcost, int64_t N, int64_t D, int64_t H, int64_t W, int dtype,
                                int device, void* stream) {
   if (N < 0 || D <= 0 || H < 0 || W < 0) return RSM_ERR_INVALID_SHAPE;
   if (N * H * W == 0) return RSM_OK;
-  if (!gout || !cost || !soft || !lse || !gcost) return RSM_ERR_NULL_POINTER;
+  if (!gout || !cost || !expect || !lse || !gcost) return RSM_ERR_NULL_POINTER;
   RSM_COMMON_CHECKS(dtype)
   return RSM_DISPATCH_DTYPE(dtype, T, [&]() -> int {
     constexpr int VEC = 16 / sizeof(T);
@@ -350,10 +352,10 @@ extern "C" int rsm_regress_bwd(const void* gout, const void* cost, const void* s
     if (!grid_ok(ceil_div(total, 256))) return (int)RSM_ERR_INVALID_SHAPE;
     const unsigned blocks = (unsigned)ceil_div(total, 256);
     if (vec)
-      regress_bwd_kernel<T, VEC><<<blocks, 256, 0, st>>>((const T*)gout, (const T*)cost, (const T*)soft, lse,
+      regress_bwd_kernel<T, VEC><<<blocks, 256, 0, st>>>((const T*)gout, (const T*)cost, expect, lse,
                                                          (T*)gcost, pv, total, (int)D, HW);
     else
-      regress_bwd_kernel<T, 1><<<blocks, 256, 0, st>>>((const T*)gout, (const T*)cost, (const T*)soft, lse,
+      regress_bwd_kernel<T, 1><<<blocks, 256, 0, st>>>((const T*)gout, (const T*)cost, expect, lse,
                                                        (T*)gcost, pv, total, (int)D, HW);
     return finish_launch("rsm_regress_bwd");
   });

@@ -325,7 +325,7 @@ __device__ __forceinline__ float fine_max(const SliceY& sl, const TailSmem& sm, 
 template <typename T, bool FAST4, bool ALL4, bool WANT_ARG>
 __global__ void __launch_bounds__(kNT)
 upsample_regress_fwd_kernel(const T* __restrict__ cost, T* __restrict__ soft, int64_t* __restrict__ amin,
-                            int64_t* __restrict__ amax, float* __restrict__ lse, TailGeom g) {
+                            int64_t* __restrict__ amax, float* __restrict__ lse, float* __restrict__ expect, TailGeom g) {
   extern __shared__ __align__(16) float smem_f[];
   const TailSmem sm(smem_f, g);
   const int b = blockIdx.z;
@@ -376,7 +376,9 @@ upsample_regress_fwd_kernel(const T* __restrict__ cost, T* __restrict__ soft, in
     }
   }
   const int64_t o = ((int64_t)b * g.H + y) * g.W + x;
-  if (soft) soft[o] = from_f<T>(ws / s);
+  const float E = ws / s;
+  if (soft) soft[o] = from_f<T>(E);
+  if (expect) expect[o] = E;
   if (lse) lse[o] = M + __logf(s);
   if constexpr (WANT_ARG) {
     if (amin) amin[o] = trk.mini;
@@ -392,7 +394,7 @@ upsample_regress_fwd_kernel(const T* __restrict__ cost, T* __restrict__ soft, in
 template <typename T, bool ALL4>
 __global__ void __launch_bounds__(kNT)
 upsample_regress_bwd_cols_kernel(const T* __restrict__ gout, const T* __restrict__ cost,
-                                 const T* __restrict__ soft, const float* __restrict__ lse,
+                                 const float* __restrict__ expect, const float* __restrict__ lse,
                                  float* __restrict__ wsp, TailGeom g) {
   extern __shared__ __align__(16) float smem_f[];
   const TailSmem sm(smem_f, g);
@@ -406,7 +408,7 @@ upsample_regress_bwd_cols_kernel(const T* __restrict__ gout, const T* __restrict
 
   const SliceY sl(sm, g, y, cy0);
   const int64_t o = ((int64_t)b * g.H + y) * g.W + x;
-  const float go = to_f(gout[o]), E = to_f(soft[o]), l2 = lse[o] * kLog2e;
+  const float go = to_f(gout[o]), E = expect[o], l2 = lse[o] * kLog2e;
   const int64_t plane = (int64_t)g.H * g.W;
   float* __restrict__ col = wsp + (int64_t)b * g.Dc * plane + (int64_t)y * g.W + x;
 
@@ -552,7 +554,7 @@ static int launch_tail_fwd(const void* cost, const rsm_regress_out& out, const T
                            cudaStream_t st) {
   auto k = upsample_regress_fwd_kernel<T, FAST4, ALL4, WANT_ARG>;
   if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k<<<grid, kNT, smem, st>>>((const T*)cost, (T*)out.soft, out.argmin, out.argmax, out.lse, g);
+  k<<<grid, kNT, smem, st>>>((const T*)cost, (T*)out.soft, out.argmin, out.argmax, out.lse, out.expect, g);
   return finish_launch("rsm_upsample_regress_fwd");
 }
 
@@ -585,7 +587,7 @@ extern "C" int64_t rsm_upsample_regress_bwd_workspace(int64_t B, int64_t Dc, int
   return B * Dc * H * W * (int64_t)sizeof(float);
 }
 
-extern "C" int rsm_upsample_regress_bwd(const void* gout, const void* cost, const void* soft,
+extern "C" int rsm_upsample_regress_bwd(const void* gout, const void* cost, const float* expect,
                                         const float* lse, void* gcost, void* workspace, int64_t B,
                                         int64_t Dc, int64_t Hc, int64_t Wc, int64_t D, int64_t H,
                                         int64_t W, int dtype, int device, void* stream) {
@@ -594,7 +596,7 @@ extern "C" int rsm_upsample_regress_bwd(const void* gout, const void* cost, cons
   size_t smem;
   if (int rc = make_geom(Dc, Hc, Wc, D, H, W, g, smem)) return rc;
   if (B == 0) return RSM_OK;
-  if (!gout || !cost || !soft || !lse || !gcost || !workspace) return RSM_ERR_NULL_POINTER;
+  if (!gout || !cost || !expect || !lse || !gcost || !workspace) return RSM_ERR_NULL_POINTER;
   if (B > 65535) return RSM_ERR_INVALID_SHAPE;
   RSM_COMMON_CHECKS(dtype)
   return RSM_DISPATCH_DTYPE(dtype, T, [&]() -> int {
@@ -602,7 +604,7 @@ extern "C" int rsm_upsample_regress_bwd(const void* gout, const void* cost, cons
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const dim3 grid((unsigned)ceil_div(W, kTX), (unsigned)ceil_div(H, kTY), (unsigned)B);
     if (grid.y > 65535) return (int)RSM_ERR_INVALID_SHAPE;
-    k<<<grid, kNT, smem, st>>>((const T*)gout, (const T*)cost, (const T*)soft, lse, (float*)workspace, g);
+    k<<<grid, kNT, smem, st>>>((const T*)gout, (const T*)cost, expect, lse, (float*)workspace, g);
     if (int rc = finish_launch("rsm_upsample_regress_bwd(cols)")) return rc;
     const int64_t total = B * Dc * Hc * Wc;
     if (!grid_ok(ceil_div(total, 256))) return (int)RSM_ERR_INVALID_SHAPE;

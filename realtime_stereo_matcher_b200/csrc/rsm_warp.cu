@@ -89,10 +89,12 @@ warp_bwd_kernel(const T* __restrict__ gout, const T* __restrict__ image, const T
     const float go = to_f(*g);
     const float vnw = bnw ? to_f(__ldg(src + onw)) : 0.f, vne = bne ? to_f(__ldg(src + one)) : 0.f;
     const float vsw = bsw ? to_f(__ldg(src + osw)) : 0.f, vse = bse ? to_f(__ldg(src + ose)) : 0.f;
-    if (bnw) atomicAdd(gi + onw, go * wx0 * wy0);
-    if (bne) atomicAdd(gi + one, go * t.wx1 * wy0);
-    if (bsw) atomicAdd(gi + osw, go * wx0 * t.wy1);
-    if (bse) atomicAdd(gi + ose, go * t.wx1 * t.wy1);
+    if (gimage) {                       // NULL: the image needs no gradient (v2 warps the raw right image)
+      if (bnw) atomicAdd(gi + onw, go * wx0 * wy0);
+      if (bne) atomicAdd(gi + one, go * t.wx1 * wy0);
+      if (bsw) atomicAdd(gi + osw, go * wx0 * t.wy1);
+      if (bse) atomicAdd(gi + ose, go * t.wx1 * t.wy1);
+    }
     gix = fmaf(go, (vne - vnw) * wy0 + (vse - vsw) * t.wy1, gix);
     giy = fmaf(go, (vsw - vnw) * wx0 + (vse - vne) * t.wx1, giy);
   }
@@ -139,10 +141,10 @@ extern "C" int rsm_warp_bwd(const void* gout, const void* image, const void* flo
   if (H > (1 << 24) || W > (1 << 24)) return RSM_ERR_INVALID_SHAPE;
   const int64_t total = N * H * W;
   if (total == 0) return RSM_OK;
-  if (!gimage || (C > 0 && (!gout || !image)) || !flow) return RSM_ERR_NULL_POINTER;
+  if ((!gimage && !gflow) || (C > 0 && (!gout || !image)) || !flow) return RSM_ERR_NULL_POINTER;
   RSM_COMMON_CHECKS(dtype)
   if (!grid_ok(ceil_div(total, 256))) return RSM_ERR_INVALID_SHAPE;
-  if (C > 0 && cudaMemsetAsync(gimage, 0, (size_t)(total * C) * sizeof(float), st) != cudaSuccess)
+  if (gimage && C > 0 && cudaMemsetAsync(gimage, 0, (size_t)(total * C) * sizeof(float), st) != cudaSuccess)
     return finish_launch("rsm_warp_bwd(memset)");
   return RSM_DISPATCH_DTYPE(dtype, T, [&]() -> int {
     warp_bwd_kernel<T><<<(unsigned)ceil_div(total, 256), 256, 0, st>>>((const T*)gout, (const T*)image, (const T*)flow,

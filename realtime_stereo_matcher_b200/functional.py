@@ -271,11 +271,15 @@ class _Warp(torch.autograd.Function):
         image, flow = ctx.saved_tensors
         dev, n, c, h, w, cf = ctx.dims
         gout = _dense(gout)
-        gimage = torch.empty((n, c, h, w), dtype=torch.float32, device=image.device)   # fp32 atomics accumulate here
+        # fp32 atomics accumulate the image gradient; skipped entirely when the image needs none (v2's RefineNet
+        # warps the raw right image and differentiates only the flow)
+        gimage = torch.empty((n, c, h, w), dtype=torch.float32, device=image.device) if ctx.needs_input_grad[0] else None
         gflow = torch.empty_like(flow) if ctx.needs_input_grad[1] else None
-        L.check(L.load().rsm_warp_bwd(gout.data_ptr(), image.data_ptr(), flow.data_ptr(), gimage.data_ptr(), L.ptr(gflow),
+        if gimage is None and gflow is None:
+            return None, None
+        L.check(L.load().rsm_warp_bwd(gout.data_ptr(), image.data_ptr(), flow.data_ptr(), L.ptr(gimage), L.ptr(gflow),
                                       n, c, h, w, cf, L.dtype_code(image), dev, L.stream_ptr(dev)), "rsm_warp_bwd")
-        return gimage.to(image.dtype), gflow
+        return (None if gimage is None else gimage.to(image.dtype)), gflow
 
 
 def warp_by_flow_map(image, flow):
@@ -444,13 +448,18 @@ def flow_map_metrics(flow_gt, flow_pred, flow_valid):
 
 
 # ---------------------------------------------------------------------------- regression
-def _regress_outputs(shape, dtype, device, soft, argmin, argmax, lse):
+def _regress_outputs(shape, dtype, device, soft, argmin, argmax, lse, expect=False):
+    """Output planes of a regression call.  ``expect`` is the fp32 copy of the expectation (rsm_regress_out.expect):
+    the backward pass reads it, and it is what a caller under autocast returns; for an fp32 cost it IS ``soft``."""
     n, h, w = shape
     so = torch.empty((n, h, w), dtype=dtype, device=device) if soft else None
     mi = torch.empty((n, h, w), dtype=torch.int64, device=device) if argmin else None
     ma = torch.empty((n, h, w), dtype=torch.int64, device=device) if argmax else None
     ls = torch.empty((n, h, w), dtype=torch.float32, device=device) if lse else None
-    return so, mi, ma, ls, L.RsmRegressOut(L.ptr(so), L.ptr(mi), L.ptr(ma), L.ptr(ls))
+    ex = None
+    if expect:
+        ex = so if (so is not None and dtype == torch.float32) else torch.empty((n, h, w), dtype=torch.float32, device=device)
+    return so, mi, ma, ls, ex, L.RsmRegressOut(L.ptr(so), L.ptr(mi), L.ptr(ma), L.ptr(ls), L.ptr(ex))
 
 
 def _check_cost(cost):
@@ -466,17 +475,20 @@ class _Regress(torch.autograd.Function):
 
     @staticmethod
     @custom_fwd(device_type="cuda")
-    def forward(ctx, cost, want_argmin, want_argmax):
+    def forward(ctx, cost, want_argmin, want_argmax, out_fp32=False):
         dev = _check_cost(cost)
         cost = _dense(cost)
         n, d, h, w = cost.shape
         need_grad = ctx.needs_input_grad[0]
-        so, mi, ma, ls, out = _regress_outputs((n, h, w), cost.dtype, cost.device, True, want_argmin,
-                                               want_argmax, need_grad)
+        out_fp32 = bool(out_fp32) and cost.dtype != torch.float32
+        so, mi, ma, ls, ex, out = _regress_outputs((n, h, w), cost.dtype, cost.device, not out_fp32, want_argmin,
+                                                   want_argmax, need_grad, need_grad or out_fp32)
         L.check(L.load().rsm_regress_fwd(cost.data_ptr(), n, d, h, w, L.dtype_code(cost), out, dev,
                                          L.stream_ptr(dev)), "rsm_regress_fwd")
+        if out_fp32:
+            so = ex
         if need_grad:
-            ctx.save_for_backward(cost, so, ls)
+            ctx.save_for_backward(cost, ex, ls)
         ctx.dims = (dev, n, d, h, w)
         empty = torch.empty(0, dtype=torch.int64, device=cost.device)
         mi = mi if mi is not None else empty
@@ -487,14 +499,14 @@ class _Regress(torch.autograd.Function):
     @staticmethod
     @custom_bwd(device_type="cuda")
     def backward(ctx, gsoft, _gmi, _gma):
-        cost, so, ls = ctx.saved_tensors
+        cost, ex, ls = ctx.saved_tensors
         dev, n, d, h, w = ctx.dims
         gsoft = _dense(gsoft.to(cost.dtype))
         gcost = torch.empty_like(cost)
-        L.check(L.load().rsm_regress_bwd(gsoft.data_ptr(), cost.data_ptr(), so.data_ptr(), ls.data_ptr(),
+        L.check(L.load().rsm_regress_bwd(gsoft.data_ptr(), cost.data_ptr(), ex.data_ptr(), ls.data_ptr(),
                                          gcost.data_ptr(), n, d, h, w, L.dtype_code(cost), dev,
                                          L.stream_ptr(dev)), "rsm_regress_bwd")
-        return gcost, None, None
+        return gcost, None, None, None
 
 
 def regress(cost, argmin=True, argmax=True):
@@ -502,13 +514,14 @@ def regress(cost, argmin=True, argmax=True):
 
     soft = sum_d d * softmax_d(+cost) (reference mobile_stereo_net.py:144-147); argmin/argmax follow
     torch.argmin/argmax(cost, 1): first index on ties, NaN is the extremum."""
-    so, mi, ma = _Regress.apply(cost, bool(argmin), bool(argmax))
+    so, mi, ma = _Regress.apply(cost, bool(argmin), bool(argmax), False)
     return so, (mi if argmin else None), (ma if argmax else None)
 
 
-def soft_argmax(cost, keepdim=False):
-    """sum_d d * softmax_d(+cost): (N,D,H,W) -> (N,H,W), or (N,1,H,W) with ``keepdim``."""
-    so, _, _ = _Regress.apply(cost, False, False)
+def soft_argmax(cost, keepdim=False, out_fp32=False):
+    """sum_d d * softmax_d(+cost): (N,D,H,W) -> (N,H,W), or (N,1,H,W) with ``keepdim``.  ``out_fp32``: return the
+    fp32 expectation for a 16-bit cost (what the reference produces under autocast, where F.softmax runs in fp32)."""
+    so, _, _ = _Regress.apply(cost, False, False, out_fp32)
     return so.unsqueeze(1) if keepdim else so
 
 
@@ -517,7 +530,7 @@ def hard_argmin(cost):
     dev = _check_cost(cost)
     cost = _dense(cost.detach())
     n, d, h, w = cost.shape
-    _, mi, _, _, out = _regress_outputs((n, h, w), cost.dtype, cost.device, False, True, False, False)
+    _, mi, _, _, _, out = _regress_outputs((n, h, w), cost.dtype, cost.device, False, True, False, False)
     L.check(L.load().rsm_regress_fwd(cost.data_ptr(), n, d, h, w, L.dtype_code(cost), out, dev,
                                      L.stream_ptr(dev)), "rsm_regress_fwd")
     return mi
@@ -528,7 +541,7 @@ def hard_argmax(cost):
     dev = _check_cost(cost)
     cost = _dense(cost.detach())
     n, d, h, w = cost.shape
-    _, _, ma, _, out = _regress_outputs((n, h, w), cost.dtype, cost.device, False, False, True, False)
+    _, _, ma, _, _, out = _regress_outputs((n, h, w), cost.dtype, cost.device, False, False, True, False)
     L.check(L.load().rsm_regress_fwd(cost.data_ptr(), n, d, h, w, L.dtype_code(cost), out, dev,
                                      L.stream_ptr(dev)), "rsm_regress_fwd")
     return ma
@@ -567,18 +580,21 @@ def expectation(prob):
 class _UpsampleRegress(torch.autograd.Function):
     @staticmethod
     @custom_fwd(device_type="cuda")
-    def forward(ctx, cost, maxdisp, out_h, out_w, want_argmin, want_argmax):
+    def forward(ctx, cost, maxdisp, out_h, out_w, want_argmin, want_argmax, out_fp32=False):
         dev = _check_cost(cost)
         cost = _dense(cost)
         b, dc, hc, wc = cost.shape
         d, h, w = int(maxdisp), int(out_h), int(out_w)
         need_grad = ctx.needs_input_grad[0]
-        so, mi, ma, ls, out = _regress_outputs((b, h, w), cost.dtype, cost.device, True, want_argmin,
-                                               want_argmax, need_grad)
+        out_fp32 = bool(out_fp32) and cost.dtype != torch.float32
+        so, mi, ma, ls, ex, out = _regress_outputs((b, h, w), cost.dtype, cost.device, not out_fp32, want_argmin,
+                                                   want_argmax, need_grad, need_grad or out_fp32)
         L.check(L.load().rsm_upsample_regress_fwd(cost.data_ptr(), b, dc, hc, wc, d, h, w, L.dtype_code(cost),
                                                   out, dev, L.stream_ptr(dev)), "rsm_upsample_regress_fwd")
+        if out_fp32:
+            so = ex
         if need_grad:
-            ctx.save_for_backward(cost, so, ls)
+            ctx.save_for_backward(cost, ex, ls)
         ctx.dims = (dev, b, dc, hc, wc, d, h, w)
         empty = torch.empty(0, dtype=torch.int64, device=cost.device)
         mi = mi if mi is not None else empty
@@ -589,24 +605,24 @@ class _UpsampleRegress(torch.autograd.Function):
     @staticmethod
     @custom_bwd(device_type="cuda")
     def backward(ctx, gsoft, _gmi, _gma):
-        cost, so, ls = ctx.saved_tensors
+        cost, ex, ls = ctx.saved_tensors
         dev, b, dc, hc, wc, d, h, w = ctx.dims
         gsoft = _dense(gsoft.to(cost.dtype))
         gcost = torch.empty_like(cost)
         nbytes = L.load().rsm_upsample_regress_bwd_workspace(b, dc, h, w)
         work = torch.empty(nbytes // 4, dtype=torch.float32, device=cost.device)
-        L.check(L.load().rsm_upsample_regress_bwd(gsoft.data_ptr(), cost.data_ptr(), so.data_ptr(),
+        L.check(L.load().rsm_upsample_regress_bwd(gsoft.data_ptr(), cost.data_ptr(), ex.data_ptr(),
                                                   ls.data_ptr(), gcost.data_ptr(), work.data_ptr(), b, dc, hc,
                                                   wc, d, h, w, L.dtype_code(cost), dev, L.stream_ptr(dev)),
                 "rsm_upsample_regress_bwd")
-        return gcost, None, None, None, None, None
+        return gcost, None, None, None, None, None, None
 
 
-def upsample_regress(cost, maxdisp, out_h, out_w, argmin=False, argmax=False):
+def upsample_regress(cost, maxdisp, out_h, out_w, argmin=False, argmax=False, out_fp32=False):
     """MobileStereoNetV4 head (mobile_stereo_net_v4.py:511-518), fused: trilinear upsample of the coarse
     (B,Dc,Hc,Wc) cost to (maxdisp,out_h,out_w) -> softmax over D -> expectation, (B,H,W).
     Optionally also the hard argmin/argmax over the upsampled volume."""
-    so, mi, ma = _UpsampleRegress.apply(cost, maxdisp, out_h, out_w, bool(argmin), bool(argmax))
+    so, mi, ma = _UpsampleRegress.apply(cost, maxdisp, out_h, out_w, bool(argmin), bool(argmax), bool(out_fp32))
     if not argmin and not argmax:
         return so
     return so, (mi if argmin else None), (ma if argmax else None)
@@ -618,7 +634,7 @@ def inner_product_regress(left, right, max_disparity, mean=False, argmin=True, a
     (N,D,H,W) volume is never written to HBM.  Inference only (no autograd)."""
     dev, n, c, h, w = _check_pair(left, right)
     d = int(max_disparity)
-    so, mi, ma, _, out = _regress_outputs((n, h, w), torch.float32, left.device, True, argmin, argmax, False)
+    so, mi, ma, _, _, out = _regress_outputs((n, h, w), torch.float32, left.device, True, argmin, argmax, False)
     red = L.RSM_REDUCE_MEAN if mean else L.RSM_REDUCE_SUM
     L.check(L.load().rsm_inner_regress_fwd(L.feat(left.detach()), L.feat(right.detach()), n, c, h, w, d, red,
                                            L.dtype_code(left), out, dev, L.stream_ptr(dev)),

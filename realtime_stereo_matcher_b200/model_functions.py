@@ -4,7 +4,16 @@
 """
 from __future__ import annotations
 
+import torch
+
 from . import functional as F_rsm
+
+
+def _autocast_fp32() -> bool:
+    """Under torch.autocast the reference's F.softmax runs in fp32 (autocast's fp32 op list), so its regressed
+    disparity is fp32 even when the cost is fp16 (evaluate_stereo.py / test_stereo.py wrap the
+    forward in autocast).  The kernels then return the fp32 expectation plane instead of rounding it to 16 bit."""
+    return torch.is_autocast_enabled("cuda")
 
 
 def make_cost_volume(left, right, max_disp):
@@ -70,18 +79,18 @@ def disparity_regression_dispnetc(corr_volume, max_disp):
     expectation, returned as (N,1,H,W)."""
     assert len(corr_volume.shape) == 4, "#dimensions of correlation volume != 4."
     assert corr_volume.shape[1] == max_disp, f"#channels of correlation volume != max_disparity ({max_disp})."
-    return F_rsm.soft_argmax(corr_volume, keepdim=True)
+    return F_rsm.soft_argmax(corr_volume, keepdim=True, out_fp32=_autocast_fp32())
 
 
 def softmax_regression(cost_volume, keepdim=True):
     """The inline regression of MobileStereoNet v1-v3 (mobile_stereo_net.py:144-147,
     mobile_stereo_net_v2.py:217-220, mobile_stereo_net_v3.py:321-324): softmax(dim=1) ->
     sum(x * arange(D)), one fused pass."""
-    return F_rsm.soft_argmax(cost_volume, keepdim=keepdim)
+    return F_rsm.soft_argmax(cost_volume, keepdim=keepdim, out_fp32=_autocast_fp32())
 
 
 def v4_head(cost, maxdisp, out_h, out_w):
     """The MobileStereoNetV4 head (mobile_stereo_net_v4.py:511-518; training heads :471-506):
     F.interpolate(cost[:,None], [maxdisp,H,W], 'trilinear') -> softmax -> disparity_regression,
     without materialising the (B,maxdisp,H,W) tensor.  Returns (B,H,W)."""
-    return F_rsm.upsample_regress(cost, maxdisp, out_h, out_w)
+    return F_rsm.upsample_regress(cost, maxdisp, out_h, out_w, out_fp32=_autocast_fp32())

@@ -123,13 +123,15 @@ def test_regress_entry_points_stay_in_bounds(L, shape, dt):
     st = L.stream_ptr(0)
     so, ls = Guarded(n * h * w, tdt), Guarded(n * h * w, torch.float32)
     mi64 = torch.full((n * h * w + 2 * GUARD,), -7, dtype=torch.int64, device="cuda")
-    ro = L.RsmRegressOut(so.ptr(), mi64[GUARD:].data_ptr(), None, ls.ptr())
+    e32 = Guarded(n * h * w, torch.float32)
+    ro = L.RsmRegressOut(so.ptr(), mi64[GUARD:].data_ptr(), None, ls.ptr(), e32.ptr())
     L.check(lib.rsm_regress_fwd(cost.data_ptr(), n, d, h, w, code, ro, 0, st), "regress")
-    so.check("rsm_regress_fwd soft"), ls.check("rsm_regress_fwd lse")
+    so.check("rsm_regress_fwd soft"), ls.check("rsm_regress_fwd lse"), e32.check("rsm_regress_fwd expect")
+    assert torch.equal(e32.payload.to(tdt), so.payload)       # soft is the fp32 expectation rounded once
     assert bool((mi64[:GUARD] == -7).all()) and bool((mi64[GUARD + n * h * w:] == -7).all())
     gout = torch.randn((n, h, w), device="cuda").to(tdt)
     gc = Guarded(n * d * h * w, tdt)
-    L.check(lib.rsm_regress_bwd(gout.data_ptr(), cost.data_ptr(), so.ptr(), ls.ptr(), gc.ptr(), n, d, h, w, code, 0, st),
+    L.check(lib.rsm_regress_bwd(gout.data_ptr(), cost.data_ptr(), e32.ptr(), ls.ptr(), gc.ptr(), n, d, h, w, code, 0, st),
             "regress_bwd")
     gc.check("rsm_regress_bwd")
     ex = Guarded(n * h * w, tdt)
@@ -147,7 +149,7 @@ def test_v4_head_entry_points_stay_in_bounds(L, geom):
     cost = torch.randn((b, dc, hc, wc), device="cuda") * 3
     st = L.stream_ptr(0)
     so, ls = Guarded(b * h * w, torch.float32), Guarded(b * h * w, torch.float32)
-    ro = L.RsmRegressOut(so.ptr(), None, None, ls.ptr())
+    ro = L.RsmRegressOut(so.ptr(), None, None, ls.ptr(), so.ptr())      # fp32 cost: soft and expect may alias
     L.check(lib.rsm_upsample_regress_fwd(cost.data_ptr(), b, dc, hc, wc, d, h, w, 0, ro, 0, st), "tail")
     so.check("rsm_upsample_regress_fwd soft"), ls.check("rsm_upsample_regress_fwd lse")
     gout = torch.randn((b, h, w), device="cuda")

@@ -1,0 +1,185 @@
+"""GPU suite: the drop-in glue meets the kernels -- the reference's own models, built by its own factory from its
+own configs on the CUDA device, run UNPATCHED (stock PyTorch / cuDNN ops) and then PATCHED (cost volumes,
+regression, warps, pre/post steps and, for v4 in eval mode, the whole per-disparity Conv3d stack on librsm_b200.so)
+with identical seeded weights:
+
+  * fp32 forward parity                          (model/mobile_stereo_net.py:120-159, _v4.py:432-524, mobile_disp_net_c.py:337-412)
+  * forward under torch.autocast(fp16), the evaluation path of the reference (evaluate_stereo.py:48,
+    test_stereo.py:117) -- this is what drives inner_tc_kernel (tcgen05) from a real call site (DispNetC, C = 16)
+  * SequenceLoss(...).backward() in train mode with parameter gradients compared (train_stereo.py:170-180)
+
+The reference is the unmodified copy in baseline/_ref (tools/install_ref.py; shipped to the GPU box by gpurun,
+never read from /root/reference at run time)."""
+import contextlib
+
+import pytest
+import torch
+
+from oracle import ref_loader
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not ref_loader.available(), reason="baseline/_ref missing: run tools/install_ref.py")]
+
+# (config, image size (H, W), batch).  v4 needs H, W % 16 == 0 and W/4 > 48; the others pad internally
+MODELS = [
+    ("stereo_net_config.json", (100, 188), 2),
+    ("stereo_net_config_v2.json", (96, 192), 2),
+    ("stereo_net_config_v3.json", (128, 192), 2),
+    ("stereo_net_config_v4.json", (64, 256), 2),
+    ("disp_net_c_config.json", (100, 180), 2),
+]
+
+
+@pytest.fixture(scope="module")
+def ref():
+    r = ref_loader.load()
+    assert ref_loader.verify_unmodified() >= 20
+    return r
+
+
+@pytest.fixture()
+def strict_fp32():
+    """fp32 means fp32: no TF32 in cuDNN / cuBLAS for the duration of a parity test, deterministic algorithms."""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
+
+
+@contextlib.contextmanager
+def patched(fuse=True):
+    import realtime_stereo_matcher_b200 as rsm
+    done = rsm.patch_reference(fuse=fuse)
+    try:
+        yield done
+    finally:
+        rsm.unpatch_reference()
+
+
+def build(ref, cfg_name, train=False):
+    cfg = ref.config(cfg_name)
+    torch.manual_seed(1234)
+    net = ref.model.build_model(cfg["model"]).cuda()
+    # BatchNorm running statistics away from (0, 1) so that eval-mode folding is actually exercised
+    g = torch.Generator().manual_seed(5)
+    for m in net.modules():
+        if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+            m.running_mean.copy_((torch.randn(m.running_mean.shape, generator=g) * 0.1).cuda())
+            m.running_var.copy_((1.0 + 0.2 * torch.rand(m.running_var.shape, generator=g)).cuda())
+            m.weight.data.copy_((1.0 + 0.1 * torch.randn(m.weight.shape, generator=g)).cuda())
+            m.bias.data.copy_((0.05 * torch.randn(m.bias.shape, generator=g)).cuda())
+    return (net.train() if train else net.eval()), cfg
+
+
+def stereo_pair(size, batch, max_shift=9):
+    """Smooth-ish random texture and a shifted copy: (N,3,H,W) in 0..255 like the reference's loaders deliver."""
+    g = torch.Generator().manual_seed(7)
+    h, w = size
+    base = torch.rand((batch, 3, h // 4 + 2, w // 4 + 8), generator=g)
+    img = torch.nn.functional.interpolate(base, size=(h, w + 4 * max_shift), mode="bilinear", align_corners=False)
+    img = (img + 0.15 * torch.rand(img.shape, generator=g)).clamp(0, 1) * 255.0
+    left = img[..., max_shift:max_shift + w].contiguous()
+    right = img[..., max_shift + 5:max_shift + 5 + w].contiguous()      # disparity 5 px
+    return left.cuda(), right.cuda()
+
+
+def rel_err(a, b):
+    scale = float(b.abs().max().clamp_min(1e-6))
+    return float((a.float() - b.float()).abs().max()) / scale
+
+
+@pytest.mark.parametrize("cfg_name,size,batch", MODELS)
+def test_model_forward_fp32_patched_vs_unpatched(ref, strict_fp32, cfg_name, size, batch):
+    net, _ = build(ref, cfg_name)
+    left, right = stereo_pair(size, batch)
+    with torch.no_grad():
+        want = net(left, right)
+        with patched() as done:
+            assert done["functions"]
+            got = net(left, right)
+        again = net(left, right)
+    assert len(got) == len(want)
+    for a, b, c in zip(got, want, again):
+        assert a.shape == b.shape and a.dtype == b.dtype
+        assert torch.isfinite(a).all()
+        # relative to the map's own scale; 2e-4 covers fp32 re-association in the conv stacks downstream of a
+        # volume that differs by ~1e-6
+        tol = 2e-4
+        assert rel_err(a, b) <= tol, (cfg_name, rel_err(a, b))
+        assert torch.equal(b, c)            # unpatch restores the reference bit for bit
+
+
+@pytest.mark.parametrize("cfg_name,size,batch", MODELS)
+def test_model_forward_autocast_fp16(ref, cfg_name, size, batch):
+    """The reference's evaluation path: forward under autocast.  Both arms are compared with the fp32 forward of the
+    unpatched model: the patched arm must not be further from it than the stock fp16 arm (plus a small floor)."""
+    net, _ = build(ref, cfg_name)
+    left, right = stereo_pair(size, batch)
+    with torch.no_grad():
+        truth = net(left, right)
+        with torch.autocast("cuda", dtype=torch.float16):
+            stock = net(left, right)
+            with patched():
+                got = net(left, right)
+    for a, b, t in zip(got, stock, truth):
+        assert a.shape == b.shape
+        assert a.dtype == b.dtype, (a.dtype, b.dtype)       # fp32 out of the regression under autocast, as the reference
+        assert torch.isfinite(a).all()
+        e_stock, e_got = rel_err(b, t), rel_err(a, t)
+        assert e_got <= 2.0 * e_stock + 5e-3, (cfg_name, e_got, e_stock)
+
+
+@pytest.mark.parametrize("cfg_name,size,batch", MODELS)
+def test_model_training_step_grads(ref, strict_fp32, cfg_name, size, batch):
+    """train_stereo.py:170-180 without the optimiser: forward in train mode, SequenceLoss, backward; the loss and
+    every parameter gradient of the patched run against the unpatched run."""
+    left, right = stereo_pair(size, batch)
+    g = torch.Generator().manual_seed(11)
+    flow_gt = -(5.0 + torch.rand((batch, 1) + size, generator=g)).cuda()          # flow = -disparity
+    valid = (torch.rand((batch,) + size, generator=g) > 0.2).float().cuda()
+
+    def step(use_patch):
+        net, cfg = build(ref, cfg_name, train=True)
+        ctx = patched() if use_patch else contextlib.nullcontext()
+        with ctx:
+            loss_fn = ref.loss.build_loss_function(cfg["train"]["loss"])          # patched: the on-device loss
+            preds = net(left, right)
+            loss = loss_fn(preds, flow_gt, valid)
+            loss.backward()
+        grads = {k: p.grad.detach().clone() for k, p in net.named_parameters() if p.grad is not None}
+        return float(loss), grads
+
+    loss_ref, g_ref = step(False)
+    loss_got, g_got = step(True)
+    assert abs(loss_got - loss_ref) <= 2e-4 * max(1.0, abs(loss_ref)), (loss_got, loss_ref)
+    assert set(g_got) == set(g_ref) and len(g_ref) > 10
+    num = sum(float((g_got[k] - g_ref[k]).double().pow(2).sum()) for k in g_ref)
+    den = sum(float(g_ref[k].double().pow(2).sum()) for k in g_ref)
+    assert den > 0
+    assert (num / den) ** 0.5 <= 2e-3, (cfg_name, (num / den) ** 0.5)
+
+
+def test_cost_volume_classes_patched_on_gpu(ref):
+    """cost_volume/*.py: after patch_reference() the reference's module attributes are the mirrors and
+    produce the reference's results on the device."""
+    g = torch.Generator().manual_seed(3)
+    l = torch.randn((2, 16, 6, 40), generator=g).cuda()
+    r = torch.randn((2, 16, 6, 40), generator=g).cuda()
+    want = {
+        "concat": ref.cv_concatenate.TorchConcatenateCost(12)(l, r),
+        "inter": ref.cv_interweave.TorchInterweaveCost()(l, r),
+        "inner": ref.cv_inner_product.TorchInnerProductCost(12)(l, r),
+        "group": ref.cv_groupwise.TorchGroupwiseCost(4, 12)(l.cpu(), r.cpu()),      # reference bug F6: CPU fp32 output
+    }
+    with patched():
+        got = {
+            "concat": ref.cv_concatenate.TorchConcatenateCost(12)(l, r),
+            "inter": ref.cv_interweave.TorchInterweaveCost()(l, r),
+            "inner": ref.cv_inner_product.TorchInnerProductCost(12)(l, r),
+            "group": ref.cv_groupwise.TorchGroupwiseCost(4, 12)(l, r),
+        }
+    assert torch.equal(got["concat"], want["concat"]) and torch.equal(got["inter"], want["inter"])
+    torch.testing.assert_close(got["inner"], want["inner"], atol=2e-5 * 4 * 25, rtol=0)
+    torch.testing.assert_close(got["group"].cpu(), want["group"], atol=2e-5 * 2 * 25, rtol=0)

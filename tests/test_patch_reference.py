@@ -33,10 +33,10 @@ def oracle_backed(monkeypatch):
     monkeypatch.setattr(F_rsm, "inner_product_volume",
                         lambda l, r, d, mean=False, out_dtype=None: _t(oracle.inner_product_volume(_np(l), _np(r), d, mean=mean), l))
     monkeypatch.setattr(F_rsm, "interweave", lambda l, r: _t(oracle.interweave(_np(l), _np(r)), l))
-    monkeypatch.setattr(F_rsm, "soft_argmax", lambda c, keepdim=False: _t(oracle.soft_argmax(_np(c), keepdim=keepdim), c))
+    monkeypatch.setattr(F_rsm, "soft_argmax", lambda c, keepdim=False, out_fp32=False: _t(oracle.soft_argmax(_np(c), keepdim=keepdim), c))
     monkeypatch.setattr(F_rsm, "expectation",
                         lambda p: _t((_np(p) * np.arange(p.shape[1], dtype=np.float32).reshape(1, -1, 1, 1)).sum(1), p))
-    monkeypatch.setattr(F_rsm, "upsample_regress", lambda c, d, h, w, argmin=False, argmax=False: _t(oracle.v4_tail(_np(c), d, h, w), c))
+    monkeypatch.setattr(F_rsm, "upsample_regress", lambda c, d, h, w, argmin=False, argmax=False, out_fp32=False: _t(oracle.v4_tail(_np(c), d, h, w), c))
     monkeypatch.setattr(F_rsm, "prepare_input", lambda img, align=1: _t(oracle.prepare_input(_np(img), align), img))
     monkeypatch.setattr(F_rsm, "finalize_disparity",
                         lambda d, padded, size=None, mode="nearest", negate=True:

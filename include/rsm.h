@@ -130,6 +130,37 @@ int rsm_shift_interweave_fwd(rsm_feat left, rsm_feat right, void* out, int64_t N
 int rsm_shift_interweave_bwd(const void* gout, void* gleft, void* gright, int64_t N, int64_t C,
                              int64_t H, int64_t W, int64_t D, int dtype, int device, void* stream);
 
+/* ---- MobileStereoNetV4's whole per-disparity learned volume in eval mode: the loop
+ * model/mobile_stereo_net_v4.py:443-458 -- for every disparity i: interweave_tensors(featL[..., i:], featR[..., :-i])
+ * -> self.conv3d (:317-333: Conv3d(1,16,(8,3,3),stride (8,1,1)) + BN + ReLU, Conv3d(16,32,(4,3,3),stride (4,1,1)) + BN +
+ * ReLU, Conv3d(32,16,(2,3,3),stride (2,1,1)) + BN + ReLU) -> self.volume11 (:335: 1x1 conv 16->1 + BN + ReLU) ->
+ * volume[:, 0, i, :, i:] -- as three kernels (layer-1 maps once per pair, layers 2 and 3 as tcgen05 implicit GEMMs with
+ * 16-bit operands and fp32 accumulation); out (B,D,H,W) in in_dtype, zero where x < d.
+ * The caller folds each BatchNorm (eval: y = (conv + bias - mean) * gamma / sqrt(var + eps) + beta) into the weights
+ * (scale per output channel) and an additive term t, and packs layers 2 / 3 into the UMMA core-matrix layout:
+ *   w1  (16,8,3,3) fp32      = conv3d[0].weight[:,0] * s1[:,None,None,None];            t1 (16) fp32
+ *   w2  (9,8,32,8) op_dtype  : [tap = dy*3+dx][chunk][co][e] = conv3d[3].weight[co, ci, kd, dy, dx] * s2[co]
+ *                              with kd*16 + ci = chunk*8 + e;                             t2 (32) fp32
+ *   w3  (9,8,16,8) op_dtype  : conv3d[6].weight[co, ci, kd, dy, dx] * s3[co] with kd*32 + ci = chunk*8 + e;  t3 (16)
+ *   w11 (16) fp32            = volume11[0][0].weight[0,:,0,0] * s11;                      t11 (1) fp32
+ * all DEVICE pointers.  op_dtype = RSM_F16 (fp32 / fp16 features; 11-bit significands like TF32, saturating at
+ * +-65504) or RSM_BF16.  C must be 32 (2C = 64 = the 8 x 4 x 2 depth the Conv3d kernels collapse). */
+typedef struct rsm_v4_weights {
+  const float* w1;
+  const float* t1;
+  const void* w2;
+  const float* t2;
+  const void* w3;
+  const float* t3;
+  const float* w11;
+  const float* t11;
+} rsm_v4_weights;
+/* bytes of device scratch rsm_v4_volume_fwd needs (layer-1 maps + the 16-bit layer-2 activations); 256-byte aligned */
+int64_t rsm_v4_volume_workspace(int64_t B, int64_t H, int64_t W, int64_t D);
+int rsm_v4_volume_fwd(rsm_feat left, rsm_feat right, rsm_v4_weights w, void* out, void* workspace, int64_t B,
+                      int64_t C, int64_t H, int64_t W, int64_t D, int in_dtype, int op_dtype, int device,
+                      void* stream);
+
 /* ---- refinement warp: warp_by_flow_map, model/mobile_stereo_net_v2.py:59-96
  * (= model/mobile_stereo_net_v3.py:60-97, tools/warp.py:5-42; call sites v2 :127, v3 :136).
  * image (N,C,H,W), flow (N,flow_channels,H,W) with flow_channels 1 or 2, all dense, same dtype.

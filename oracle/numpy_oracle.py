@@ -432,25 +432,35 @@ def warp_by_flow_map_bwd(gout, image, flow):
 
 
 # ------------------------------------------------------------------ pre / post steps
-def prepare_input(img, align=1):
+def _div255(x, device_div):
+    """``x / 255.0`` as torch evaluates it: a true division on the CPU; on a CUDA tensor ATen's div-by-scalar kernel
+    multiplies by the reciprocal rounded to fp32 once (BinaryDivTrueKernel.cu), computing in fp32 for 16-bit tensors."""
+    dt = x.dtype.type
+    if not device_div:
+        return x / dt(255.0)
+    return (x.astype(np.float32) * (np.float32(1.0) / np.float32(255.0))).astype(x.dtype)
+
+
+def prepare_input(img, align=1, device_div=False):
     """(N,C,H,W) -> (N,C,Hp,Wp): model/mobile_stereo_net.py:121-130 (= _v2.py:194-203, _v3.py:296-305,
     mobile_disp_net_c.py:339-351): 2 * (img / 255) - 1 in the tensor's dtype, then zero padding on the right /
-    bottom to a multiple of ``align``."""
+    bottom to a multiple of ``align``.  ``device_div``: the division as torch's CUDA kernel performs it (what the
+    reference computes on a GPU, and what rsm_prepare_fwd follows); default = the CPU's true division (goldens)."""
     img = np.asarray(img)
     dt = img.dtype.type
-    x = dt(2.0) * (img / dt(255.0)) - dt(1.0)
+    x = dt(2.0) * _div255(img, device_div) - dt(1.0)
     h, w = img.shape[2:]
     h_pad = (align - (h % align)) % align
     w_pad = (align - (w % align)) % align
     return np.pad(x, ((0, 0), (0, 0), (0, h_pad), (0, w_pad)))
 
 
-def prepare_input_bwd(gout, size):
+def prepare_input_bwd(gout, size, device_div=False):
     """adjoint of prepare_input: (gout[:, :, :H, :W] * 2) / 255."""
     gout = np.asarray(gout)
     dt = gout.dtype.type
     h, w = size
-    return (gout[:, :, :h, :w] * dt(2.0)) / dt(255.0)
+    return _div255(gout[:, :, :h, :w] * dt(2.0), device_div)
 
 
 def _resize_taps(out_size, in_size, mode):

@@ -14,7 +14,7 @@ from .functional import (concat_volume, difference_volume, expectation, finalize
                          groupwise_volume, hard_argmax, hard_argmin, inner_product_regress,
                          inner_product_volume, interweave, prepare_input, regress, sequence_loss_term,
                          shift_interweave_volume,
-                         soft_argmax, upsample_regress, warp_by_flow_map)
+                         soft_argmax, upsample_regress, v4_cost_volume, warp_by_flow_map)
 from .loss import SequenceLoss, build_loss_function, get_flow_map_metrics
 from .model_functions import (disparity_regression_dispnetc, disparity_regression_v4, interweave_tensors,
                               make_correlation_volume, make_cost_volume, softmax_regression, v4_head)

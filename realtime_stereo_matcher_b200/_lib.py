@@ -30,6 +30,11 @@ class RsmRegressOut(C.Structure):
                 ("expect", C.c_void_p)]
 
 
+class RsmV4Weights(C.Structure):
+    _fields_ = [("w1", C.c_void_p), ("t1", C.c_void_p), ("w2", C.c_void_p), ("t2", C.c_void_p), ("w3", C.c_void_p),
+                ("t3", C.c_void_p), ("w11", C.c_void_p), ("t11", C.c_void_p)]
+
+
 i64, vp, ci, cf = C.c_int64, C.c_void_p, C.c_int, C.c_float
 
 RSM_REDUCE_WS_DOUBLES = 1184 * 8   # include/rsm.h
@@ -49,6 +54,7 @@ SIGNATURES = {
     "rsm_difference_bwd": [vp, vp, vp, i64, i64, i64, i64, i64, ci, ci, vp],
     "rsm_shift_interweave_fwd": [RsmFeat, RsmFeat, vp, i64, i64, i64, i64, i64, ci, ci, vp],
     "rsm_shift_interweave_bwd": [vp, vp, vp, i64, i64, i64, i64, i64, ci, ci, vp],
+    "rsm_v4_volume_fwd": [RsmFeat, RsmFeat, RsmV4Weights, vp, vp, i64, i64, i64, i64, i64, ci, ci, ci, vp],
     "rsm_warp_fwd": [vp, vp, vp, i64, i64, i64, i64, ci, ci, ci, vp],
     "rsm_warp_bwd": [vp, vp, vp, vp, vp, i64, i64, i64, i64, ci, ci, ci, vp],
     "rsm_pfm_write": [C.c_char_p, vp, i64, i64, ci, C.c_double, ci],
@@ -69,7 +75,7 @@ SIGNATURES = {
     "rsm_upsample_regress_bwd": [vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, i64, ci, ci, vp],
     "rsm_inner_regress_fwd": [RsmFeat, RsmFeat, i64, i64, i64, i64, i64, ci, ci, RsmRegressOut, ci, vp],
 }
-OTHER_SYMBOLS = ("rsm_version", "rsm_last_error", "rsm_upsample_regress_bwd_workspace")
+OTHER_SYMBOLS = ("rsm_version", "rsm_last_error", "rsm_upsample_regress_bwd_workspace", "rsm_v4_volume_workspace")
 
 _lib = None
 
@@ -94,6 +100,8 @@ def load() -> C.CDLL:
     lib.rsm_last_error.restype = C.c_char_p
     lib.rsm_upsample_regress_bwd_workspace.argtypes = [i64, i64, i64, i64]
     lib.rsm_upsample_regress_bwd_workspace.restype = i64
+    lib.rsm_v4_volume_workspace.argtypes = [i64, i64, i64, i64]
+    lib.rsm_v4_volume_workspace.restype = i64
     got = lib.rsm_version()
     if got != RSM_VERSION:
         # the .so is git-ignored and copied between boxes: a stale binary would be called with the wrong layouts

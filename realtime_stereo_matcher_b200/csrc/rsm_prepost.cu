@@ -19,7 +19,12 @@ template <typename T> __device__ __forceinline__ float round_through(float v) { 
 template <> __device__ __forceinline__ float round_through<float>(float v) { return v; }
 
 template <typename T> __device__ __forceinline__ float normalise_pixel(float v) {
-  const float a = round_through<T>(__fdiv_rn(v, 255.f));
+  // `img / 255.0` on a CUDA tensor is ATen's div-by-a-CPU-scalar kernel: a * (1 / b) with the reciprocal rounded to
+  // fp32 once (BinaryDivTrueKernel.cu), not a true division -- the two differ by one ulp for about a third of the
+  // 8-bit pixel values.  The drop-in follows the DEVICE convention, so that the patched model is bit-identical to the
+  // unpatched model on the same GPU (a one-ulp change of the input moves a randomly initialised BatchNorm-in-train-mode
+  // network's gradients by ~10 %: tools/diag_v4_train.py).  The CPU goldens (true division) agree within one ulp.
+  const float a = round_through<T>(__fmul_rn(v, 1.0f / 255.0f));
   const float b = round_through<T>(__fmul_rn(2.f, a));
   return round_through<T>(__fsub_rn(b, 1.f));
 }
@@ -83,7 +88,7 @@ prepare_bwd_kernel(const T* __restrict__ gout, T* __restrict__ gimg, int H, int 
   const int x = blockIdx.y * 128 + threadIdx.x;
   if (x >= W) return;
   const float g = to_f(gout[(plane * Hp + y) * (int64_t)Wp + x]);
-  gimg[row * W + x] = from_f<T>(round_through<T>(__fdiv_rn(round_through<T>(__fmul_rn(g, 2.f)), 255.f)));
+  gimg[row * W + x] = from_f<T>(round_through<T>(__fmul_rn(round_through<T>(__fmul_rn(g, 2.f)), 1.0f / 255.0f)));
 }
 
 enum : int { RESIZE_NEAREST = 0, RESIZE_BILINEAR = 1 };

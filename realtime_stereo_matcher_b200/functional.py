@@ -243,6 +243,69 @@ def shift_interweave_volume(left, right, max_disparity):
     return _ShiftInterweave.apply(left, right, max_disparity)
 
 
+# ------------------------------------------------------------- v4 learned per-disparity volume
+_V4_WEIGHT_CACHE = {}
+
+
+def _fold_bn(conv_w, conv_b, bn):
+    """Eval-mode BatchNorm folded into the convolution before it: scale per output channel + additive term."""
+    s = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+    b = conv_b.detach().float() if conv_b is not None else torch.zeros_like(s)
+    t = (b - bn.running_mean.detach().float()) * s + bn.bias.detach().float()
+    return conv_w.detach().float() * s.view(-1, *([1] * (conv_w.dim() - 1))), t
+
+
+def pack_v4_weights(conv3d, volume11, op_dtype):
+    """Fold + pack the weights of MobileStereoNetV4.conv3d / .volume11 (mobile_stereo_net_v4.py:317-335) for
+    rsm_v4_volume_fwd (layouts in include/rsm.h).  Cached per module pair until a parameter / buffer changes."""
+    mods = [conv3d[0], conv3d[1], conv3d[3], conv3d[4], conv3d[6], conv3d[7], volume11[0][0], volume11[0][1]]
+    tensors = [t for m in mods for t in list(m.parameters()) + list(m.buffers())]
+    key = (id(conv3d), id(volume11), op_dtype, tuple((t.data_ptr(), t._version) for t in tensors))
+    hit = _V4_WEIGHT_CACHE.get(id(conv3d))
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    c1, b1, c2, b2, c3, b3, c11, b11 = mods
+    if (tuple(c1.weight.shape) != (16, 1, 8, 3, 3) or tuple(c2.weight.shape) != (32, 16, 4, 3, 3)
+            or tuple(c3.weight.shape) != (16, 32, 2, 3, 3) or tuple(c11.weight.shape) != (1, 16, 1, 1)):
+        raise RuntimeError("v4_cost_volume: unexpected Conv3d / volume11 shapes (not MobileStereoNetV4's)")
+    with torch.no_grad():
+        w1, t1 = _fold_bn(c1.weight[:, 0], c1.bias, b1)                       # (16,8,3,3)
+        w2, t2 = _fold_bn(c2.weight, c2.bias, b2)                             # (32,16,4,3,3) [co,ci,kd,dy,dx]
+        w3, t3 = _fold_bn(c3.weight, c3.bias, b3)                             # (16,32,2,3,3)
+        w11, t11 = _fold_bn(c11.weight, c11.bias, b11)                        # (1,16,1,1)
+
+        def pack(w):                                                          # -> (9, 8, co, 8): kk = kd*Cin + ci
+            co = w.shape[0]
+            k = w.permute(3, 4, 2, 1, 0).reshape(9, 64, co)                   # [tap][kd*Cin + ci][co]
+            return k.reshape(9, 8, 8, co).permute(0, 1, 3, 2).contiguous().to(op_dtype)
+
+        packed = {"w1": w1.contiguous(), "t1": t1.contiguous(), "w2": pack(w2), "t2": t2.contiguous(), "w3": pack(w3),
+                  "t3": t3.contiguous(), "w11": w11.reshape(16).contiguous(), "t11": t11.reshape(1).contiguous()}
+    _V4_WEIGHT_CACHE[id(conv3d)] = (key, packed)
+    return packed
+
+
+def v4_cost_volume(left, right, conv3d, volume11, max_disparity, op_dtype=None):
+    """MobileStereoNetV4's per-disparity learned volume (mobile_stereo_net_v4.py:443-458), all ``max_disparity``
+    iterations and the three Conv3d + 1x1 conv in one fused op (eval mode: BatchNorm folded).  (B,32,H,W) x2 ->
+    (B,D,H,W), zero where x < d.  Operands are fp16 (bf16 for bf16 features), accumulation fp32.  Inference only."""
+    dev, n, c, h, w = _check_pair(left, right)
+    if conv3d.training or volume11.training:
+        raise RuntimeError("v4_cost_volume folds BatchNorm: eval mode only (the training forward keeps the loop)")
+    d = int(max_disparity)
+    op_dtype = op_dtype or (torch.bfloat16 if left.dtype == torch.bfloat16 else torch.float16)
+    pk = pack_v4_weights(conv3d, volume11, op_dtype)
+    lib = L.load()
+    out = torch.empty((n, d, h, w), dtype=left.dtype, device=left.device)
+    nbytes = lib.rsm_v4_volume_workspace(n, h, w, d)
+    work = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=left.device)
+    wts = L.RsmV4Weights(*(pk[k].data_ptr() for k in ("w1", "t1", "w2", "t2", "w3", "t3", "w11", "t11")))
+    L.check(lib.rsm_v4_volume_fwd(L.feat(left.detach()), L.feat(right.detach()), wts, out.data_ptr(), work.data_ptr(),
+                                  n, c, h, w, d, L.dtype_code(left), L._DTYPES[op_dtype], dev, L.stream_ptr(dev)),
+            "rsm_v4_volume_fwd")
+    return out
+
+
 # ----------------------------------------------------------------------- refinement warp
 class _Warp(torch.autograd.Function):
     @staticmethod

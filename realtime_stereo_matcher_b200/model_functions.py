@@ -40,9 +40,20 @@ def shift_interweave_stack(refimg_fea, targetimg_fea, volume_size):
     return F_rsm.shift_interweave_volume(refimg_fea, targetimg_fea, volume_size)
 
 
+def v4_cost_volume(featL, featR, conv3d, volume11, volume_size):
+    """The whole per-disparity volume loop of MobileStereoNetV4.forward (model/mobile_stereo_net_v4.py:443-458) with
+    the module's own ``conv3d`` / ``volume11`` weights, eval mode: (B,32,H,W) x2 -> (B,volume_size,H,W)."""
+    return F_rsm.v4_cost_volume(featL, featR, conv3d, volume11, volume_size)
+
+
 def warp_by_flow_map(image, flow):
     """model/mobile_stereo_net_v2.py:59-96 (= mobile_stereo_net_v3.py:60-97, tools/warp.py:5-42): the
     refinement warp of RefineNet (call sites v2 :127, v3 :136); same AssertionError on a bad flow shape."""
+    if image.dtype != flow.dtype or (_autocast_fp32() and image.dtype != torch.float32):
+        # the reference's F.grid_sample is on autocast's fp32 list (and type-promotes otherwise): under autocast the
+        # v3 RefineNet warps fp16 feature maps with the fp32 disparity and gets an fp32 map back
+        dt = torch.float32 if _autocast_fp32() else torch.promote_types(image.dtype, flow.dtype)
+        image, flow = image.to(dt), flow.to(dt)
     return F_rsm.warp_by_flow_map(image, flow)
 
 
@@ -63,6 +74,8 @@ def disparity_interpolate(disp, shape):
     a map already at ``shape`` is returned untouched."""
     if tuple(disp.shape[2:]) == tuple(shape):
         return disp
+    if _autocast_fp32() and disp.dtype != torch.float32:
+        disp = disp.float()      # F.interpolate (upsample_bilinear2d) is on autocast's fp32 list: fp32 in, fp32 out
     return F_rsm.finalize_disparity(disp, shape, None, mode="bilinear", negate=False)
 
 

@@ -107,6 +107,7 @@ def v4_volume_batched(self, featL, featR, chunk=None):
 
 
 def forward_v4(self, L, R):
+    import torch
     """MobileStereoNetV4.forward (mobile_stereo_net_v4.py:432-524) with interweave and the
     trilinear -> softmax -> expectation head on the fused kernels."""
     L, R = mf.prepare_input(L), mf.prepare_input(R)          # :433-434 (v4 does not pad)
@@ -122,8 +123,11 @@ def forward_v4(self, L, R):
             x = self.volume11(self.conv3d(x.unsqueeze(1)).squeeze(2))
             volume[:, :, i, :, i:] = x
         volume = volume.squeeze(1)
+    elif torch.is_grad_enabled() and (featL.requires_grad or featR.requires_grad):
+        volume = v4_volume_batched(self, featL, featR)         # eval mode but differentiable: cuDNN convolutions
     else:
-        volume = v4_volume_batched(self, featL, featR)
+        # the whole loop -- 48 x (interweave -> 3 Conv3d -> 1x1 conv) -- as one fused op on tcgen05
+        volume = mf.v4_cost_volume(featL, featR, self.conv3d, self.volume11, self.volume_size)
     cost0 = self.dres0(volume)
     cost0 = self.dres1(cost0) + cost0
     out1 = self.encoder_decoder1(cost0)

@@ -44,10 +44,15 @@ class HostPipeline:
         """Yield ``(i, host_out[i % len(host_out)])`` once batch i's result has landed on the host.
 
         ``host_batches`` yields tuples of PINNED host tensors; ``host_out`` is a ring of pinned result
-        buffers (len >= depth + 1).  Per batch the region covers its H2D copy, the kernels and the D2H copy."""
+        buffers (depth + 1 of them for full overlap; fewer only shortens the pipeline).  Per batch the region covers its H2D copy, the kernels and the D2H copy."""
         compute = torch.cuda.current_stream(self.device)
         inflight = []   # (index, done_event, out_buffer)
+        limit = max(1, min(self.depth + 1, len(host_out)))      # a result buffer is rewritten only after it was yielded
         for i, batch in enumerate(host_batches):
+            while len(inflight) >= limit:
+                j, ev, buf = inflight.pop(0)
+                ev.synchronize()
+                yield j, buf
             self._ensure_slots(batch)
             k = i % len(self._slots)
             dev_in = self._slots[k]
@@ -73,10 +78,6 @@ class HostPipeline:
                 done = torch.cuda.Event()
                 done.record(self.copy_out)
             inflight.append((i, done, out))
-            if len(inflight) > self.depth:
-                j, ev, buf = inflight.pop(0)
-                ev.synchronize()
-                yield j, buf
         for j, ev, buf in inflight:
             ev.synchronize()
             yield j, buf

@@ -124,11 +124,11 @@ def test_random_shapes_prepost_and_loss(rsm, seed):
     tag = f"n{n} c{c} h{h} w{w} align{align}"
     x = dev(img, grad=True)
     out = rsm.prepare_input(x, align)
-    ref = oracle.prepare_input(img, align)
+    ref = oracle.prepare_input(img, align, device_div=True)
     np.testing.assert_array_equal(host(out), ref, err_msg=tag)
     gout = rng.standard_normal(ref.shape).astype(np.float32)
     out.backward(dev(gout))
-    np.testing.assert_array_equal(host(x.grad), oracle.prepare_input_bwd(gout, (h, w)), err_msg=tag)
+    np.testing.assert_array_equal(host(x.grad), oracle.prepare_input_bwd(gout, (h, w), device_div=True), err_msg=tag)
 
     hp, wp = ref.shape[2:]
     hs, ws = int(rng.integers(1, hp + 6)), int(rng.integers(1, wp + 6))

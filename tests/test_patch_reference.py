@@ -12,6 +12,8 @@ import torch
 
 import oracle
 
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
 REF = os.environ.get("RSM_REFERENCE", "/root/reference")
 pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "model")),
                                 reason="reference checkout not present (GPU box)")
@@ -42,6 +44,11 @@ def oracle_backed(monkeypatch):
                         lambda d, padded, size=None, mode="nearest", negate=True:
                         _t((1.0 if negate else -1.0) * oracle.finalize_disparity(_np(d), tuple(padded), None if size is None else tuple(size), mode), d))
     monkeypatch.setattr(F_rsm, "warp_by_flow_map", lambda im, fl: _t(oracle.warp_by_flow_map(_np(im), _np(fl)), im))
+    def v4_volume_cpu(l, r, conv3d, volume11, d, op_dtype=None):      # the kernels' algebra restated with torch CPU ops
+        from test_v4_volume_math import decomposed_volume
+        with torch.no_grad():
+            return decomposed_volume(F_rsm.pack_v4_weights(conv3d, volume11, torch.float32), l, r, d)
+    monkeypatch.setattr(F_rsm, "v4_cost_volume", v4_volume_cpu)
     monkeypatch.setattr(F_rsm, "shift_interweave_volume", lambda l, r, d: _t(oracle.shift_interweave_volume(_np(l), _np(r), d), l))
     sys.path.insert(0, REF)
     yield

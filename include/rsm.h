@@ -161,6 +161,12 @@ int rsm_v4_volume_fwd(rsm_feat left, rsm_feat right, rsm_v4_weights w, void* out
                       int64_t C, int64_t H, int64_t W, int64_t D, int in_dtype, int op_dtype, int device,
                       void* stream);
 
+/* diagnostic twin of rsm_v4_volume_fwd: `prof` = 32 zero-initialised uint64 on the device; the two GEMM kernels add
+ * clock64 cycles per warp role (waiting for rows / accumulators / ring slots, working, total), summed over CTAs */
+int rsm_v4_volume_fwd_profile(rsm_feat left, rsm_feat right, rsm_v4_weights w, void* out, void* workspace, int64_t B,
+                              int64_t C, int64_t H, int64_t W, int64_t D, int in_dtype, int op_dtype, int device,
+                              void* stream, uint64_t* prof);
+
 /* ---- refinement warp: warp_by_flow_map, model/mobile_stereo_net_v2.py:59-96
  * (= model/mobile_stereo_net_v3.py:60-97, tools/warp.py:5-42; call sites v2 :127, v3 :136).
  * image (N,C,H,W), flow (N,flow_channels,H,W) with flow_channels 1 or 2, all dense, same dtype.

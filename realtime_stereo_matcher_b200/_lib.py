@@ -55,6 +55,7 @@ SIGNATURES = {
     "rsm_shift_interweave_fwd": [RsmFeat, RsmFeat, vp, i64, i64, i64, i64, i64, ci, ci, vp],
     "rsm_shift_interweave_bwd": [vp, vp, vp, i64, i64, i64, i64, i64, ci, ci, vp],
     "rsm_v4_volume_fwd": [RsmFeat, RsmFeat, RsmV4Weights, vp, vp, i64, i64, i64, i64, i64, ci, ci, ci, vp],
+    "rsm_v4_volume_fwd_profile": [RsmFeat, RsmFeat, RsmV4Weights, vp, vp, i64, i64, i64, i64, i64, ci, ci, ci, vp, vp],
     "rsm_warp_fwd": [vp, vp, vp, i64, i64, i64, i64, ci, ci, ci, vp],
     "rsm_warp_bwd": [vp, vp, vp, vp, vp, i64, i64, i64, i64, ci, ci, ci, vp],
     "rsm_pfm_write": [C.c_char_p, vp, i64, i64, ci, C.c_double, ci],

@@ -70,32 +70,51 @@ template <typename T16> __device__ __forceinline__ uint4 pack8(const float (&f)[
   return make_uint4(pack2<T16>(f[0], f[1]), pack2<T16>(f[2], f[3]), pack2<T16>(f[4], f[5]), pack2<T16>(f[6], f[7]));
 }
 
+// relu(a + b) on two packed 16-bit values, clamped to the largest finite value (the sum of two saturated maps may
+// overflow fp16).  A correctly rounded 16-bit add of two 16-bit values equals their exact sum rounded once, i.e. the
+// same result as adding in fp32 and rounding -- at a quarter of the instructions.
+template <typename T16> __device__ __forceinline__ uint32_t add_relu2(uint32_t a, uint32_t b);
+template <> __device__ __forceinline__ uint32_t add_relu2<__half>(uint32_t a, uint32_t b) {
+  const __half2 z = __float2half2_rn(0.f), m = __float2half2_rn(65504.f);
+  __half2 s = __hadd2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+  s = __hmin2(__hmax2(s, z), m);
+  return *reinterpret_cast<const uint32_t*>(&s);
+}
+template <> __device__ __forceinline__ uint32_t add_relu2<__nv_bfloat16>(uint32_t a, uint32_t b) {
+  const __nv_bfloat162 z = __float2bfloat162_rn(0.f), m = __float2bfloat162_rn(3.3895314e38f);
+  __nv_bfloat162 s = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  s = __hmin2(__hmax2(s, z), m);
+  return *reinterpret_cast<const uint32_t*>(&s);
+}
+
 // ================================================================================================ K1: layer-1 maps
-// grid (ceil(W/32), H, B), 256 threads: warp = depth block k (interleaved channels 8k..8k+7 = left 4k..4k+3 at even
+// grid (ceil(W/32), H, 2B: left / right maps), 256 threads: warp = depth block k (interleaved channels 8k..8k+7 = left 4k..4k+3 at even
 // depths, right 4k..4k+3 at odd depths), lane = pixel.  w1 (16, 8, 3, 3) fp32 with BatchNorm folded, t1 (16) the
 // folded bias (goes into PL).  Map channel = k*16 + o, stored [b][chunk = 2k + o/8][y][x][o%8].
 template <typename Tin, typename T16>
 __global__ void __launch_bounds__(256)
 v4_premap_kernel(FeatView L, FeatView R, const float* __restrict__ w1, const float* __restrict__ t1,
                  uint4* __restrict__ PL, uint4* __restrict__ PR, uint4* __restrict__ EL, uint4* __restrict__ ER, int H, int W) {
-  __shared__ float sw[8 * 9 * 16];     // [kd][tap][o]
+  __shared__ float sw[4 * 9 * 16];     // this side's depths: [cl][tap][o]
   __shared__ float st[16];
-  for (int i = threadIdx.x; i < 8 * 9 * 16; i += 256) {
-    const int o = i & 15, tap = (i >> 4) % 9, kd = i / 144;
-    sw[i] = w1[(o * 8 + kd) * 9 + tap];
+  const int side = blockIdx.z & 1, b = blockIdx.z >> 1;     // 0: left maps (PL, EL), 1: right maps (PR, ER)
+  for (int i = threadIdx.x; i < 4 * 9 * 16; i += 256) {
+    const int o = i & 15, tap = (i >> 4) % 9, cl = i / 144;
+    sw[i] = w1[(o * 8 + 2 * cl + side) * 9 + tap];
   }
-  if (threadIdx.x < 16) st[threadIdx.x] = t1[threadIdx.x];
+  if (threadIdx.x < 16) st[threadIdx.x] = side == 0 ? t1[threadIdx.x] : 0.f;   // the folded bias goes into PL
   __syncthreads();
   const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int x = blockIdx.x * 32 + lane, y = blockIdx.y, b = blockIdx.z;
+  const int x = blockIdx.x * 32 + lane, y = blockIdx.y;
   if (x >= W) return;
-  float aL[16], aR[16], eL[16], eR[16];
+  float acc[16], edg[16];
 #pragma unroll
-  for (int o = 0; o < 16; ++o) { aL[o] = st[o]; aR[o] = 0.f; eL[o] = 0.f; eR[o] = 0.f; }
-  const Tin* __restrict__ pl = reinterpret_cast<const Tin*>(L.data) + (int64_t)b * L.sn;
-  const Tin* __restrict__ pr = reinterpret_cast<const Tin*>(R.data) + (int64_t)b * R.sn;
+  for (int o = 0; o < 16; ++o) { acc[o] = st[o]; edg[o] = 0.f; }
+  const FeatView& F = side == 0 ? L : R;
+  const Tin* __restrict__ pf = reinterpret_cast<const Tin*>(F.data) + (int64_t)b * F.sn + (int64_t)(4 * k) * F.sc;
+  const int edge_dx = side == 0 ? 0 : 2;                    // EL: the column that reads x - 1; ER: the one that reads x + 1
+#pragma unroll
   for (int cl = 0; cl < 4; ++cl) {
-    const int ch = 4 * k + cl;
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy) {
       const int yy = y + dy - 1;
@@ -103,42 +122,33 @@ v4_premap_kernel(FeatView L, FeatView R, const float* __restrict__ w1, const flo
 #pragma unroll
       for (int dx = 0; dx < 3; ++dx) {
         const int xx = x + dx - 1;
-        const bool in = xx >= 0 && xx < W;
-        const float vl = in ? to_f(__ldg(pl + (int64_t)ch * L.sc + (int64_t)yy * L.sh + (int64_t)xx * L.sw)) : 0.f;
-        const float vr = in ? to_f(__ldg(pr + (int64_t)ch * R.sc + (int64_t)yy * R.sh + (int64_t)xx * R.sw)) : 0.f;
-        const float4* wl = reinterpret_cast<const float4*>(sw + ((2 * cl) * 9 + dy * 3 + dx) * 16);
-        const float4* wr = reinterpret_cast<const float4*>(sw + ((2 * cl + 1) * 9 + dy * 3 + dx) * 16);
+        const float v = (xx >= 0 && xx < W) ? to_f(__ldg(pf + (int64_t)cl * F.sc + (int64_t)yy * F.sh + (int64_t)xx * F.sw)) : 0.f;
+        const float4* wp = reinterpret_cast<const float4*>(sw + (cl * 9 + dy * 3 + dx) * 16);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float4 a = wl[q], c = wr[q];
-          const float la[4] = {a.x, a.y, a.z, a.w}, ra[4] = {c.x, c.y, c.z, c.w};
+          const float4 a = wp[q];
+          const float wa[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            aL[4 * q + i] = fmaf(la[i], vl, aL[4 * q + i]);
-            aR[4 * q + i] = fmaf(ra[i], vr, aR[4 * q + i]);
-            if (dx == 0) eL[4 * q + i] = fmaf(la[i], vl, eL[4 * q + i]);
-            if (dx == 2) eR[4 * q + i] = fmaf(ra[i], vr, eR[4 * q + i]);
+            acc[4 * q + i] = fmaf(wa[i], v, acc[4 * q + i]);
+            if (dx == edge_dx) edg[4 * q + i] = fmaf(wa[i], v, edg[4 * q + i]);
           }
         }
       }
     }
   }
+  uint4* __restrict__ P = side == 0 ? PL : PR;
+  uint4* __restrict__ E = side == 0 ? EL : ER;
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     const int64_t o = (((int64_t)b * 16 + 2 * k + half) * H + y) * W + x;
     float v[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = aL[8 * half + i];
-    PL[o] = pack8<T16>(v);
+    for (int i = 0; i < 8; ++i) v[i] = acc[8 * half + i];
+    P[o] = pack8<T16>(v);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = aR[8 * half + i];
-    PR[o] = pack8<T16>(v);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = eL[8 * half + i];
-    EL[o] = pack8<T16>(v);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = eR[8 * half + i];
-    ER[o] = pack8<T16>(v);
+    for (int i = 0; i < 8; ++i) v[i] = edg[8 * half + i];
+    E[o] = pack8<T16>(v);
   }
 }
 
@@ -177,7 +187,7 @@ __global__ void __launch_bounds__(GEN ? 13 * 32 : 6 * 32, 1)
 v4_conv_kernel(const uint4* __restrict__ PL, const uint4* __restrict__ PR, const uint4* __restrict__ EL,
                const uint4* __restrict__ ER, const __grid_constant__ CUtensorMap tmIn, const uint4* __restrict__ wpacked,
                const float* __restrict__ bias, const float* __restrict__ w11, const float* __restrict__ t11,
-               uint4* __restrict__ act_out, Tout* __restrict__ vol, V4Geom g) {
+               uint4* __restrict__ act_out, Tout* __restrict__ vol, V4Geom g, unsigned long long* __restrict__ prof) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   unsigned char* ring = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   constexpr int WBYTES = 9 * V4_KCH * NOUT * 16;
@@ -220,39 +230,56 @@ v4_conv_kernel(const uint4* __restrict__ PL, const uint4* __restrict__ PR, const
 
   if (warp == 4) {
     // ================================================================================ UMMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | ((uint32_t)g.fmt << 7) | ((uint32_t)g.fmt << 10) | ((uint32_t)(NOUT >> 3) << 17) |
-                             ((uint32_t)(V4_TM >> 4) << 24);        // K-major A and B, fp32 accumulate
-      // K-major, SWIZZLE_NONE: LBO = stride between the two 8-channel core matrices of a K = 16 step (the next chunk),
-      // SBO = stride between 8-row groups along M / N (8 pixels or 8 output channels x 16 B) -- verified on B200
-      // against the reference loop (the swapped assignment produces garbage)
-      constexpr uint32_t lboA = V4_PX * 16, sboA = 128, lboB = NOUT * 16, sboB = 128;
-      const uint32_t ring_a = smem_u32(ring), w_a = smem_u32(wsm);
-      uint32_t rid0 = 0;          // row id of this strip's row 0 (ids run on across the CTA's strips)
-      uint32_t waited = 0;        // rows [0, waited) of the id sequence have been waited for
-      uint32_t it = 0;            // output rows issued so far
-      for (int s = blockIdx.x; s < g.strips; s += gridDim.x, rid0 += (uint32_t)H) {
-        for (int y = 0; y < H; ++y, ++it) {
-          const uint32_t need = rid0 + (uint32_t)min(y + 1, H - 1) + 1;       // rows up to y+1 must have landed
-          for (; waited < need; ++waited) mbar_wait(full + 8 * (waited % V4_NROWS), (waited / V4_NROWS) & 1);
-          const uint32_t ab = it % V4_NACC;
-          mbar_wait(accempty + 8 * ab, ((it / V4_NACC) & 1) ^ 1);             // epilogue drained this accumulator
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t td = tmem_base + ab * NOUT;
+    // The whole warp runs the loop converged (every value below is warp-uniform, so the compiler keeps it in uniform
+    // registers) and ONE elected lane issues.  The first version branched on lane == 0 and rebuilt both 64-bit
+    // descriptors per MMA: 13 dependent instructions, ~68 cycles per tcgen05.mma measured with clock64 -- the issue
+    // stream, not the tensor pipe, set the pace (tensor pipe 10-15 % busy).  Now: descriptor high words are constants,
+    // low words are a base plus an immediate.
+    uint32_t leader;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+    const uint32_t idesc = (1u << 4) | ((uint32_t)g.fmt << 7) | ((uint32_t)g.fmt << 10) | ((uint32_t)(NOUT >> 3) << 17) |
+                           ((uint32_t)(V4_TM >> 4) << 24);        // K-major A and B, fp32 accumulate
+    // K-major, SWIZZLE_NONE: LBO = stride between the two 8-channel core matrices of a K = 16 step (the next chunk),
+    // SBO = stride between 8-row groups along M / N (8 pixels or 8 output channels x 16 B) -- verified on B200
+    // against the reference loop (the swapped assignment produces garbage)
+    constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);                       // SBO = 128 B, descriptor version 1
+    const uint32_t alo0 = ((smem_u32(ring) >> 4) & 0x3FFF) | ((uint32_t)(V4_PX * 16 >> 4) << 16);
+    const uint32_t blo0 = ((smem_u32(wsm) >> 4) & 0x3FFF) | ((uint32_t)(NOUT * 16 >> 4) << 16);
+    uint32_t rid0 = 0;          // row id of this strip's row 0 (ids run on across the CTA's strips)
+    uint32_t waited = 0;        // rows [0, waited) of the id sequence have been waited for
+    uint32_t it = 0;            // output rows issued so far
+    long long c_full = 0, c_acc = 0;
+    const long long c_beg = prof ? clock64() : 0;
+    for (int s = blockIdx.x; s < g.strips; s += gridDim.x, rid0 += (uint32_t)H) {
+      for (int y = 0; y < H; ++y, ++it) {
+        const uint32_t need = rid0 + (uint32_t)min(y + 1, H - 1) + 1;       // rows up to y+1 must have landed
+        const long long c0 = prof ? clock64() : 0;
+        for (; waited < need; ++waited) mbar_wait(full + 8 * (waited % V4_NROWS), (waited / V4_NROWS) & 1);
+        const long long c1 = prof ? clock64() : 0;
+        const uint32_t ab = it % V4_NACC;
+        mbar_wait(accempty + 8 * ab, ((it / V4_NACC) & 1) ^ 1);             // epilogue drained this accumulator
+        if (prof) { c_full += c1 - c0; c_acc += clock64() - c1; }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t td = tmem_base + ab * NOUT;
+        if (leader) {
           uint32_t acc = 0;
 #pragma unroll
           for (int dy = 0; dy < 3; ++dy) {
             const int yy = y + dy - 1;
             if (yy < 0 || yy >= H) continue;                                  // zero padding rows: no MMAs at all
-            const uint32_t slot = (rid0 + (uint32_t)yy) % V4_NROWS;
+            const uint32_t alo = alo0 + ((rid0 + (uint32_t)yy) % V4_NROWS) * (V4_ROW_BYTES >> 4);
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) {
-              const uint32_t a0 = ring_a + slot * V4_ROW_BYTES + dx * 16;
-              const uint32_t b0 = w_a + (dy * 3 + dx) * (V4_KCH * NOUT * 16);
 #pragma unroll
               for (int ks = 0; ks < V4_KCH / 2; ++ks) {                        // K = 16 per UMMA: two 8-channel chunks
-                umma_f16(td, umma_desc(a0 + ks * 2 * (V4_PX * 16), lboA, sboA), umma_desc(b0 + ks * 2 * (NOUT * 16), lboB, sboB),
-                         idesc, acc);
+                const uint32_t a = alo + (uint32_t)(dx + ks * 2 * V4_PX);                               // 16-byte units
+                const uint32_t b = blo0 + (uint32_t)(((dy * 3 + dx) * V4_KCH + 2 * ks) * NOUT);
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+                    "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+                    "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+                    ::"r"(td), "r"(a), "r"(b), "r"(DESC_HI), "r"(idesc), "r"(acc)
+                    : "memory");
                 acc = 1;
               }
             }
@@ -261,85 +288,130 @@ v4_conv_kernel(const uint4* __restrict__ PL, const uint4* __restrict__ PR, const
           if (y >= 1) umma_commit(empty + 8 * ((rid0 + (uint32_t)y - 1) % V4_NROWS));   // row y-1 is no longer needed
           if (y == H - 1) umma_commit(empty + 8 * ((rid0 + (uint32_t)y) % V4_NROWS));
         }
+        __syncwarp();
       }
+    }
+    if (prof && leader) {
+      atomicAdd(prof + 0, (unsigned long long)c_full);
+      atomicAdd(prof + 1, (unsigned long long)c_acc);
+      atomicAdd(prof + 2, (unsigned long long)(clock64() - c_beg));
+      atomicAdd(prof + 11, (unsigned long long)it);
     }
   } else if (warp >= 5) {
     // ================================================================================== producers
     if constexpr (GEN) {
       const int grp = (warp - 5) >> 2, t = (threadIdx.x - 5 * 32) & 127;
-      const int64_t plane = (int64_t)H * W;
+      const int plane = H * W;                                                // (B * 16 * H * W < 2^31: checked on the host)
+      constexpr int NIT = (V4_KCH * V4_PX + 127) / 128;                       // 9 items of 16 B per thread and row
+      const bool rec = prof && t == 0;
+      long long c_wait = 0, c_load = 0;
+      const long long c_beg = rec ? clock64() : 0;
       uint32_t rid0 = 0;
       for (int s = blockIdx.x; s < g.strips; s += gridDim.x, rid0 += (uint32_t)H) {
         const V4Strip st = v4_strip(s, g);
-        const int64_t cbase = ((int64_t)st.b * 16 + 8 * st.j) * plane;      // first of this depth block's 8 chunks
+        // per strip: where each of this thread's items lives in the maps (row 0), whether it is inside the cropped
+        // image (x >= d, x < W: else the staged value is zero) and whether it is one of the two edge columns
+        int off[NIT];
+        uint32_t live = 0, edge = 0;
+#pragma unroll
+        for (int i = 0; i < NIT; ++i) {
+          const int item = t + 128 * i, c = item / V4_PX, p = item - c * V4_PX, x = st.x0 - 1 + p;
+          const bool ok = item < V4_KCH * V4_PX && x >= st.d && x < W;
+          off[i] = (st.b * 16 + 8 * st.j + c) * plane + x;
+          live |= (uint32_t)ok << i;
+          edge |= (uint32_t)(ok && (x == st.d || x == W - 1)) << i;
+        }
         for (int y = 0; y < H; ++y) {
           const uint32_t rid = rid0 + (uint32_t)y;
           if ((int)(rid & 1) != grp) continue;
           const uint32_t slot = rid % V4_NROWS;
+          const long long c0 = rec ? clock64() : 0;
           mbar_wait(empty + 8 * slot, ((rid / V4_NROWS) & 1) ^ 1);           // UMMAs that read this slot have completed
-          unsigned char* dst = ring + slot * V4_ROW_BYTES;
-          constexpr int NIT = (V4_KCH * V4_PX + 127) / 128;                   // 9 items per thread (last one partial)
+          const long long c1 = rec ? clock64() : 0;
+          uint4* dst = reinterpret_cast<uint4*>(ring + slot * V4_ROW_BYTES) + t;
+          const int ro = y * W;
           uint4 vl[NIT], vr[NIT];
 #pragma unroll
           for (int i = 0; i < NIT; ++i) {                                     // all of the row's loads in flight first
-            const int item = t + 128 * i, c = item / V4_PX, p = item - c * V4_PX, x = st.x0 - 1 + p;
-            const bool live = item < V4_KCH * V4_PX && x >= st.d && x < W;    // (x >= d >= 0)
-            const int64_t o = cbase + (int64_t)c * plane + (int64_t)y * W;
-            vl[i] = live ? __ldg(PL + o + x) : make_uint4(0u, 0u, 0u, 0u);
-            vr[i] = live ? __ldg(PR + o + (x - st.d)) : make_uint4(0u, 0u, 0u, 0u);
+            const bool ok = (live >> i) & 1;
+            vl[i] = ok ? __ldg(PL + off[i] + ro) : make_uint4(0u, 0u, 0u, 0u);
+            vr[i] = ok ? __ldg(PR + off[i] + ro - st.d) : make_uint4(0u, 0u, 0u, 0u);
           }
 #pragma unroll
           for (int i = 0; i < NIT; ++i) {
-            const int item = t + 128 * i, c = item / V4_PX, p = item - c * V4_PX, x = st.x0 - 1 + p;
-            if (item >= V4_KCH * V4_PX) break;
-            float a[8], r[8];
-            unpack8<T16>(vl[i], a);
-            unpack8<T16>(vr[i], r);
+            if (i == NIT - 1 && t + 128 * i >= V4_KCH * V4_PX) break;
+            uint4 v;
+            if ((edge >> i) & 1) {                                            // the cropped tensor's zero padding (rare)
+              float a[8], r[8];
+              unpack8<T16>(vl[i], a);
+              unpack8<T16>(vr[i], r);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) a[e] += r[e];
-            if (x >= st.d && x < W && (x == st.d || x == W - 1)) {            // the cropped tensor's zero padding
-              const int64_t o = cbase + (int64_t)c * plane + (int64_t)y * W;
+              for (int e = 0; e < 8; ++e) a[e] += r[e];
+              const int x = st.x0 - 1 + (t + 128 * i) % V4_PX;
               if (x == st.d) {
-                unpack8<T16>(__ldg(EL + o + x), r);
+                unpack8<T16>(__ldg(EL + off[i] + ro), r);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) a[e] -= r[e];
               }
               if (x == W - 1) {
-                unpack8<T16>(__ldg(ER + o + (x - st.d)), r);
+                unpack8<T16>(__ldg(ER + off[i] + ro - st.d), r);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) a[e] -= r[e];
               }
-            }
 #pragma unroll
-            for (int e = 0; e < 8; ++e) a[e] = fmaxf(a[e], 0.f);            // ReLU (zeros stay zeros)
-            *reinterpret_cast<uint4*>(dst + (c * V4_PX + p) * 16) = pack8<T16>(a);
+              for (int e = 0; e < 8; ++e) a[e] = fmaxf(a[e], 0.f);
+              v = pack8<T16>(a);
+            } else {                                                          // relu(PL + PR); dead items stay zero
+              v = make_uint4(add_relu2<T16>(vl[i].x, vr[i].x), add_relu2<T16>(vl[i].y, vr[i].y),
+                             add_relu2<T16>(vl[i].z, vr[i].z), add_relu2<T16>(vl[i].w, vr[i].w));
+            }
+            dst[128 * i] = v;                                                 // ring row = [chunk][pixel] = linear in item
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async proxy (UMMA)
           mbar_arrive(full + 8 * slot);
+          if (rec) { c_wait += c1 - c0; c_load += clock64() - c1; }
         }
+      }
+      if (rec) {
+        atomicAdd(prof + 3 + 3 * grp, (unsigned long long)c_wait);
+        atomicAdd(prof + 4 + 3 * grp, (unsigned long long)c_load);
+        atomicAdd(prof + 5 + 3 * grp, (unsigned long long)(clock64() - c_beg));
       }
     } else if (warp == 5 && lane == 0) {
       uint32_t rid0 = 0;
+      long long c_wait = 0;
+      const long long c_beg = prof ? clock64() : 0;
       for (int s = blockIdx.x; s < g.strips; s += gridDim.x, rid0 += (uint32_t)H) {
         const V4Strip st = v4_strip(s, g);
         for (int y = 0; y < H; ++y) {
           const uint32_t rid = rid0 + (uint32_t)y, slot = rid % V4_NROWS;
+          const long long c0 = prof ? clock64() : 0;
           mbar_wait(empty + 8 * slot, ((rid / V4_NROWS) & 1) ^ 1);
+          if (prof) c_wait += clock64() - c0;
           mbar_expect_tx(full + 8 * slot, V4_ROW_BYTES);
           tma_load_5d(smem_u32(ring + slot * V4_ROW_BYTES), &tmIn, full + 8 * slot, 0, st.x0 - 1, y, 0, st.d * g.B + st.b);
         }
+      }
+      if (prof) {
+        atomicAdd(prof + 3, (unsigned long long)c_wait);
+        atomicAdd(prof + 5, (unsigned long long)(clock64() - c_beg));
       }
     }
   } else {
     // ==================================================================================== epilogue
     uint32_t it = 0;
+    const bool rec = prof && threadIdx.x == 0;
+    long long c_wait = 0;
+    const long long c_beg = rec ? clock64() : 0;
     for (int s = blockIdx.x; s < g.strips; s += gridDim.x) {
       const V4Strip st = v4_strip(s, g);
       const int x = st.x0 + 32 * warp + lane;
       const bool keep = x >= st.d;
       for (int y = 0; y < H; ++y, ++it) {
         const uint32_t ab = it % V4_NACC;
+        const long long c0 = rec ? clock64() : 0;
         mbar_wait(accfull + 8 * ab, (it / V4_NACC) & 1);
+        if (rec) c_wait += clock64() - c0;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t taddr = tmem_base + ab * NOUT + ((uint32_t)(32 * warp) << 16);
         uint32_t r[NOUT / 16][16];
@@ -371,6 +443,10 @@ v4_conv_kernel(const uint4* __restrict__ PL, const uint4* __restrict__ PR, const
           vol[(((int64_t)st.b * g.D + st.d) * H + y) * (int64_t)W + x] = from_f<Tout>(keep ? fmaxf(acc, 0.f) : 0.f);
         }
       }
+    }
+    if (rec) {
+      atomicAdd(prof + 9, (unsigned long long)c_wait);
+      atomicAdd(prof + 10, (unsigned long long)(clock64() - c_beg));
     }
   }
 
@@ -409,14 +485,14 @@ extern "C" int64_t rsm_v4_volume_workspace(int64_t B, int64_t H, int64_t W, int6
 
 template <typename Tin, typename T16>
 static int v4_run(const rsm_feat& left, const rsm_feat& right, const rsm_v4_weights& w, void* out, void* workspace,
-                  int64_t B, int64_t H, int64_t W, int64_t D, int fmt, cudaStream_t st) {
+                  int64_t B, int64_t H, int64_t W, int64_t D, int fmt, cudaStream_t st, unsigned long long* prof) {
   const V4Workspace ws = v4_workspace(B, H, W, D);
   unsigned char* base = reinterpret_cast<unsigned char*>(workspace);
   uint4 *PL = (uint4*)(base + ws.pl), *PR = (uint4*)(base + ws.pr), *EL = (uint4*)(base + ws.el), *ER = (uint4*)(base + ws.er),
         *ACT = (uint4*)(base + ws.act);
   // K1
   {
-    const dim3 grid((unsigned)ceil_div(W, 32), (unsigned)H, (unsigned)B);
+    const dim3 grid((unsigned)ceil_div(W, 32), (unsigned)H, (unsigned)(2 * B));
     v4_premap_kernel<Tin, T16><<<grid, 256, 0, st>>>(view_of(left), view_of(right), w.w1, w.t1, PL, PR, EL, ER, (int)H, (int)W);
     if (int rc = finish_launch("rsm_v4_volume_fwd(premap)")) return rc;
   }
@@ -432,7 +508,7 @@ static int v4_run(const rsm_feat& left, const rsm_feat& right, const rsm_v4_weig
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return finish_launch("rsm_v4_volume_fwd(attr2)");
     const unsigned grid = (unsigned)(g.strips < kNumSMs ? g.strips : kNumSMs);
-    k<<<grid, 13 * 32, smem, st>>>(PL, PR, EL, ER, tm, (const uint4*)w.w2, w.t2, nullptr, nullptr, ACT, (Tin*)nullptr, g);
+    k<<<grid, 13 * 32, smem, st>>>(PL, PR, EL, ER, tm, (const uint4*)w.w2, w.t2, nullptr, nullptr, ACT, (Tin*)nullptr, g, prof);
     if (int rc = finish_launch("rsm_v4_volume_fwd(conv2)")) return rc;
   }
   // K3
@@ -453,20 +529,20 @@ static int v4_run(const rsm_feat& left, const rsm_feat& right, const rsm_v4_weig
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return finish_launch("rsm_v4_volume_fwd(attr3)");
     const unsigned grid = (unsigned)(g.strips < kNumSMs ? g.strips : kNumSMs);
-    k<<<grid, 6 * 32, smem, st>>>(nullptr, nullptr, nullptr, nullptr, tm, (const uint4*)w.w3, w.t3, w.w11, w.t11, nullptr, (Tin*)out, g);
+    k<<<grid, 6 * 32, smem, st>>>(nullptr, nullptr, nullptr, nullptr, tm, (const uint4*)w.w3, w.t3, w.w11, w.t11, nullptr, (Tin*)out, g, prof ? prof + 16 : nullptr);
     return finish_launch("rsm_v4_volume_fwd(conv3)");
   }
 }
 
-extern "C" int rsm_v4_volume_fwd(rsm_feat left, rsm_feat right, rsm_v4_weights w, void* out, void* workspace, int64_t B,
-                                 int64_t C, int64_t H, int64_t W, int64_t D, int in_dtype, int op_dtype, int device,
-                                 void* stream) {
+static int v4_entry(rsm_feat left, rsm_feat right, rsm_v4_weights w, void* out, void* workspace, int64_t B,
+                    int64_t C, int64_t H, int64_t W, int64_t D, int in_dtype, int op_dtype, int device,
+                    void* stream, unsigned long long* prof) {
   if (B < 0 || H < 0 || W < 0 || D < 0) return RSM_ERR_INVALID_SHAPE;
   if (C != V4_C) return RSM_ERR_UNSUPPORTED_CONFIG;                 // the module's Conv3d depths (8, 4, 2) need 2C = 64
   if (op_dtype != RSM_F16 && op_dtype != RSM_BF16) return RSM_ERR_UNSUPPORTED_DTYPE;
   if (!valid_dtype(in_dtype)) return RSM_ERR_UNSUPPORTED_DTYPE;
   if (B * H * W * D == 0) return RSM_OK;
-  if (B > 65535 || H > 65535 || B * D * 2 * ceil_div(W, V4_TM) > 2147483647LL || (int64_t)H * W > 2147483647LL)
+  if (B > 32767 || H > 65535 || B * D * 2 * ceil_div(W, V4_TM) > 2147483647LL || B * 16 * H * W > 2147483647LL)
     return RSM_ERR_INVALID_SHAPE;
   if (!left.data || !right.data || !out || !workspace || !w.w1 || !w.t1 || !w.w2 || !w.t2 || !w.w3 || !w.t3 || !w.w11 || !w.t11)
     return RSM_ERR_NULL_POINTER;
@@ -476,13 +552,30 @@ extern "C" int rsm_v4_volume_fwd(rsm_feat left, rsm_feat right, rsm_v4_weights w
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int fmt = op_dtype == RSM_F16 ? 0 : 1;
   if (in_dtype == RSM_F32) {
-    return fmt == 0 ? v4_run<float, __half>(left, right, w, out, workspace, B, H, W, D, fmt, st)
-                    : v4_run<float, __nv_bfloat16>(left, right, w, out, workspace, B, H, W, D, fmt, st);
+    return fmt == 0 ? v4_run<float, __half>(left, right, w, out, workspace, B, H, W, D, fmt, st, prof)
+                    : v4_run<float, __nv_bfloat16>(left, right, w, out, workspace, B, H, W, D, fmt, st, prof);
   }
   if (in_dtype == RSM_F16) {
-    return fmt == 0 ? v4_run<__half, __half>(left, right, w, out, workspace, B, H, W, D, fmt, st)
-                    : v4_run<__half, __nv_bfloat16>(left, right, w, out, workspace, B, H, W, D, fmt, st);
+    return fmt == 0 ? v4_run<__half, __half>(left, right, w, out, workspace, B, H, W, D, fmt, st, prof)
+                    : v4_run<__half, __nv_bfloat16>(left, right, w, out, workspace, B, H, W, D, fmt, st, prof);
   }
-  return fmt == 0 ? v4_run<__nv_bfloat16, __half>(left, right, w, out, workspace, B, H, W, D, fmt, st)
-                  : v4_run<__nv_bfloat16, __nv_bfloat16>(left, right, w, out, workspace, B, H, W, D, fmt, st);
+  return fmt == 0 ? v4_run<__nv_bfloat16, __half>(left, right, w, out, workspace, B, H, W, D, fmt, st, prof)
+                  : v4_run<__nv_bfloat16, __nv_bfloat16>(left, right, w, out, workspace, B, H, W, D, fmt, st, prof);
+}
+
+extern "C" int rsm_v4_volume_fwd(rsm_feat left, rsm_feat right, rsm_v4_weights w, void* out, void* workspace, int64_t B,
+                                 int64_t C, int64_t H, int64_t W, int64_t D, int in_dtype, int op_dtype, int device,
+                                 void* stream) {
+  return v4_entry(left, right, w, out, workspace, B, C, H, W, D, in_dtype, op_dtype, device, stream, nullptr);
+}
+
+// diagnostic twin: `prof` = 32 zero-initialised uint64 on the device; the kernels add clock64 cycles per role
+// ([0..10] layer 2, [16..26] layer 3: issuer {waiting for rows, waiting for an accumulator, total}, producers
+// {waiting for a slot, working, total} x 2 groups, [8] rows issued, epilogue {waiting, total}), summed over CTAs
+extern "C" int rsm_v4_volume_fwd_profile(rsm_feat left, rsm_feat right, rsm_v4_weights w, void* out, void* workspace,
+                                         int64_t B, int64_t C, int64_t H, int64_t W, int64_t D, int in_dtype,
+                                         int op_dtype, int device, void* stream, uint64_t* prof) {
+  if (!prof) return RSM_ERR_NULL_POINTER;
+  return v4_entry(left, right, w, out, workspace, B, C, H, W, D, in_dtype, op_dtype, device, stream,
+                  reinterpret_cast<unsigned long long*>(prof));
 }

@@ -309,6 +309,46 @@ def tensor_core_kernels(rsm, dev, peak):
         ms = time_op(fn, 10, flush)
         out[name] = {"ms": ms, "algorithmic_GBps": bytes_ / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": bytes_ / (ms * 1e-3) / 1e9 / peak,
                      "useful_TFLOPs": flops / (ms * 1e-3) / 1e12}
+    del sets
+    out.update(v4_model_numbers(rsm, dev, flush))
+    return out
+
+
+def v4_model_numbers(rsm, dev, flush):
+    """SURVEY 8f-1 / BASELINE config 3 as a MODEL inference: MobileStereoNetV4's per-disparity volume as the fused
+    tcgen05 op, and the whole reference model (baseline/_ref, seeded random weights, eval) unpatched vs patched at
+    (8,3,384,1248).  Skipped when the reference is not installed."""
+    try:
+        from oracle import ref_loader
+        if not ref_loader.available():
+            return {}
+        ref = ref_loader.load()
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("rsm_model_bench", os.path.join(ROOT, "tools", "model_bench.py"))
+        mb = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mb)
+    except Exception as e:                                   # the bench line must not depend on the checker
+        return {"full_model_error": repr(e)[:200]}
+    out = {}
+    torch.manual_seed(1234)
+    net = ref.model.build_model(ref.config("stereo_net_config_v4.json")["model"]).to(dev).eval()
+    b = 8
+    L, R = torch.randn((b, 32, 96, 312), device=dev), torch.randn((b, 32, 96, 312), device=dev)
+    with torch.no_grad():
+        fn = lambda: rsm.v4_cost_volume(L, R, net.conv3d, net.volume11, 48)
+        for _ in range(2):
+            fn()
+        ms = time_op(fn, 5, flush)
+    px = b * 96 * 312 * 48
+    flops = 2.0 * px * (8 * 72 * 16 + 2 * 576 * 32 + 576 * 16 + 16)        # the reference loop's MACs x 2
+    out["v4_cost_volume_fused[f32 features, fp16 operands, 8 pairs, tcgen05]"] = {
+        "ms": ms, "ms_per_pair": ms / b, "reference_loop_TFLOPs_equivalent": flops / (ms * 1e-3) / 1e12}
+    del net, L, R
+    for autocast in (False, True):
+        r = mb.measure(ref, rsm, "stereo_net_config_v4.json", (8, 3, 384, 1248), autocast, reps=3, warmup=2)
+        out[f"full_model_v4_384x1248_b8[{r['precision']}]"] = {
+            "unpatched_ms": r["unpatched_ms"], "patched_ms": r["patched_ms"], "unpatched_pairs_per_s": r["unpatched_pairs_per_s"],
+            "patched_pairs_per_s": r["patched_pairs_per_s"], "max_abs_diff_px": r["max_abs_diff"], "disparity_scale_px": r["disparity_scale"]}
     return out
 
 

@@ -4,15 +4,21 @@
 Each op is timed alone with CUDA events on the launching stream, L2 flushed (a 512 MB memset)
 before every timed launch, median of `--iters` launches after 3 warm-ups.  achieved GB/s uses the
 ALGORITHMIC bytes (each input element read once, each output element written once); the fraction
-is against MEASURED_PEAKS.json hbm_gbs.  One JSON object per line on stdout.
+is against MEASURED_PEAKS.json hbm_gbs.  One JSON object per line on stdout, each carrying the
+nvidia-smi clock / throttle-reason samples taken while that row was being measured (a background
+sampler with timestamps; rows are printed when the sweep ends).
 
     python tools/sweep.py [--iters 10] [--only cfg3]
 """
 import argparse
+import datetime
 import json
 import os
 import statistics
+import subprocess
 import sys
+import tempfile
+import time
 
 import torch
 
@@ -49,13 +55,85 @@ def timed(fn, iters):
     return statistics.median(ts)
 
 
+class TimedClockSampler:
+    """nvidia-smi sampled every 50 ms with timestamps for the whole sweep; window(t0, t1) -> the clocks record of
+    the samples taken in [t0 - 0.1 s, t1 + 0.1 s]."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self):
+        self.proc, self.path, self.samples = None, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+                                          "-i", "0"], stdout=fd, stderr=subprocess.DEVNULL)
+            os.close(fd)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        self.samples = []
+        if not self.proc:
+            return
+        time.sleep(0.2)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        for line in open(self.path).read().strip().splitlines():
+            f = [c.strip() for c in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                t = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                self.samples.append((t, float(f[1]), float(f[2]), float(f[3]), [n for n, v in zip(
+                    ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]) if v.lower().startswith("active")]))
+            except ValueError:
+                continue
+        os.unlink(self.path)
+
+    def window(self, t0, t1):
+        sel = [s for s in self.samples if t0 - 0.1 <= s[0] <= t1 + 0.1]
+        if not sel:
+            return {"sm_mhz": None, "samples": 0, "reasons": []}
+        return {"sm_mhz": statistics.median(s[1] for s in sel), "sm_max_mhz": sel[0][2], "power_w_max": max(s[3] for s in sel),
+                "reasons": sorted({r for s in sel for r in s[4]}), "samples": len(sel)}
+
+
+_ROWS = []
+_T0 = [time.time()]
+
+
 def report(cfg, op, dtype, shape, ms, nbytes, flops=0):
     gbs = nbytes / (ms * 1e-3) / 1e9
     rec = {"cfg": cfg, "op": op, "dtype": dtype, "shape": shape, "ms": round(ms, 5), "algorithmic_bytes": nbytes,
            "GBps": round(gbs, 1), "frac_of_measured_hbm": round(gbs / PEAK, 3)}
     if flops:
         rec["TFLOPs"] = round(flops / (ms * 1e-3) / 1e12, 2)
-    print(json.dumps(rec), flush=True)
+    now = time.time()
+    _ROWS.append((rec, _T0[0], now))      # measured between the previous report and this one
+    _T0[0] = now
+    print(f"  .. {cfg} {op} {dtype} {rec['ms']} ms {rec['frac_of_measured_hbm']}", file=sys.stderr, flush=True)
+
+
+def sustained(cfg, op, dtype, shape, fn, nbytes, seconds=2.0):
+    """>= `seconds` of back-to-back launches (no L2 flush: the working sets are >> L2): does the fraction hold under load?"""
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); fn(); b.record(); torch.cuda.synchronize()
+    reps = max(20, int(seconds / (a.elapsed_time(b) * 1e-3)))
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    report(cfg, op + f" [sustained {a.elapsed_time(b) * 1e-3:.1f} s, {reps} launches back to back]", dtype, shape, ms, nbytes)
 
 
 def feats(n, c, h, w, dt):
@@ -146,6 +224,41 @@ def sweep_tail(cfg, b, dc, hc, wc, iters):
     go = torch.randn_like(out)
     report(cfg, "v4_head_bwd", "f32", shp, timed(lambda: torch.autograd.grad(out, cg, go, retain_graph=True), iters),
            nb + 2 * b * dc * h * w * 4)
+
+
+def sweep_v4_volume(cfg, iters):
+    """MobileStereoNetV4's whole per-disparity volume (48 x (interweave -> 3 Conv3d -> 1x1)) as the fused op,
+    with the reference's own module weights when baseline/_ref is installed; flops = the reference loop's 2*MACs."""
+    try:
+        from oracle import ref_loader
+        ref = ref_loader.load()
+    except Exception:
+        return
+    torch.manual_seed(1234)
+    net = ref.model.build_model(ref.config("stereo_net_config_v4.json")["model"]).cuda().eval()
+    for b in (1, 8):
+        for dt in ("f32", "f16"):
+            L, R = feats(b, 32, 96, 312, dt)
+            px = b * 96 * 312 * 48
+            flops = 2.0 * px * (8 * 72 * 16 + 2 * 576 * 32 + 576 * 16 + 16)
+            e = 2 if dt != "f32" else 4
+            with torch.no_grad():
+                report(cfg, "v4_cost_volume_fused (K1 maps + 2 tcgen05 implicit GEMMs)", dt, dict(B=b, C=32, H=96, W=312, D=48),
+                       timed(lambda: rsm.v4_cost_volume(L, R, net.conv3d, net.volume11, 48), iters),
+                       2 * b * 32 * 96 * 312 * e + px * e, flops)
+    L, R = feats(1, 32, 96, 312, "f32")
+    v4 = ref.v4
+
+    def loop():
+        vol = L.new_zeros([1, 48, 96, 312])
+        for i in range(48):
+            x = v4.interweave_tensors(L[:, :, :, i:], R[:, :, :, : 312 - i])
+            vol[:, i, :, i:] = net.volume11(torch.squeeze(net.conv3d(torch.unsqueeze(x, 1)), 2))[:, 0]
+        return vol
+    with torch.no_grad():
+        report(cfg, "v4_cost_volume_reference_loop (cuDNN, TF32 allowed; reference op sequence on GPU)", "f32",
+               dict(B=1, C=32, H=96, W=312, D=48), timed(loop, 3), 2 * 32 * 96 * 312 * 4 + 96 * 312 * 48 * 4,
+               2.0 * 96 * 312 * 48 * (8 * 72 * 16 + 2 * 576 * 32 + 576 * 16 + 16))
 
 
 def sweep_warp(cfg, n, c, h, w, iters):
@@ -250,6 +363,9 @@ def main():
     a = ap.parse_args()
     want = lambda c: not a.only or c in a.only.split(",")
     rsm.load_library()
+    sampler = TimedClockSampler()
+    sampler.start()
+    _T0[0] = time.time()
     if want("cfg1"):
         sweep_volumes("cfg1", 1, 32, 48, 156, 24, 8, ["f32"], a.iters, {"difference", "bwd"})
         sweep_volumes("cfg1", 8, 32, 48, 156, 24, 8, ["f32", "bf16"], a.iters, {"difference", "bwd"})   # training batch of 8
@@ -267,13 +383,37 @@ def main():
         sweep_prepost("cfg3", 8, 384, 1248, 8, 8, a.iters)
         sweep_loss("cfg3", 8, 384, 1248, [(96, 312), (192, 624), (384, 1248)], a.iters)
         sweep_loss("cfg3", 8, 384, 1248, [(384, 1248)] * 6, a.iters)      # DispNetC: six full-size predictions
+        sweep_v4_volume("cfg3", a.iters)
+        L, R = feats(8, 32, 96, 312, "f32")
+        with torch.no_grad():
+            sustained("cfg3", "concat_fwd", "f32", dict(N=8, C=32, H=96, W=312, D=48), lambda: rsm.concat_volume(L, R, 48),
+                      2 * 8 * 32 * 96 * 312 * 4 * (1 + 48))
+        del L, R
     if want("cfg4"):
-        for c, g, d in ((32, 8, 48), (64, 16, 96), (128, 32, 192)):
-            sweep_volumes("cfg4", 1, c, 270, 480, d, g, ["f32", "bf16"], a.iters, {"concat", "groupwise", "inner", "fused"})
+        # the full (C, G, D) grid, forward and backward: concat / inner depend on (C, D) only and are run once per pair
+        seen = set()
+        for c in (32, 64, 128):
+            for d in (48, 96, 192):
+                for g in (8, 16, 32):
+                    ops = {"groupwise", "bwd"}
+                    if (c, d) not in seen:
+                        ops |= {"concat", "inner", "fused"}
+                        seen.add((c, d))
+                    sweep_volumes("cfg4", 1, c, 270, 480, d, g, ["f32", "bf16"], a.iters, ops)
     if want("cfg5"):
+        cost = torch.randn((4, 192, 1080, 1920), device="cuda") * 4
+        with torch.no_grad():
+            sustained("cfg5", "soft_argmax_fwd", "f32", dict(N=4, D=192, H=1080, W=1920), lambda: rsm.soft_argmax(cost),
+                      4 * 192 * 1080 * 1920 * 4 + 4 * 1080 * 1920 * 4)
+        del cost
+        torch.cuda.empty_cache()
         sweep_regress("cfg5", 1, 192, 1080, 1920, ["f32", "bf16"], a.iters)
         sweep_regress("cfg5", 4, 192, 1080, 1920, ["f32"], a.iters)
         sweep_tail("cfg5", 1, 48, 270, 480, a.iters)
+    sampler.stop()
+    for rec, t0, t1 in _ROWS:
+        rec["clocks"] = sampler.window(t0, t1)
+        print(json.dumps(rec), flush=True)
 
 
 if __name__ == "__main__":

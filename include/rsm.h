@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RSM_VERSION 105 /* major*10000 + minor*100 + patch */
+#define RSM_VERSION 106 /* major*10000 + minor*100 + patch */
 
 typedef enum rsm_dtype {
   RSM_F32 = 0,
@@ -271,6 +271,13 @@ int rsm_upsample_regress_bwd(const void* gout, const void* cost, const float* ex
 int rsm_inner_regress_fwd(rsm_feat left, rsm_feat right, int64_t N, int64_t C, int64_t H,
                           int64_t W, int64_t D, int reduce, int in_dtype, rsm_regress_out out,
                           int device, void* stream);
+/* diagnostic twin: `prof` = 8 zero-initialised uint64 on the device; the row-streaming tcgen05 kernel adds clock64
+ * cycles per warp role, summed over CTAs: [0] issuer waiting for operands, [1] issuer waiting for a free TMEM block,
+ * [2] issuer total, [3] TMA producer waiting for a free ring slot, [4] producer total, [5] epilogue warps waiting
+ * for an accumulator block, [6] epilogue warps total */
+int rsm_inner_regress_fwd_profile(rsm_feat left, rsm_feat right, int64_t N, int64_t C, int64_t H,
+                                  int64_t W, int64_t D, int reduce, int in_dtype, rsm_regress_out out,
+                                  int device, void* stream, uint64_t* prof);
 
 #ifdef __cplusplus
 }

@@ -38,7 +38,7 @@ class RsmV4Weights(C.Structure):
 i64, vp, ci, cf = C.c_int64, C.c_void_p, C.c_int, C.c_float
 
 RSM_REDUCE_WS_DOUBLES = 1184 * 8   # include/rsm.h
-RSM_VERSION = 105                  # include/rsm.h; the argument layouts below were written for this ABI
+RSM_VERSION = 106                  # include/rsm.h; the argument layouts below were written for this ABI
 
 # name -> argtypes, exactly the prototypes of include/rsm.h (tests/test_abi.py checks the header)
 SIGNATURES = {
@@ -75,6 +75,7 @@ SIGNATURES = {
     "rsm_upsample_regress_fwd": [vp, i64, i64, i64, i64, i64, i64, i64, ci, RsmRegressOut, ci, vp],
     "rsm_upsample_regress_bwd": [vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, i64, ci, ci, vp],
     "rsm_inner_regress_fwd": [RsmFeat, RsmFeat, i64, i64, i64, i64, i64, ci, ci, RsmRegressOut, ci, vp],
+    "rsm_inner_regress_fwd_profile": [RsmFeat, RsmFeat, i64, i64, i64, i64, i64, ci, ci, RsmRegressOut, ci, vp, vp],
 }
 OTHER_SYMBOLS = ("rsm_version", "rsm_last_error", "rsm_upsample_regress_bwd_workspace", "rsm_v4_volume_workspace")
 

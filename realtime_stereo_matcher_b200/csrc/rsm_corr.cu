@@ -21,6 +21,9 @@ namespace rsm {
 
 int launch_inner_tc(const rsm_feat& left, const rsm_feat& right, void* out, int64_t N, int64_t C, int64_t H, int64_t W,
                     int64_t D, int mean, int in_dtype, int out_dtype, cudaStream_t st);
+int launch_inner_regress_rows(const rsm_feat& left, const rsm_feat& right, int64_t N, int64_t C, int64_t H, int64_t W,
+                              int64_t D, int mean, int in_dtype, const rsm_regress_out& out, cudaStream_t st,
+                              unsigned long long* prof);
 int launch_inner_regress_tc(const rsm_feat& left, const rsm_feat& right, int64_t N, int64_t C, int64_t H, int64_t W,
                             int64_t D, int mean, int in_dtype, const rsm_regress_out& out, cudaStream_t st);
 
@@ -866,9 +869,9 @@ extern "C" int rsm_groupwise_bwd(const void* gout, rsm_feat left, rsm_feat right
   });
 }
 
-extern "C" int rsm_inner_regress_fwd(rsm_feat left, rsm_feat right, int64_t N, int64_t C, int64_t H,
-                                     int64_t W, int64_t D, int reduce, int in_dtype, rsm_regress_out out,
-                                     int device, void* stream) {
+static int inner_regress_fwd(rsm_feat left, rsm_feat right, int64_t N, int64_t C, int64_t H, int64_t W, int64_t D,
+                             int reduce, int in_dtype, rsm_regress_out out, int device, void* stream,
+                             unsigned long long* prof) {
   CorrGeom g;
   if (D <= 0) return RSM_ERR_INVALID_SHAPE;
   if (out.soft && out.expect && out.soft != (void*)out.expect) return RSM_ERR_UNSUPPORTED_CONFIG;   // both are the fp32 plane here
@@ -880,7 +883,12 @@ extern "C" int rsm_inner_regress_fwd(rsm_feat left, rsm_feat right, int64_t N, i
   RSM_COMMON_CHECKS(in_dtype)
   {
     const char* no_tc = getenv("RSM_DISABLE_TC");
-    if (!(no_tc && no_tc[0] == '1')) {   // 16-bit features, D <= 128: tcgen05 tiles reduced straight out of TMEM
+    if (!(no_tc && no_tc[0] == '1')) {   // 16-bit features: tcgen05 blocks reduced straight out of TMEM
+      const char* old_tc = getenv("RSM_TC_REGRESS_CHUNKED");   // A/B: the first (disparity-chunked) tensor-core form
+      if (!(old_tc && old_tc[0] == '1')) {
+        const int rc = launch_inner_regress_rows(left, right, N, C, H, W, D, reduce == RSM_REDUCE_MEAN, in_dtype, out, st, prof);
+        if (rc != RSM_ERR_UNSUPPORTED_CONFIG) return rc;
+      }
       const int rc = launch_inner_regress_tc(left, right, N, C, H, W, D, reduce == RSM_REDUCE_MEAN, in_dtype, out, st);
       if (rc != RSM_ERR_UNSUPPORTED_CONFIG) return rc;
     }
@@ -925,4 +933,20 @@ extern "C" int rsm_inner_regress_fwd(rsm_feat left, rsm_feat right, int64_t N, i
                                                out.argmax, out.lse, g);
     return finish_launch("rsm_inner_regress_fwd");
   });
+}
+
+extern "C" int rsm_inner_regress_fwd(rsm_feat left, rsm_feat right, int64_t N, int64_t C, int64_t H,
+                                     int64_t W, int64_t D, int reduce, int in_dtype, rsm_regress_out out,
+                                     int device, void* stream) {
+  return inner_regress_fwd(left, right, N, C, H, W, D, reduce, in_dtype, out, device, stream, nullptr);
+}
+
+// diagnostic twin: `prof` = 8 zero-initialised uint64 on the device; the row-streaming tcgen05 kernel adds clock64
+// cycles per warp role (other paths leave it untouched)
+extern "C" int rsm_inner_regress_fwd_profile(rsm_feat left, rsm_feat right, int64_t N, int64_t C, int64_t H,
+                                             int64_t W, int64_t D, int reduce, int in_dtype, rsm_regress_out out,
+                                             int device, void* stream, uint64_t* prof) {
+  if (!prof) return RSM_ERR_NULL_POINTER;
+  return inner_regress_fwd(left, right, N, C, H, W, D, reduce, in_dtype, out, device, stream,
+                           reinterpret_cast<unsigned long long*>(prof));
 }

@@ -75,6 +75,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
 // past a failed wait (it would overwrite a shared-memory stage or a TMEM buffer that is still in use), so the
 // kernel cannot return RSM_OK with a poisoned volume.
 __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+#pragma unroll 1   // (unrolled 16x by default: ~560 instructions per call site)
   for (int it = 0; it < (1 << 12); ++it) {
     uint32_t ok;
     asm volatile(

@@ -271,10 +271,10 @@ int rsm_upsample_regress_bwd(const void* gout, const void* cost, const float* ex
 int rsm_inner_regress_fwd(rsm_feat left, rsm_feat right, int64_t N, int64_t C, int64_t H,
                           int64_t W, int64_t D, int reduce, int in_dtype, rsm_regress_out out,
                           int device, void* stream);
-/* diagnostic twin: `prof` = 8 zero-initialised uint64 on the device; the row-streaming tcgen05 kernel adds clock64
+/* diagnostic twin: `prof` = 16 zero-initialised uint64 on the device; the row-streaming tcgen05 kernel adds clock64
  * cycles per warp role, summed over CTAs: [0] issuer waiting for operands, [1] issuer waiting for a free TMEM block,
  * [2] issuer total, [3] TMA producer waiting for a free ring slot, [4] producer total, [5] epilogue warps waiting
- * for an accumulator block, [6] epilogue warps total */
+ * for an accumulator group, [6] epilogue warps total, [7] scanning, [8] fence + arrive, [9] merging + storing */
 int rsm_inner_regress_fwd_profile(rsm_feat left, rsm_feat right, int64_t N, int64_t C, int64_t H,
                                   int64_t W, int64_t D, int reduce, int in_dtype, rsm_regress_out out,
                                   int device, void* stream, uint64_t* prof);

@@ -941,7 +941,7 @@ extern "C" int rsm_inner_regress_fwd(rsm_feat left, rsm_feat right, int64_t N, i
   return inner_regress_fwd(left, right, N, C, H, W, D, reduce, in_dtype, out, device, stream, nullptr);
 }
 
-// diagnostic twin: `prof` = 8 zero-initialised uint64 on the device; the row-streaming tcgen05 kernel adds clock64
+// diagnostic twin: `prof` = 16 zero-initialised uint64 on the device; the row-streaming tcgen05 kernel adds clock64
 // cycles per warp role (other paths leave it untouched)
 extern "C" int rsm_inner_regress_fwd_profile(rsm_feat left, rsm_feat right, int64_t N, int64_t C, int64_t H,
                                              int64_t W, int64_t D, int reduce, int in_dtype, rsm_regress_out out,

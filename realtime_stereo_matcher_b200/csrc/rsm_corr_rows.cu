@@ -20,16 +20,17 @@
 //     columns outside [0, D) for a lane are masked (one compare + select per value), which only happens in the two
 //     31-column edges of a quadrant's range.  j ascends = d descends, so ties take the LATER column (torch: first
 //     index wins).
-// Warp roles (576 threads, one persistent CTA per SM, a contiguous range of x-tiles each):
-//   warps 0-15  epilogue: TMEM lane quadrant q = warp % 4 (also the warp's scheduler), the 8-column chunks of the
-//               quadrant's range dealt round-robin to its four warps; partial states merged through shared memory
-//   warp 16     UMMA issuer (whole warp converged, one elected lane issues)      warp 17  TMA producer (one lane)
+// Warp roles (320 threads, one persistent CTA per SM):
+//   warps 0-7   epilogue: TMEM lane quadrant q = warp % 4 (also the warp's scheduler), the 8-column chunks of the
+//               quadrant's range dealt alternately to its two warps; partial states merged through shared memory
+//   warp 8      UMMA issuer (whole warp converged, one elected lane issues)      warp 9   TMA producer (one lane)
 // mbarriers: a_full/a_empty (left tile ring), b_full/b_empty (right atom ring), t_full/t_empty (TMEM halves).  All
 // waits are bounded and trap on expiry (rsm_tc.cuh).
-// Measured while building it (tools/rows_trace.py, clock64 stamps per role): hand-offs are expensive -- a warp that
-// only waits, fences and arrives needs 300-450 cycles per hand-off, the single-lane producer ~600 cycles per box it
-// issues with divisions in its loop -- so hand-offs are per group, not per atom, and ring positions are kept
-// incrementally.
+// Measured while building it (clock64 stamps per role and atom, first version: one hand-off per 64-column atom, 12
+// epilogue warps): a warp that only waits, fences and arrives needs 300-450 cycles per hand-off, a single-lane
+// producer with divisions in its loop ~600 cycles per box, and one warp alone needs ~500 cycles per 8-column chunk
+// (TMEM round trip + a serial scan) -- so hand-offs are per group, ring positions are kept incrementally, and every
+// warp scans two chunks at a time into two independent states.
 #include <cuda.h>
 
 #include "rsm_common.cuh"
@@ -42,10 +43,11 @@ constexpr int RR_ATOM = 64;         // pixels per operand atom
 constexpr int RR_GATOMS = 4;        // atoms per accumulator group (256 TMEM columns = one half)
 constexpr int RR_MAXA = 4;          // left-tile ring slots (upper bound)
 constexpr int RR_MAXB = 16;         // right-atom ring slots (upper bound)
-constexpr int RR_NSPLIT = 4;        // epilogue warps per TMEM lane quadrant
+constexpr int RR_NSPLIT = 2;        // epilogue warps per TMEM lane quadrant (4 measured the same or slower: the scan is
+                                    // bound by the MUFU pipe and TMEM reads, which the warps of a quadrant share)
 constexpr int RR_EPI_WARPS = 4 * RR_NSPLIT;
 constexpr int RR_THREADS = 32 * (RR_EPI_WARPS + 2);
-constexpr int RR_PART_BYTES = 2 * (RR_NSPLIT - 1) * 128 * 8 * 4;   // parked partial states: 2 buffers x 3 parts x 128 lanes x 8 words
+constexpr int RR_PART_BYTES = 2 * RR_NSPLIT * 128 * 8 * 4;   // parked partial states: 2 buffers x 2 parts x 128 lanes x 8 words
 constexpr int RR_BAR_BYTES = 512;   // 2*4 + 2*16 + 2*2 = 44 mbarriers + the TMEM address slot
 constexpr int RR_SMEM_MAX = 227 * 1024;
 
@@ -70,7 +72,8 @@ struct RrOut {
   float* lse;
 };
 
-// x-tile iterator: (n, y, xt) in row-major order
+// The x-tiles of one CTA, in order: a contiguous range of (n, y, xt) tiles.  (Dealing whole rows round-robin over the
+// CTAs, so that the grid reads neighbouring rows of every channel plane at any time, measured the same.)
 struct RowTile {
   int n, y, xt;
   __device__ __forceinline__ void advance(const RrGeom& g) {
@@ -80,14 +83,20 @@ struct RowTile {
     y = 0; ++n;
   }
 };
-__device__ __forceinline__ RowTile row_tile(int64_t t64, const RrGeom& g) {
-  const uint32_t t = (uint32_t)t64;
-  const uint32_t row = t / (uint32_t)g.xtiles;
-  RowTile r;
-  r.xt = (int)(t - row * (uint32_t)g.xtiles);
-  r.n = (int)(row / (uint32_t)g.H);
-  r.y = (int)(row - (uint32_t)r.n * (uint32_t)g.H);
-  return r;
+struct TileRange {
+  RowTile first;
+  uint32_t ntl;
+};
+__device__ __forceinline__ TileRange tile_range(const RrGeom& g) {
+  TileRange tr;
+  const int64_t per = (g.tiles + gridDim.x - 1) / gridDim.x;
+  const int64_t t_beg = min((int64_t)blockIdx.x * per, g.tiles), t_end = min(t_beg + per, g.tiles);
+  const uint32_t t = (uint32_t)t_beg, row = t / (uint32_t)g.xtiles;
+  tr.ntl = (uint32_t)(t_end - t_beg);
+  tr.first.xt = (int)(t - row * (uint32_t)g.xtiles);
+  tr.first.n = (int)(row / (uint32_t)g.H);
+  tr.first.y = (int)(row - (uint32_t)tr.first.n * (uint32_t)g.H);
+  return tr;
 }
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
@@ -109,10 +118,10 @@ struct RrState {
 
 // 8 consecutive window columns of this lane: disparities dtop, dtop-1, ..., dtop-7.
 // MODE 0: every column is a disparity in [0, D) for every lane of the warp (interior of the band);
-// MODE 1: the low-column edge (dtop may exceed D-1);  MODE 2: the high-column edge (dtop-k may fall below 0);
-// MODE 3: both at once (D < 39), and / or columns below jfill (x' < 0), which read as the reference's fill value 0.
-// Masked columns do not take part.  k2 = log2(e) * scale folded into the exponent; extrema are tracked on the raw
-// sums (the scale is a positive power of two there, or has been applied by an exact division -- DIV -- when not).
+// MODE 4: an edge of the quadrant's range: columns whose disparity falls outside [0, D) for this lane do not take part;
+// MODE 3: as 4, and columns below jfill (x' < 0) read as the reference's fill value 0 (first tiles of a row only).
+// k2 = log2(e) * scale folded into the exponent; extrema are tracked on the raw sums (the scale is a positive power of
+// two there, or has been applied by an exact division -- DIV -- when it is not).
 template <bool EXT, bool DIV, int MODE>
 __device__ __forceinline__ void rr_chunk8(RrState& st, const uint32_t (&raw)[8], int c0, int dtop, int D, int jfill, float k2, float cnt) {
   float vx[8], vn[8];
@@ -121,12 +130,8 @@ __device__ __forceinline__ void rr_chunk8(RrState& st, const uint32_t (&raw)[8],
     float f = __uint_as_float(raw[k]);
     if (DIV) f = __fdiv_rn(f, cnt);
     bool ok = true;
-    if (MODE == 1) ok = dtop - D < k;
-    if (MODE == 2) ok = k <= dtop;
-    if (MODE == 3) {
-      if (c0 + k < jfill) f = 0.f;                             // warp-uniform predicate
-      ok = (unsigned)(dtop - k) < (unsigned)D;
-    }
+    if (MODE == 3 && c0 + k < jfill) f = 0.f;                  // warp-uniform predicate
+    if (MODE != 0) ok = (unsigned)(dtop - k) < (unsigned)D;
     vx[k] = (MODE == 0 || ok) ? f : -INFINITY;
     if (EXT) vn[k] = (MODE == 0 || ok) ? f : INFINITY;
   }
@@ -164,6 +169,29 @@ __device__ __forceinline__ void rr_chunk8(RrState& st, const uint32_t (&raw)[8],
   }
 }
 
+// classify one chunk (warp-uniform) and scan it
+template <bool EXT, bool DIV>
+__device__ __forceinline__ void rr_any(RrState& st, const uint32_t (&v)[8], int c0w, int dtop, int D, int jfill, int llo, int lhi,
+                                       float k2, float cnt) {
+  if (c0w < jfill) rr_chunk8<EXT, DIV, 3>(st, v, c0w, dtop, D, jfill, k2, cnt);
+  else if (c0w >= llo && c0w + 7 <= lhi) rr_chunk8<EXT, DIV, 0>(st, v, c0w, dtop, D, jfill, k2, cnt);
+  else rr_chunk8<EXT, DIV, 4>(st, v, c0w, dtop, D, jfill, k2, cnt);
+}
+
+// fold state b into a (same pixel, disjoint disparities): equal extrema keep the smaller disparity
+template <bool EXT>
+__device__ __forceinline__ void rr_merge(RrState& a, float m2, float s2, float w2, float minv2, float maxv2, int mini2, int maxi2,
+                                         int nani2, float k2) {
+  const float M = fmaxf(a.m, m2);
+  const float a1 = fast_exp2((a.m - M) * k2), a2 = fast_exp2((m2 - M) * k2);
+  a.s = a.s * a1 + s2 * a2; a.ws = a.ws * a1 + w2 * a2; a.m = M;
+  if (EXT) {
+    if (minv2 < a.minv || (minv2 == a.minv && mini2 < a.mini)) { a.minv = minv2; a.mini = mini2; }
+    if (maxv2 > a.maxv || (maxv2 == a.maxv && maxi2 < a.maxi)) { a.maxv = maxv2; a.maxi = maxi2; }
+    a.nani = min(a.nani, nani2);
+  }
+}
+
 template <bool EXT, bool DIV>
 __global__ void __launch_bounds__(RR_THREADS, 1)
 inner_regress_rows_kernel(RrOut out, RrGeom g, const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUtensorMap tmR,
@@ -196,10 +224,9 @@ inner_regress_rows_kernel(RrOut out, RrGeom g, const __grid_constant__ CUtensorM
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
-  // contiguous range of x-tiles of this CTA; consecutive tiles of one row share their right-window atoms
-  const int64_t per = (g.tiles + gridDim.x - 1) / gridDim.x;
-  const int64_t t_beg = min((int64_t)blockIdx.x * per, g.tiles), t_end = min(t_beg + per, g.tiles);
-  const uint32_t ntl = (uint32_t)(t_end - t_beg);
+  // the x-tiles of this CTA; consecutive tiles of one row share their right-window atoms
+  const TileRange tr = tile_range(g);
+  const uint32_t ntl = tr.ntl;
   const uint32_t na = (uint32_t)g.na, nb = (uint32_t)g.nb, nabuf = (uint32_t)g.nabuf, ng = (uint32_t)g.ng;
 
   if (warp == RR_EPI_WARPS) {
@@ -225,7 +252,7 @@ inner_regress_rows_kernel(RrOut out, RrGeom g, const __grid_constant__ CUtensorM
       // ring positions kept incrementally (no divisions): left-tile slot / fill parity; slot / fill parity of the
       // window's first atom; how many atoms at the end of the window are new (not yet waited for); group counter
       uint32_t as = 0, apar = 0, bs0 = 0, bpar0 = 0, fresh = na, gc = 0;
-      int xt = row_tile(t_beg, g).xt;
+      int xt = tr.first.xt;
       for (uint32_t tl = 0; tl < ntl; ++tl) {
         long long c0 = prof ? clock64() : 0;
         mbar_wait(a_full + 8 * as, apar);
@@ -296,7 +323,7 @@ inner_regress_rows_kernel(RrOut out, RrGeom g, const __grid_constant__ CUtensorM
       long long c_wait = 0;
       const long long c_beg = prof ? clock64() : 0;
       uint32_t as = 0, apar = 0, bs = 0, bpar = 0;
-      RowTile tc = row_tile(t_beg, g);
+      RowTile tc = tr.first;
       for (uint32_t tl = 0; tl < ntl; ++tl, tc.advance(g)) {
         const bool first = tl == 0 || tc.xt == 0;
         const int x0 = tc.xt * RR_TM;
@@ -327,7 +354,7 @@ inner_regress_rows_kernel(RrOut out, RrGeom g, const __grid_constant__ CUtensorM
     const int q = warp & 3, hh = warp >> 2;
     const int r = 32 * q + lane;
     const bool pmean = g.mean && g.pow2;
-    const float scale = pmean ? 1.f / (float)g.C : 1.f, cnt = (float)g.C;
+    const float scale = pmean ? 1.f / (float)g.C : 1.f, cnt_f = (float)g.C;
     const float k2 = kLog2e * scale;
     const int D = g.D, Dp = g.Dp;
     const int dbw = r + Dp;                                     // disparity of this lane at window column j: dbw - j
@@ -335,49 +362,72 @@ inner_regress_rows_kernel(RrOut out, RrGeom g, const __grid_constant__ CUtensorM
     const int llo = ulo + 31, lhi = 32 * q + Dp;                  // columns every lane of the quadrant needs
     const int c8lo = ulo >> 3, c8hi = (uhi >> 3) + 1;             // ... as a range of 8-column chunks of the window
     const bool rec = prof && lane == 0;
-    long long c_wait = 0;
+    long long c_wait = 0, c_scan = 0, c_arr = 0, c_merge = 0;
     const long long c_beg = rec ? clock64() : 0;
-    RrState st;
+    RrState st, st2;
     uint32_t gc = 0;
     int turn = 0;                                                // whose chunk is next among the quadrant's warps
-    RowTile tc = row_tile(t_beg, g);
+    RowTile tc = tr.first;
     for (uint32_t tl = 0; tl < ntl; ++tl, tc.advance(g)) {
       const int x0 = tc.xt * RR_TM, x = x0 + r;
       const int jfill = Dp - x0;                                 // window columns below this one have x' < 0
-      st.reset();
+      st.reset(); st2.reset();
       int gat = 0;                                               // first atom of the group
       for (uint32_t grp = 0; grp < ng; ++grp, ++gc) {
         const int gsz = grp == 0 ? g.gsz0 : (int)na - g.gsz0;
         const uint32_t half = gc & 1;
         long long c0 = rec ? clock64() : 0;
         mbar_wait(t_full + 8 * half, (gc >> 1) & 1);
-        if (rec) c_wait += clock64() - c0;
+        if (rec) { const long long c1 = clock64(); c_wait += c1 - c0; c0 = c1; }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // this group's 8-column chunks inside the quadrant's range, every fourth one from this warp's turn on
         const int g8lo = max(c8lo, 8 * gat), g8hi = min(c8hi, 8 * (gat + gsz));
         const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + half * 256 - 64 * gat;   // + window column
         int c8 = g8lo + ((hh - turn) & (RR_NSPLIT - 1));
-        for (; c8 < g8hi; c8 += RR_NSPLIT) {
-          const int c0w = 8 * c8, dtop = dbw - c0w;
+        // two chunks per TMEM round trip, scanned into two independent states (st, st2): the two dependency chains
+        // interleave, which is what a warp needs here -- a lone chunk is a ~250-cycle load + a ~250-cycle serial scan.
+        // (Keeping the next pair's loads in flight during the scan measured 4-20 % SLOWER: the scan is bound by the
+        // MUFU pipe, 9 ex2 per chunk, and by TMEM read bandwidth together, not by the round-trip latency.)
+        for (; c8 + RR_NSPLIT < g8hi; c8 += 2 * RR_NSPLIT) {
+          const int ca = 8 * c8, cb = ca + 8 * RR_NSPLIT;
+          uint32_t va[8], vb[8];
+          tmem_ld8(taddr + ca, va);
+          tmem_ld8(taddr + cb, vb);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (ca >= jfill && ca >= llo && cb + 7 <= lhi) {       // both in the interior of the band
+            rr_chunk8<EXT, DIV, 0>(st, va, ca, dbw - ca, D, jfill, k2, cnt_f);
+            rr_chunk8<EXT, DIV, 0>(st2, vb, cb, dbw - cb, D, jfill, k2, cnt_f);
+          } else if (ca >= jfill) {
+            rr_chunk8<EXT, DIV, 4>(st, va, ca, dbw - ca, D, jfill, k2, cnt_f);
+            rr_chunk8<EXT, DIV, 4>(st2, vb, cb, dbw - cb, D, jfill, k2, cnt_f);
+          } else {
+            rr_chunk8<EXT, DIV, 3>(st, va, ca, dbw - ca, D, jfill, k2, cnt_f);
+            rr_chunk8<EXT, DIV, 3>(st2, vb, cb, dbw - cb, D, jfill, k2, cnt_f);
+          }
+        }
+        if (c8 < g8hi) {
+          const int c0w = 8 * c8;
           uint32_t v[8];
           tmem_ld8(taddr + c0w, v);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          const bool lo_ok = c0w >= llo, hi_ok = c0w + 7 <= lhi;
-          if (c0w < jfill || !(lo_ok || hi_ok)) rr_chunk8<EXT, DIV, 3>(st, v, c0w, dtop, D, jfill, k2, cnt);
-          else if (!lo_ok) rr_chunk8<EXT, DIV, 1>(st, v, c0w, dtop, D, jfill, k2, cnt);
-          else if (!hi_ok) rr_chunk8<EXT, DIV, 2>(st, v, c0w, dtop, D, jfill, k2, cnt);
-          else rr_chunk8<EXT, DIV, 0>(st, v, c0w, dtop, D, jfill, k2, cnt);
+          rr_any<EXT, DIV>(st, v, c0w, dbw - c0w, D, jfill, llo, lhi, k2, cnt_f);
         }
         if (g8hi > g8lo) turn = (turn + (g8hi - g8lo)) & (RR_NSPLIT - 1);
+        if (rec) { const long long c1 = clock64(); c_scan += c1 - c0; c0 = c1; }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(t_empty + 8 * half);
+        if (rec) c_arr += clock64() - c0;
         gat += gsz;
       }
-      // ---- merge the partial states of a lane (parts 1.. park theirs; part 0 merges and stores)
-      float* pbase = parts + (size_t)(tl & 1) * ((RR_NSPLIT - 1) * 128 * 8);
-      if (hh >= 1) {
-        float* p = pbase + ((size_t)(hh - 1) * 128 + r) * 8;
+      const long long cm0 = rec ? clock64() : 0;
+      // ---- merge: the warp's two states, then the four warps of the quadrant through shared memory (every warp parks
+      // its state; the merging warp rotates with the tile so that no warp is the straggler every time)
+      rr_merge<EXT>(st, st2.m, st2.s, st2.ws, st2.minv, st2.maxv, st2.mini, st2.maxi, st2.nani, k2);
+      float* pbase = parts + (size_t)(tl & 1) * (RR_NSPLIT * 128 * 8);
+      const int merger = (int)(tl & (RR_NSPLIT - 1));
+      if (hh != merger) {
+        float* p = pbase + ((size_t)hh * 128 + r) * 8;
         if (EXT) {
           *reinterpret_cast<float4*>(p) = make_float4(st.m, st.s, st.ws, st.minv);
           *reinterpret_cast<float4*>(p + 4) = make_float4(st.maxv, __int_as_float(st.mini), __int_as_float(st.maxi), __int_as_float(st.nani));
@@ -386,23 +436,14 @@ inner_regress_rows_kernel(RrOut out, RrGeom g, const __grid_constant__ CUtensorM
         }
       }
       asm volatile("bar.sync %0, %1;" ::"r"(2 + q), "r"(32 * RR_NSPLIT) : "memory");
-      if (hh == 0 && x < g.W) {
+      if (hh == merger && x < g.W) {
 #pragma unroll
-        for (int k = 0; k < RR_NSPLIT - 1; ++k) {
-          const float* p = pbase + ((size_t)k * 128 + r) * 8;
+        for (int k = 1; k < RR_NSPLIT; ++k) {
+          const float* p = pbase + ((size_t)((merger + k) & (RR_NSPLIT - 1)) * 128 + r) * 8;
           const float4 p0 = *reinterpret_cast<const float4*>(p);
-          const float m2 = p0.x, s2 = p0.y, w2 = p0.z;
-          const float M = fmaxf(st.m, m2);
-          const float a1 = fast_exp2((st.m - M) * k2), a2 = fast_exp2((m2 - M) * k2);
-          st.s = st.s * a1 + s2 * a2; st.ws = st.ws * a1 + w2 * a2; st.m = M;
-          if (EXT) {
-            const float4 p1 = *reinterpret_cast<const float4*>(p + 4);
-            const float minv2 = p0.w, maxv2 = p1.x;
-            const int mini2 = __float_as_int(p1.y), maxi2 = __float_as_int(p1.z), nani2 = __float_as_int(p1.w);
-            if (minv2 < st.minv || (minv2 == st.minv && mini2 < st.mini)) { st.minv = minv2; st.mini = mini2; }
-            if (maxv2 > st.maxv || (maxv2 == st.maxv && maxi2 < st.maxi)) { st.maxv = maxv2; st.maxi = maxi2; }
-            st.nani = min(st.nani, nani2);
-          }
+          float4 p1 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (EXT) p1 = *reinterpret_cast<const float4*>(p + 4);
+          rr_merge<EXT>(st, p0.x, p0.y, p0.z, p0.w, p1.x, __float_as_int(p1.y), __float_as_int(p1.z), __float_as_int(p1.w), k2);
         }
         const int64_t o = ((int64_t)tc.n * g.H + tc.y) * g.W + x;
         if (out.soft) out.soft[o] = __fdividef(st.ws, st.s);
@@ -415,8 +456,12 @@ inner_regress_rows_kernel(RrOut out, RrGeom g, const __grid_constant__ CUtensorM
           if (out.amax) out.amax[o] = st.maxi;
         }
       }
+      if (rec) c_merge += clock64() - cm0;
     }
     if (rec) {
+      atomicAdd(prof + 7, (unsigned long long)c_scan);
+      atomicAdd(prof + 8, (unsigned long long)c_arr);
+      atomicAdd(prof + 9, (unsigned long long)c_merge);
       atomicAdd(prof + 5, (unsigned long long)c_wait);
       atomicAdd(prof + 6, (unsigned long long)(clock64() - c_beg));
     }

@@ -108,13 +108,14 @@ def profile(lt, rt, d, mean, argmin, argmax):
     mi = torch.empty((n, h, w), dtype=torch.int64, device="cuda") if argmin else None
     ma = torch.empty((n, h, w), dtype=torch.int64, device="cuda") if argmax else None
     out = L.RsmRegressOut(L.ptr(so), L.ptr(mi), L.ptr(ma), L.ptr(None), L.ptr(None))
-    prof = torch.zeros(8, dtype=torch.int64, device="cuda")
+    prof = torch.zeros(16, dtype=torch.int64, device="cuda")
     L.check(L.load().rsm_inner_regress_fwd_profile(L.feat(lt), L.feat(rt), n, c, h, w, d, L.RSM_REDUCE_MEAN if mean else L.RSM_REDUCE_SUM,
                                                   L.dtype_code(lt), out, 0, L.stream_ptr(0), prof.data_ptr()), "profile")
     torch.cuda.synchronize()
     p = prof.cpu().numpy().astype(np.float64)
     return {"issuer_wait_operands": p[0] / max(p[2], 1), "issuer_wait_tmem": p[1] / max(p[2], 1), "issuer_cycles_per_cta": p[2] / 148,
-            "producer_wait_slots": p[3] / max(p[4], 1), "epilogue_wait_accumulator": p[5] / max(p[6], 1), "epilogue_cycles_per_warp": p[6] / (148 * 12)}
+            "producer_wait_slots": p[3] / max(p[4], 1), "epilogue_wait_accumulator": p[5] / max(p[6], 1), "epilogue_scan": p[7] / max(p[6], 1), "epilogue_arrive": p[8] / max(p[6], 1),
+            "epilogue_merge": p[9] / max(p[6], 1), "epilogue_cycles_per_warp": p[6] / (148 * 16)}
 
 
 cases = [("cfg2 C=64", 32, 64, 144, 240, 48, True), ("cfg2 C=16", 32, 16, 144, 240, 48, True),

@@ -24,8 +24,6 @@ int launch_inner_tc(const rsm_feat& left, const rsm_feat& right, void* out, int6
 int launch_inner_regress_rows(const rsm_feat& left, const rsm_feat& right, int64_t N, int64_t C, int64_t H, int64_t W,
                               int64_t D, int mean, int in_dtype, const rsm_regress_out& out, cudaStream_t st,
                               unsigned long long* prof);
-int launch_inner_regress_tc(const rsm_feat& left, const rsm_feat& right, int64_t N, int64_t C, int64_t H, int64_t W,
-                            int64_t D, int mean, int in_dtype, const rsm_regress_out& out, cudaStream_t st);
 
 constexpr int TX = 64;        // pixels per CTA tile
 constexpr int XT = 4;         // pixels per thread
@@ -651,10 +649,9 @@ static int launch_bwd(const void* gout, const rsm_feat& left, const rsm_feat& ri
   int cbs = 0;
   for (int c = BW_CB; c >= 4; c -= 4)
     if (g.cpg % c == 0) { cbs = c; break; }
-  const char* naive = getenv("RSM_BWD_NAIVE");
   // narrow groups of a D-innermost volume: one CTA per (n, group, y) row stages the gradient row once and
   // produces both gradients from it (groupwise_bwd_row_kernel)
-  if (LAYOUT == LAYOUT_NGHWD && (g.cpg == 4 || g.cpg == 8) && g.D > 0 && gl && gr && !(naive && naive[0] == '1')) {
+  if (LAYOUT == LAYOUT_NGHWD && (g.cpg == 4 || g.cpg == 8) && g.D > 0 && gl && gr) {
     GroupRowGeom rg;
     rg.nq = (g.D + 3) / 4;
     const int D4 = 4 * rg.nq;
@@ -684,17 +681,15 @@ static int launch_bwd(const void* gout, const rsm_feat& left, const rsm_feat& ri
     }
   }
   // inner product: 8(x) x 4(c) register tiles when every row and window starts on a 16-byte boundary (fp32: W % 4,
-  // 16-bit: W % 8) and all three tensors share one dtype (RSM_BWD_SMALL_TILE=1 keeps the 4x4 kernel: A/B runs)
+  // 16-bit: W % 8) and all three tensors share one dtype
   if constexpr (LAYOUT == LAYOUT_NDHW && std::is_same<Tin, Tout>::value) {
-    const char* small = getenv("RSM_BWD_SMALL_TILE");
     constexpr int EPV = 16 / (int)sizeof(Tin);
     auto v16 = [&](const rsm_feat& f) {
       return f.stride_w == 1 && f.stride_n % EPV == 0 && f.stride_c % EPV == 0 && f.stride_h % EPV == 0 && aligned_to(f.data, 16);
     };
     // (16-bit tensors are widened synchronously while staging, a few loads in flight per thread)
     if (g.G == 1 && g.C >= 16 && g.D > 0 && g.W % EPV == 0 && v16(left) && v16(right) && aligned_to(gout, 16) &&
-        (!gl || aligned_to(gl, 16)) && (!gr || aligned_to(gr, 16)) && !(naive && naive[0] == '1') &&
-        !(small && small[0] == '1')) {
+        (!gl || aligned_to(gl, 16)) && (!gr || aligned_to(gr, 16))) {
       const int xtiles = (int)ceil_div(g.W, BB_TX), cblocks = (int)ceil_div(g.C, BB_CB);
       const int64_t bx = N * g.H * (int64_t)cblocks * xtiles;
       if (grid_ok(bx)) {
@@ -717,7 +712,7 @@ static int launch_bwd(const void* gout, const rsm_feat& left, const rsm_feat& ri
       }
     }
   }
-  if (cbs > 0 && g.D > 0 && !(naive && naive[0] == '1')) {
+  if (cbs > 0 && g.D > 0) {
     const int cblocks = g.C / cbs;
     const int64_t bx = N * g.H * (int64_t)cblocks * g.xtiles;
     if (!grid_ok(bx)) return RSM_ERR_INVALID_SHAPE;
@@ -775,21 +770,18 @@ extern "C" int rsm_inner_fwd(rsm_feat left, rsm_feat right, void* out, int64_t N
   if (!valid_dtype(out_dtype)) return RSM_ERR_UNSUPPORTED_DTYPE;
   if (!aligned_to(out, dtype_size(out_dtype))) return RSM_ERR_MISALIGNED;
   // 16-bit features: banded per-row GEMM on the tcgen05 tensor cores (rsm_corr_tc.cu); fp32 features and
-  // shapes it does not cover (C % 16 != 0) use the SIMT kernel.  RSM_DISABLE_TC=1 forces SIMT (A/B runs).
-  const char* no_tc = getenv("RSM_DISABLE_TC");
-  if (!(no_tc && no_tc[0] == '1')) {
+  // shapes it does not cover (C % 16 != 0) use the SIMT kernel.
+  {
     const int rc = launch_inner_tc(left, right, out, N, C, H, W, D, reduce == RSM_REDUCE_MEAN, in_dtype, out_dtype, st);
     if (rc != RSM_ERR_UNSUPPORTED_CONFIG) return rc;
   }
   // fp32 features: 8x16 register tiles when rows and windows start on 16-byte boundaries
-  // (RSM_INNER_SMALL_TILE=1 keeps the 4x8 kernel: A/B runs)
   {
-    const char* small = getenv("RSM_INNER_SMALL_TILE");
     auto v4 = [&](const rsm_feat& f) {
       return f.stride_w == 1 && f.stride_n % 4 == 0 && f.stride_c % 4 == 0 && f.stride_h % 4 == 0 && aligned_to(f.data, 16);
     };
     if (in_dtype == RSM_F32 && out_dtype == RSM_F32 && C >= 16 && D >= 16 && W % 4 == 0 && v4(left) && v4(right) &&
-        aligned_to(out, 16) && !(small && small[0] == '1')) {
+        aligned_to(out, 16)) {
       // (DT, ntd) with an even ntd (whole warps): the smallest chunk DT * ntd covering min(D, 64)
       static const int kDT[5] = {8, 12, 8, 12, 16}, kNTD[5] = {2, 2, 4, 4, 4};   // chunks 16, 24, 32, 48, 64
       int pick = 4;
@@ -881,27 +873,17 @@ static int inner_regress_fwd(rsm_feat left, rsm_feat right, int64_t N, int64_t C
   if (C > 0 && (!left.data || !right.data)) return RSM_ERR_NULL_POINTER;
   if (NTX * g.ntd > 1024) return RSM_ERR_UNSUPPORTED_CONFIG;  // D <= 512
   RSM_COMMON_CHECKS(in_dtype)
-  {
-    const char* no_tc = getenv("RSM_DISABLE_TC");
-    if (!(no_tc && no_tc[0] == '1')) {   // 16-bit features: tcgen05 blocks reduced straight out of TMEM
-      const char* old_tc = getenv("RSM_TC_REGRESS_CHUNKED");   // A/B: the first (disparity-chunked) tensor-core form
-      if (!(old_tc && old_tc[0] == '1')) {
-        const int rc = launch_inner_regress_rows(left, right, N, C, H, W, D, reduce == RSM_REDUCE_MEAN, in_dtype, out, st, prof);
-        if (rc != RSM_ERR_UNSUPPORTED_CONFIG) return rc;
-      }
-      const int rc = launch_inner_regress_tc(left, right, N, C, H, W, D, reduce == RSM_REDUCE_MEAN, in_dtype, out, st);
-      if (rc != RSM_ERR_UNSUPPORTED_CONFIG) return rc;
-    }
+  {   // 16-bit features (C % 16 == 0, C <= 128, D <= 384, TMA-addressable views): tcgen05 accumulators reduced in TMEM
+    const int rc = launch_inner_regress_rows(left, right, N, C, H, W, D, reduce == RSM_REDUCE_MEAN, in_dtype, out, st, prof);
+    if (rc != RSM_ERR_UNSUPPORTED_CONFIG) return rc;
   }
   // fp32 features, all disparities in one 64-wide chunk, rows on 16-byte boundaries: the 8xDT-tile kernel with
-  // the regression scan as its epilogue (RSM_INNER_SMALL_TILE=1 keeps the 4x8 kernel: A/B runs)
+  // the regression scan as its epilogue
   {
-    const char* small = getenv("RSM_INNER_SMALL_TILE");
     auto v4 = [&](const rsm_feat& f) {
       return f.stride_w == 1 && f.stride_n % 4 == 0 && f.stride_c % 4 == 0 && f.stride_h % 4 == 0 && aligned_to(f.data, 16);
     };
-    if (in_dtype == RSM_F32 && C >= 16 && D >= 16 && D <= 16 * BG_MAXNTD && W % 4 == 0 && v4(left) && v4(right) &&
-        !(small && small[0] == '1')) {
+    if (in_dtype == RSM_F32 && C >= 16 && D >= 16 && D <= 16 * BG_MAXNTD && W % 4 == 0 && v4(left) && v4(right)) {
       static const int kDT[5] = {8, 12, 8, 12, 16}, kNTD[5] = {2, 2, 4, 4, 4};   // chunks 16, 24, 32, 48, 64
       int pick = 4;
       for (int k = 0; k < 5; ++k)

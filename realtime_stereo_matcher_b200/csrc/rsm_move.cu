@@ -445,9 +445,8 @@ extern "C" int rsm_concat_fwd(rsm_feat left, rsm_feat right, void* out, int64_t 
     if (smem > 200 * 1024) return (int)RSM_ERR_UNSUPPORTED_CONFIG;
     const dim3 grid((unsigned)(N * 2 * C * H));
     if constexpr (sizeof(T) == 4) {
-      const char* v8 = getenv("RSM_CONCAT_V8");
       // measured on B200: 256-bit stores win 1-5 % up to D = 96 and lose ~3 % at D = 192
-      if (D % 8 == 0 && D <= 128 && aligned_to(out, 32) && !(v8 && v8[0] == '0')) {
+      if (D % 8 == 0 && D <= 128 && aligned_to(out, 32)) {
         auto k = concat_fwd_kernel<T, 8>;      // fp32: 256-bit stores
         if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k<<<grid, kThreads, smem, st>>>(view_of(left), view_of(right), (T*)out, (int)C, (int)H, (int)W, (int)D);
@@ -476,11 +475,9 @@ extern "C" int rsm_concat_bwd(const void* gout, void* gleft, void* gright, int64
   RSM_COMMON_CHECKS(dtype)
   if (!grid_ok(ceil_div(total, kThreads))) return RSM_ERR_INVALID_SHAPE;
   return RSM_DISPATCH_DTYPE(dtype, T, [&]() -> int {
-    // row-tiled kernel: whole words per pixel, word-aligned rows, at most 1024 disparities; RSM_BWD_NAIVE=1
-    // keeps the per-element gather (A/B runs)
+    // row-tiled kernel: whole words per pixel, word-aligned rows, at most 1024 disparities (else the per-element gather)
     constexpr int EPW = 4 / (int)sizeof(T);
-    const char* naive = getenv("RSM_BWD_NAIVE");
-    if (D > 0 && D <= 1024 && D % EPW == 0 && aligned_to(gout, 4) && grid_ok(N * 2 * C * H) && !(naive && naive[0] == '1')) {
+    if (D > 0 && D <= 1024 && D % EPW == 0 && aligned_to(gout, 4) && grid_ok(N * 2 * C * H)) {
       const int DW = (int)D / EPW;
       const int P = DW | 1;                                          // odd word pitch
       int64_t tx = (96 * 1024) / (4 * (int64_t)P) - (D - 1);         // pixels per tile within 96 KB, halo included
@@ -572,14 +569,13 @@ extern "C" int rsm_difference_fwd(rsm_feat left, rsm_feat right, void* out, int6
     constexpr int VEC = 16 / sizeof(T);
     const bool vec = W % VEC == 0 && aligned_to(out, 16);
     // row-block kernel: 8 image rows per CTA, the widest store the row length and the output alignment allow
-    // (RSM_DIFF_ELEMENTWISE=1 keeps the per-vector kernel: A/B runs)
+    // (rows too long for its shared-memory tile take the per-vector kernel)
     {
-      const char* e = getenv("RSM_DIFF_ELEMENTWISE");
       const int YB = 8;
       constexpr int AL = 16 / (int)sizeof(T);
       const int64_t yblocks = ceil_div(H, YB), bx = N * C * yblocks;
       const size_t smem = ((size_t)2 * (YB * W + AL) + (D + 2 * AL - 1) / AL * AL + AL) * sizeof(T);
-      if (smem <= 96 * 1024 && grid_ok(bx) && !(e && e[0] == '1')) {
+      if (smem <= 96 * 1024 && grid_ok(bx)) {
         auto launch = [&](auto k) -> int {
           if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
           k<<<(unsigned)bx, kThreads, smem, st>>>(view_of(left), view_of(right), (T*)out, (int)C, (int)H, (int)W, (int)D, fill,

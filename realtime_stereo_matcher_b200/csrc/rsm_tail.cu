@@ -529,11 +529,7 @@ static int make_geom(int64_t Dc, int64_t Hc, int64_t Wc, int64_t D, int64_t H, i
   g.fast4 = (D == 4 * Dc) ? 1 : 0;
   g.fastx = (W == 4 * Wc) ? 1 : 0;
   g.fasty = (H == 4 * Hc) ? 1 : 0;
-  {
-    const char* e = getenv("RSM_TAIL_GENERIC");   // A/B switch: keep the all-x4 specialisation off
-    g.all4 = g.fast4 && g.fastx && g.fasty && g.FH == 4 && g.FW == 10 && Dc * Hc * Wc < 2147483647LL &&
-             !(e && e[0] == '1');
-  }
+  g.all4 = g.fast4 && g.fastx && g.fasty && g.FH == 4 && g.FW == 10 && Dc * Hc * Wc < 2147483647LL;
   smem = tail_smem_bytes(g);
   if (smem > 200 * 1024) return RSM_ERR_UNSUPPORTED_CONFIG;
   return RSM_OK;

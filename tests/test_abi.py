@@ -37,6 +37,7 @@ def test_ctypes_prototypes_cover_header():
 def test_version_and_error_strings(lib):
     lib.rsm_version.restype = ctypes.c_int
     lib.rsm_last_error.restype = ctypes.c_char_p
+    from realtime_stereo_matcher_b200 import _lib
     assert lib.rsm_version() == _lib.RSM_VERSION
     assert lib.rsm_last_error(0) == b"ok"
     assert b"C % G" in lib.rsm_last_error(1)

@@ -406,20 +406,18 @@ def test_epe_delta_synthetic(rsm):
 @pytest.mark.parametrize("shape", [(1, 16, 3, 240, 48), (2, 64, 4, 240, 48), (1, 32, 2, 312, 48),
                                    (1, 128, 2, 480, 192), (1, 16, 2, 67, 19), (1, 48, 2, 130, 130)])
 @pytest.mark.parametrize("dn", ["bf16", "fp16"])
-def test_tcgen05_inner_vs_oracle_and_simt(rsm, shape, dn, monkeypatch):
+def test_tcgen05_inner_vs_oracle_and_simt(rsm, shape, dn):
     """16-bit features with C % 16 == 0 take the tcgen05 banded-GEMM kernel: check it against the fp32
-    oracle on the same rounded inputs AND against the SIMT kernel (RSM_DISABLE_TC=1)."""
+    oracle on the same rounded inputs AND against the SIMT fp32 kernel fed the same (rounded) values."""
     n, c, h, w, d = shape
     rng = np.random.default_rng(31)
     l = round_to(rng.standard_normal((n, c, h, w)).astype(np.float32), dn)
     r = round_to(rng.standard_normal((n, c, h, w)).astype(np.float32), dn)
     L, R = dev(l, dn), dev(r, dn)
     ref = oracle.inner_product_volume(l, r, d, mean=True, out_dtype=np.float32)
-    monkeypatch.delenv("RSM_DISABLE_TC", raising=False)
     tc32 = rsm.inner_product_volume(L, R, d, mean=True, out_dtype=torch.float32)
     tc16 = rsm.inner_product_volume(L, R, d, mean=True)
-    monkeypatch.setenv("RSM_DISABLE_TC", "1")
-    simt32 = rsm.inner_product_volume(L, R, d, mean=True, out_dtype=torch.float32)
+    simt32 = rsm.inner_product_volume(dev(l), dev(r), d, mean=True)
     atol = 1e-5 * np.sqrt(c) * np.abs(l).max() * np.abs(r).max()
     close(tc32, ref, atol)
     close(simt32, ref, atol)
@@ -449,41 +447,12 @@ def test_tcgen05_fused_regress(rsm, shape):
     equal(rsm.inner_product_volume(dev(l, "bf16"), dev(r, "bf16"), d, out_dtype=torch.float32), vol)
 
 
-@pytest.mark.parametrize("shape", [(1, 8, 2, 128, 16), (2, 64, 4, 240, 48), (1, 24, 3, 312, 48), (1, 128, 2, 480, 192),
-                                   (1, 16, 2, 68, 19), (1, 40, 3, 67, 33)])
-def test_tcgen05_fp32_3xtf32_opt_in(rsm, shape, monkeypatch):
-    """fp32 features on the tensor cores (RSM_TC_FP32=1: kind::tf32 on an exact hi/lo operand split, three
-    UMMAs per k-step).  Within the fp32 tolerance of the float64 result, bit-exact on dyadic inputs, and the
-    fused regression agrees with the oracle on the volume."""
-    n, c, h, w, d = shape
-    rng = np.random.default_rng(51)
-    l = rng.standard_normal((n, c, h, w)).astype(np.float32)
-    r = rng.standard_normal((n, c, h, w)).astype(np.float32)
-    ref = oracle.inner_product_volume(l, r, d, acc_dtype=np.float64, out_dtype=np.float64)
-    monkeypatch.setenv("RSM_TC_FP32", "1")
-    tc = rsm.inner_product_volume(dev(l), dev(r), d)
-    soft, amin, amax = rsm.inner_product_regress(dev(l * 0.5), dev(r * 0.5), d)
-    monkeypatch.delenv("RSM_TC_FP32")
-    simt = rsm.inner_product_volume(dev(l), dev(r), d)
-    atol = corr_atol_fp32(c, np.abs(l).max(), np.abs(r).max())
-    close(tc, ref.astype(np.float32), atol)
-    close(simt, ref.astype(np.float32), atol)
-    vol = oracle.inner_product_volume(l * 0.5, r * 0.5, d)
-    close(soft, oracle.soft_argmax(vol), soft_argmax_atol(d) * 4)
-    assert (amin.cpu().numpy() != oracle.hard_argmin(vol)).mean() < 1e-3
-    assert (amax.cpu().numpy() != oracle.hard_argmax(vol)).mean() < 1e-3
-    l = (rng.integers(-8, 9, (n, c, h, w)) / 8.0).astype(np.float32)
-    r = (rng.integers(-8, 9, (n, c, h, w)) / 8.0).astype(np.float32)
-    monkeypatch.setenv("RSM_TC_FP32", "1")
-    equal(rsm.inner_product_volume(dev(l), dev(r), d), oracle.inner_product_volume(l, r, d))
-
-
 @pytest.mark.parametrize("scale", [3.0, 60.0, 400.0])
-def test_v4_tail_all_x4_stabiliser(rsm, scale, monkeypatch):
+def test_v4_tail_all_x4_stabiliser(rsm, scale):
     """x4 along all three axes takes the specialised staging whose softmax stabiliser is an upper BOUND
     (max of the two source rows) with an exact-maximum fallback when the bound is too loose: costs whose
-    neighbouring columns differ by hundreds must still match the oracle, the generic path
-    (RSM_TAIL_GENERIC=1) and interpolate+softmax on the device; lse and the arg-extrema too."""
+    neighbouring columns differ by hundreds must still match the oracle and interpolate+softmax on the device; the
+    arg-extrema too."""
     rng = np.random.default_rng(61)
     b, dc, hc, wc = 2, 48, 10, 23
     d, h, w = 4 * dc, 4 * hc, 4 * wc
@@ -492,13 +461,8 @@ def test_v4_tail_all_x4_stabiliser(rsm, scale, monkeypatch):
     cost[0, 7, 4, ::2] = scale * 5         # isolated peaks: the bound of the rows next to them is loose
     c = dev(cost)
     pred, amin, amax = rsm.upsample_regress(c, d, h, w, argmin=True, argmax=True)
-    monkeypatch.setenv("RSM_TAIL_GENERIC", "1")
-    pred_g, amin_g, amax_g = rsm.upsample_regress(c, d, h, w, argmin=True, argmax=True)
-    monkeypatch.delenv("RSM_TAIL_GENERIC")
     assert torch.isfinite(pred).all()
     close(pred, oracle.v4_tail(cost, d, h, w), V4_TAIL_ATOL * max(1.0, scale / 3))
-    torch.testing.assert_close(pred, pred_g, atol=V4_TAIL_ATOL * max(1.0, scale / 3), rtol=0)
-    assert (amin != amin_g).float().mean() < 1e-3 and (amax != amax_g).float().mean() < 1e-3
     fine = torch.nn.functional.interpolate(c.unsqueeze(1), [d, h, w], mode="trilinear").squeeze(1)
     assert (amax != fine.argmax(1)).float().mean() < 1e-3
     assert (amin != fine.argmin(1)).float().mean() < 1e-3
@@ -506,22 +470,18 @@ def test_v4_tail_all_x4_stabiliser(rsm, scale, monkeypatch):
 
 @pytest.mark.parametrize("shape", [(1, 32, 3, 330, 40, 4), (2, 16, 2, 50, 24, 2), (1, 8, 2, 161, 33, 2), (1, 24, 2, 312, 48, 6)])
 @pytest.mark.parametrize("dn", ["fp32", "bf16"])
-def test_groupwise_bwd_row_parts(rsm, shape, dn, monkeypatch):
+def test_groupwise_bwd_row_parts(rsm, shape, dn):
     """Narrow groups (4 or 8 channels) take the row-part adjoint kernel: several parts per row, ragged
-    last part, D not a multiple of 8, 8-channel groups, 16-bit tensors -- against the oracle and against
-    the per-element gather kernel (RSM_BWD_NAIVE=1)."""
+    last part, D not a multiple of 8, 8-channel groups, 16-bit tensors -- against the oracle."""
     n, c, h, w, d, ng = shape
     rng = np.random.default_rng(71)
     l = round_to(rng.standard_normal((n, c, h, w)).astype(np.float32), dn)
     r = round_to(rng.standard_normal((n, c, h, w)).astype(np.float32), dn)
     gout = round_to(rng.standard_normal((n, ng, h, w, d)).astype(np.float32), dn)
     gl, gr = oracle.groupwise_volume_bwd(gout, l, r, ng)
-    res = []
-    for naive in ("0", "1"):
-        monkeypatch.setenv("RSM_BWD_NAIVE", naive)
-        L, R = dev(l, dn, grad=True), dev(r, dn, grad=True)
-        rsm.groupwise_volume(L, R, ng, d).backward(dev(gout, dn))
-        res.append((L.grad, R.grad))
+    L, R = dev(l, dn, grad=True), dev(r, dn, grad=True)
+    rsm.groupwise_volume(L, R, ng, d).backward(dev(gout, dn))
+    res = [(L.grad, R.grad)]
     atol = GRAD_RTOL * np.sqrt(d) * 16 if dn == "fp32" else RTOL_16[dn] * np.sqrt(d) * 4
     for a, b in res:
         close(a, gl, atol)
@@ -811,9 +771,9 @@ def test_empty_and_degenerate_inputs(rsm):
 @pytest.mark.parametrize("shape", [(1, 64, 3, 240, 48), (2, 40, 2, 136, 70), (1, 32, 2, 128, 24)])
 @pytest.mark.parametrize("dn", ["bf16", "fp16"])
 @pytest.mark.parametrize("mean", [False, True])
-def test_inner_bwd_16bit_big_tiles(rsm, shape, dn, mean, monkeypatch):
+def test_inner_bwd_16bit_big_tiles(rsm, shape, dn, mean):
     """16-bit tensors through the 8x8-tile inner-product adjoint (rows on 16-byte boundaries: W % 8 == 0),
-    against the fp32 oracle on the same rounded inputs and against the per-element gather kernel."""
+    against the fp32 oracle on the same rounded inputs."""
     n, c, h, w, d = shape
     rng = np.random.default_rng(91)
     l = round_to(rng.standard_normal((n, c, h, w)).astype(np.float32), dn)
@@ -821,9 +781,7 @@ def test_inner_bwd_16bit_big_tiles(rsm, shape, dn, mean, monkeypatch):
     gout = round_to(rng.standard_normal((n, d, h, w)).astype(np.float32), dn)
     gl, gr = oracle.inner_product_volume_bwd(gout, l, r, mean=mean)
     atol = RTOL_16[dn] * np.sqrt(d) * 4 / (c if mean else 1)
-    for naive in ("0", "1"):
-        monkeypatch.setenv("RSM_BWD_NAIVE", naive)
-        L, R = dev(l, dn, grad=True), dev(r, dn, grad=True)
-        rsm.inner_product_volume(L, R, d, mean=mean).backward(dev(gout, dn))
-        close(L.grad, gl, atol, RTOL_16[dn])
-        close(R.grad, gr, atol, RTOL_16[dn])
+    L, R = dev(l, dn, grad=True), dev(r, dn, grad=True)
+    rsm.inner_product_volume(L, R, d, mean=mean).backward(dev(gout, dn))
+    close(L.grad, gl, atol, RTOL_16[dn])
+    close(R.grad, gr, atol, RTOL_16[dn])

@@ -1,6 +1,6 @@
 """Row-streaming fused inner-product -> regression kernel (csrc/rsm_corr_rows.cu) on the GPU box: parity against the
 oracle on small shapes (soft, lse-free; argmin / argmax; dyadic bit-exact; mean / sum; fill region; NaN), then timing
-with the per-role cycle counters at the cfg2 / cfg4 sizes, next to the first (disparity-chunked) tensor-core form.
+with the per-role cycle counters at the cfg2 / cfg4 sizes next to volume + regression as two launches.
 
     python tools/rows_check.py [--no-time]
 """
@@ -126,13 +126,10 @@ for name, n, c, h, w, d, mean in cases:
     rt = (torch.randn(n, c, h, w, device="cuda") * 0.5).bfloat16()
     row = {"case": name, "shape": [n, c, h, w, d], "dtype": "bf16"}
     for label, am in (("soft", False), ("soft+argmin+argmax", True)):
-        os.environ.pop("RSM_TC_REGRESS_CHUNKED", None)
         med, best = timeit(lambda: run(lt, rt, d, mean, am, am))
-        os.environ["RSM_TC_REGRESS_CHUNKED"] = "1"
-        med0, best0 = timeit(lambda: run(lt, rt, d, mean, am, am))
-        os.environ.pop("RSM_TC_REGRESS_CHUNKED", None)
+        med0, best0 = timeit(lambda: rsm.regress(rsm.inner_product_volume(lt, rt, d, mean=mean), argmin=am, argmax=am))
         alg = 2 * n * c * h * w * 2 + n * h * w * (4 + (16 if am else 0))
-        row[label] = {"rows_us": round(med, 1), "rows_best_us": round(best, 1), "chunked_us": round(med0, 1),
+        row[label] = {"rows_us": round(med, 1), "rows_best_us": round(best, 1), "volume_then_regress_us": round(med0, 1),
                       "frac_hbm": round(alg / (med * 1e-6) / 6452.5e9, 3), "useful_TFLOPs": round(2 * n * c * h * w * d / (med * 1e-6) / 1e12, 1),
                       "roles": {k: round(v, 3) for k, v in profile(lt, rt, d, mean, am, am).items()}}
     print(json.dumps(row), flush=True)

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RSM_VERSION 106 /* major*10000 + minor*100 + patch */
+#define RSM_VERSION 107 /* major*10000 + minor*100 + patch */
 
 typedef enum rsm_dtype {
   RSM_F32 = 0,
@@ -102,6 +102,13 @@ int rsm_inner_fwd(rsm_feat left, rsm_feat right, void* out, int64_t N, int64_t C
 int rsm_inner_bwd(const void* gout, rsm_feat left, rsm_feat right, void* gleft, void* gright,
                   int64_t N, int64_t C, int64_t H, int64_t W, int64_t D, int reduce, int in_dtype,
                   int out_dtype, int device, void* stream);
+/* diagnostic twin: `prof` = 16 zero-initialised uint64 on the device; the tcgen05 adjoint kernel (16-bit tensors,
+ * D <= 64) adds clock64 cycles per warp role, summed over CTAs: issuer [0] waiting for a free accumulator, [1] for a band
+ * matrix, [2] for feature atoms, [3] total; builder warp 0 [4] waiting for the gradient tile, [5] for a free band matrix,
+ * [6] building, [7] total; epilogue warp 0 [8] waiting for an accumulator, [9] total */
+int rsm_inner_bwd_profile(const void* gout, rsm_feat left, rsm_feat right, void* gleft, void* gright,
+                  int64_t N, int64_t C, int64_t H, int64_t W, int64_t D, int reduce, int in_dtype,
+                  int out_dtype, int device, void* stream, uint64_t* prof);
 
 /* ---- group-wise correlation: TorchGroupwiseCost.forward / .groupwise, cost_volume/groupwise.py:12-56
  * out (N,G,H,W,D) = (1/(C/G)) * sum_{c in group g} L[c,x] R[c,x-d] for x>=d, else 0 */

@@ -38,7 +38,7 @@ class RsmV4Weights(C.Structure):
 i64, vp, ci, cf = C.c_int64, C.c_void_p, C.c_int, C.c_float
 
 RSM_REDUCE_WS_DOUBLES = 1184 * 8   # include/rsm.h
-RSM_VERSION = 106                  # include/rsm.h; the argument layouts below were written for this ABI
+RSM_VERSION = 107                  # include/rsm.h; the argument layouts below were written for this ABI
 
 # name -> argtypes, exactly the prototypes of include/rsm.h (tests/test_abi.py checks the header)
 SIGNATURES = {
@@ -48,6 +48,7 @@ SIGNATURES = {
     "rsm_interweave_bwd": [vp, vp, vp, i64, i64, i64, i64, ci, ci, vp],
     "rsm_inner_fwd": [RsmFeat, RsmFeat, vp, i64, i64, i64, i64, i64, ci, ci, ci, ci, vp],
     "rsm_inner_bwd": [vp, RsmFeat, RsmFeat, vp, vp, i64, i64, i64, i64, i64, ci, ci, ci, ci, vp],
+    "rsm_inner_bwd_profile": [vp, RsmFeat, RsmFeat, vp, vp, i64, i64, i64, i64, i64, ci, ci, ci, ci, vp, vp],
     "rsm_groupwise_fwd": [RsmFeat, RsmFeat, vp, i64, i64, i64, i64, i64, i64, ci, ci, ci, vp],
     "rsm_groupwise_bwd": [vp, RsmFeat, RsmFeat, vp, vp, i64, i64, i64, i64, i64, i64, ci, ci, ci, vp],
     "rsm_difference_fwd": [RsmFeat, RsmFeat, vp, i64, i64, i64, i64, i64, cf, ci, ci, vp],

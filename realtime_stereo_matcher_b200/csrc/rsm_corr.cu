@@ -21,6 +21,9 @@ namespace rsm {
 
 int launch_inner_tc(const rsm_feat& left, const rsm_feat& right, void* out, int64_t N, int64_t C, int64_t H, int64_t W,
                     int64_t D, int mean, int in_dtype, int out_dtype, cudaStream_t st);
+int launch_inner_bwd_tc(const void* gout, const rsm_feat& left, const rsm_feat& right, void* gl, void* gr, int64_t N,
+                        int64_t C, int64_t H, int64_t W, int64_t D, int mean, int in_dtype, int out_dtype, cudaStream_t st,
+                        unsigned long long* prof);
 int launch_inner_regress_rows(const rsm_feat& left, const rsm_feat& right, int64_t N, int64_t C, int64_t H, int64_t W,
                               int64_t D, int mean, int in_dtype, const rsm_regress_out& out, cudaStream_t st,
                               unsigned long long* prof);
@@ -816,9 +819,9 @@ extern "C" int rsm_inner_fwd(rsm_feat left, rsm_feat right, void* out, int64_t N
   });
 }
 
-extern "C" int rsm_inner_bwd(const void* gout, rsm_feat left, rsm_feat right, void* gleft, void* gright,
-                             int64_t N, int64_t C, int64_t H, int64_t W, int64_t D, int reduce,
-                             int in_dtype, int out_dtype, int device, void* stream) {
+static int inner_bwd(const void* gout, rsm_feat left, rsm_feat right, void* gleft, void* gright, int64_t N, int64_t C,
+                     int64_t H, int64_t W, int64_t D, int reduce, int in_dtype, int out_dtype, int device, void* stream,
+                     unsigned long long* prof) {
   CorrGeom g;
   if (int rc = make_geom(N, C, H, W, D, 1, reduce == RSM_REDUCE_MEAN, false, g)) return rc;
   if (N * C * H * W == 0) return RSM_OK;
@@ -826,9 +829,30 @@ extern "C" int rsm_inner_bwd(const void* gout, rsm_feat left, rsm_feat right, vo
   if (!gleft && !gright) return RSM_OK;
   RSM_COMMON_CHECKS(in_dtype)
   if (!valid_dtype(out_dtype)) return RSM_ERR_UNSUPPORTED_DTYPE;
+  {   // 16-bit tensors, D <= 64: band matrices + tcgen05 (rsm_corr_bwd_tc.cu)
+    const int rc = launch_inner_bwd_tc(gout, left, right, gleft, gright, N, C, H, W, D, reduce == RSM_REDUCE_MEAN, in_dtype,
+                                       out_dtype, st, prof);
+    if (rc != RSM_ERR_UNSUPPORTED_CONFIG) return rc;
+  }
   return RSM_DISPATCH_IO(in_dtype, out_dtype, Tin, Tout, [&]() -> int {
     return launch_bwd<Tin, Tout, LAYOUT_NDHW>(gout, left, right, gleft, gright, N, g, st, "rsm_inner_bwd");
   });
+}
+
+extern "C" int rsm_inner_bwd(const void* gout, rsm_feat left, rsm_feat right, void* gleft, void* gright,
+                             int64_t N, int64_t C, int64_t H, int64_t W, int64_t D, int reduce,
+                             int in_dtype, int out_dtype, int device, void* stream) {
+  return inner_bwd(gout, left, right, gleft, gright, N, C, H, W, D, reduce, in_dtype, out_dtype, device, stream, nullptr);
+}
+
+// diagnostic twin: `prof` = 16 zero-initialised uint64 on the device; the tcgen05 adjoint kernel adds clock64 cycles
+// per warp role (other paths leave it untouched)
+extern "C" int rsm_inner_bwd_profile(const void* gout, rsm_feat left, rsm_feat right, void* gleft, void* gright,
+                                     int64_t N, int64_t C, int64_t H, int64_t W, int64_t D, int reduce,
+                                     int in_dtype, int out_dtype, int device, void* stream, uint64_t* prof) {
+  if (!prof) return RSM_ERR_NULL_POINTER;
+  return inner_bwd(gout, left, right, gleft, gright, N, C, H, W, D, reduce, in_dtype, out_dtype, device, stream,
+                   reinterpret_cast<unsigned long long*>(prof));
 }
 
 extern "C" int rsm_groupwise_fwd(rsm_feat left, rsm_feat right, void* out, int64_t N, int64_t C, int64_t H,

@@ -21,6 +21,8 @@ namespace rsm {
 
 int launch_inner_tc(const rsm_feat& left, const rsm_feat& right, void* out, int64_t N, int64_t C, int64_t H, int64_t W,
                     int64_t D, int mean, int in_dtype, int out_dtype, cudaStream_t st);
+int launch_groupwise_tma(const rsm_feat& left, const rsm_feat& right, void* out, int64_t N, int64_t C, int64_t H, int64_t W,
+                         int64_t D, int64_t G, int in_dtype, int out_dtype, cudaStream_t st);
 int launch_inner_bwd_tc(const void* gout, const rsm_feat& left, const rsm_feat& right, void* gl, void* gr, int64_t N,
                         int64_t C, int64_t H, int64_t W, int64_t D, int mean, int in_dtype, int out_dtype, cudaStream_t st,
                         unsigned long long* prof);
@@ -865,6 +867,10 @@ extern "C" int rsm_groupwise_fwd(rsm_feat left, rsm_feat right, void* out, int64
   RSM_COMMON_CHECKS(in_dtype)
   if (!valid_dtype(out_dtype)) return RSM_ERR_UNSUPPORTED_DTYPE;
   if (!aligned_to(out, dtype_size(out_dtype))) return RSM_ERR_MISALIGNED;
+  {   // groups of <= 32 channels, rows TMA can address: the persistent TMA-fed kernel (rsm_groupwise_tma.cu)
+    const int rc = launch_groupwise_tma(left, right, out, N, C, H, W, D, G, in_dtype, out_dtype, st);
+    if (rc != RSM_ERR_UNSUPPORTED_CONFIG) return rc;
+  }
   return RSM_DISPATCH_IO(in_dtype, out_dtype, Tin, Tout, [&]() -> int {
     return launch_fwd<Tin, Tout, LAYOUT_NGHWD>(left, right, out, N, g, st, "rsm_groupwise_fwd");
   });

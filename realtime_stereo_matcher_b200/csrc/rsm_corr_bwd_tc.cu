@@ -14,10 +14,11 @@
 // Operands: the gradient tile gV[0..D) x [x0, x0 + 192) arrives as ONE TMA box (plain rows); feature windows are
 // 64-pixel x C-block TMA boxes with SWIZZLE_128B -- as K-major UMMA operands a box row is one channel with 64 K
 // elements -- streamed through rings exactly as in rsm_corr_rows.cu (consecutive tiles of a row share one atom).
-// Warps: 0-7 band builders (row = thread % 128, half of the disparities each), 8-11 epilogue (TMEM lane quadrant each:
-// tcgen05.ld -> scale -> round -> staging tile -> one TMA store per gradient and tile), 12 UMMA issuer (converged warp, one elected
-// lane), 13 TMA producer (one lane).  A_L and A_R are single buffers with their own ready / free barriers, so building
-// one overlaps the MMAs on the other; two TMEM accumulator pairs decouple the MMAs from the epilogue.
+// Warps: 0-7 band builders (a row per thread, half of the disparities each), 8-15 epilogue (TMEM lane quadrant = warp % 4,
+// two parts sharing a tile's (gradient, 16-channel round) jobs: tcgen05.ld -> scale -> round -> staging tile -> TMA store),
+// 16 UMMA issuer (converged warp, one elected lane), 17 TMA producer (one lane).  A_L and A_R are single buffers with their
+// own ready / free barriers, so building one overlaps the MMAs on the other; two TMEM accumulator pairs decouple the MMAs
+// from the epilogue.
 #include <cuda.h>
 
 #include "rsm_common.cuh"
@@ -30,13 +31,14 @@ constexpr int BT_ATOM = 64;                // pixels per feature atom / K elemen
 constexpr int BT_DP = 64;                  // disparity reach of a window (D <= 64)
 constexpr int BT_KATOMS = (BT_TM + BT_DP) / BT_ATOM;   // 3: K = 192 window pixels
 constexpr int BT_GW = BT_TM + BT_DP;       // gradient tile width (pixels)
-constexpr int BT_RING = 5;                 // slots per feature ring: window 3 + 2 ahead (g.ring = 4 when shared memory is short)
-constexpr int BT_BUILD_WARPS = 8, BT_EPI_WARPS = 4;
+constexpr int BT_RING = 5;                 // slots per feature ring: window 3 + 2 ahead (4 where shared memory is short)
+constexpr int BT_BUILD_WARPS = 8, BT_EPI_WARPS = 8;
 constexpr int BT_THREADS = 32 * (BT_BUILD_WARPS + BT_EPI_WARPS + 2);
 constexpr int BT_A_BYTES = BT_KATOMS * BT_TM * 128;    // one band matrix: 3 atoms of 128 rows x 128 bytes = 48 KB
 constexpr int BT_BAR_BYTES = 512;         // mbarriers, the TMEM address slot and the builders' trash slot
-constexpr int BT_SC = 32;                  // channels per output store
-constexpr int BT_STAGE_BYTES = BT_SC * BT_TM * 2;      // output staging: 32 channel rows of 128 pixels
+constexpr int BT_SC = 16;                  // channels per output store
+constexpr int BT_STILE = BT_SC * BT_TM * 2;             // one staging tile: 16 channel rows x 128 pixels
+constexpr int BT_STAGE_BYTES = 4 * BT_STILE;           // two per epilogue part: the store of a round reads one while the next is written
 
 struct BtGeom {
   int C, CB, cblocks;     // channels, channels per pass (<= 64, multiple of 16), passes
@@ -47,7 +49,7 @@ struct BtGeom {
   int atom_bytes;         // CB * 128
   int g_bytes;            // gradient tile buffer: D * 192 * 2 rounded up to 1 KB
   int tmem_cols;          // allocation: power of two >= 4 * CB
-  int ring;               // feature ring slots in use (5, or 4)
+  int ring_r, ring_l;     // slots in use of the right- / left-feature ring (5, or 4)
   int64_t rows, tiles;    // N * H; cblocks * rows * xtiles
 };
 
@@ -69,6 +71,14 @@ __device__ __forceinline__ uint32_t band_off(uint32_t rowbase, uint32_t rx16, in
   return rowbase + (uint32_t)(k >> 6) * (BT_TM * 128) + ((((uint32_t)k << 1) & 126u) ^ rx16);
 }
 
+struct BtRing {   // slot / fill parity of a ring position
+  uint32_t s, p, n;
+  __device__ __forceinline__ void step(uint32_t k = 1) {
+    s += k;
+    if (s >= n) { s -= n; p ^= 1; }
+  }
+};
+
 template <typename T, int ND>
 __global__ void __launch_bounds__(BT_THREADS, 1)
 inner_bwd_tc_kernel(BtGeom g, int N, const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmL,
@@ -81,8 +91,8 @@ inner_bwd_tc_kernel(BtGeom g, int N, const __grid_constant__ CUtensorMap tmG, co
   unsigned char* sAR = sAL + BT_A_BYTES;                       // ... of the right gradient
   unsigned char* sG = sAR + BT_A_BYTES;                        // 2 gradient tiles, rows of 192 pixels
   unsigned char* sRr = sG + 2 * (size_t)g.g_bytes;             // ring of right-feature atoms (operand of the left gradient)
-  unsigned char* sLr = sRr + g.ring * (size_t)ab;              // ring of left-feature atoms
-  unsigned char* sOut = sLr + g.ring * (size_t)ab;             // output staging [channel][128 pixels]
+  unsigned char* sLr = sRr + g.ring_r * (size_t)ab;            // ring of left-feature atoms
+  unsigned char* sOut = sLr + g.ring_l * (size_t)ab;           // output staging tiles [channel][128 pixels]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + BT_STAGE_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 40);
   const uint32_t g_full = smem_u32(bars), g_empty = g_full + 16, al_ready = g_full + 32, al_free = g_full + 40,
@@ -130,7 +140,7 @@ inner_bwd_tc_kernel(BtGeom g, int N, const __grid_constant__ CUtensorMap tmG, co
     first.n = (int)(t % (uint32_t)N);
     first.cb = (int)(t / (uint32_t)N);
   }
-  const uint32_t CB = (uint32_t)g.CB, RING = (uint32_t)g.ring;
+  const uint32_t CB = (uint32_t)g.CB;
 
   if (warp == BT_BUILD_WARPS + BT_EPI_WARPS) {
     // ================================================================ UMMA issuer (converged warp, one elected lane)
@@ -145,21 +155,21 @@ inner_bwd_tc_kernel(BtGeom g, int N, const __grid_constant__ CUtensorMap tmG, co
       const uint32_t al_lo = ((smem_u32(sAL) >> 4) & 0x3FFFu) | LBO1, ar_lo = ((smem_u32(sAR) >> 4) & 0x3FFFu) | LBO1;
       const uint32_t rr_lo = ((smem_u32(sRr) >> 4) & 0x3FFFu) | LBO1, lr_lo = ((smem_u32(sLr) >> 4) & 0x3FFFu) | LBO1;
       const uint32_t ab16 = ab >> 4;
-      uint32_t s0 = 0, p0 = 0, fresh = BT_KATOMS;            // ring slot / fill parity of the windows' first atom
+      BtRing r0{0, 0, (uint32_t)g.ring_r}, l0{0, 0, (uint32_t)g.ring_l};   // the windows' first atoms
+      uint32_t fresh = BT_KATOMS;
       int xt = first.xt;
       long long c_t = 0, c_a = 0, c_ring = 0;
       const long long c_beg = prof ? clock64() : 0;
-      auto side = [&](uint32_t a_lo, uint32_t ring_lo, uint32_t ring_full, uint32_t td) {
-        uint32_t s = s0, p = p0;
+      auto side = [&](uint32_t a_lo, uint32_t ring_lo, uint32_t ring_full, BtRing w, uint32_t td) {
         for (uint32_t kb = 0; kb < BT_KATOMS; ++kb) {
           if (kb + fresh >= BT_KATOMS) {                                   // one of the window's new atoms
             const long long c0 = prof ? clock64() : 0;
-            mbar_wait(ring_full + 8 * s, p);
+            mbar_wait(ring_full + 8 * w.s, w.p);
             if (prof) c_ring += clock64() - c0;
           }
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (leader) {
-            const uint32_t a = a_lo + kb * ((BT_TM * 128) >> 4), b = ring_lo + s * ab16;
+            const uint32_t a = a_lo + kb * ((BT_TM * 128) >> 4), b = ring_lo + w.s * ab16;
 #pragma unroll
             for (uint32_t ks = 0; ks < 4; ++ks)
               asm volatile(
@@ -170,7 +180,7 @@ inner_bwd_tc_kernel(BtGeom g, int N, const __grid_constant__ CUtensorMap tmG, co
                   : "memory");
           }
           __syncwarp();
-          if (++s == RING) { s = 0; p ^= 1; }
+          w.step();
         }
       };
       for (uint32_t tl = 0; tl < ntl; ++tl) {
@@ -181,29 +191,28 @@ inner_bwd_tc_kernel(BtGeom g, int N, const __grid_constant__ CUtensorMap tmG, co
         if (g.do_l) {
           mbar_wait(al_ready, tl & 1);
           if (prof) c_a += clock64() - c0;
-          side(al_lo, rr_lo, rr_full, td);
+          side(al_lo, rr_lo, rr_full, r0, td);
           if (leader) umma_commit(al_free);
         }
         if (g.do_r) {
           c0 = prof ? clock64() : 0;
           mbar_wait(ar_ready, tl & 1);
           if (prof) c_a += clock64() - c0;
-          side(ar_lo, lr_lo, lr_full, td + CB);
+          side(ar_lo, lr_lo, lr_full, l0, td + CB);
           if (leader) umma_commit(ar_free);
         }
         const bool cont = tl + 1 < ntl && xt + 1 < g.xtiles;
         const uint32_t nrel = cont ? 2u : (uint32_t)BT_KATOMS;
         if (leader) {
           umma_commit(t_full + 8 * buf);
-          uint32_t rs = s0;
-          for (uint32_t i = 0; i < nrel; ++i) {
-            if (g.do_l) umma_commit(rr_empty + 8 * rs);
-            if (g.do_r) umma_commit(lr_empty + 8 * rs);
-            if (++rs == RING) rs = 0;
+          BtRing rr = r0, ll = l0;
+          for (uint32_t i = 0; i < nrel; ++i, rr.step(), ll.step()) {
+            if (g.do_l) umma_commit(rr_empty + 8 * rr.s);
+            if (g.do_r) umma_commit(lr_empty + 8 * ll.s);
           }
         }
         __syncwarp();
-        s0 += nrel; if (s0 >= RING) { s0 -= RING; p0 ^= 1; }
+        r0.step(nrel); l0.step(nrel);
         fresh = nrel;
         if (++xt == g.xtiles) xt = 0;
       }
@@ -217,27 +226,34 @@ inner_bwd_tc_kernel(BtGeom g, int N, const __grid_constant__ CUtensorMap tmG, co
   } else if (warp == BT_BUILD_WARPS + BT_EPI_WARPS + 1) {
     // ================================================================ TMA producer (one lane)
     if (lane == 0 && ntl > 0) {
-      uint32_t s = 0, p = 0;
-      BtTile tc = first;
-      for (uint32_t tl = 0; tl < ntl; ++tl, tc.advance(g, N)) {
-        const bool fst = tl == 0 || tc.xt == 0;
-        const int x0 = tc.xt * BT_TM, c0 = tc.cb * (int)CB;
+      BtRing rr{0, 0, (uint32_t)g.ring_r}, ll{0, 0, (uint32_t)g.ring_l};
+      // the gradient tile runs one tile ahead of the feature atoms: its buffer frees up as soon as the builders are
+      // done with the tile before last, while atoms wait for ring slots the MMAs of the previous tile still hold -- issued
+      // in tile order, those waits kept the next gradient tile from being requested (builders 35 % idle waiting for it)
+      auto load_g = [&](uint32_t tl, const BtTile& t) {
         const uint32_t gb = tl & 1;
         mbar_wait(g_empty + 8 * gb, ((tl >> 1) & 1) ^ 1);
         mbar_expect_tx(g_full + 8 * gb, (uint32_t)(g.D * BT_GW * 2));
-        tma_load_4d(smem_u32(sG) + gb * (uint32_t)g.g_bytes, &tmG, g_full + 8 * gb, x0, tc.y, 0, tc.n);
+        tma_load_4d(smem_u32(sG) + gb * (uint32_t)g.g_bytes, &tmG, g_full + 8 * gb, t.xt * BT_TM, t.y, 0, t.n);
+      };
+      BtTile tc = first, tg = first;
+      load_g(0, tg);
+      for (uint32_t tl = 0; tl < ntl; ++tl, tc.advance(g, N)) {
+        const bool fst = tl == 0 || tc.xt == 0;
+        const int x0 = tc.xt * BT_TM, c0 = tc.cb * (int)CB;
+        if (tl + 1 < ntl) { tg.advance(g, N); load_g(tl + 1, tg); }
         for (uint32_t a = fst ? 0u : 1u; a < BT_KATOMS; ++a) {
           if (g.do_l) {
-            mbar_wait(rr_empty + 8 * s, p ^ 1);
-            mbar_expect_tx(rr_full + 8 * s, ab);
-            tma_load_4d(smem_u32(sRr) + s * ab, &tmR, rr_full + 8 * s, x0 - BT_DP + BT_ATOM * (int)a, tc.y, c0, tc.n);
+            mbar_wait(rr_empty + 8 * rr.s, rr.p ^ 1);
+            mbar_expect_tx(rr_full + 8 * rr.s, ab);
+            tma_load_4d(smem_u32(sRr) + rr.s * ab, &tmR, rr_full + 8 * rr.s, x0 - BT_DP + BT_ATOM * (int)a, tc.y, c0, tc.n);
           }
           if (g.do_r) {
-            mbar_wait(lr_empty + 8 * s, p ^ 1);
-            mbar_expect_tx(lr_full + 8 * s, ab);
-            tma_load_4d(smem_u32(sLr) + s * ab, &tmL, lr_full + 8 * s, x0 + BT_ATOM * (int)a, tc.y, c0, tc.n);
+            mbar_wait(lr_empty + 8 * ll.s, ll.p ^ 1);
+            mbar_expect_tx(lr_full + 8 * ll.s, ab);
+            tma_load_4d(smem_u32(sLr) + ll.s * ab, &tmL, lr_full + 8 * ll.s, x0 + BT_ATOM * (int)a, tc.y, c0, tc.n);
           }
-          if (++s == RING) { s = 0; p ^= 1; }
+          rr.step(); ll.step();
         }
       }
     }
@@ -250,7 +266,10 @@ inner_bwd_tc_kernel(BtGeom g, int N, const __grid_constant__ CUtensorMap tmG, co
     // registers, disparities past the end point at a trash slot -- per element the loop is one LDS with an immediate
     // offset and one STS (the first version recomputed the swizzled address and three predicates per element: ~15
     // instructions, 3500 cycles per tile, the bound of the kernel at 16 channels).
-    const int r = threadIdx.x & 127, dh = threadIdx.x >> 7;
+    // row of this thread: a warp takes every other 8-row group of its 64-row half (rows 8(2i + w%2) + l%8), which spreads
+    // the scatter stores over the banks better than 32 consecutive rows (1.5 instead of 2 wavefronts per store)
+    const int wq = (threadIdx.x >> 5) & 3, dh = threadIdx.x >> 7;
+    const int r = 64 * (wq >> 1) + 16 * (lane >> 3) + 8 * (wq & 1) + (lane & 7);
     const int d_beg = dh ? (g.D + 1) / 2 : 0, d_end = dh ? g.D : (g.D + 1) / 2;
     const uint32_t rowbase = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u, rx16 = (uint32_t)(r & 7) << 4;
     const uint32_t trash = (uint32_t)(reinterpret_cast<unsigned char*>(bars) + 448 - smem);
@@ -322,13 +341,17 @@ inner_bwd_tc_kernel(BtGeom g, int N, const __grid_constant__ CUtensorMap tmG, co
     // (a warp writes 64 contiguous bytes per channel) -> ONE TMA store per gradient and tile: whole 256-byte row
     // segments per channel, pixels past W clipped by the TMA unit.  (Storing straight from registers -- 2 bytes per lane,
     // 64-bit address arithmetic per channel -- kept the four epilogue warps 97 % busy and bounded the kernel at C = 64.)
-    const int q = warp - BT_BUILD_WARPS;                        // warps 8-11: warp % 4 = TMEM lane quadrant
+    // Eight warps: TMEM lane quadrant q = warp % 4, part = which half of the (gradient, 16-channel round) jobs of a tile;
+    // each part has its own staging tile, named barrier and storing lane.  (Four warps doing all of it were 95 % busy
+    // and set the tile period at C = 64.)
+    const int ew = warp - BT_BUILD_WARPS;
+    const int q = ew & 3, part = ew >> 2;
     const int r = 32 * q + lane;
-    const bool rec = prof && q == 0 && lane == 0;
+    const bool rec = prof && ew == 0 && lane == 0;
     const bool storer = q == 0 && lane == 0;
     long long c_w = 0;
     const long long c_beg = rec ? clock64() : 0;
-    T* stage = reinterpret_cast<T*>(sOut) + r;
+    uint32_t nround = 0;                                        // staging rounds of this part so far
     BtTile tc = first;
     for (uint32_t tl = 0; tl < ntl; ++tl, tc.advance(g, N)) {
       const uint32_t buf = tl & 1;
@@ -337,25 +360,27 @@ inner_bwd_tc_kernel(BtGeom g, int N, const __grid_constant__ CUtensorMap tmG, co
       if (rec) c_w += clock64() - c0;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + buf * 2 * CB;
+      int job = 0;
 #pragma unroll 1
       for (int sd = 0; sd < 2; ++sd) {
         if (!(sd == 0 ? g.do_l : g.do_r)) continue;
 #pragma unroll 1
-        for (uint32_t cs = 0; cs < CB; cs += BT_SC) {             // <= 32 channels per staging round
-          if (storer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous store has read the staging tile
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          for (uint32_t c = 0; c < BT_SC && cs + c < CB; c += 16) {
-            uint32_t v[16];
-            tmem_ld16(taddr + sd * CB + cs + c, v);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (uint32_t cs = 0; cs < CB; cs += BT_SC, ++job) {       // 16 channels per staging round
+          if ((job & 1) != part) continue;
+          unsigned char* stile = sOut + (2 * part + (nround++ & 1)) * BT_STILE;
+          T* stage = reinterpret_cast<T*>(stile) + r;
+          if (storer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store before the previous one has read this tile
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + part) : "memory");
+          uint32_t v[16];
+          tmem_ld16(taddr + sd * CB + cs, v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int i = 0; i < 16; ++i) stage[(c + i) * BT_TM] = from_f<T>(__uint_as_float(v[i]) * g.scale);
-          }
+          for (int i = 0; i < 16; ++i) stage[i * BT_TM] = from_f<T>(__uint_as_float(v[i]) * g.scale);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> async proxy (TMA)
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + part) : "memory");
           if (storer) {
             asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                         ::"l"(sd == 0 ? &tmGL : &tmGR), "r"(smem_u32(sOut)), "r"(tc.xt * BT_TM), "r"(tc.y),
+                         ::"l"(sd == 0 ? &tmGL : &tmGR), "r"(smem_u32(stile)), "r"(tc.xt * BT_TM), "r"(tc.y),
                            "r"(tc.cb * (int)CB + (int)cs), "r"(tc.n)
                          : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -437,8 +462,10 @@ int launch_inner_bwd_tc(const void* gout, const rsm_feat& left, const rsm_feat& 
   g.tiles = (int64_t)g.cblocks * g.rows * g.xtiles;
   if (g.tiles > 2147483647LL) return RSM_ERR_UNSUPPORTED_CONFIG;
   const size_t fixed = 2 * (size_t)BT_A_BYTES + 2 * (size_t)g.g_bytes + BT_STAGE_BYTES + BT_BAR_BYTES + 1024;
-  g.ring = fixed + 2 * BT_RING * (size_t)g.atom_bytes <= 227 * 1024 ? BT_RING : BT_RING - 1;
-  const size_t smem = fixed + 2 * g.ring * (size_t)g.atom_bytes;
+  g.ring_r = g.ring_l = BT_RING;
+  if (fixed + (size_t)(g.ring_r + g.ring_l) * g.atom_bytes > 227 * 1024) g.ring_l = BT_RING - 1;
+  if (fixed + (size_t)(g.ring_r + g.ring_l) * g.atom_bytes > 227 * 1024) g.ring_r = BT_RING - 1;
+  const size_t smem = fixed + (size_t)(g.ring_r + g.ring_l) * g.atom_bytes;
   if (smem > 227 * 1024) return RSM_ERR_UNSUPPORTED_CONFIG;
   alignas(64) CUtensorMap tmG, tmL, tmR, tmGL, tmGR;
   memset(&tmG, 0, sizeof(tmG)); memset(&tmL, 0, sizeof(tmL)); memset(&tmR, 0, sizeof(tmR));
@@ -455,7 +482,7 @@ int launch_inner_bwd_tc(const void* gout, const rsm_feat& left, const rsm_feat& 
   };
   if (!feat_map(&tmL, left) || !feat_map(&tmR, right)) return RSM_ERR_UNSUPPORTED_CONFIG;
   const unsigned grid = (unsigned)(g.tiles < kNumSMs ? g.tiles : kNumSMs);
-  // outputs: dense (N, C, H, W); box = 128 pixels x <= 32 channels, plain rows (the staging tile)
+  // outputs: dense (N, C, H, W); box = 128 pixels x 16 channels, plain rows (the staging tile)
   auto out_map = [&](CUtensorMap* m, void* p) {
     if (!p) return true;
     const int64_t dims[4] = {W, H, C, N}, strides[3] = {W * 2, H * W * 2, C * H * W * 2};

@@ -43,7 +43,7 @@ constexpr int RR_ATOM = 64;         // pixels per operand atom
 constexpr int RR_GATOMS = 4;        // atoms per accumulator group (256 TMEM columns = one half)
 constexpr int RR_MAXA = 4;          // left-tile ring slots (upper bound)
 constexpr int RR_MAXB = 16;         // right-atom ring slots (upper bound)
-constexpr int RR_NSPLIT = 2;        // epilogue warps per TMEM lane quadrant (4 measured the same or slower: the scan is
+constexpr int RR_NSPLIT = 2;        // epilogue warps per TMEM lane quadrant (3 and 4 measured the same or slower: the scan is
                                     // bound by the MUFU pipe and TMEM reads, which the warps of a quadrant share)
 constexpr int RR_EPI_WARPS = 4 * RR_NSPLIT;
 constexpr int RR_THREADS = 32 * (RR_EPI_WARPS + 2);
@@ -383,7 +383,7 @@ inner_regress_rows_kernel(RrOut out, RrGeom g, const __grid_constant__ CUtensorM
         // this group's 8-column chunks inside the quadrant's range, every fourth one from this warp's turn on
         const int g8lo = max(c8lo, 8 * gat), g8hi = min(c8hi, 8 * (gat + gsz));
         const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + half * 256 - 64 * gat;   // + window column
-        int c8 = g8lo + ((hh - turn) & (RR_NSPLIT - 1));
+        int c8 = g8lo + (hh - turn + RR_NSPLIT) % RR_NSPLIT;
         // two chunks per TMEM round trip, scanned into two independent states (st, st2): the two dependency chains
         // interleave, which is what a warp needs here -- a lone chunk is a ~250-cycle load + a ~250-cycle serial scan.
         // (Keeping the next pair's loads in flight during the scan measured 4-20 % SLOWER: the scan is bound by the
@@ -412,7 +412,7 @@ inner_regress_rows_kernel(RrOut out, RrGeom g, const __grid_constant__ CUtensorM
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           rr_any<EXT, DIV>(st, v, c0w, dbw - c0w, D, jfill, llo, lhi, k2, cnt_f);
         }
-        if (g8hi > g8lo) turn = (turn + (g8hi - g8lo)) & (RR_NSPLIT - 1);
+        if (g8hi > g8lo) turn = (turn + (g8hi - g8lo)) % RR_NSPLIT;
         if (rec) { const long long c1 = clock64(); c_scan += c1 - c0; c0 = c1; }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
@@ -425,7 +425,7 @@ inner_regress_rows_kernel(RrOut out, RrGeom g, const __grid_constant__ CUtensorM
       // its state; the merging warp rotates with the tile so that no warp is the straggler every time)
       rr_merge<EXT>(st, st2.m, st2.s, st2.ws, st2.minv, st2.maxv, st2.mini, st2.maxi, st2.nani, k2);
       float* pbase = parts + (size_t)(tl & 1) * (RR_NSPLIT * 128 * 8);
-      const int merger = (int)(tl & (RR_NSPLIT - 1));
+      const int merger = (int)(tl % RR_NSPLIT);
       if (hh != merger) {
         float* p = pbase + ((size_t)hh * 128 + r) * 8;
         if (EXT) {
@@ -439,7 +439,7 @@ inner_regress_rows_kernel(RrOut out, RrGeom g, const __grid_constant__ CUtensorM
       if (hh == merger && x < g.W) {
 #pragma unroll
         for (int k = 1; k < RR_NSPLIT; ++k) {
-          const float* p = pbase + ((size_t)((merger + k) & (RR_NSPLIT - 1)) * 128 + r) * 8;
+          const float* p = pbase + ((size_t)((merger + k) % RR_NSPLIT) * 128 + r) * 8;
           const float4 p0 = *reinterpret_cast<const float4*>(p);
           float4 p1 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (EXT) p1 = *reinterpret_cast<const float4*>(p + 4);

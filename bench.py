@@ -337,6 +337,7 @@ def tensor_core_kernels(rsm, dev, peak):
         "ms": ms, "algorithmic_GBps": b4 / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": b4 / (ms * 1e-3) / 1e9 / peak,
         "useful_TFLOPs": 2.0 * n4 * c4 * h4 * w4 * d4 / (ms * 1e-3) / 1e12}
     del sets, s4
+    out.update(cfg5_regression_numbers(rsm, dev, peak, flush))
     out.update(v4_model_numbers(rsm, dev, flush))
     return out
 
@@ -376,6 +377,39 @@ def v4_model_numbers(rsm, dev, flush):
         out[f"full_model_v4_384x1248_b8[{r['precision']}]"] = {
             "unpatched_ms": r["unpatched_ms"], "patched_ms": r["patched_ms"], "unpatched_pairs_per_s": r["unpatched_pairs_per_s"],
             "patched_pairs_per_s": r["patched_pairs_per_s"], "max_abs_diff_px": r["max_abs_diff"], "disparity_scale_px": r["disparity_scale"]}
+    # BASELINE configs 1 and 2 as MODEL inferences: MobileStereoNet v1 on one 384x1248 pair, MobileDispNetC
+    # on 32 pairs at 540x960 -- the unmodified reference unpatched vs patched, fp32
+    for tag, cfg_name, shape in (("cfg1_model_v1_384x1248_b1", "stereo_net_config.json", (1, 3, 384, 1248)),
+                                 ("cfg2_model_dispnetc_540x960_b32", "disp_net_c_config.json", (32, 3, 540, 960))):
+        r = mb.measure(ref, rsm, cfg_name, shape, False, reps=3, warmup=2)
+        out[f"{tag}[{r['precision']}]"] = {
+            "unpatched_ms": r["unpatched_ms"], "patched_ms": r["patched_ms"], "unpatched_pairs_per_s": r["unpatched_pairs_per_s"],
+            "patched_pairs_per_s": r["patched_pairs_per_s"], "max_abs_diff_px": r["max_abs_diff"], "disparity_scale_px": r["disparity_scale"]}
+    return out
+
+
+def cfg5_regression_numbers(rsm, dev, peak, flush):
+    """BASELINE config 5's kernels on one 1080p pair, (1, 192, 1080, 1920) fp32: regression forward (soft + argmin in one
+    pass) and backward, against the HBM roofline."""
+    n, d, h, w = 1, 192, 1080, 1920
+    g = torch.Generator(device=dev).manual_seed(7)
+    cost = (torch.randn((n, d, h, w), device=dev, generator=g) * 4).requires_grad_(True)
+    out = {}
+    fwd = lambda: rsm.regress(cost.detach(), argmin=True, argmax=False)
+    for _ in range(3):
+        fwd()
+    ms = time_op(fwd, 10, flush)
+    b = n * d * h * w * 4 + n * h * w * 12
+    out["regress_fwd_soft+argmin[f32,cfg5 1080p D=192]"] = {"ms": ms, "algorithmic_GBps": b / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": b / (ms * 1e-3) / 1e9 / peak}
+    with torch.enable_grad():
+        soft = rsm.soft_argmax(cost)
+    gsoft = torch.ones_like(soft)
+    bwd = lambda: torch.autograd.grad(soft, cost, gsoft, retain_graph=True)
+    for _ in range(3):
+        bwd()
+    ms = time_op(bwd, 10, flush)
+    b = 2 * n * d * h * w * 4 + 3 * n * h * w * 4
+    out["soft_argmax_bwd[f32,cfg5 1080p D=192]"] = {"ms": ms, "algorithmic_GBps": b / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": b / (ms * 1e-3) / 1e9 / peak}
     return out
 
 

@@ -20,10 +20,11 @@
 //     columns outside [0, D) for a lane are masked (one compare + select per value), which only happens in the two
 //     31-column edges of a quadrant's range.  j ascends = d descends, so ties take the LATER column (torch: first
 //     index wins).
-// Warp roles (320 threads, one persistent CTA per SM):
+// Warp roles (352 threads, one persistent CTA per SM):
 //   warps 0-7   epilogue: TMEM lane quadrant q = warp % 4 (also the warp's scheduler), the 8-column chunks of the
 //               quadrant's range dealt alternately to its two warps; partial states merged through shared memory
-//   warp 8      UMMA issuer (whole warp converged, one elected lane issues)      warp 9   TMA producer (one lane)
+//   warp 8      UMMA issuer (whole warp converged, one elected lane issues)
+//   warps 9, 10 TMA producers (one lane each): right-atom ring, left-tile ring
 // mbarriers: a_full/a_empty (left tile ring), b_full/b_empty (right atom ring), t_full/t_empty (TMEM halves).  All
 // waits are bounded and trap on expiry (rsm_tc.cuh).
 // Measured while building it (clock64 stamps per role and atom, first version: one hand-off per 64-column atom, 12
@@ -31,6 +32,11 @@
 // producer with divisions in its loop ~600 cycles per box, and one warp alone needs ~500 cycles per 8-column chunk
 // (TMEM round trip + a serial scan) -- so hand-offs are per group, ring positions are kept incrementally, and every
 // warp scans two chunks at a time into two independent states.
+// Where the time goes now (experiment builds, config 2 C = 64 / config 4 C = 128 D = 192 x 8 images, same box): loads +
+// hand-offs alone, no MMAs and no scan, 71 / 110 us = 4.0 / 4.8 TB/s -- what TMA boxes of 128-byte rows gathered from C
+// channel planes deliver from HBM, whatever the ring depths (2 .. 8 left tiles, 5 .. 16 right atoms: no change) and
+// whether one lane or two issue them; + MMAs 77 / 131 us; + scan 98 / 188 us.  Taking the exponentials or the TMEM
+// loads OUT of the scan changes nothing (<= 5 %): the scan's cost is its ~75 plain instructions per 16 values.
 #include <cuda.h>
 
 #include "rsm_common.cuh"
@@ -43,10 +49,9 @@ constexpr int RR_ATOM = 64;         // pixels per operand atom
 constexpr int RR_GATOMS = 4;        // atoms per accumulator group (256 TMEM columns = one half)
 constexpr int RR_MAXA = 4;          // left-tile ring slots (upper bound)
 constexpr int RR_MAXB = 16;         // right-atom ring slots (upper bound)
-constexpr int RR_NSPLIT = 2;        // epilogue warps per TMEM lane quadrant (3 and 4 measured the same or slower: the scan is
-                                    // bound by the MUFU pipe and TMEM reads, which the warps of a quadrant share)
+constexpr int RR_NSPLIT = 2;        // epilogue warps per TMEM lane quadrant (3 and 4 measured the same or slower)
 constexpr int RR_EPI_WARPS = 4 * RR_NSPLIT;
-constexpr int RR_THREADS = 32 * (RR_EPI_WARPS + 2);
+constexpr int RR_THREADS = 32 * (RR_EPI_WARPS + 3);
 constexpr int RR_PART_BYTES = 2 * RR_NSPLIT * 128 * 8 * 4;   // parked partial states: 2 buffers x 2 parts x 128 lanes x 8 words
 constexpr int RR_BAR_BYTES = 512;   // 2*4 + 2*16 + 2*2 = 44 mbarriers + the TMEM address slot
 constexpr int RR_SMEM_MAX = 227 * 1024;
@@ -318,25 +323,19 @@ inner_regress_rows_kernel(RrOut out, RrGeom g, const __grid_constant__ CUtensorM
       }
     }
   } else if (warp == RR_EPI_WARPS + 1) {
-    // ================================================================ TMA producer (one lane)
+    // ================================================================ TMA producer of the right-atom ring (one lane)
+    // (Two producer lanes in two warps, one per ring: a single lane issuing both in tile order was busy half of the
+    // time at 64 channels -- ~350 cycles per box -- and a full ring stalled the requests for the other one.)
     if (lane == 0 && ntl > 0) {
       long long c_wait = 0;
       const long long c_beg = prof ? clock64() : 0;
-      uint32_t as = 0, apar = 0, bs = 0, bpar = 0;
+      uint32_t bs = 0, bpar = 0;
       RowTile tc = tr.first;
       for (uint32_t tl = 0; tl < ntl; ++tl, tc.advance(g)) {
         const bool first = tl == 0 || tc.xt == 0;
         const int x0 = tc.xt * RR_TM;
-        long long c0 = prof ? clock64() : 0;
-        mbar_wait(a_empty + 8 * as, apar ^ 1);
-        if (prof) c_wait += clock64() - c0;
-        const uint32_t dA = smem_u32(sA) + as * 2 * ab;
-        mbar_expect_tx(a_full + 8 * as, 2 * ab);
-        tma_load_4d(dA, &tmL, a_full + 8 * as, x0, tc.y, 0, tc.n);
-        tma_load_4d(dA + ab, &tmL, a_full + 8 * as, x0 + RR_ATOM, tc.y, 0, tc.n);
-        if (++as == nabuf) { as = 0; apar ^= 1; }
         for (uint32_t a = first ? 0u : na - 2u; a < na; ++a) {
-          c0 = prof ? clock64() : 0;
+          const long long c0 = prof ? clock64() : 0;
           mbar_wait(b_empty + 8 * bs, bpar ^ 1);
           if (prof) c_wait += clock64() - c0;
           mbar_expect_tx(b_full + 8 * bs, ab);
@@ -347,6 +346,21 @@ inner_regress_rows_kernel(RrOut out, RrGeom g, const __grid_constant__ CUtensorM
       if (prof) {
         atomicAdd(prof + 3, (unsigned long long)c_wait);
         atomicAdd(prof + 4, (unsigned long long)(clock64() - c_beg));
+      }
+    }
+  } else if (warp == RR_EPI_WARPS + 2) {
+    // ================================================================ TMA producer of the left-tile ring (one lane)
+    if (lane == 0 && ntl > 0) {
+      uint32_t as = 0, apar = 0;
+      RowTile tc = tr.first;
+      for (uint32_t tl = 0; tl < ntl; ++tl, tc.advance(g)) {
+        const int x0 = tc.xt * RR_TM;
+        mbar_wait(a_empty + 8 * as, apar ^ 1);
+        const uint32_t dA = smem_u32(sA) + as * 2 * ab;
+        mbar_expect_tx(a_full + 8 * as, 2 * ab);
+        tma_load_4d(dA, &tmL, a_full + 8 * as, x0, tc.y, 0, tc.n);
+        tma_load_4d(dA + ab, &tmL, a_full + 8 * as, x0 + RR_ATOM, tc.y, 0, tc.n);
+        if (++as == nabuf) { as = 0; apar ^= 1; }
       }
     }
   } else {
@@ -384,10 +398,9 @@ inner_regress_rows_kernel(RrOut out, RrGeom g, const __grid_constant__ CUtensorM
         const int g8lo = max(c8lo, 8 * gat), g8hi = min(c8hi, 8 * (gat + gsz));
         const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + half * 256 - 64 * gat;   // + window column
         int c8 = g8lo + (hh - turn + RR_NSPLIT) % RR_NSPLIT;
-        // two chunks per TMEM round trip, scanned into two independent states (st, st2): the two dependency chains
-        // interleave, which is what a warp needs here -- a lone chunk is a ~250-cycle load + a ~250-cycle serial scan.
-        // (Keeping the next pair's loads in flight during the scan measured 4-20 % SLOWER: the scan is bound by the
-        // MUFU pipe, 9 ex2 per chunk, and by TMEM read bandwidth together, not by the round-trip latency.)
+        // two chunks per TMEM round trip, scanned into two independent states (st, st2) so that the two dependency chains
+        // interleave -- a lone chunk is a ~250-cycle load + a ~250-cycle serial scan.  (Four chunks into four states, and
+        // keeping the next pair's loads in flight during the scan, measured the same or slower.)
         for (; c8 + RR_NSPLIT < g8hi; c8 += 2 * RR_NSPLIT) {
           const int ca = 8 * c8, cb = ca + 8 * RR_NSPLIT;
           uint32_t va[8], vb[8];

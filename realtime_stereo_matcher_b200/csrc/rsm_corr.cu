@@ -645,6 +645,7 @@ static int launch_fwd(const rsm_feat& left, const rsm_feat& right, void* out, in
 
 }  // namespace rsm
 #include "rsm_corr_bwd.cuh"
+#include "rsm_groupwise_bwd.cuh"
 namespace rsm {
 
 template <typename Tin, typename Tout, int LAYOUT>
@@ -654,36 +655,11 @@ static int launch_bwd(const void* gout, const rsm_feat& left, const rsm_feat& ri
   int cbs = 0;
   for (int c = BW_CB; c >= 4; c -= 4)
     if (g.cpg % c == 0) { cbs = c; break; }
-  // narrow groups of a D-innermost volume: one CTA per (n, group, y) row stages the gradient row once and
-  // produces both gradients from it (groupwise_bwd_row_kernel)
-  if (LAYOUT == LAYOUT_NGHWD && (g.cpg == 4 || g.cpg == 8) && g.D > 0 && gl && gr) {
-    GroupRowGeom rg;
-    rg.nq = (g.D + 3) / 4;
-    const int D4 = 4 * rg.nq;
-    // parts of <= 160 pixels (one register tile per thread), balanced over the row
-    rg.nparts = (g.W + 159) / 160;
-    rg.XP = ((g.W + rg.nparts - 1) / rg.nparts + 3) / 4 * 4;
-    rg.nparts = (g.W + rg.XP - 1) / rg.XP;
-    int P = rg.XP + D4 + 8;
-    if (P % 8 == 0) P += 4;
-    rg.P = P;
-    rg.DPAD = D4 + 4;
-    rg.FP = rg.DPAD + rg.XP + D4 + 8;
-    const int xqn = rg.XP / 4;
-    rg.dsplit = GR_THREADS / (2 * xqn);
-    if (rg.dsplit > rg.nq) rg.dsplit = rg.nq;
-    if (rg.dsplit < 1) rg.dsplit = 1;
-    const size_t tile = (size_t)D4 * rg.P, parts = (size_t)2 * g.cpg * rg.dsplit * rg.XP;
-    const size_t smem = ((tile > parts ? tile : parts) + 2 * (size_t)g.cpg * rg.FP) * sizeof(float);
-    const int64_t bx = N * g.G * (int64_t)g.H * rg.nparts;
-    if (smem <= 100 * 1024 && 2 * xqn * rg.dsplit <= GR_THREADS && grid_ok(bx)) {
-      auto launch = [&](auto kern) -> int {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<(unsigned)bx, GR_THREADS, smem, st>>>((const Tout*)gout, view_of(left), view_of(right), (Tin*)gl, (Tin*)gr, g, rg);
-        return finish_launch(where);
-      };
-      return g.cpg == 4 ? launch(groupwise_bwd_row_kernel<Tin, Tout, 4>) : launch(groupwise_bwd_row_kernel<Tin, Tout, 8>);
-    }
+  // D-innermost volume, 1..16 channels per group: one CTA per (n, group, y) row streams the gradient row once through
+  // 16-disparity slabs and produces both gradients from it (rsm_groupwise_bwd.cuh)
+  if constexpr (LAYOUT == LAYOUT_NGHWD) {
+    int rc = RSM_OK;
+    if (launch_groupwise_bwd_slab<Tin, Tout>(gout, left, right, gl, gr, N, g, st, where, rc)) return rc;
   }
   // inner product: 8(x) x 4(c) register tiles when every row and window starts on a 16-byte boundary (fp32: W % 4,
   // 16-bit: W % 8) and all three tensors share one dtype

@@ -434,231 +434,4 @@ inner_bwd_big_kernel(const T* __restrict__ gout, FeatView L, FeatView R, T* __re
   }
 }
 
-// ===================================================================== group-wise rows (D innermost)
-// Adjoint of the (N,G,H,W,D) group-wise volume for narrow groups (cpg = 4 or 8 channels): one CTA per
-// (n, group, y) row PART of XP pixels.  The gradient of the part plus a D-pixel halo -- a contiguous
-// (XP + D) x D matrix -- is staged ONCE, transposed to sG[d][x] (4-byte LDGSTS with zero-fill past the row
-// end, a warp taking 4 pixels x 8 disparities: 32-byte runs in memory, all 32 banks in shared memory because
-// the pitch is 4 (mod 8) words), together with the group's channels of both feature rows (zero margins stand
-// in for the x < d fill and the right edge), and BOTH gradients come out of that one tile:
-//     gL[c,x] = s sum_d gV[d][x] R[c][x-d],        gR[c,x'] = s sum_d gV[d][x'+d] L[c][x'+d].
-// Work item = (side, pixel quad, disparity part), one per thread: a 4(x) x CPG(c) register tile walking its
-// disparity quads with aligned LDS.128 only, exactly like corr_bwd_tiled_kernel; the disparity parts of an
-// output are then reduced through shared memory (overlaying the dead gradient tile) in a fixed order.
-// Atomic-free and deterministic.
-constexpr int GR_THREADS = 256;
-
-struct GroupRowGeom {
-  int XP;       // pixels per part (multiple of 4)
-  int nparts;   // parts per row
-  int P;        // pitch of sG rows (floats): >= XP + D4 + 8, = 4 (mod 8)
-  int FP;       // pitch of a feature row (floats): DPAD + XP + D4 + 8
-  int DPAD;     // zero margin in front of the right-feature window (D4 + 4)
-  int nq;       // disparity quads = ceil(D / 4)
-  int dsplit;   // disparity parts per (side, pixel quad); 2 * (XP/4) * dsplit <= GR_THREADS
-};
-
-template <typename Tin, typename Tout, int CPG>
-__global__ void __launch_bounds__(GR_THREADS)
-groupwise_bwd_row_kernel(const Tout* __restrict__ gout, FeatView L, FeatView R, Tin* __restrict__ gl,
-                         Tin* __restrict__ gr, CorrGeom g, GroupRowGeom rg) {
-  extern __shared__ __align__(16) float smem[];
-  const int D4 = rg.nq * 4;
-  float* sG = smem;                                   // [D4][P]: gV[d][x0 + j], zero for d >= D or x0 + j >= W
-  float* sL = sG + (size_t)D4 * rg.P;                 // [CPG][FP]: L[c][x0 + j] at FP*c + j
-  float* sR = sL + CPG * rg.FP;                       // [CPG][FP]: R[c][x0 - DPAD + j] at FP*c + j
-  int64_t bid = blockIdx.x;
-  const int xp = (int)(bid % rg.nparts); bid /= rg.nparts;
-  const int y = (int)(bid % g.H); bid /= g.H;
-  const int grp = (int)(bid % g.G);
-  const int64_t n = bid / g.G;
-  const int c0 = grp * CPG;
-  const int x0 = xp * rg.XP;
-  const int npx = min(rg.XP, g.W - x0);               // output pixels of this part
-  const Tout* __restrict__ grow = gout + ((((int64_t)n * g.G + grp) * g.H + y) * (int64_t)g.W + x0) * g.D;
-
-  // ---- stage the gradient tile transposed; warp -> (pixel quad xg, disparity octet dg), octet index
-  // r = xg * D8 + dg advances by the 8 warps of the CTA
-  {
-    const int D8 = (D4 + 7) >> 3;
-    const int lane = threadIdx.x & 31, xl = lane & 3, dl = lane >> 2;
-    const int nxg = (rg.XP + D4) >> 2;                // staged pixel quads (part + halo)
-    int r = threadIdx.x >> 5;
-    int xg = r / D8, dg = r - xg * D8;
-    const int stepd = (GR_THREADS / 32) % D8, stepx = (GR_THREADS / 32) / D8;
-    const int noct = nxg * D8;
-    const int wleft = g.W - x0;                       // columns j >= wleft are past the row end
-    if (sizeof(Tout) == 4 && g.D % 8 == 0) {
-      // whole octets along d: a warp walks the D8 octets of one pixel quad with constant strides; the only
-      // test (row end) is made once per quad
-      const uint32_t sstep = 32u * rg.P;
-      for (xg = threadIdx.x >> 5; xg < nxg; xg += GR_THREADS / 32) {
-        const int j = 4 * xg + xl;
-        const bool valid = j < wleft;
-        const Tout* gp = valid ? grow + (int64_t)j * g.D + dl : grow;
-        uint32_t sp = (uint32_t)__cvta_generic_to_shared(sG + dl * rg.P + j);
-        const int nbytes = valid ? 4 : 0, gstep = valid ? 8 : 0;
-#pragma unroll 2
-        for (int o = 0; o < D8; ++o) {
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sp), "l"(gp), "r"(nbytes) : "memory");
-          gp += gstep; sp += sstep;
-        }
-      }
-      r = noct;
-    }
-    if constexpr (sizeof(Tout) == 2) {
-      // 16-bit gradient, even D, word-aligned rows: a warp takes 4 pixels x 16 disparities as 32-bit pairs (32-byte
-      // runs), a quad at a time with four independent loads in flight per thread, widened on the way into sG
-      if (g.D % 2 == 0 && (reinterpret_cast<uintptr_t>(grow) & 3) == 0) {
-        const int D16 = (D4 + 15) >> 4, dp = lane >> 2;
-        const int nitem = nxg * D16;
-        const uint32_t* __restrict__ gw = reinterpret_cast<const uint32_t*>(grow);
-        const int DW = g.D >> 1;
-        for (int it0 = threadIdx.x >> 5; it0 < nitem; it0 += 4 * (GR_THREADS / 32)) {
-          uint32_t w[4];
-          int jj[4], dd[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int it = it0 + u * (GR_THREADS / 32);
-            const int xq = it / D16, d16 = it - xq * D16;
-            jj[u] = 4 * xq + xl; dd[u] = 16 * d16 + 2 * dp;
-            const bool valid = it < nitem && jj[u] < wleft && dd[u] < g.D;
-            w[u] = valid ? __ldg(gw + (int64_t)jj[u] * DW + (dd[u] >> 1)) : 0u;
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (it0 + u * (GR_THREADS / 32) < nitem && dd[u] < D4) {
-              const float2 f = unpack2<Tout>(w[u]);
-              sG[dd[u] * rg.P + jj[u]] = f.x;
-              sG[(dd[u] + 1) * rg.P + jj[u]] = f.y;
-            }
-          }
-        }
-        r = noct;
-      }
-    }
-    for (; r < noct; r += GR_THREADS / 32) {
-      const int j = 4 * xg + xl, d = 8 * dg + dl;
-      const bool valid = j < wleft && d < g.D;
-      if (d < D4) {
-        float* dst = sG + d * rg.P + j;
-        if constexpr (sizeof(Tout) == 4) {
-          const Tout* src = valid ? grow + (int64_t)j * g.D + d : grow;
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)),
-                       "l"(src), "r"(valid ? 4 : 0)
-                       : "memory");
-        } else {
-          *dst = valid ? to_f(__ldg(grow + (int64_t)j * g.D + d)) : 0.f;
-        }
-      }
-      dg += stepd; xg += stepx;
-      if (dg >= D8) { dg -= D8; ++xg; }
-    }
-  }
-  // ---- features of the group: fp32, zero margins (one row per channel and side, no divisions)
-  // (one warp per row: the per-row address set-up is paid once per warp, not once per thread and row)
-#pragma unroll 1
-  for (int sc = threadIdx.x >> 5; sc < 2 * CPG; sc += GR_THREADS / 32) {
-    const bool rside = sc >= CPG;
-    const int c = rside ? sc - CPG : sc;
-    const FeatView& F = rside ? R : L;
-    const Tin* __restrict__ frow =
-        reinterpret_cast<const Tin*>(F.data) + n * F.sn + (int64_t)(c0 + c) * F.sc + (int64_t)y * F.sh;
-    const int shift = x0 - (rside ? rg.DPAD : 0);
-    float* drow = sL + sc * rg.FP;
-    for (int j = threadIdx.x & 31; j < rg.FP; j += 32) {
-      const int x = j + shift;
-      const bool valid = x >= 0 && x < g.W;
-      if constexpr (sizeof(Tin) == 4) {
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(drow + j)),
-                     "l"(valid ? frow + (int64_t)x * F.sw : frow), "r"(valid ? 4 : 0)
-                     : "memory");
-      } else {
-        drow[j] = valid ? to_f(__ldg(frow + (int64_t)x * F.sw)) : 0.f;
-      }
-    }
-  }
-  asm volatile("cp.async.wait_all;" ::: "memory");
-  __syncthreads();
-
-  // ---- one register tile per thread
-  const int xqn = rg.XP >> 2;
-  const int item = threadIdx.x;
-  const bool active = item < 2 * xqn * rg.dsplit;
-  const int xq = item % xqn, rest = item / xqn;
-  const int dpart = rest % rg.dsplit, side = rest / rg.dsplit;
-  const int xb = 4 * xq;
-  float acc[CPG][4];
-#pragma unroll
-  for (int j = 0; j < CPG; ++j)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
-  if (active && xb < npx) {
-    const int q0 = dpart * rg.nq / rg.dsplit, q1 = (dpart + 1) * rg.nq / rg.dsplit;
-    if (side == SIDE_LEFT) {
-      for (int q = q0; q < q1; ++q) {
-        float gq[4][4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const float4 t = *reinterpret_cast<const float4*>(sG + (4 * q + r) * rg.P + xb);
-          gq[r][0] = t.x; gq[r][1] = t.y; gq[r][2] = t.z; gq[r][3] = t.w;
-        }
-        const int wb = rg.DPAD + xb - 4 * q - 4;      // R[x - d] = w[4 + i - r]
-#pragma unroll
-        for (int j = 0; j < CPG; ++j) {
-          const float4* wp = reinterpret_cast<const float4*>(sR + j * rg.FP + wb);
-          const float4 w0 = wp[0], w1 = wp[1];
-          const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-          for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[j][i] = fmaf(gq[r][i], w[4 + i - r], acc[j][i]);
-        }
-      }
-    } else {
-      for (int q = q0; q < q1; ++q) {
-        const int wb = xb + 4 * q;                    // u = x' + d: index wb + (i + r) in sG (row d) and sL
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const float4* gp = reinterpret_cast<const float4*>(sG + (4 * q + r) * rg.P + wb);
-          const float4 a = gp[0], b = gp[1];
-          const float p[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-          for (int j = 0; j < CPG; ++j) {
-            // L[c][x' + d] for i = 0..3 is sL[wb + r + i]: two aligned quads cover it
-            const float4* lp = reinterpret_cast<const float4*>(sL + j * rg.FP + wb);
-            const float4 l0 = lp[0], l1 = lp[1];
-            const float l[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[j][i] = fmaf(p[i + r], l[i + r], acc[j][i]);
-          }
-        }
-      }
-    }
-  }
-  __syncthreads();                                    // the gradient tile is dead: its space takes the partials
-  float* part = sG;                                   // [(side*CPG + c) * dsplit + dpart][XP]
-  if (active) {
-#pragma unroll
-    for (int j = 0; j < CPG; ++j)
-      *reinterpret_cast<float4*>(part + (size_t)((side * CPG + j) * rg.dsplit + dpart) * rg.XP + xb) =
-          make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
-  }
-  __syncthreads();
-  // ---- reduce the disparity parts in ascending order, scale, store (x contiguous)
-  const float inv = g.mean ? 1.f / (float)g.cpg : 1.f;   // cpg is 4 or 8: exact
-#pragma unroll 1
-  for (int sc = threadIdx.x >> 5; sc < 2 * CPG; sc += GR_THREADS / 32) {   // one warp per output row
-    Tin* dstp = sc < CPG ? gl : gr;
-    if (!dstp) continue;
-    dstp += (((int64_t)n * g.C + c0 + (sc < CPG ? sc : sc - CPG)) * g.H + y) * g.W + x0;
-    const float* pp = part + (size_t)sc * rg.dsplit * rg.XP;
-    for (int x = threadIdx.x & 31; x < npx; x += 32) {
-      float sum = pp[x];
-      for (int dp = 1; dp < rg.dsplit; ++dp) sum += pp[dp * rg.XP + x];
-      dstp[x] = from_f<Tin>(sum * inv);
-    }
-  }
-}
-
 }  // namespace rsm

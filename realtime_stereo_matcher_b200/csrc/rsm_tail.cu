@@ -387,11 +387,11 @@ upsample_regress_fwd_kernel(const T* __restrict__ cost, T* __restrict__ soft, in
 }
 
 // ==================================================================================== backward
-// stage 1: per fine pixel, the gradient with respect to its slice values c_k -> wsp (B,Dc,H,W) fp32.
+// General ratios, stage 1: per fine pixel, the gradient with respect to its slice values c_k -> wsp (B,Dc,H,W) fp32.
 //   p(d') = exp(f(d') - lse);  gf = g * p * (d' - E);  gc[i0] += (1-w) gf;  gc[i1] += w gf.
 // Deterministic (no atomics): intervals are visited in order, so slice k is complete once
 // interval k has been processed.
-template <typename T, bool ALL4>
+template <typename T>
 __global__ void __launch_bounds__(kNT)
 upsample_regress_bwd_cols_kernel(const T* __restrict__ gout, const T* __restrict__ cost,
                                  const float* __restrict__ expect, const float* __restrict__ lse,
@@ -402,8 +402,7 @@ upsample_regress_bwd_cols_kernel(const T* __restrict__ gout, const T* __restrict
   const int x = blockIdx.x * kTX + (threadIdx.x & (kTX - 1)), y = blockIdx.y * kTY + threadIdx.x / kTX;
   const int cy0 = lin_index(blockIdx.y * kTY, g.sh, g.Hc).i0;
   const int cx0 = lin_index(blockIdx.x * kTX, g.sw, g.Wc).i0;
-  if constexpr (ALL4) stage_tile_all4(cost + (int64_t)b * g.Dc * g.Hc * g.Wc, sm, g, cy0, cx0);
-  else stage_tile(cost + (int64_t)b * g.Dc * g.Hc * g.Wc, sm, g, cy0, cx0);
+  stage_tile(cost + (int64_t)b * g.Dc * g.Hc * g.Wc, sm, g, cy0, cx0);
   if (x >= g.W || y >= g.H) return;
 
   const SliceY sl(sm, g, y, cy0);
@@ -412,16 +411,16 @@ upsample_regress_bwd_cols_kernel(const T* __restrict__ gout, const T* __restrict
   const int64_t plane = (int64_t)g.H * g.W;
   float* __restrict__ col = wsp + (int64_t)b * g.Dc * plane + (int64_t)y * g.W + x;
 
-  float cs0 = sl.template scaled<ALL4>(0, -l2);
+  float cs0 = sl.template scaled<false>(0, -l2);
   float acc0 = 0.f;   // gradient of slice k accumulated so far
-  if (ALL4 || g.fast4) {
+  if (g.fast4) {
     {
       const float p = fast_exp2(cs0);
       acc0 = go * p * ((0.f - E) + (1.f - E));
     }
     float base = 2.f;
     for (int k = 0; k + 1 < g.Dc; ++k) {
-      const float cs1 = sl.template scaled<ALL4>(k + 1, -l2);
+      const float cs1 = sl.template scaled<false>(k + 1, -l2);
       const float dl = cs1 - cs0;
       float acc1 = 0.f;
 #pragma unroll
@@ -461,6 +460,167 @@ upsample_regress_bwd_cols_kernel(const T* __restrict__ gout, const T* __restrict
       cs0 = cs1;
     }
   }
+}
+
+// ---- x4 x4 x4 head: stage 1 with the transposed bilinear interpolation done inside the CTA.
+// The general stage 1 above writes one fp32 value per (slice, FINE pixel) -- a (B,Dc,H,W) workspace, 16x the
+// gradient itself -- and stage 2 gathers 64 taps per coarse voxel from it: at (8,48,96,312) -> (8,192,384,1248) that is
+// 1.47 GB of HBM traffic and a 358 us gather next to a 367 us stage 1.  Here a CTA reduces its 32 x 8 fine pixels
+// to the 4 x 10 coarse voxels they touch, eight slices at a time, with the x4 rule's constant weights: fine
+// columns 4j .. 4j+3 give (3 v0 + v1)/8 to coarse column j-1, (5 v0 + 7 v1 + 7 v2 + 5 v3)/8 to j and (v2 + 3 v3)/8 to
+// j+1, the same along y.  The footprint is addressed UNCLAMPED (origin (8 bx - 1, 2 by - 1), possibly -1): the
+// align_corners=False clamp at the image border moves a weight from voxel -1 to voxel 0 (or from Wc to Wc-1), which
+// the second kernel does by folding those cells -- so the tile kernel has no border cases at all, and out-of-image
+// pixels just contribute zeros.  The CTA writes 40 partial sums per slice; the second kernel adds, for every coarse
+// voxel, the cells of the <= 4 tiles that hold it, in a fixed order.  Deterministic, no atomics; the workspace is
+// (B, tiles, Dc, 40): 6.4x smaller than (B,Dc,H,W).
+// The exponentials of an interval's four fine values come from two ex2 and three multiplies (geometric
+// progression, as in the forward pass) whenever the pixel's value range leaves 2^-126 out of reach.
+constexpr int kKB = 8;            // slices per reduction batch
+constexpr int kAP = kTX + 4;      // pitch of a staged gradient row (16-byte aligned rows)
+constexpr int kTileCells = 40;    // 4 x 10 coarse voxels per tile and slice
+constexpr int kBwdExtra = kKB * kTY * kAP + kKB * kTY * 10;   // A | B (floats)
+
+// one interval: slices k, k + 1 = cs0, cs1; adds the four fine values' gradient to acc0 (slice k), returns slice k+1's
+template <bool ROBUST>
+__device__ __forceinline__ float tail_bwd_interval(float cs0, float cs1, float u, float go, float& acc0) {
+  const float dl = cs1 - cs0;
+  float p0, p1, p2, p3;
+  p0 = fast_exp2(fmaf(0.125f, dl, cs0));
+  if constexpr (!ROBUST) {
+    const float q = fast_exp2(0.25f * dl);
+    p1 = p0 * q; p2 = p1 * q; p3 = p2 * q;
+  } else {
+    p1 = fast_exp2(fmaf(0.375f, dl, cs0)); p2 = fast_exp2(fmaf(0.625f, dl, cs0)); p3 = fast_exp2(fmaf(0.875f, dl, cs0));
+  }
+  const float g0 = p0 * u, g1 = p1 * (u + go), g2 = p2 * fmaf(2.f, go, u), g3 = p3 * fmaf(3.f, go, u);
+  acc0 = fmaf(0.875f, g0, acc0); acc0 = fmaf(0.625f, g1, acc0); acc0 = fmaf(0.375f, g2, acc0); acc0 = fmaf(0.125f, g3, acc0);
+  return fmaf(0.875f, g3, fmaf(0.625f, g2, fmaf(0.375f, g1, 0.125f * g0)));
+}
+
+// slices [k0, k0 + nk) of one pixel -> column (ty, tx) of the staged gradients; FULL = eight whole intervals
+template <bool ROBUST, bool FULL>
+__device__ __forceinline__ void tail_bwd_batch(const SliceY& sl, float* __restrict__ a, int k0, int nk, int Dc, int D,
+                                               float l2, float E, float go, bool valid, float& cs0, float& acc0, float& u) {
+#pragma unroll
+  for (int kk = 0; kk < kKB; ++kk) {
+    if (!FULL && kk >= nk) break;
+    float acc1 = 0.f;
+    if (FULL || k0 + kk + 1 < Dc) {
+      const float cs1 = sl.template scaled<true>(k0 + kk + 1, -l2);
+      acc1 = tail_bwd_interval<ROBUST>(cs0, cs1, u, go, acc0);
+      u = fmaf(4.f, go, u);
+      cs0 = cs1;
+    } else {
+      acc0 += go * fast_exp2(cs0) * (((float)(D - 2) - E) + ((float)(D - 1) - E));   // the last two fine values
+    }
+    a[kk * kTY * kAP] = valid ? acc0 : 0.f;
+    acc0 = acc1;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kNT)
+upsample_regress_bwd_tile_kernel(const T* __restrict__ gout, const T* __restrict__ cost,
+                                 const float* __restrict__ expect, const float* __restrict__ lse,
+                                 float* __restrict__ part, TailGeom g) {
+  extern __shared__ __align__(16) float smem_f[];
+  const TailSmem sm(smem_f, g);
+  float* sA = sm.rowmax + 2 * 4 * kTX;         // [kKB][kTY][kAP]
+  float* sB = sA + kKB * kTY * kAP;            // [kKB][kTY][10]
+  const int b = blockIdx.z;
+  const int tx = threadIdx.x & (kTX - 1), ty = threadIdx.x / kTX;
+  const int x = blockIdx.x * kTX + tx, y = blockIdx.y * kTY + ty;
+  const int cy0 = lin_index(blockIdx.y * kTY, g.sh, g.Hc).i0;
+  const int cx0 = lin_index(blockIdx.x * kTX, g.sw, g.Wc).i0;
+  stage_tile_all4(cost + (int64_t)b * g.Dc * g.Hc * g.Wc, sm, g, cy0, cx0);
+
+  const bool valid = x < g.W && y < g.H;
+  const SliceY sl(sm, g, min(y, g.H - 1), cy0);
+  const int64_t o = ((int64_t)b * g.H + min(y, g.H - 1)) * g.W + min(x, g.W - 1);
+  const float go = valid ? to_f(gout[o]) : 0.f, E = expect[o], l2 = lse[o] * kLog2e;
+  // progression only when no fine value of the pixel can come within 2^-126 of flushing: range + log2(D) < 118
+  const bool robust = !((sl.bound(sm) - sl.lower_bound(sm)) * kLog2e + __log2f((float)g.D) < 118.f);
+  float* __restrict__ ptile = part + ((((int64_t)b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * g.Dc) * kTileCells;
+  float* __restrict__ acol = sA + ty * kAP + tx;
+
+  float cs0 = sl.template scaled<true>(0, -l2);
+  float acc0 = go * fast_exp2(cs0) * ((0.f - E) + (1.f - E));   // d' = 0, 1 sit on slice 0
+  float u = go * (2.f - E);                                      // go * (first fine index of the interval - E)
+#pragma unroll 1
+  for (int k0 = 0; k0 < g.Dc; k0 += kKB) {
+    const int nk = min(kKB, g.Dc - k0);
+    if (k0 + kKB < g.Dc) {
+      if (!robust) tail_bwd_batch<false, true>(sl, acol, k0, nk, g.Dc, g.D, l2, E, go, valid, cs0, acc0, u);
+      else tail_bwd_batch<true, true>(sl, acol, k0, nk, g.Dc, g.D, l2, E, go, valid, cs0, acc0, u);
+    } else {
+      tail_bwd_batch<true, false>(sl, acol, k0, nk, g.Dc, g.D, l2, E, go, valid, cs0, acc0, u);
+    }
+    __syncthreads();
+    // ---- along x: item (row = kk * 8 + ty, q) reads its fine quad and exchanges with its neighbours in the warp
+#pragma unroll 1
+    for (int it = threadIdx.x; it < nk * kTY * 8; it += kNT) {
+      const int q = it & 7, row = it >> 3;
+      const float4 v = *reinterpret_cast<const float4*>(sA + row * kAP + 4 * q);
+      const float sm_ = fmaf(0.375f, v.x, 0.125f * v.y);
+      const float sc = fmaf(0.625f, v.x + v.w, 0.875f * (v.y + v.z));
+      const float sp = fmaf(0.375f, v.w, 0.125f * v.z);
+      // footprint column fx (coarse 8 bx - 1 + fx) = sm[fx] + sc[fx - 1] + sp[fx - 2]
+      const float sc1 = __shfl_up_sync(0xffffffffu, sc, 1, 8), sp1 = __shfl_up_sync(0xffffffffu, sp, 1, 8);
+      const float sp2 = __shfl_up_sync(0xffffffffu, sp, 2, 8);
+      float* brow = sB + row * 10;
+      brow[q] = sm_ + (q >= 1 ? sc1 : 0.f) + (q >= 2 ? sp2 : 0.f);
+      if (q == 7) { brow[8] = sc + sp1; brow[9] = sp; }
+    }
+    __syncthreads();
+    // ---- along y: item (kk, fx) reads the column's 8 rows; footprint row fy (coarse 2 by - 1 + fy)
+#pragma unroll 1
+    for (int it = threadIdx.x; it < nk * 10; it += kNT) {
+      const int kk = it / 10, fx = it - kk * 10;
+      const float* bb = sB + kk * kTY * 10 + fx;
+      const float r0 = bb[0], r1 = bb[10], r2 = bb[20], r3 = bb[30], r4 = bb[40], r5 = bb[50], r6 = bb[60], r7 = bb[70];
+      const float m0 = fmaf(0.375f, r0, 0.125f * r1), c0 = fmaf(0.625f, r0 + r3, 0.875f * (r1 + r2)), p0 = fmaf(0.375f, r3, 0.125f * r2);
+      const float m1 = fmaf(0.375f, r4, 0.125f * r5), c1 = fmaf(0.625f, r4 + r7, 0.875f * (r5 + r6)), p1 = fmaf(0.375f, r7, 0.125f * r6);
+      float* o4 = ptile + (int64_t)(k0 + kk) * kTileCells + fx;
+      o4[0] = m0; o4[10] = c0 + m1; o4[20] = p0 + c1; o4[30] = p1;
+    }
+    // (the next batch's A stores do not touch B, and its first barrier orders its B stores after these reads)
+  }
+}
+
+// stage 2 of the tile form: every coarse voxel adds the cells that hold it -- tile (bx, by) holds coarse columns
+// 8 bx - 1 .. 8 bx + 8 and rows 2 by - 1 .. 2 by + 2 -- plus, at the image border, the cells one step outside
+// (the clamp of align_corners=False).  grid = (ceil(Wc / 64), Hc, B * Dc).
+template <typename T>
+__global__ void __launch_bounds__(64)
+upsample_regress_bwd_combine_kernel(const float* __restrict__ part, T* __restrict__ gcost, TailGeom g, int tiles_x,
+                                    int tiles_y) {
+  const int xc = blockIdx.x * 64 + threadIdx.x, yc = blockIdx.y;
+  if (xc >= g.Wc) return;
+  const int k = blockIdx.z % g.Dc, b = blockIdx.z / g.Dc;
+  float acc = 0.f;
+  // unclamped coarse coordinates folded onto this voxel: itself, -1 onto 0, Hc onto Hc - 1 (same along x)
+  const int ny = 1 + (yc == 0) + (yc == g.Hc - 1), nx = 1 + (xc == 0) + (xc == g.Wc - 1);
+  for (int iy = 0; iy < ny; ++iy) {
+    const int yy = iy == 0 ? yc : (iy == 1 && yc == 0 ? -1 : g.Hc);
+    // cells (by, fy) with 2 by - 1 + fy == yy: fy = (yy + 1) & 1 (+ 2), by = (yy + 1 - fy) / 2
+    const int fy0 = (yy + 1) & 1;
+    for (int jy = 0; jy < 2; ++jy) {
+      const int fy = fy0 + 2 * jy, by = (yy + 1 - fy) >> 1;
+      if (by < 0 || by >= tiles_y) continue;
+      for (int ix = 0; ix < nx; ++ix) {
+        const int xx = ix == 0 ? xc : (ix == 1 && xc == 0 ? -1 : g.Wc);
+        // cells (bx, fx) with 8 bx - 1 + fx == xx: fx = (xx + 1) & 7 (+ 8 when <= 1), bx = (xx + 1 - fx) / 8
+        const int fx0 = (xx + 1) & 7;
+        for (int jx = 0; jx < 2; ++jx) {
+          const int fx = fx0 + 8 * jx, bx = (xx + 1 - fx) >> 3;
+          if (fx > 9 || bx < 0 || bx >= tiles_x) continue;
+          acc += __ldg(part + ((((int64_t)b * tiles_y + by) * tiles_x + bx) * g.Dc + k) * kTileCells + fy * 10 + fx);
+        }
+      }
+    }
+  }
+  gcost[(((int64_t)b * g.Dc + k) * g.Hc + yc) * g.Wc + xc] = from_f<T>(acc);
 }
 
 // range of fine indices whose (i0 or i1) can equal coarse index ic (conservative; exact test inside)
@@ -596,7 +756,20 @@ extern "C" int rsm_upsample_regress_bwd(const void* gout, const void* cost, cons
   if (B > 65535) return RSM_ERR_INVALID_SHAPE;
   RSM_COMMON_CHECKS(dtype)
   return RSM_DISPATCH_DTYPE(dtype, T, [&]() -> int {
-    auto k = g.all4 ? upsample_regress_bwd_cols_kernel<T, true> : upsample_regress_bwd_cols_kernel<T, false>;
+    if (g.all4) {
+      // x4 x4 x4 head: per-tile partial sums (B, tiles, Dc, 40) + combine
+      const size_t smem_t = smem + kBwdExtra * sizeof(float);
+      const dim3 grid((unsigned)ceil_div(W, kTX), (unsigned)ceil_div(H, kTY), (unsigned)B);
+      if (grid.y > 65535 || Hc > 65535 || B * Dc > 65535 || smem_t > 200 * 1024) return (int)RSM_ERR_INVALID_SHAPE;
+      auto kt = upsample_regress_bwd_tile_kernel<T>;
+      if (smem_t > 48 * 1024) cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t);
+      kt<<<grid, kNT, smem_t, st>>>((const T*)gout, (const T*)cost, expect, lse, (float*)workspace, g);
+      if (int rc = finish_launch("rsm_upsample_regress_bwd(tiles)")) return rc;
+      upsample_regress_bwd_combine_kernel<T><<<dim3((unsigned)ceil_div(Wc, 64), (unsigned)Hc, (unsigned)(B * Dc)), 64, 0, st>>>(
+          (const float*)workspace, (T*)gcost, g, (int)grid.x, (int)grid.y);
+      return finish_launch("rsm_upsample_regress_bwd(combine)");
+    }
+    auto k = upsample_regress_bwd_cols_kernel<T>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const dim3 grid((unsigned)ceil_div(W, kTX), (unsigned)ceil_div(H, kTY), (unsigned)B);
     if (grid.y > 65535) return (int)RSM_ERR_INVALID_SHAPE;

@@ -267,7 +267,7 @@ def test_regress_ties_everywhere(rsm):
 
 
 @pytest.mark.parametrize("geom", [(1, 48, 6, 10, 192, 24, 40), (2, 12, 5, 7, 48, 20, 28), (1, 5, 3, 4, 13, 7, 10),
-                                  (1, 9, 8, 8, 9, 4, 4)])
+                                  (1, 9, 8, 8, 9, 4, 4), (2, 11, 23, 37, 44, 92, 148), (1, 8, 4, 10, 32, 16, 40)])
 def test_v4_tail_vs_oracle(rsm, geom):
     b, dc, hc, wc, d, h, w = geom
     rng = np.random.default_rng(11)
@@ -468,11 +468,34 @@ def test_v4_tail_all_x4_stabiliser(rsm, scale):
     assert (amin != fine.argmin(1)).float().mean() < 1e-3
 
 
-@pytest.mark.parametrize("shape", [(1, 32, 3, 330, 40, 4), (2, 16, 2, 50, 24, 2), (1, 8, 2, 161, 33, 2), (1, 24, 2, 312, 48, 6)])
+def test_v4_tail_bwd_wide_range(rsm):
+    """The x4 head's adjoint takes its exponentials from a geometric progression unless the pixel's value range could
+    flush one of them; both forms, several tiles, ragged right / bottom edges and the folded border cells are checked
+    against autograd through interpolate -> softmax -> expectation on the device."""
+    rng = np.random.default_rng(62)
+    b, dc, hc, wc = 2, 16, 21, 45
+    d, h, w = 4 * dc, 4 * hc, 4 * wc
+    for scale in (2.0, 80.0):
+        cost = (rng.standard_normal((b, dc, hc, wc)) * scale).astype(np.float32)
+        cost[0, :, 5, :] = -scale * 4
+        gout = rng.standard_normal((b, h, w)).astype(np.float32)
+        c = dev(cost, grad=True)
+        rsm.upsample_regress(c, d, h, w).backward(dev(gout))
+        ref = dev(cost, grad=True)
+        fine = torch.nn.functional.interpolate(ref.unsqueeze(1), [d, h, w], mode="trilinear").squeeze(1)
+        e = (torch.softmax(fine, 1) * torch.arange(d, device="cuda", dtype=torch.float32).view(1, -1, 1, 1)).sum(1)
+        e.backward(dev(gout))
+        err = (c.grad - ref.grad).abs().max().item()
+        assert err <= GRAD_RTOL * d * max(1.0, ref.grad.abs().max().item()), (scale, err)
+
+
+@pytest.mark.parametrize("shape", [(1, 32, 3, 330, 40, 4), (2, 16, 2, 50, 24, 2), (1, 8, 2, 161, 33, 2), (1, 24, 2, 312, 48, 6),
+                                   (1, 16, 3, 77, 96, 16), (2, 32, 2, 100, 20, 2), (1, 8, 2, 45, 12, 4), (1, 6, 2, 64, 16, 2)])
 @pytest.mark.parametrize("dn", ["fp32", "bf16"])
 def test_groupwise_bwd_row_parts(rsm, shape, dn):
-    """Narrow groups (4 or 8 channels) take the row-part adjoint kernel: several parts per row, ragged
-    last part, D not a multiple of 8, 8-channel groups, 16-bit tensors -- against the oracle."""
+    """The row-streaming adjoint kernel (1 / 2 / 4 / 8 / 16 channels per group, D % 4 == 0): ragged rows, last slab
+    partly past D, several slabs, 16-bit tensors; and the shapes it leaves to the tiled kernel (D % 4 != 0, 3 channels
+    per group) -- against the oracle."""
     n, c, h, w, d, ng = shape
     rng = np.random.default_rng(71)
     l = round_to(rng.standard_normal((n, c, h, w)).astype(np.float32), dn)

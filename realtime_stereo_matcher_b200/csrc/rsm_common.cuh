@@ -114,11 +114,13 @@ __device__ __forceinline__ float fast_exp2(float x) {
 struct ArgTrack {
   float minv = INFINITY, maxv = -INFINITY;
   int mini = 0, maxi = 0;
-  __device__ __forceinline__ void update(float v, int d) {
-    const bool vnan = v != v;
-    if ((v < minv) || (vnan && minv == minv)) { minv = v; mini = d; }
-    if ((v > maxv) || (vnan && maxv == maxv)) { maxv = v; maxi = d; }
+  __device__ __forceinline__ void update_min(float v, int d) {
+    if ((v < minv) || (v != v && minv == minv)) { minv = v; mini = d; }
   }
+  __device__ __forceinline__ void update_max(float v, int d) {
+    if ((v > maxv) || (v != v && maxv == maxv)) { maxv = v; maxi = d; }
+  }
+  __device__ __forceinline__ void update(float v, int d) { update_min(v, d); update_max(v, d); }
 };
 
 // Per-pixel running soft-argmax / arg-extrema state, fed 8 disparities at a time in ascending order (torch

@@ -245,6 +245,8 @@ struct SliceY {
 
 struct NoTrack {
   __device__ __forceinline__ void update(float, int) {}
+  __device__ __forceinline__ void update_min(float, int) {}
+  __device__ __forceinline__ void update_max(float, int) {}
 };
 
 // ===================================================================================== forward
@@ -289,9 +291,13 @@ __device__ __forceinline__ void pass2_x4(const SliceY& sl, float neg_ml, int Dc,
       s += S;
       ws = fmaf(base, S, ws) + Tm;
     }
+    // the four fine values of an interval are monotone: only its ends can be extrema -- the far end on a strict
+    // slope, the first value otherwise (flat interval: first index; NaN slice: the interval's first value is the
+    // first NaN)
     const int d0 = 4 * k + 2;
-    trk.update(fmaf(0.125f, dl, cs0), d0); trk.update(fmaf(0.375f, dl, cs0), d0 + 1);
-    trk.update(fmaf(0.625f, dl, cs0), d0 + 2); trk.update(fmaf(0.875f, dl, cs0), d0 + 3);
+    const float flo = fmaf(0.125f, dl, cs0), fhi = fmaf(0.875f, dl, cs0);
+    trk.update_max(dl > 0.f ? fhi : flo, dl > 0.f ? d0 + 3 : d0);
+    trk.update_min(dl < 0.f ? fhi : flo, dl < 0.f ? d0 + 3 : d0);
     base += 4.f;
     cs0 = cs1;
   }
@@ -498,15 +504,16 @@ __device__ __forceinline__ float tail_bwd_interval(float cs0, float cs1, float u
   return fmaf(0.875f, g3, fmaf(0.625f, g2, fmaf(0.375f, g1, 0.125f * g0)));
 }
 
-// slices [k0, k0 + nk) of one pixel -> column (ty, tx) of the staged gradients; FULL = eight whole intervals
-template <bool ROBUST, bool FULL>
+// slices [k0, k0 + nk) of one pixel -> column (ty, tx) of the staged gradients.  MODE 0: eight whole intervals;
+// MODE 1: seven intervals and the last slice (the final batch when Dc % 8 == 0); MODE 2: any nk, tested per slice
+template <bool ROBUST, int MODE>
 __device__ __forceinline__ void tail_bwd_batch(const SliceY& sl, float* __restrict__ a, int k0, int nk, int Dc, int D,
                                                float l2, float E, float go, bool valid, float& cs0, float& acc0, float& u) {
 #pragma unroll
   for (int kk = 0; kk < kKB; ++kk) {
-    if (!FULL && kk >= nk) break;
+    if (MODE == 2 && kk >= nk) break;
     float acc1 = 0.f;
-    if (FULL || k0 + kk + 1 < Dc) {
+    if (MODE == 0 || (MODE == 1 && kk < kKB - 1) || (MODE == 2 && k0 + kk + 1 < Dc)) {
       const float cs1 = sl.template scaled<true>(k0 + kk + 1, -l2);
       acc1 = tail_bwd_interval<ROBUST>(cs0, cs1, u, go, acc0);
       u = fmaf(4.f, go, u);
@@ -551,10 +558,13 @@ upsample_regress_bwd_tile_kernel(const T* __restrict__ gout, const T* __restrict
   for (int k0 = 0; k0 < g.Dc; k0 += kKB) {
     const int nk = min(kKB, g.Dc - k0);
     if (k0 + kKB < g.Dc) {
-      if (!robust) tail_bwd_batch<false, true>(sl, acol, k0, nk, g.Dc, g.D, l2, E, go, valid, cs0, acc0, u);
-      else tail_bwd_batch<true, true>(sl, acol, k0, nk, g.Dc, g.D, l2, E, go, valid, cs0, acc0, u);
+      if (!robust) tail_bwd_batch<false, 0>(sl, acol, k0, nk, g.Dc, g.D, l2, E, go, valid, cs0, acc0, u);
+      else tail_bwd_batch<true, 0>(sl, acol, k0, nk, g.Dc, g.D, l2, E, go, valid, cs0, acc0, u);
+    } else if (nk == kKB) {
+      if (!robust) tail_bwd_batch<false, 1>(sl, acol, k0, nk, g.Dc, g.D, l2, E, go, valid, cs0, acc0, u);
+      else tail_bwd_batch<true, 1>(sl, acol, k0, nk, g.Dc, g.D, l2, E, go, valid, cs0, acc0, u);
     } else {
-      tail_bwd_batch<true, false>(sl, acol, k0, nk, g.Dc, g.D, l2, E, go, valid, cs0, acc0, u);
+      tail_bwd_batch<true, 2>(sl, acol, k0, nk, g.Dc, g.D, l2, E, go, valid, cs0, acc0, u);
     }
     __syncthreads();
     // ---- along x: item (row = kk * 8 + ty, q) reads its fine quad and exchanges with its neighbours in the warp
@@ -590,37 +600,61 @@ upsample_regress_bwd_tile_kernel(const T* __restrict__ gout, const T* __restrict
 
 // stage 2 of the tile form: every coarse voxel adds the cells that hold it -- tile (bx, by) holds coarse columns
 // 8 bx - 1 .. 8 bx + 8 and rows 2 by - 1 .. 2 by + 2 -- plus, at the image border, the cells one step outside
-// (the clamp of align_corners=False).  grid = (ceil(Wc / 64), Hc, B * Dc).
+// (the clamp of align_corners=False).  A thread finds the <= 4 (border: <= 16) cells of its (y, x) once and then walks
+// its share of the slices (the cell offsets do not depend on k).  grid = (ceil(Wc / 64), Hc, B * ksplit): the split of
+// the slices only adds loads in flight (the kernel is bound by their latency, not by issue or bandwidth).
 template <typename T>
 __global__ void __launch_bounds__(64)
 upsample_regress_bwd_combine_kernel(const float* __restrict__ part, T* __restrict__ gcost, TailGeom g, int tiles_x,
-                                    int tiles_y) {
-  const int xc = blockIdx.x * 64 + threadIdx.x, yc = blockIdx.y;
+                                    int tiles_y, int ksplit) {
+  const int xc = blockIdx.x * 64 + threadIdx.x, yc = blockIdx.y, b = blockIdx.z / ksplit, ks = blockIdx.z % ksplit;
   if (xc >= g.Wc) return;
-  const int k = blockIdx.z % g.Dc, b = blockIdx.z / g.Dc;
-  float acc = 0.f;
-  // unclamped coarse coordinates folded onto this voxel: itself, -1 onto 0, Hc onto Hc - 1 (same along x)
+  const int kbeg = g.Dc * ks / ksplit, kend = g.Dc * (ks + 1) / ksplit;
+  const float* __restrict__ pb = part + (int64_t)b * tiles_y * tiles_x * g.Dc * kTileCells;
+  T* __restrict__ out = gcost + ((int64_t)b * g.Dc * g.Hc + yc) * g.Wc + xc;
+  const int64_t plane = (int64_t)g.Hc * g.Wc;
+  const int tstride = g.Dc * kTileCells;
+  // cell offsets (tile * Dc * 40 + fy * 10 + fx) in the fixed order (row, column) ascending; -1 = none
+  auto cells_of = [&](int yy, int xx, int (&off)[4]) {
+    const int fy0 = (yy + 1) & 1, fx0 = (xx + 1) & 7;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int fy = fy0 + 2 * (j >> 1), fx = fx0 + 8 * (j & 1);
+      const int by = (yy + 1 - fy) >> 1, bx = (xx + 1 - fx) >> 3;
+      off[j] = (fx > 9 || by < 0 || by >= tiles_y || bx < 0 || bx >= tiles_x) ? -1 : (by * tiles_x + bx) * tstride + fy * 10 + fx;
+    }
+  };
+  const bool border = yc == 0 || yc == g.Hc - 1 || xc == 0 || xc == g.Wc - 1;
+  if (!border) {
+    int off[4];
+    cells_of(yc, xc, off);
+#pragma unroll 4
+    for (int k = kbeg; k < kend; ++k) {
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (off[j] >= 0) acc += __ldg(pb + off[j] + k * kTileCells);
+      out[k * plane] = from_f<T>(acc);
+    }
+    return;
+  }
+  // border voxels: the unclamped coordinates folded onto this voxel: itself, -1 onto 0, Hc onto Hc - 1 (same along x)
   const int ny = 1 + (yc == 0) + (yc == g.Hc - 1), nx = 1 + (xc == 0) + (xc == g.Wc - 1);
-  for (int iy = 0; iy < ny; ++iy) {
-    const int yy = iy == 0 ? yc : (iy == 1 && yc == 0 ? -1 : g.Hc);
-    // cells (by, fy) with 2 by - 1 + fy == yy: fy = (yy + 1) & 1 (+ 2), by = (yy + 1 - fy) / 2
-    const int fy0 = (yy + 1) & 1;
-    for (int jy = 0; jy < 2; ++jy) {
-      const int fy = fy0 + 2 * jy, by = (yy + 1 - fy) >> 1;
-      if (by < 0 || by >= tiles_y) continue;
+  for (int k = kbeg; k < kend; ++k) {
+    float acc = 0.f;
+    for (int iy = 0; iy < ny; ++iy) {
+      const int yy = iy == 0 ? yc : (iy == 1 && yc == 0 ? -1 : g.Hc);
       for (int ix = 0; ix < nx; ++ix) {
         const int xx = ix == 0 ? xc : (ix == 1 && xc == 0 ? -1 : g.Wc);
-        // cells (bx, fx) with 8 bx - 1 + fx == xx: fx = (xx + 1) & 7 (+ 8 when <= 1), bx = (xx + 1 - fx) / 8
-        const int fx0 = (xx + 1) & 7;
-        for (int jx = 0; jx < 2; ++jx) {
-          const int fx = fx0 + 8 * jx, bx = (xx + 1 - fx) >> 3;
-          if (fx > 9 || bx < 0 || bx >= tiles_x) continue;
-          acc += __ldg(part + ((((int64_t)b * tiles_y + by) * tiles_x + bx) * g.Dc + k) * kTileCells + fy * 10 + fx);
-        }
+        int off[4];
+        cells_of(yy, xx, off);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (off[j] >= 0) acc += __ldg(pb + off[j] + k * kTileCells);
       }
     }
+    out[k * plane] = from_f<T>(acc);
   }
-  gcost[(((int64_t)b * g.Dc + k) * g.Hc + yc) * g.Wc + xc] = from_f<T>(acc);
 }
 
 // range of fine indices whose (i0 or i1) can equal coarse index ic (conservative; exact test inside)
@@ -760,13 +794,19 @@ extern "C" int rsm_upsample_regress_bwd(const void* gout, const void* cost, cons
       // x4 x4 x4 head: per-tile partial sums (B, tiles, Dc, 40) + combine
       const size_t smem_t = smem + kBwdExtra * sizeof(float);
       const dim3 grid((unsigned)ceil_div(W, kTX), (unsigned)ceil_div(H, kTY), (unsigned)B);
-      if (grid.y > 65535 || Hc > 65535 || B * Dc > 65535 || smem_t > 200 * 1024) return (int)RSM_ERR_INVALID_SHAPE;
+      if (grid.y > 65535 || Hc > 65535 || smem_t > 200 * 1024 || (int64_t)grid.x * grid.y * Dc * kTileCells > 2147483647LL)
+        return (int)RSM_ERR_INVALID_SHAPE;
       auto kt = upsample_regress_bwd_tile_kernel<T>;
       if (smem_t > 48 * 1024) cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t);
       kt<<<grid, kNT, smem_t, st>>>((const T*)gout, (const T*)cost, expect, lse, (float*)workspace, g);
       if (int rc = finish_launch("rsm_upsample_regress_bwd(tiles)")) return rc;
-      upsample_regress_bwd_combine_kernel<T><<<dim3((unsigned)ceil_div(Wc, 64), (unsigned)Hc, (unsigned)(B * Dc)), 64, 0, st>>>(
-          (const float*)workspace, (T*)gcost, g, (int)grid.x, (int)grid.y);
+      // enough CTAs for ~4 waves of 32 x 64 threads per SM
+      int64_t ksplit = ceil_div((int64_t)4 * kNumSMs * 32, ceil_div(Wc, 64) * Hc * B);
+      ksplit = ksplit < 1 ? 1 : (ksplit > Dc ? Dc : ksplit);
+      if (B * ksplit > 65535) ksplit = 1;
+      if (B > 65535) return (int)RSM_ERR_INVALID_SHAPE;
+      upsample_regress_bwd_combine_kernel<T><<<dim3((unsigned)ceil_div(Wc, 64), (unsigned)Hc, (unsigned)(B * ksplit)), 64, 0, st>>>(
+          (const float*)workspace, (T*)gcost, g, (int)grid.x, (int)grid.y, (int)ksplit);
       return finish_launch("rsm_upsample_regress_bwd(combine)");
     }
     auto k = upsample_regress_bwd_cols_kernel<T>;

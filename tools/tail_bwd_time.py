@@ -1,4 +1,4 @@
-"""Times the MobileStereoNetV4 head backward (cols + gather kernels) at cfg3 and cfg5 sizes."""
+"""Times the MobileStereoNetV4 head (forward, forward with arg-extrema, backward) at cfg3 and cfg5 sizes."""
 import os
 import sys
 
@@ -31,6 +31,11 @@ def main():
             go = torch.randn_like(out)
             ms = timed(lambda: torch.autograd.grad(out, cost, go, retain_graph=True))
             print(f"v4_head_bwd {dt} {b}x{dc}x{hc}x{wc}: {ms * 1e3:.1f} us", flush=True)
+            with torch.no_grad():
+                c = cost.detach()
+                ms = timed(lambda: rsm.v4_head(c, d, h, w))
+                ms2 = timed(lambda: rsm.upsample_regress(c, d, h, w, argmin=True, argmax=True))
+            print(f"v4_head_fwd {dt} {b}x{dc}x{hc}x{wc}: {ms * 1e3:.1f} us, with argmin+argmax {ms2 * 1e3:.1f} us", flush=True)
 
 
 if __name__ == "__main__":

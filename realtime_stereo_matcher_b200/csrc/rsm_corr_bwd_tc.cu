@@ -1,4 +1,5 @@
-// Adjoint of the inner-product / correlation volume on tcgen05 (16-bit tensors, D <= 64):
+// Adjoint of the inner-product / correlation volume on tcgen05 (16-bit tensors; 64 disparities per launch, see
+// launch_inner_bwd_tc for D > 64):
 //     gL[c, x]  = s * sum_d gV[d, x]      * R[c, x - d]        (x >= d)
 //     gR[c, x'] = s * sum_d gV[d, x' + d] * L[c, x' + d]       (x' + d < W)
 // -- what autograd derives from the slice-assign loop of TorchInnerProductCost.forward (cost_volume/inner_product.py:29-41)
@@ -46,6 +47,10 @@ struct BtGeom {
   int fmt;                // 0 = fp16, 1 = bf16
   int do_l, do_r;
   float scale;
+  int d0;                 // first disparity of this launch's chunk (D = disparities of the chunk, <= 64)
+  int gx;                 // x offset of the gradient box: 0, or d0 for the right gradient of a later chunk
+  int rshift, lshift;     // feature windows: right pixels start at x0 - 64 - rshift, left pixels at x0 + lshift
+  int accum;              // outputs are added to (TMA reduce-add), not stored: chunks after the first
   int atom_bytes;         // CB * 128
   int g_bytes;            // gradient tile buffer: D * 192 * 2 rounded up to 1 KB
   int tmem_cols;          // allocation: power of two >= 4 * CB
@@ -234,7 +239,7 @@ inner_bwd_tc_kernel(BtGeom g, int N, const __grid_constant__ CUtensorMap tmG, co
         const uint32_t gb = tl & 1;
         mbar_wait(g_empty + 8 * gb, ((tl >> 1) & 1) ^ 1);
         mbar_expect_tx(g_full + 8 * gb, (uint32_t)(g.D * BT_GW * 2));
-        tma_load_4d(smem_u32(sG) + gb * (uint32_t)g.g_bytes, &tmG, g_full + 8 * gb, t.xt * BT_TM, t.y, 0, t.n);
+        tma_load_4d(smem_u32(sG) + gb * (uint32_t)g.g_bytes, &tmG, g_full + 8 * gb, t.xt * BT_TM + g.gx, t.y, g.d0, t.n);
       };
       BtTile tc = first, tg = first;
       load_g(0, tg);
@@ -246,12 +251,12 @@ inner_bwd_tc_kernel(BtGeom g, int N, const __grid_constant__ CUtensorMap tmG, co
           if (g.do_l) {
             mbar_wait(rr_empty + 8 * rr.s, rr.p ^ 1);
             mbar_expect_tx(rr_full + 8 * rr.s, ab);
-            tma_load_4d(smem_u32(sRr) + rr.s * ab, &tmR, rr_full + 8 * rr.s, x0 - BT_DP + BT_ATOM * (int)a, tc.y, c0, tc.n);
+            tma_load_4d(smem_u32(sRr) + rr.s * ab, &tmR, rr_full + 8 * rr.s, x0 - BT_DP - g.rshift + BT_ATOM * (int)a, tc.y, c0, tc.n);
           }
           if (g.do_r) {
             mbar_wait(lr_empty + 8 * ll.s, ll.p ^ 1);
             mbar_expect_tx(lr_full + 8 * ll.s, ab);
-            tma_load_4d(smem_u32(sLr) + ll.s * ab, &tmL, lr_full + 8 * ll.s, x0 + BT_ATOM * (int)a, tc.y, c0, tc.n);
+            tma_load_4d(smem_u32(sLr) + ll.s * ab, &tmL, lr_full + 8 * ll.s, x0 + g.lshift + BT_ATOM * (int)a, tc.y, c0, tc.n);
           }
           rr.step(); ll.step();
         }
@@ -288,7 +293,8 @@ inner_bwd_tc_kernel(BtGeom g, int N, const __grid_constant__ CUtensorMap tmG, co
       const uint32_t gb = tl & 1;
       // row d_beg of the gradient tile at this thread's pixel (rows past D read whatever follows: they go to the trash slot)
       const unsigned short* G = reinterpret_cast<const unsigned short*>(sG + gb * (size_t)g.g_bytes) + d_beg * BT_GW + r;
-      const int dmask = tc.xt == 0 ? r - d_beg : 0x7fffffff;     // x < d (first tile of a row): the forward never wrote that entry
+      // x < d (the first tiles of a row; d counts from the chunk's first disparity): the forward never wrote that entry
+      const int dmask = tc.xt * BT_TM + r - g.d0 - d_beg;
       long long c0 = rec ? clock64() : 0;
       mbar_wait(g_full + 8 * gb, (tl >> 1) & 1);
       if (rec) { const long long c1 = clock64(); c_g += c1 - c0; c0 = c1; }
@@ -379,10 +385,16 @@ inner_bwd_tc_kernel(BtGeom g, int N, const __grid_constant__ CUtensorMap tmG, co
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> async proxy (TMA)
           asm volatile("bar.sync %0, 128;" ::"r"(1 + part) : "memory");
           if (storer) {
-            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                         ::"l"(sd == 0 ? &tmGL : &tmGR), "r"(smem_u32(stile)), "r"(tc.xt * BT_TM), "r"(tc.y),
-                           "r"(tc.cb * (int)CB + (int)cs), "r"(tc.n)
-                         : "memory");
+            if (!g.accum)
+              asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                           ::"l"(sd == 0 ? &tmGL : &tmGR), "r"(smem_u32(stile)), "r"(tc.xt * BT_TM), "r"(tc.y),
+                             "r"(tc.cb * (int)CB + (int)cs), "r"(tc.n)
+                           : "memory");
+            else   // a later disparity chunk: add to what the earlier chunks stored
+              asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                           ::"l"(sd == 0 ? &tmGL : &tmGR), "r"(smem_u32(stile)), "r"(tc.xt * BT_TM), "r"(tc.y),
+                             "r"(tc.cb * (int)CB + (int)cs), "r"(tc.n)
+                           : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
@@ -438,43 +450,35 @@ static int bt_launch(const BtGeom& g, int N, const CUtensorMap& tmG, const CUten
 
 // returns RSM_ERR_UNSUPPORTED_CONFIG when this form does not apply (the caller falls back to the SIMT kernels):
 // gout (N,D,H,W), gl / gr (N,C,H,W) dense and of the features' 16-bit dtype, C a multiple of 16 and either <= 64 or a
-// multiple of 64, D <= 64, rows TMA can address (W % 8 == 0)
+// multiple of 64, D <= 512, rows TMA can address (W % 8 == 0).
+// D > 64 runs as chunks of 64 disparities, one launch each (two from the second chunk on: the right gradient of chunk
+// d0 reads the gradient box and the left window d0 pixels further right, the left gradient reads the right window d0
+// pixels further left -- same kernel, shifted TMA coordinates); later chunks add to the stored result with TMA
+// reduce-add.  Each launch re-reads the features (2 C H W) and its share of the gradient: at C = 128, D = 192 that is
+// 2.2x the algorithmic traffic instead of the SIMT kernel's 0.04 of the HBM roofline.
 int launch_inner_bwd_tc(const void* gout, const rsm_feat& left, const rsm_feat& right, void* gl, void* gr, int64_t N,
                         int64_t C, int64_t H, int64_t W, int64_t D, int mean, int in_dtype, int out_dtype, cudaStream_t st,
                         unsigned long long* prof) {
   if ((in_dtype != RSM_F16 && in_dtype != RSM_BF16) || out_dtype != in_dtype) return RSM_ERR_UNSUPPORTED_CONFIG;
-  if (C <= 0 || C % 16 != 0 || (C > 64 && C % 64 != 0) || D <= 0 || D > BT_DP || W % 8 != 0 || N <= 0 || H <= 0)
+  if (C <= 0 || C % 16 != 0 || (C > 64 && C % 64 != 0) || D <= 0 || D > 8 * BT_DP || W % 8 != 0 || N <= 0 || H <= 0)
     return RSM_ERR_UNSUPPORTED_CONFIG;
   if (left.stride_w != 1 || right.stride_w != 1) return RSM_ERR_UNSUPPORTED_CONFIG;
   if ((gl && !aligned_to(gl, 16)) || (gr && !aligned_to(gr, 16))) return RSM_ERR_UNSUPPORTED_CONFIG;
   BtGeom g;
   g.C = (int)C; g.CB = C < 64 ? (int)C : 64; g.cblocks = (int)(C / g.CB);
-  g.H = (int)H; g.W = (int)W; g.D = (int)D;
+  g.H = (int)H; g.W = (int)W;
   g.xtiles = (int)ceil_div(W, BT_TM);
   g.fmt = in_dtype == RSM_F16 ? 0 : 1;
-  g.do_l = gl != nullptr; g.do_r = gr != nullptr;
   g.scale = mean ? 1.f / (float)C : 1.f;
   g.atom_bytes = g.CB * 128;
-  g.g_bytes = (int)((D * BT_GW * 2 + 1023) / 1024 * 1024);
   g.tmem_cols = 32;
   while (g.tmem_cols < 4 * g.CB) g.tmem_cols *= 2;
   g.rows = N * H;
   g.tiles = (int64_t)g.cblocks * g.rows * g.xtiles;
   if (g.tiles > 2147483647LL) return RSM_ERR_UNSUPPORTED_CONFIG;
-  const size_t fixed = 2 * (size_t)BT_A_BYTES + 2 * (size_t)g.g_bytes + BT_STAGE_BYTES + BT_BAR_BYTES + 1024;
-  g.ring_r = g.ring_l = BT_RING;
-  if (fixed + (size_t)(g.ring_r + g.ring_l) * g.atom_bytes > 227 * 1024) g.ring_l = BT_RING - 1;
-  if (fixed + (size_t)(g.ring_r + g.ring_l) * g.atom_bytes > 227 * 1024) g.ring_r = BT_RING - 1;
-  const size_t smem = fixed + (size_t)(g.ring_r + g.ring_l) * g.atom_bytes;
-  if (smem > 227 * 1024) return RSM_ERR_UNSUPPORTED_CONFIG;
-  alignas(64) CUtensorMap tmG, tmL, tmR, tmGL, tmGR;
-  memset(&tmG, 0, sizeof(tmG)); memset(&tmL, 0, sizeof(tmL)); memset(&tmR, 0, sizeof(tmR));
+  alignas(64) CUtensorMap tmL, tmR, tmGL, tmGR;
+  memset(&tmL, 0, sizeof(tmL)); memset(&tmR, 0, sizeof(tmR));
   memset(&tmGL, 0, sizeof(tmGL)); memset(&tmGR, 0, sizeof(tmGR));
-  {
-    const int64_t dims[4] = {W, H, D, N}, strides[3] = {W * 2, H * W * 2, D * H * W * 2};
-    const uint32_t box[4] = {(uint32_t)BT_GW, 1, (uint32_t)D, 1};
-    if (!bt_tmap(&tmG, gout, g.fmt, dims, strides, box, false)) return RSM_ERR_UNSUPPORTED_CONFIG;
-  }
   auto feat_map = [&](CUtensorMap* m, const rsm_feat& f) {
     const int64_t dims[4] = {W, H, C, N}, strides[3] = {f.stride_h * 2, f.stride_c * 2, f.stride_n * 2};
     const uint32_t box[4] = {(uint32_t)BT_ATOM, 1, (uint32_t)g.CB, 1};
@@ -490,18 +494,48 @@ int launch_inner_bwd_tc(const void* gout, const rsm_feat& left, const rsm_feat& 
     return bt_tmap(m, p, g.fmt, dims, strides, box, false);
   };
   if (!out_map(&tmGL, gl) || !out_map(&tmGR, gr)) return RSM_ERR_UNSUPPORTED_CONFIG;
-  const int nd = (int)(((D + 1) / 2 + 7) / 8 * 8);               // disparities per builder thread, rounded up to 8
-  auto go = [&](auto tag) -> int {
-    using T = decltype(tag);
-    switch (nd) {
-      case 8: return bt_launch<T, 8>(g, (int)N, tmG, tmL, tmR, tmGL, tmGR, grid, smem, st, prof);
-      case 16: return bt_launch<T, 16>(g, (int)N, tmG, tmL, tmR, tmGL, tmGR, grid, smem, st, prof);
-      case 24: return bt_launch<T, 24>(g, (int)N, tmG, tmL, tmR, tmGL, tmGR, grid, smem, st, prof);
-      default: return bt_launch<T, 32>(g, (int)N, tmG, tmL, tmR, tmGL, tmGR, grid, smem, st, prof);
-    }
+
+  // one launch: disparities [d0, d0 + dc) into the gradients named by do_l / do_r
+  auto chunk = [&](int d0, int dc, bool do_l, bool do_r) -> int {
+    g.D = dc; g.d0 = d0;
+    g.do_l = do_l; g.do_r = do_r;
+    g.gx = do_r ? d0 : 0; g.lshift = d0; g.rshift = d0;
+    g.accum = d0 > 0;
+    g.g_bytes = (dc * BT_GW * 2 + 1023) / 1024 * 1024;
+    const size_t fixed = 2 * (size_t)BT_A_BYTES + 2 * (size_t)g.g_bytes + BT_STAGE_BYTES + BT_BAR_BYTES + 1024;
+    g.ring_r = g.ring_l = BT_RING;
+    if (fixed + (size_t)(g.ring_r + g.ring_l) * g.atom_bytes > 227 * 1024) g.ring_l = BT_RING - 1;
+    if (fixed + (size_t)(g.ring_r + g.ring_l) * g.atom_bytes > 227 * 1024) g.ring_r = BT_RING - 1;
+    const size_t smem = fixed + (size_t)(g.ring_r + g.ring_l) * g.atom_bytes;
+    if (smem > 227 * 1024) return (int)RSM_ERR_UNSUPPORTED_CONFIG;
+    alignas(64) CUtensorMap tmG;
+    memset(&tmG, 0, sizeof(tmG));
+    const int64_t dims[4] = {W, H, D, N}, strides[3] = {W * 2, H * W * 2, D * H * W * 2};
+    const uint32_t box[4] = {(uint32_t)BT_GW, 1, (uint32_t)dc, 1};
+    if (!bt_tmap(&tmG, gout, g.fmt, dims, strides, box, false)) return (int)RSM_ERR_UNSUPPORTED_CONFIG;
+    const int nd = ((dc + 1) / 2 + 7) / 8 * 8;                 // disparities per builder thread, rounded up to 8
+    auto go = [&](auto tag) -> int {
+      using T = decltype(tag);
+      switch (nd) {
+        case 8: return bt_launch<T, 8>(g, (int)N, tmG, tmL, tmR, tmGL, tmGR, grid, smem, st, prof);
+        case 16: return bt_launch<T, 16>(g, (int)N, tmG, tmL, tmR, tmGL, tmGR, grid, smem, st, prof);
+        case 24: return bt_launch<T, 24>(g, (int)N, tmG, tmL, tmR, tmGL, tmGR, grid, smem, st, prof);
+        default: return bt_launch<T, 32>(g, (int)N, tmG, tmL, tmR, tmGL, tmGR, grid, smem, st, prof);
+      }
+    };
+    if (in_dtype == RSM_F16) return go(__half{});
+    return go(__nv_bfloat16{});
   };
-  if (in_dtype == RSM_F16) return go(__half{});
-  return go(__nv_bfloat16{});
+  for (int d0 = 0; d0 < (int)D; d0 += BT_DP) {
+    const int dc = (int)D - d0 < BT_DP ? (int)D - d0 : BT_DP;
+    if (d0 == 0) {
+      if (int rc = chunk(0, dc, gl != nullptr, gr != nullptr)) return rc;
+    } else {
+      if (gl) { if (int rc = chunk(d0, dc, true, false)) return rc; }
+      if (gr) { if (int rc = chunk(d0, dc, false, true)) return rc; }
+    }
+  }
+  return RSM_OK;
 }
 
 }  // namespace rsm

@@ -294,8 +294,9 @@ groupwise_bwd_slab_kernel(const Tout* __restrict__ gout, FeatView L, FeatView R,
       const float* __restrict__ frow = rside ? sL + xb + d0 : sR + sg.DPAD + xb - d0 - 4;
       // a left tile only meets the zero margin once d > x + 3; a right tile only zeros once x' + d >= W
       if (active && (rside ? xb + d0 < g.W : d0 <= xb + 3)) {
-        if (!rside) gs_left<Tout, CPG>(acc, sGt, frow, sg.FPR, 0, S::DC / 4);
-        else gs_right<Tout, CPG>(acc, sGt, frow, sg.FPL, xb + d0, g.W, 0, S::DC / 4);
+        const int nq = min(S::DC, g.D - d0) >> 2;      // disparity quads of this slab below D
+        if (!rside) gs_left<Tout, CPG>(acc, sGt, frow, sg.FPR, 0, nq);
+        else gs_right<Tout, CPG>(acc, sGt, frow, sg.FPL, xb + d0, g.W, 0, nq);
       }
     }
 

@@ -1,6 +1,7 @@
-"""GPU parity of the tcgen05 inner-product adjoint (csrc/rsm_corr_bwd_tc.cu: 16-bit tensors, D <= 64) against the fp32
+"""GPU parity of the tcgen05 inner-product adjoint (csrc/rsm_corr_bwd_tc.cu: 16-bit tensors) against the fp32
 oracle on the same rounded inputs: both gradients and one gradient alone, channel sum and mean, 16 .. 192 channels
-(one and several 64-channel passes), D = 1 .. 64, rows narrower than a tile and ragged last tiles, the x < d fill
+(one and several 64-channel passes), D = 1 .. 64 in one launch and D = 65 .. 200 as chunks of 64 added with TMA
+reduce-add, rows narrower than a tile (and narrower than D) and ragged last tiles, the x < d fill
 region with non-finite upstream gradients, strided feature views, and the SIMT fall-back for shapes it does not cover.
 Reference: autograd through TorchInnerProductCost.forward (cost_volume/inner_product.py:29-41) / make_correlation_volume
 (model/mobile_disp_net_c.py:188-205); SURVEY.md 8a "Backward contracts"."""
@@ -16,7 +17,8 @@ pytestmark = pytest.mark.gpu
 
 DT = {"fp16": torch.float16, "bf16": torch.bfloat16}
 SHAPES = [(1, 16, 2, 128, 16), (1, 64, 3, 240, 48), (2, 64, 5, 240, 48), (1, 32, 4, 312, 48), (1, 16, 2, 72, 19), (1, 128, 2, 480, 64),
-          (1, 48, 2, 136, 1), (1, 16, 2, 8, 24), (3, 32, 7, 96, 64), (1, 16, 1, 520, 33), (2, 192, 2, 264, 40)]
+          (1, 48, 2, 136, 1), (1, 16, 2, 8, 24), (3, 32, 7, 96, 64), (1, 16, 1, 520, 33), (2, 192, 2, 264, 40),
+          (1, 64, 2, 480, 96), (1, 128, 2, 480, 192), (2, 32, 3, 200, 65), (1, 16, 2, 72, 130), (1, 16, 2, 312, 200)]
 
 
 @pytest.fixture(scope="module")
@@ -65,7 +67,15 @@ def test_inner_bwd_tc(rsm, shape, dn, mean):
 def test_inner_bwd_tc_fill_region_is_ignored(rsm):
     """Upstream gradient entries with x < d belong to the volume's fill region: the reference's slice assignment never
     reads them, so NaN / inf there must not reach either gradient."""
-    shape = (2, 32, 3, 200, 48)
+    _fill_region_case(rsm, (2, 32, 3, 200, 48))
+
+
+def test_inner_bwd_tc_fill_region_is_ignored_chunked(rsm):
+    """the same with three disparity chunks: the fill region of a later chunk reaches into the second tile of a row"""
+    _fill_region_case(rsm, (1, 32, 2, 328, 160))
+
+
+def _fill_region_case(rsm, shape):
     n, c, h, w, d = shape
     l, r, go = _case(shape, "bf16", seed=11)
     for dd in range(d):

@@ -222,8 +222,11 @@ def sweep_tail(cfg, b, dc, hc, wc, iters):
     cg = cost.requires_grad_(True)
     out = rsm.v4_head(cg, d, h, w)
     go = torch.randn_like(out)
-    report(cfg, "v4_head_bwd", "f32", shp, timed(lambda: torch.autograd.grad(out, cg, go, retain_graph=True), iters),
-           nb + 2 * b * dc * h * w * 4)
+    # algorithmic bytes: cost read, its gradient written, incoming gradient + expectation + lse read (the tile-partial
+    # workspace of the x4 head, 40 floats per tile and slice, is not algorithmic); the op is issue-bound like the forward
+    ms = timed(lambda: torch.autograd.grad(out, cg, go, retain_graph=True), iters)
+    report(cfg, "v4_head_bwd", "f32", {**shp, "Gexp_per_s": round(b * d * h * w / (ms * 1e-3) / 1e9, 1)}, ms,
+           2 * b * dc * hc * wc * 4 + 3 * b * h * w * 4)
 
 
 def sweep_v4_volume(cfg, iters):

@@ -154,21 +154,27 @@ template <typename T>
 __device__ __forceinline__ void stage_tile_all4(const T* __restrict__ cost_b, const TailSmem& sm, const TailGeom& g,
                                                 int cy0, int cx0) {
   constexpr int FW = 10;
-  const int n = g.Dc * 4 * FW;
   const int plane = g.Hc * g.Wc;           // Dc * Hc * Wc < 2^31 (host check): 32-bit offsets inside a batch item
-  // ---- 1. raw[(k*4 + fy)*10 + fx]
-  for (int e0 = threadIdx.x; e0 < n; e0 += 4 * kNT) {
-    float v[4];
+  // ---- 1. raw[(k*4 + fy)*10 + fx]: a thread keeps its footprint cell (fy, fx) and walks the slices six apart (240 of
+  // the 256 threads; one division per thread, not per element: the flat-index form spent 25 instructions per value)
+  {
+    const int kk = threadIdx.x / 40, r = threadIdx.x - kk * 40;
+    if (kk < 6) {
+      const int fy = r / FW, fx = r - fy * FW;
+      const int cy = min(cy0 + fy, g.Hc - 1), cx = min(cx0 + fx, g.Wc - 1);
+      const T* __restrict__ src = cost_b + ((int64_t)kk * plane + cy * g.Wc + cx);
+      float* dst = sm.raw + threadIdx.x;                 // (kk * 4 + fy) * 10 + fx == kk * 40 + r
+      const int64_t step = 6 * (int64_t)plane;
+      int k = kk;
+      for (; k + 18 < g.Dc; k += 24, src += 4 * step, dst += 4 * 240) {
+        float v[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int e = e0 + u * kNT;
-      const int p = e / FW, fx = e - p * FW;
-      const int cy = min(cy0 + (p & 3), g.Hc - 1), cx = min(cx0 + fx, g.Wc - 1);
-      v[u] = e < n ? to_f(__ldg(cost_b + ((p >> 2) * plane + cy * g.Wc + cx))) : 0.f;
+        for (int u = 0; u < 4; ++u) v[u] = to_f(__ldg(src + u * step));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dst[u * 240] = v[u];
+      }
+      for (; k < g.Dc; k += 6, src += step, dst += 240) *dst = to_f(__ldg(src));
     }
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (e0 + u * kNT < n) sm.raw[e0 + u * kNT] = v[u];
   }
   __syncthreads();
   // ---- 2. x-interpolation (constant weights, see stage_tile) + running column maxima

@@ -338,7 +338,42 @@ def tensor_core_kernels(rsm, dev, peak):
         "useful_TFLOPs": 2.0 * n4 * c4 * h4 * w4 * d4 / (ms * 1e-3) / 1e12}
     del sets, s4
     out.update(cfg5_regression_numbers(rsm, dev, peak, flush))
+    out.update(cfg3_backward_numbers(rsm, dev, peak, flush))
     out.update(v4_model_numbers(rsm, dev, flush))
+    return out
+
+
+def cfg3_backward_numbers(rsm, dev, peak, flush):
+    """The training half of BASELINE config 3's step: adjoints of the three kernels of `value` at the same shapes
+    (8 pairs, C = 32, 96 x 312, D = 48, G = 8; head to 384 x 1248), fp32, against the HBM roofline (the head's adjoint is
+    issue-bound: its figure is fine disparities per second)."""
+    n, c, h, w, d, ng = 8, 32, 96, 312, 48, 8
+    g = torch.Generator(device=dev).manual_seed(11)
+    L = torch.randn((n, c, h, w), device=dev, generator=g).requires_grad_(True)
+    R = torch.randn((n, c, h, w), device=dev, generator=g).requires_grad_(True)
+    out = {}
+    feat = n * c * h * w * 4
+    for name, vol_fn, vol_elems in (("groupwise_bwd[f32,cfg3]", lambda: rsm.groupwise_volume(L, R, ng, d), n * ng * h * w * d),
+                                    ("concat_bwd[f32,cfg3]", lambda: rsm.concat_volume(L, R, d), n * 2 * c * h * w * d)):
+        with torch.enable_grad():
+            vol = vol_fn()
+        go = torch.randn(vol.shape, device=dev, generator=g)
+        fn = lambda: torch.autograd.grad(vol, (L, R), go, retain_graph=True)
+        for _ in range(3):
+            fn()
+        ms = time_op(fn, 10, flush)
+        b = vol_elems * 4 + (2 if name.startswith("concat") else 4) * feat     # gradient read, both feature gradients written (+ features read)
+        out[name] = {"ms": ms, "algorithmic_GBps": b / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": b / (ms * 1e-3) / 1e9 / peak}
+        del vol, go
+    cost = (torch.randn((n, d, h, w), device=dev, generator=g) * 3).requires_grad_(True)
+    with torch.enable_grad():
+        disp = rsm.v4_head(cost, 4 * d, 4 * h, 4 * w)
+    go = torch.randn(disp.shape, device=dev, generator=g)
+    fn = lambda: torch.autograd.grad(disp, cost, go, retain_graph=True)
+    for _ in range(3):
+        fn()
+    ms = time_op(fn, 10, flush)
+    out["v4_head_bwd[f32,cfg3]"] = {"ms": ms, "G_fine_disparities_per_s": n * 4 * d * 4 * h * 4 * w / (ms * 1e-3) / 1e9}
     return out
 
 

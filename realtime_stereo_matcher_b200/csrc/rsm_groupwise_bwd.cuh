@@ -48,6 +48,7 @@ struct GroupSlabGeom {
   int half;      // threads per side: ceil32(ceil(W / 4))
   int nslab;     // ceil(D / DC)
   int fvec;      // feature rows can be copied 16 bytes at a time (unit stride, aligned rows, W % (16 / sizeof) == 0)
+  int nfb;       // feature buffers: 2 (the next row's features arrive under this row's FMAs), or 1 where two do not fit
   int64_t rows;  // N * G * H
 };
 
@@ -215,7 +216,7 @@ groupwise_bwd_slab_kernel(const Tout* __restrict__ gout, FeatView L, FeatView R,
   const int slab = sg.NQ * S::QP + (sg.NQ * S::QP & 1);   // words per stage (16-byte multiple)
   const int fsz = CPG * (sg.FPL + sg.FPR);
   float* sG = smem;                                    // [GS_NS][NQ][4][DC] (quad pitch QP)
-  float* sF = sG + GS_NS * (slab + (slab & 2));        // [2][ CPG x FPL | CPG x FPR ]
+  float* sF = sG + GS_NS * (slab + (slab & 2));        // [nfb][ CPG x FPL | CPG x FPR ]
   const int stage = slab + (slab & 2);
   // this CTA's run of rows
   const int64_t r0 = sg.rows * blockIdx.x / gridDim.x, r1 = sg.rows * (blockIdx.x + 1) / gridDim.x;
@@ -225,7 +226,7 @@ groupwise_bwd_slab_kernel(const Tout* __restrict__ gout, FeatView L, FeatView R,
   const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sG);
 
   // ---- zero the stages (quads past the row are never written) and the feature buffers (margins)
-  for (int i = threadIdx.x; i < (GS_NS * stage + 2 * fsz) / 4; i += blockDim.x)
+  for (int i = threadIdx.x; i < (GS_NS * stage + sg.nfb * fsz) / 4; i += blockDim.x)
     reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
 
@@ -259,7 +260,7 @@ groupwise_bwd_slab_kernel(const Tout* __restrict__ gout, FeatView L, FeatView R,
 
 #pragma unroll 1
   for (int64_t r = r0; r < r1; ++r) {
-    const int fb = (int)(r - r0) & 1;
+    const int fb = sg.nfb == 2 ? (int)(r - r0) & 1 : 0;
     const float* __restrict__ sL = sF + fb * fsz;
     const float* __restrict__ sR = sL + CPG * sg.FPL;
     float acc[CPG][4];
@@ -275,11 +276,16 @@ groupwise_bwd_slab_kernel(const Tout* __restrict__ gout, FeatView L, FeatView R,
       if (sg.nslab < GS_NS - 1) asm volatile("cp.async.wait_all;" ::: "memory");
       else asm volatile("cp.async.wait_group %0;" ::"n"(GS_NS - 2) : "memory");
       __syncthreads();
-      if (s == 0 && r + 1 < r1) {                      // next row's features into the other buffer
+      if (s == 0 && sg.nfb == 2 && r + 1 < r1) {       // next row's features into the other buffer
         const int64_t rn = r + 1;
         const int y = (int)(rn % g.H);
         const int64_t t = rn / g.H;
         gs_stage_features<Tin, CPG>(sF + (fb ^ 1) * fsz, L, R, t / g.G, (int)(t % g.G) * CPG, y, g.W, sg);
+      }
+      if (s == 0 && sg.nfb == 1 && r > r0) {           // one buffer: everyone is done with the previous row's features now
+        const int y = (int)(r % g.H);
+        const int64_t t = r / g.H;
+        gs_stage_features<Tin, CPG>(sF, L, R, t / g.G, (int)(t % g.G) * CPG, y, g.W, sg);
       }
       if (iu < nunits) {
         cp.issue(sbase + 4u * (uint32_t)((iu % GS_NS) * stage), irow, g.W, g.D, is * S::DC);
@@ -287,6 +293,10 @@ groupwise_bwd_slab_kernel(const Tout* __restrict__ gout, FeatView L, FeatView R,
         if (++is == sg.nslab) { is = 0; irow += WD; }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
+      if (s == 0 && sg.nfb == 1 && r > r0) {           // (exposed once per row; only shapes whose features fill the SM)
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();
+      }
 
       const int d0 = s * S::DC;
       // left: the slab at this thread's quad, the right features at x - d0 - 4;  right: both at x' + d0
@@ -353,7 +363,12 @@ static bool launch_groupwise_bwd_slab(const void* gout, const rsm_feat& left, co
   sg.fvec = g.W % FEPV == 0 && vec_ok(left) && vec_ok(right);
   const int slab = sg.NQ * S::QP + (sg.NQ * S::QP & 1), stage = slab + (slab & 2);
   const int ns = GS_STAGES;
-  const size_t smem = ((size_t)ns * stage + (size_t)2 * g.cpg * (sg.FPL + sg.FPR)) * sizeof(float);
+  sg.nfb = 2;
+  size_t smem = ((size_t)ns * stage + (size_t)2 * g.cpg * (sg.FPL + sg.FPR)) * sizeof(float);
+  if (smem > 200 * 1024) {
+    sg.nfb = 1;
+    smem = ((size_t)ns * stage + (size_t)g.cpg * (sg.FPL + sg.FPR)) * sizeof(float);
+  }
   if (smem > 200 * 1024 || sg.rows <= 0 || sg.rows > 2147483647LL) return false;
   const int nt = 2 * sg.half;
   auto launch = [&](auto kern) -> int {

@@ -135,7 +135,8 @@ concat_bwd_kernel(const T* __restrict__ gout, T* __restrict__ gl, T* __restrict_
 // flight, fully coalesced) into rows of an ODD word pitch, so that both reductions
 //     left  half:  gL[x]  = sum_{d <= x}        M[x][d]        (row sums, masked like the forward fill)
 //     right half:  gR[x'] = sum_{d, x'+d < W}   M[x'+d][d]     (diagonal sums; the tile carries a D-1 pixel halo)
-// read shared memory conflict-free with one pixel per thread.  Sums run in ascending d (deterministic).
+// read shared memory conflict-free with one pixel per thread (two when the tile is wider than the CTA).  Sums run in
+// ascending d (deterministic), D in chunks of <= 64 words per pixel.
 // 16-bit volumes move as 32-bit words holding two disparities (D even).  (A variant with 16-byte copies,
 // a pitch of 4 (mod 8) words and LDS.128 row sums measured 20% slower on B200: the reductions, not the
 // copies, set the pace.)
@@ -151,7 +152,7 @@ __device__ __forceinline__ float word_elem(uint32_t w, int d) {
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 concat_bwd_row_kernel(const T* __restrict__ gout, T* __restrict__ gl, T* __restrict__ gr, int C, int H, int W,
-                      int D, int TX, int P) {
+                      int D, int TX, int P, int DCH) {
   extern __shared__ __align__(16) uint32_t tile[];
   constexpr int EPW = 4 / (int)sizeof(T);          // elements per 32-bit word
   const int DW = D / EPW;                          // words per pixel
@@ -162,40 +163,59 @@ concat_bwd_row_kernel(const T* __restrict__ gout, T* __restrict__ gl, T* __restr
   const bool right = ch >= C;
   const uint32_t* __restrict__ src = reinterpret_cast<const uint32_t*>(gout + row * (int64_t)W * D);
   T* __restrict__ dst = (right ? gr : gl) + ((n * C + (right ? ch - C : ch)) * H + y) * (int64_t)W;
-  // word w of a tile -> pixel w / DW, word w % DW of it; a thread's words are kThreads apart, so both the
-  // shared-memory address and the wrap test advance by constants (no division in the loop)
-  const int stepk = kThreads % DW;
-  const uint32_t dstep = 4u * ((kThreads / DW) * P + stepk), wrapfix = 4u * (P - DW);
-  const int px0 = threadIdx.x / DW, kk0 = threadIdx.x - px0 * DW;
   const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
   for (int x0 = 0; x0 < W; x0 += TX) {
-    const int npx = min(TX + (right ? D - 1 : 0), W - x0);
-    __syncthreads();
-    {
-      int kk = kk0;
-      uint32_t sdst = tile_s + 4u * (px0 * P + kk0);
-      const uint32_t* g = src + (int64_t)x0 * DW + threadIdx.x;
-      const int nword = npx * DW;
-      for (int w = threadIdx.x; w < nword; w += kThreads) {
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst), "l"(g) : "memory");
-        g += kThreads; sdst += dstep; kk += stepk;
-        if (kk >= DW) { kk -= DW; sdst += wrapfix; }
+    const int ntx = min(TX, W - x0);               // output pixels of this tile: threadIdx.x and threadIdx.x + kThreads
+    float acc[2] = {0.f, 0.f};
+    // disparity chunks of DCH (one chunk when D <= DCH): a chunk of the right half needs the pixels x' + d of ITS
+    // disparities only, so the halo stays DCH - 1 pixels however large D is (a single pass over D = 192 re-read a
+    // 191-pixel halo per 32-pixel tile: 7x the traffic)
+    for (int d0 = 0; d0 < D; d0 += DCH) {
+      const int dch = min(DCH, D - d0), DWc = dch / EPW;
+      const int start = x0 + (right ? d0 : 0);     // first pixel staged
+      const int npx = min(ntx + (right ? dch - 1 : 0), W - start);
+      // word w of the tile -> pixel w / DWc, word w % DWc of the chunk; a thread's words are kThreads apart, so the
+      // shared-memory address, the source address and the wrap test advance by constants (no division in the loop)
+      const int stepk = kThreads % DWc, stepp = kThreads / DWc;
+      const uint32_t dstep = 4u * (stepp * P + stepk), wrapfix = 4u * (P - DWc);
+      const int px0 = threadIdx.x / DWc, kk0 = threadIdx.x - px0 * DWc;
+      __syncthreads();
+      if (npx > 0) {
+        int kk = kk0;
+        uint32_t sdst = tile_s + 4u * (px0 * P + kk0);
+        const uint32_t* g = src + (int64_t)(start + px0) * DW + d0 / EPW + kk0;
+        const int64_t gstep = (int64_t)stepp * DW + stepk;
+        const int nword = npx * DWc;
+        for (int w = threadIdx.x; w < nword; w += kThreads) {
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst), "l"(g) : "memory");
+          g += gstep; sdst += dstep; kk += stepk;
+          if (kk >= DWc) { kk -= DWc; sdst += wrapfix; g += DW - DWc; }
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
       }
-      asm volatile("cp.async.wait_all;" ::: "memory");
+      __syncthreads();
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int xi = threadIdx.x + u * kThreads;
+        if (xi >= ntx) break;
+        const int x = x0 + xi;
+        float a = acc[u];
+        if (!right) {
+          const uint32_t* r = tile + xi * P;
+          const int nd = min(x - d0, dch - 1) + 1;             // disparities d0 .. of this chunk with d <= x
+          for (int d = 0; d < nd; ++d) a += word_elem<T>(r[d / EPW], d);
+        } else {
+          const uint32_t* r = tile + xi * P;
+          const int nd = min(dch, W - x - d0);                 // x + d0 + d < W
+          for (int d = 0; d < nd; ++d) a += word_elem<T>(r[d * P + d / EPW], d);
+        }
+        acc[u] = a;
+      }
     }
-    __syncthreads();
-    for (int xi = threadIdx.x; xi < min(TX, W - x0); xi += kThreads) {
-      const int x = x0 + xi;
-      float acc = 0.f;
-      const uint32_t* r = tile + xi * P;
-      if (!right) {
-        const int nd = min(x, D - 1) + 1;
-        for (int d = 0; d < nd; ++d) acc += word_elem<T>(r[d / EPW], d);
-      } else {
-        const int nd = min(D, W - x);
-        for (int d = 0; d < nd; ++d) acc += word_elem<T>(r[d * P + d / EPW], d);
-      }
-      dst[x] = from_f<T>(acc);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int xi = threadIdx.x + u * kThreads;
+      if (xi < ntx) dst[x0 + xi] = from_f<T>(acc[u]);
     }
   }
 }
@@ -475,20 +495,23 @@ extern "C" int rsm_concat_bwd(const void* gout, void* gleft, void* gright, int64
   RSM_COMMON_CHECKS(dtype)
   if (!grid_ok(ceil_div(total, kThreads))) return RSM_ERR_INVALID_SHAPE;
   return RSM_DISPATCH_DTYPE(dtype, T, [&]() -> int {
-    // row-tiled kernel: whole words per pixel, word-aligned rows, at most 1024 disparities (else the per-element gather)
+    // row-tiled kernel: whole words per pixel, word-aligned rows (else the per-element gather)
     constexpr int EPW = 4 / (int)sizeof(T);
-    if (D > 0 && D <= 1024 && D % EPW == 0 && aligned_to(gout, 4) && grid_ok(N * 2 * C * H)) {
-      const int DW = (int)D / EPW;
-      const int P = DW | 1;                                          // odd word pitch
-      int64_t tx = (96 * 1024) / (4 * (int64_t)P) - (D - 1);         // pixels per tile within 96 KB, halo included
+    if (D > 0 && D % EPW == 0 && aligned_to(gout, 4) && grid_ok(N * 2 * C * H)) {
+      const int DW = (int)(D / EPW);
+      const int CW = DW <= 64 ? DW : 48;                             // words per pixel and disparity chunk
+      const int dch = CW * EPW;
+      const int P = CW | 1;                                          // odd word pitch
+      int64_t tx = (96 * 1024) / (4 * (int64_t)P) - (dch - 1);       // pixels per tile within 96 KB, halo included
       tx = tx < 32 ? 32 : tx;
+      if (tx > 2 * kThreads) tx = 2 * kThreads;                      // two pixels per thread
       if (tx > W) tx = W;
-      const size_t smem = (size_t)(tx + D - 1) * P * 4;
+      const size_t smem = (size_t)(tx + dch - 1) * P * 4;
       if (smem <= 200 * 1024) {
         auto k = concat_bwd_row_kernel<T>;
         if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k<<<(unsigned)(N * 2 * C * H), kThreads, smem, st>>>((const T*)gout, (T*)gleft, (T*)gright, (int)C, (int)H,
-                                                             (int)W, (int)D, (int)tx, P);
+                                                             (int)W, (int)D, (int)tx, P, dch);
         return finish_launch("rsm_concat_bwd");
       }
     }

@@ -511,6 +511,60 @@ def test_groupwise_bwd_row_parts(rsm, shape, dn):
         close(b, gr, atol)
 
 
+def test_groupwise_bwd_one_side_and_views(rsm):
+    """The row-streaming adjoint with only one gradient asked for, with strided (channel-sliced, width-cropped) feature
+    views (the 4-byte staging path) and with rows wider than one CTA covers (W > 1024: the tiled kernel)."""
+    rng = np.random.default_rng(73)
+    n, c, h, w, d, ng = 2, 16, 3, 200, 24, 4
+    l = rng.standard_normal((n, c, h, w)).astype(np.float32)
+    r = rng.standard_normal((n, c, h, w)).astype(np.float32)
+    gout = rng.standard_normal((n, ng, h, w, d)).astype(np.float32)
+    gl, gr = oracle.groupwise_volume_bwd(gout, l, r, ng)
+    atol = GRAD_RTOL * np.sqrt(d) * 16
+    L = dev(l, grad=True)
+    rsm.groupwise_volume(L, dev(r), ng, d).backward(dev(gout))
+    close(L.grad, gl, atol)
+    R = dev(r, grad=True)
+    rsm.groupwise_volume(dev(l), R, ng, d).backward(dev(gout))
+    close(R.grad, gr, atol)
+    # views: channels 4..20 of a 24-channel tensor, columns 3..203 of a 208-wide one
+    big_l = torch.zeros((n, c + 8, h, w + 8), device="cuda")
+    big_r = torch.zeros((n, c + 8, h, w + 8), device="cuda")
+    big_l[:, 4:4 + c, :, 3:3 + w] = dev(l)
+    big_r[:, 4:4 + c, :, 3:3 + w] = dev(r)
+    big_l.requires_grad_(True); big_r.requires_grad_(True)
+    rsm.groupwise_volume(big_l[:, 4:4 + c, :, 3:3 + w], big_r[:, 4:4 + c, :, 3:3 + w], ng, d).backward(dev(gout))
+    close(big_l.grad[:, 4:4 + c, :, 3:3 + w], gl, atol)
+    close(big_r.grad[:, 4:4 + c, :, 3:3 + w], gr, atol)
+    assert big_l.grad[:, :4].abs().max().item() == 0 and big_l.grad[..., :3].abs().max().item() == 0
+    # a row wider than the streaming kernel's CTA
+    n2, c2, h2, w2, d2, g2 = 1, 8, 2, 1100, 8, 2
+    l2 = rng.standard_normal((n2, c2, h2, w2)).astype(np.float32)
+    r2 = rng.standard_normal((n2, c2, h2, w2)).astype(np.float32)
+    go2 = rng.standard_normal((n2, g2, h2, w2, d2)).astype(np.float32)
+    gl2, gr2 = oracle.groupwise_volume_bwd(go2, l2, r2, g2)
+    L2, R2 = dev(l2, grad=True), dev(r2, grad=True)
+    rsm.groupwise_volume(L2, R2, g2, d2).backward(dev(go2))
+    close(L2.grad, gl2, atol)
+    close(R2.grad, gr2, atol)
+
+
+@pytest.mark.parametrize("dn", ["fp32", "bf16"])
+def test_concat_bwd_disparity_chunks(rsm, dn):
+    """The concatenation adjoint stages at most 64 words per pixel at a time: D = 192 (fp32: four chunks, bf16: two)
+    and a D that leaves a short last chunk, ragged rows -- against the oracle."""
+    rng = np.random.default_rng(74)
+    for (n, c, h, w, d) in ((1, 3, 2, 230, 192), (2, 2, 3, 75, 100)):
+        gout = round_to(rng.standard_normal((n, 2 * c, h, w, d)).astype(np.float32), dn)
+        gl, gr = oracle.concat_volume_bwd(gout)
+        L = dev(np.zeros((n, c, h, w), np.float32), dn, grad=True)
+        R = dev(np.zeros((n, c, h, w), np.float32), dn, grad=True)
+        rsm.concat_volume(L, R, d).backward(dev(gout, dn))
+        atol = GRAD_RTOL * np.sqrt(d) * 16 if dn == "fp32" else RTOL_16[dn] * np.sqrt(d) * 4
+        close(L.grad, gl, atol)
+        close(R.grad, gr, atol)
+
+
 # ------------------------------------------------------------ refinement warp (SURVEY 8f-2)
 @pytest.mark.parametrize("name", names("warp_"))
 def test_warp_goldens(rsm, name):

@@ -354,6 +354,70 @@ def test_fullsize_v4_tail_cfg3(rsm):
     torch.testing.assert_close(pred, ref, atol=V4_TAIL_ATOL, rtol=0)
 
 
+def _dot(a, b):
+    return (a.double() * b.double()).sum().item()
+
+
+def test_fullsize_adjoint_identities_cfg3(rsm):
+    """cfg3 shapes, the whole per-GPU batch: every volume is (bi)linear in the features, so for any upstream gradient
+    <gV, V(L, R)> = <gL, L> = <gR, R> (group-wise) and <gV, V> = <gL, L> + <gR, R> (concatenation) -- a
+    size-independent check of the adjoint kernels against the forward kernels (which the tests above pin to torch)."""
+    n, c, h, w, d, ng = 8, 32, 96, 312, 48, 8
+    gen = torch.Generator(device="cuda").manual_seed(4321)
+    L = torch.randn((n, c, h, w), device="cuda", generator=gen).requires_grad_(True)
+    R = torch.randn((n, c, h, w), device="cuda", generator=gen).requires_grad_(True)
+    for dt, tol in ((torch.float32, 2e-5), (torch.bfloat16, 1e-2)):
+        l, r = L.detach().to(dt).requires_grad_(True), R.detach().to(dt).requires_grad_(True)
+        vol = rsm.groupwise_volume(l, r, ng, d)
+        gv = torch.randn(vol.shape, device="cuda", generator=gen).to(dt)
+        gl, gr = torch.autograd.grad(vol, (l, r), gv)
+        ref = _dot(gv, vol)
+        scale = (gv.double().abs() * vol.double().abs()).sum().item()
+        assert abs(_dot(gl, l) - ref) <= tol * scale, (dt, _dot(gl, l), ref)
+        assert abs(_dot(gr, r) - ref) <= tol * scale, (dt, _dot(gr, r), ref)
+        del vol, gv
+        vol = rsm.concat_volume(l, r, d)
+        gv = torch.randn(vol.shape, device="cuda", generator=gen).to(dt)
+        gl, gr = torch.autograd.grad(vol, (l, r), gv)
+        ref = _dot(gv, vol)
+        scale = (gv.double().abs() * vol.double().abs()).sum().item()
+        assert abs(_dot(gl, l) + _dot(gr, r) - ref) <= tol * scale, (dt, ref)
+        del vol, gv
+
+
+@pytest.mark.parametrize("shape", [(8, 64, 144, 240, 48), (1, 128, 270, 480, 192), (1, 64, 270, 480, 96)])
+def test_fullsize_inner_adjoint_identity(rsm, shape):
+    """cfg2 (DispNetC's correlation, 8 of the 32 pairs) and cfg4's large-D points: <gV, V> = <gL, L> = <gR, R> for the
+    inner-product volume, fp32 (SIMT adjoint) and bf16 (tcgen05 adjoint; D = 96 / 192 as chunks of 64 disparities)."""
+    n, c, h, w, d = shape
+    gen = torch.Generator(device="cuda").manual_seed(99)
+    for dt, tol in ((torch.float32, 2e-5), (torch.bfloat16, 1e-2)):
+        l = torch.randn((n, c, h, w), device="cuda", generator=gen).to(dt).requires_grad_(True)
+        r = torch.randn((n, c, h, w), device="cuda", generator=gen).to(dt).requires_grad_(True)
+        vol = rsm.inner_product_volume(l, r, d, mean=True)
+        gv = torch.randn(vol.shape, device="cuda", generator=gen).to(dt)
+        gl, gr = torch.autograd.grad(vol, (l, r), gv)
+        ref = _dot(gv, vol)
+        scale = (gv.double().abs() * vol.double().abs()).sum().item()
+        assert abs(_dot(gl, l) - ref) <= tol * scale, (dt, _dot(gl, l), ref)
+        assert abs(_dot(gr, r) - ref) <= tol * scale, (dt, _dot(gr, r), ref)
+
+
+def test_fullsize_v4_head_adjoint_cfg3(rsm):
+    """cfg3 head, one pair at full size (48 x 96 x 312 -> 192 x 384 x 1248): the tile + combine adjoint against autograd
+    through interpolate -> softmax -> expectation on the device."""
+    gen = torch.Generator(device="cuda").manual_seed(77)
+    cost = (torch.randn((1, 48, 96, 312), device="cuda", generator=gen) * 3)
+    gout = torch.randn((1, 384, 1248), device="cuda", generator=gen)
+    c = cost.clone().requires_grad_(True)
+    rsm.v4_head(c, 192, 384, 1248).backward(gout)
+    ref = cost.clone().requires_grad_(True)
+    fine = torch.nn.functional.interpolate(ref.unsqueeze(1), [192, 384, 1248], mode="trilinear").squeeze(1)
+    (torch.softmax(fine, 1) * torch.arange(192, device="cuda", dtype=torch.float32).view(1, -1, 1, 1)).sum(1).backward(gout)
+    err = (c.grad - ref.grad).abs().max().item()
+    assert err <= GRAD_RTOL * 192 * max(1.0, ref.grad.abs().max().item()), err
+
+
 # ------------------------------------------------------------------------ error behaviour
 def test_errors(rsm):
     x = torch.zeros((1, 6, 2, 8), device="cuda")

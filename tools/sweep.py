@@ -29,6 +29,7 @@ import realtime_stereo_matcher_b200 as rsm  # noqa: E402
 DT = {"f32": torch.float32, "bf16": torch.bfloat16, "f16": torch.float16}
 PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
     os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+FFMA_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # fp32 FMA pipe at the boost clock the sweeps record
 _flush = None
 
 
@@ -113,6 +114,8 @@ def report(cfg, op, dtype, shape, ms, nbytes, flops=0):
            "GBps": round(gbs, 1), "frac_of_measured_hbm": round(gbs / PEAK, 3)}
     if flops:
         rec["TFLOPs"] = round(flops / (ms * 1e-3) / 1e12, 2)
+        if dtype == "f32":      # SIMT kernels: 148 SMs x 128 FMA lanes x 2 flops x 1.965 GHz = 74.4 TFLOP/s
+            rec["frac_of_fp32_fma_peak"] = round(flops / (ms * 1e-3) / 1e12 / FFMA_PEAK_TFLOPS, 3)
     now = time.time()
     _ROWS.append((rec, _T0[0], now))      # measured between the previous report and this one
     _T0[0] = now
@@ -166,16 +169,16 @@ def sweep_volumes(cfg, n, c, h, w, d, g, dtypes, iters, ops):
                        fin + n * h * w * 20, 2 * n * c * h * w * d)
         if "bwd" in ops:
             Lg, Rg = L.clone().requires_grad_(True), R.clone().requires_grad_(True)
-            for name, fn, nb in (
-                ("concat_bwd", lambda: rsm.concat_volume(Lg, Rg, d), 2 * n * c * h * w * d * e + fin),
-                ("groupwise_bwd", lambda: rsm.groupwise_volume(Lg, Rg, g, d), n * g * h * w * d * e + 2 * fin),
-                ("inner_mean_bwd", lambda: rsm.inner_product_volume(Lg, Rg, d, mean=True), n * d * h * w * e + 2 * fin),
+            for name, fn, nb, fl in (
+                ("concat_bwd", lambda: rsm.concat_volume(Lg, Rg, d), 2 * n * c * h * w * d * e + fin, 0),
+                ("groupwise_bwd", lambda: rsm.groupwise_volume(Lg, Rg, g, d), n * g * h * w * d * e + 2 * fin, 4 * n * c * h * w * d),
+                ("inner_mean_bwd", lambda: rsm.inner_product_volume(Lg, Rg, d, mean=True), n * d * h * w * e + 2 * fin, 4 * n * c * h * w * d),
             ):
                 if name.split("_")[0] not in ops:
                     continue
                 out = fn()
                 go = torch.randn_like(out)
-                report(cfg, name, dt, shp, timed(lambda: torch.autograd.grad(out, (Lg, Rg), go, retain_graph=True), iters), nb)
+                report(cfg, name, dt, shp, timed(lambda: torch.autograd.grad(out, (Lg, Rg), go, retain_graph=True), iters), nb, fl)
                 del out, go
         del L, R
         torch.cuda.empty_cache()

@@ -102,8 +102,8 @@ int rsm_inner_fwd(rsm_feat left, rsm_feat right, void* out, int64_t N, int64_t C
 int rsm_inner_bwd(const void* gout, rsm_feat left, rsm_feat right, void* gleft, void* gright,
                   int64_t N, int64_t C, int64_t H, int64_t W, int64_t D, int reduce, int in_dtype,
                   int out_dtype, int device, void* stream);
-/* diagnostic twin: `prof` = 16 zero-initialised uint64 on the device; the tcgen05 adjoint kernel (16-bit tensors,
- * D <= 64) adds clock64 cycles per warp role, summed over CTAs: issuer [0] waiting for a free accumulator, [1] for a band
+/* diagnostic twin: `prof` = 16 zero-initialised uint64 on the device; the tcgen05 adjoint kernel (16-bit tensors;
+ * every 64-disparity launch of it) adds clock64 cycles per warp role, summed over CTAs: issuer [0] waiting for a free accumulator, [1] for a band
  * matrix, [2] for feature atoms, [3] total; builder warp 0 [4] waiting for the gradient tile, [5] for a free band matrix,
  * [6] building, [7] total; epilogue warp 0 [8] waiting for an accumulator, [9] total */
 int rsm_inner_bwd_profile(const void* gout, rsm_feat left, rsm_feat right, void* gleft, void* gright,
@@ -265,7 +265,8 @@ int rsm_expect_bwd(const void* gout, void* gprob, int64_t N, int64_t D, int64_t 
 int rsm_upsample_regress_fwd(const void* cost, int64_t B, int64_t Dc, int64_t Hc, int64_t Wc,
                              int64_t D, int64_t H, int64_t W, int dtype, rsm_regress_out out,
                              int device, void* stream);
-/* bytes of scratch the backward needs (a (B,Dc,H,W) fp32 tensor) */
+/* bytes of scratch the backward needs: an upper bound, (B,Dc,H,W) fp32 -- what the general two-stage form writes; the
+ * x4 x4 x4 head (D = 4 Dc, H = 4 Hc, W = 4 Wc) uses (B, tiles of 32 x 8 fine pixels, Dc, 40) of it */
 int64_t rsm_upsample_regress_bwd_workspace(int64_t B, int64_t Dc, int64_t H, int64_t W);
 int rsm_upsample_regress_bwd(const void* gout, const void* cost, const float* expect,
                              const float* lse, void* gcost, void* workspace, int64_t B,

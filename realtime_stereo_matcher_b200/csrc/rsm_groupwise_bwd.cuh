@@ -30,6 +30,7 @@
 namespace rsm {
 
 constexpr int GS_MAXT = 512;           // threads per CTA (2 sides x <= 256 pixel quads: W <= 1024)
+constexpr int GS_UNROLL_CPG = 8;        // whole slabs are unrolled up to this many channels per group (16: register spills)
 constexpr int GS_STAGES = 2;           // slab stages of the ring: with three, only two CTAs fit an SM at W = 312 (measured 163 vs 134 us)
 
 template <typename Tout> struct GsSlab {
@@ -102,12 +103,13 @@ __device__ __forceinline__ float4 gs_ld4(const float* __restrict__ sGq, int i, i
 }
 
 // one side's FMAs for disparity quads [Q0, Q1) of a slab; sGq = the slab at this thread's pixel quad
-template <typename Tout, int CPG>
+template <typename Tout, int CPG, int NQ>
 __device__ __forceinline__ void gs_left(float (&acc)[CPG][4], const float* __restrict__ sGq, const float* __restrict__ wrow,
                                         int FPR, int Q0, int Q1) {
   // R[c][x + i - d], d = d0 + 4q + r: window w[0..8) = wrow[c * FPR - 4q ..], element 4 + i - r
-#pragma unroll 1
-  for (int q = Q0; q < Q1; ++q) {
+  // (NQ > 0: the first NQ quads of the slab, unrolled -- every address is then an immediate offset)
+#pragma unroll(NQ > 0 ? NQ : 1)
+  for (int q = NQ > 0 ? 0 : Q0; q < (NQ > 0 ? NQ : Q1); ++q) {
     float gq[4][4];                                    // [r][i]
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -128,14 +130,14 @@ __device__ __forceinline__ void gs_left(float (&acc)[CPG][4], const float* __res
 }
 
 // sGu / lrow = the slab / the left features at pixel x' + d0 (u = x' + d)
-template <typename Tout, int CPG>
+template <typename Tout, int CPG, int NQ>
 __device__ __forceinline__ void gs_right(float (&acc)[CPG][4], const float* __restrict__ sGu, const float* __restrict__ lrow,
                                          int FPL, int ub, int W, int Q0, int Q1) {
   // u0 = x' + d0 + 4q: gV[d0 + 4q + r][u0 + r + i] is component r of pixel m = r + i of the two quads at u0;
   // L[c][u0 + r + i] is element r + i of the aligned octet at u0
   constexpr int QP = GsSlab<Tout>::QP;
-#pragma unroll 1
-  for (int q = Q0; q < Q1; ++q) {
+#pragma unroll(NQ > 0 ? NQ : 1)
+  for (int q = NQ > 0 ? 0 : Q0; q < (NQ > 0 ? NQ : Q1); ++q) {
     if (ub + 4 * q >= W) break;                        // nothing but zeros further right
     float p[4][4];                                     // [r][i]
 #pragma unroll
@@ -305,8 +307,17 @@ groupwise_bwd_slab_kernel(const Tout* __restrict__ gout, FeatView L, FeatView R,
       // a left tile only meets the zero margin once d > x + 3; a right tile only zeros once x' + d >= W
       if (active && (rside ? xb + d0 < g.W : d0 <= xb + 3)) {
         const int nq = min(S::DC, g.D - d0) >> 2;      // disparity quads of this slab below D
-        if (!rside) gs_left<Tout, CPG>(acc, sGt, frow, sg.FPR, 0, nq);
-        else gs_right<Tout, CPG>(acc, sGt, frow, sg.FPL, xb + d0, g.W, 0, nq);
+        constexpr int UQ = S::DC / 4;                  // quads of a whole slab: unrolled (4 or 8 at a time)
+        if (CPG <= GS_UNROLL_CPG && nq == UQ) {
+          if (!rside) gs_left<Tout, CPG, UQ>(acc, sGt, frow, sg.FPR, 0, UQ);
+          else gs_right<Tout, CPG, UQ>(acc, sGt, frow, sg.FPL, xb + d0, g.W, 0, UQ);
+        } else if (!S::F32 && CPG <= GS_UNROLL_CPG && nq == 4) {   // half a 16-bit slab (D = 48: 32 + 16)
+          if (!rside) gs_left<Tout, CPG, 4>(acc, sGt, frow, sg.FPR, 0, 4);
+          else gs_right<Tout, CPG, 4>(acc, sGt, frow, sg.FPL, xb + d0, g.W, 0, 4);
+        } else {
+          if (!rside) gs_left<Tout, CPG, 0>(acc, sGt, frow, sg.FPR, 0, nq);
+          else gs_right<Tout, CPG, 0>(acc, sGt, frow, sg.FPL, xb + d0, g.W, 0, nq);
+        }
       }
     }
 

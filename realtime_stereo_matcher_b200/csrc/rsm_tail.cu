@@ -315,6 +315,44 @@ __device__ __forceinline__ void pass2_x4(const SliceY& sl, float neg_ml, int Dc,
   }
 }
 
+// The same pass for TWO horizontally adjacent pixels per thread in packed fp32 (sm_100's FFMA2 / FMUL2 / FADD2: two
+// lanes of arithmetic per issue slot -- the one-pixel loop above is bound by instruction issue, 21 instructions per
+// interval of which 17 are fp32 arithmetic).  Per interval and pixel pair: two 64-bit LDS, 17 packed operations and four
+// ex2, the same operations in the same order as pass2_x4<true, false> on each half.  The 256 threads of a CTA are 128
+// pixel pairs x two halves of the disparity range: intervals [kb, ke) here, the caller adds the two halves' sums.
+struct PairY {
+  const float* p0;   // rows + fy0 * 32 + 2 * (pair column): both pixels share the coarse rows (same y)
+  const float* p1;
+  float2 w0l, w1l;   // wy * log2(e), the same in both halves
+  __device__ __forceinline__ float2 scaled(int k, float2 neg_ml) const {
+    const float2 a = *reinterpret_cast<const float2*>(p0 + k * (4 * kTX));
+    const float2 b = *reinterpret_cast<const float2*>(p1 + k * (4 * kTX));
+    return __ffma2_rn(w0l, a, __ffma2_rn(w1l, b, neg_ml));
+  }
+};
+__device__ __forceinline__ void pass2_x4_pair(const PairY& sl, float2 neg_ml, int kb, int ke, float2& s, float2& ws) {
+  const float2 c8 = make_float2(0.125f, 0.125f), c4 = make_float2(0.25f, 0.25f), m1 = make_float2(-1.f, -1.f);
+  const float2 two = make_float2(2.f, 2.f), three = make_float2(3.f, 3.f), four = make_float2(4.f, 4.f);
+  float2 cs0 = sl.scaled(kb, neg_ml);
+  float2 base = make_float2((float)(4 * kb + 2), (float)(4 * kb + 2));   // first fine index of the interval
+#pragma unroll 4
+  for (int k = kb; k < ke; ++k) {
+    const float2 cs1 = sl.scaled(k + 1, neg_ml);
+    const float2 dl = __ffma2_rn(cs0, m1, cs1);                           // cs1 - cs0, exactly
+    const float2 f0 = __ffma2_rn(c8, dl, cs0), fq = __fmul2_rn(c4, dl);
+    float2 e0, q;
+    e0.x = fast_exp2(f0.x); e0.y = fast_exp2(f0.y);
+    q.x = fast_exp2(fq.x); q.y = fast_exp2(fq.y);
+    const float2 e1 = __fmul2_rn(e0, q), e2 = __fmul2_rn(e1, q), e3 = __fmul2_rn(e2, q);
+    const float2 S = __fadd2_rn(__fadd2_rn(e0, e1), __fadd2_rn(e2, e3));
+    const float2 Tm = __ffma2_rn(three, e3, __ffma2_rn(two, e2, e1));     // sum_j j * e_j
+    s = __fadd2_rn(s, S);
+    ws = __fadd2_rn(__ffma2_rn(base, S, ws), Tm);
+    base = __fadd2_rn(base, four);
+    cs0 = cs1;
+  }
+}
+
 // exact maximum over the FINE values of a pixel (linear inside an interval: attained at an interval end)
 template <bool FAST4, bool ALL4>
 __device__ __forceinline__ float fine_max(const SliceY& sl, const TailSmem& sm, const TailGeom& g) {
@@ -346,6 +384,58 @@ upsample_regress_fwd_kernel(const T* __restrict__ cost, T* __restrict__ soft, in
   const int cx0 = lin_index(blockIdx.x * kTX, g.sw, g.Wc).i0;
   if constexpr (ALL4) stage_tile_all4(cost + (int64_t)b * g.Dc * g.Hc * g.Wc, sm, g, cy0, cx0);
   else stage_tile(cost + (int64_t)b * g.Dc * g.Hc * g.Wc, sm, g, cy0, cx0);
+
+  if constexpr (ALL4 && !WANT_ARG) {
+    // The x4 head without arg-extrema (what MobileStereoNetV4 evaluates): pixel pairs in packed fp32 (pass2_x4_pair).
+    // Thread -> (pair of columns 2 * txp, 2 * txp + 1 of row py, half of the disparity intervals); W % 4 == 0, so a pair
+    // is inside the image or outside it as a whole.  A tile with a pixel whose value range could flush (or with NaNs)
+    // takes the one-pixel-per-thread path below as a whole.
+    const int pi = threadIdx.x & (kNT / 2 - 1), half = threadIdx.x / (kNT / 2);
+    const int txp = pi & 15, py = blockIdx.y * kTY + (pi >> 4), px = blockIdx.x * kTX + 2 * txp;
+    const bool pvalid = px < g.W && py < g.H;
+    const Lin ly = lin_index(py, g.sh, g.Hc);
+    const int o0 = min(ly.i0 - cy0, 3) * kTX + 2 * txp, o1 = min(ly.i1 - cy0, 3) * kTX + 2 * txp;
+    const float2 ua = *reinterpret_cast<const float2*>(sm.rowmax + o0), ub = *reinterpret_cast<const float2*>(sm.rowmax + o1);
+    const float2 la = *reinterpret_cast<const float2*>(sm.rowmax + 4 * kTX + o0),
+                 lb = *reinterpret_cast<const float2*>(sm.rowmax + 4 * kTX + o1);
+    const float2 M2 = make_float2(fmaxf(ua.x, ub.x), fmaxf(ua.y, ub.y));
+    const bool wide = !((M2.x - fminf(la.x, lb.x)) * kLog2e < 120.f) || !((M2.y - fminf(la.y, lb.y)) * kLog2e < 120.f);
+    if (!__syncthreads_or(pvalid && wide)) {
+      PairY pr;
+      pr.p0 = sm.rows + o0; pr.p1 = sm.rows + o1;
+      pr.w0l = make_float2(ly.w0 * kLog2e, ly.w0 * kLog2e); pr.w1l = make_float2(ly.w1 * kLog2e, ly.w1 * kLog2e);
+      const float2 nml = make_float2(-M2.x * kLog2e, -M2.y * kLog2e);
+      const int kmid = min(g.Dc >> 1, g.Dc - 1);
+      float2 s2 = make_float2(0.f, 0.f), ws2 = s2;
+      if (pvalid) {
+        if (half == 0) {   // d' = 0, 1 sit on slice 0
+          const float2 c = pr.scaled(0, nml);
+          const float ex = fast_exp2(c.x), ey = fast_exp2(c.y);
+          s2 = make_float2(ex + ex, ey + ey); ws2 = make_float2(ex, ey);
+          pass2_x4_pair(pr, nml, 0, kmid, s2, ws2);
+        } else {           // d' = D-2, D-1 sit on the last slice
+          pass2_x4_pair(pr, nml, kmid, g.Dc - 1, s2, ws2);
+          const float2 c = pr.scaled(g.Dc - 1, nml);
+          const float ex = fast_exp2(c.x), ey = fast_exp2(c.y), wl = (float)(2 * g.D - 3);
+          s2.x += ex + ex; s2.y += ey + ey;
+          ws2.x = fmaf(wl, ex, ws2.x); ws2.y = fmaf(wl, ey, ws2.y);
+        }
+      }
+      float4* xch = reinterpret_cast<float4*>(sm.part);            // free since the end of the staging
+      xch[threadIdx.x] = make_float4(s2.x, s2.y, ws2.x, ws2.y);
+      __syncthreads();
+      if (pvalid && ((pi >> 5) & 1) == half) {                     // whole warps: each half finishes half of the pairs
+        const float4 ot = xch[threadIdx.x ^ (kNT / 2)];
+        const float sx = s2.x + ot.x, sy = s2.y + ot.y;
+        const float Ex = (ws2.x + ot.z) / sx, Ey = (ws2.y + ot.w) / sy;
+        const int64_t o = ((int64_t)b * g.H + py) * g.W + px;
+        if (soft) { soft[o] = from_f<T>(Ex); soft[o + 1] = from_f<T>(Ey); }
+        if (expect) { expect[o] = Ex; expect[o + 1] = Ey; }        // (scalar stores: the caller's planes need not be 8-byte aligned)
+        if (lse) { lse[o] = M2.x + __logf(sx); lse[o + 1] = M2.y + __logf(sy); }
+      }
+      return;
+    }
+  }
   if (x >= g.W || y >= g.H) return;
 
   const SliceY sl(sm, g, y, cy0);

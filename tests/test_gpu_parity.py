@@ -926,3 +926,33 @@ def test_inner_bwd_16bit_big_tiles(rsm, shape, dn, mean):
     rsm.inner_product_volume(L, R, d, mean=mean).backward(dev(gout, dn))
     close(L.grad, gl, atol, RTOL_16[dn])
     close(R.grad, gr, atol, RTOL_16[dn])
+
+
+@pytest.mark.parametrize("shape", [(3, 64, 130, 132, 48), (2, 48, 40, 260, 96), (1, 40, 5, 132, 70), (2, 32, 7, 128, 20),
+                                   (1, 16, 2, 516, 200)])
+@pytest.mark.parametrize("mean", [False, True])
+def test_inner_bwd_fp32_stream(rsm, shape, mean):
+    """fp32 inner-product adjoint, persistent two-stage kernel (inner_bwd_stream_kernel): more tiles than CTAs (every
+    CTA walks several items), one / two / four disparity chunks, a ragged last channel block, rows that end inside a
+    tile -- against the oracle, and bit-exact on dyadic inputs (fp32 sums are then order-independent)."""
+    n, c, h, w, d = shape
+    rng = np.random.default_rng(17)
+    for dyadic in (False, True):
+        if dyadic:
+            l, r, gout = ((rng.integers(-8, 9, s) / 8.0).astype(np.float32) for s in ((n, c, h, w), (n, c, h, w), (n, d, h, w)))
+        else:
+            l, r, gout = (rng.standard_normal(s).astype(np.float32) for s in ((n, c, h, w), (n, c, h, w), (n, d, h, w)))
+        if h * w * n > 20000:      # the numpy oracle walks disparities: keep it to a few rows of the big cases
+            rows = slice(0, h, max(1, h // 3))
+        else:
+            rows = slice(None)
+        gl, gr = oracle.inner_product_volume_bwd(gout[:, :, rows], l[:, :, rows], r[:, :, rows], mean=mean)
+        L, R = dev(l, grad=True), dev(r, grad=True)
+        rsm.inner_product_volume(L, R, d, mean=mean).backward(dev(gout))
+        if dyadic and (not mean or c & (c - 1) == 0):
+            equal(L.grad[:, :, rows], gl)
+            equal(R.grad[:, :, rows], gr)
+        else:
+            atol = GRAD_RTOL * np.sqrt(d) * 16 / (c if mean else 1)
+            close(L.grad[:, :, rows], gl, atol)
+            close(R.grad[:, :, rows], gr, atol)

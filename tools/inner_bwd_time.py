@@ -11,11 +11,11 @@ def timed(fn, iters=10):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters * 1e3
 for (n, c, h, w, d) in ((1, 64, 270, 480, 96), (1, 128, 270, 480, 96), (1, 128, 270, 480, 192), (1, 64, 270, 480, 192), (8, 128, 270, 480, 192), (32, 64, 144, 240, 48)):
-    for dt in (torch.bfloat16,):
+    for dt in ((torch.float32, torch.bfloat16) if 'f32' in sys.argv else (torch.bfloat16,)):
         L = torch.randn(n, c, h, w, device='cuda', dtype=dt).requires_grad_(True)
         R = torch.randn(n, c, h, w, device='cuda', dtype=dt).requires_grad_(True)
         out = rsm.inner_product_volume(L, R, d)
         go = torch.randn_like(out)
         us = timed(lambda: torch.autograd.grad(out, (L, R), go, retain_graph=True))
-        nb = (n * d * h * w + 4 * n * c * h * w) * 2
-        print(f"inner_bwd bf16 N={n} C={c} D={d}: {us:.1f} us, {nb / us * 1e-3:.0f} GB/s algorithmic", flush=True)
+        nb = (n * d * h * w + 4 * n * c * h * w) * L.element_size()
+        print(f"inner_bwd {str(dt)[6:]} N={n} C={c} D={d}: {us:.1f} us, {nb / us * 1e-3:.0f} GB/s algorithmic", flush=True)

@@ -30,7 +30,8 @@
 namespace rsm {
 
 constexpr int GS_MAXT = 512;           // threads per CTA (2 sides x <= 256 pixel quads: W <= 1024)
-constexpr int GS_UNROLL_CPG = 8;        // whole slabs are unrolled up to this many channels per group (16: register spills)
+constexpr int GS_UNROLL_CPG = 8;        // whole slabs are unrolled up to this many channels per group (16: register spills);
+                                        // 16-bit gradients (8 quads per slab) up to 4: with 8 the unrolled form measured 10-17 % slower
 constexpr int GS_STAGES = 2;           // slab stages of the ring: with three, only two CTAs fit an SM at W = 312 (measured 163 vs 134 us)
 
 template <typename Tout> struct GsSlab {
@@ -308,10 +309,11 @@ groupwise_bwd_slab_kernel(const Tout* __restrict__ gout, FeatView L, FeatView R,
       if (active && (rside ? xb + d0 < g.W : d0 <= xb + 3)) {
         const int nq = min(S::DC, g.D - d0) >> 2;      // disparity quads of this slab below D
         constexpr int UQ = S::DC / 4;                  // quads of a whole slab: unrolled (4 or 8 at a time)
-        if (CPG <= GS_UNROLL_CPG && nq == UQ) {
+        constexpr bool UNROLL = CPG <= (S::F32 ? GS_UNROLL_CPG : GS_UNROLL_CPG / 2);
+        if (UNROLL && nq == UQ) {
           if (!rside) gs_left<Tout, CPG, UQ>(acc, sGt, frow, sg.FPR, 0, UQ);
           else gs_right<Tout, CPG, UQ>(acc, sGt, frow, sg.FPL, xb + d0, g.W, 0, UQ);
-        } else if (!S::F32 && CPG <= GS_UNROLL_CPG && nq == 4) {   // half a 16-bit slab (D = 48: 32 + 16)
+        } else if (!S::F32 && UNROLL && nq == 4) {   // half a 16-bit slab (D = 48: 32 + 16)
           if (!rside) gs_left<Tout, CPG, 4>(acc, sGt, frow, sg.FPR, 0, 4);
           else gs_right<Tout, CPG, 4>(acc, sGt, frow, sg.FPL, xb + d0, g.W, 0, 4);
         } else {

@@ -601,6 +601,13 @@ def run_b200(args, wl):
     achieved = ab[names[dom]] / (op_ms[dom] * 1e-3) / 1e9
     kernels = {n: {"ms": op_ms[j], "algorithmic_GBps": ab[n] / (op_ms[j] * 1e-3) / 1e9,
                    "frac_of_hbm_peak": ab[n] / (op_ms[j] * 1e-3) / 1e9 / peak} for j, n in enumerate(names)}
+    if "v4_head" in kernels and getattr(wl, "D", 0):
+        # the head is bound by the MUFU / FMA pipes, not by HBM: two ex2 per four fine disparities at
+        # 16 ex2 / clk / SM is its floor on this GPU
+        fine = wl.pairs_per_step * wl.D * wl.H * wl.W
+        floor_ms = fine / 2 / (148 * 16 * 1.965e9) * 1e3
+        kernels["v4_head"].update({"bound": "mufu/fma pipes (not hbm)", "G_fine_disparities_per_s": fine / (kernels["v4_head"]["ms"] * 1e-3) / 1e9,
+                                   "mufu_floor_ms": floor_ms, "frac_of_mufu_floor": floor_ms / kernels["v4_head"]["ms"]})
     kernels.update(extra)
     line = {
         "metric": "stereo_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": K,

@@ -149,18 +149,28 @@ __device__ __forceinline__ float word_elem(uint32_t w, int d) {
   }
 }
 
-template <typename T, bool CHUNKED>
+// CWT = words per pixel and chunk when it is one of the usual ones (48: D = 48 / 96 / 192 in fp32, 96 / 192 in 16 bits;
+// 24: D = 48 in 16 bits), else 0: with it the pitch is a constant and the full-length sums -- every pixel but the ones
+// at the row's ends -- are unrolled with immediate offsets (the rolled loop spent ~6 instructions per element; ncu: 421 M
+// warp instructions for 2.9 GB at cfg3).  RIGHT_ONLY: the grid covers the right half's rows only (the left half's plain
+// row sums go through concat_bwd_left_kernel without shared memory).
+template <typename T, bool CHUNKED, int CWT, bool RIGHT_ONLY>
 __global__ void __launch_bounds__(kThreads)
 concat_bwd_row_kernel(const T* __restrict__ gout, T* __restrict__ gl, T* __restrict__ gr, int C, int H, int W,
-                      int D, int TX, int P, int DCH) {
+                      int D, int TX, int P_, int DCH) {
   extern __shared__ __align__(16) uint32_t tile[];
   constexpr int EPW = 4 / (int)sizeof(T);          // elements per 32-bit word
+  const int P = CWT ? (CWT | 1) : P_;
   const int DW = D / EPW;                          // words per pixel
-  const int64_t row = blockIdx.x;
+  int64_t row = blockIdx.x;                        // (n, channel of the 2C, y)
+  if (RIGHT_ONLY) {                                // blockIdx.x = (n, c, y) of the right half
+    const int64_t nc = row / H;
+    row = ((nc / C) * 2 * C + C + nc % C) * H + row % H;
+  }
   const int y = (int)(row % H);
   const int ch = (int)((row / H) % (2 * C));
   const int64_t n = row / ((int64_t)H * 2 * C);
-  const bool right = ch >= C;
+  const bool right = RIGHT_ONLY || ch >= C;
   const uint32_t* __restrict__ src = reinterpret_cast<const uint32_t*>(gout + row * (int64_t)W * D);
   T* __restrict__ dst = (right ? gr : gl) + ((n * C + (right ? ch - C : ch)) * H + y) * (int64_t)W;
   const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
@@ -207,11 +217,21 @@ concat_bwd_row_kernel(const T* __restrict__ gout, T* __restrict__ gl, T* __restr
         if (!right) {
           const uint32_t* r = tile + xi * P;
           const int nd = min(x - d0, dch - 1) + 1;             // disparities d0 .. of this chunk with d <= x
-          for (int d = 0; d < nd; ++d) a += word_elem<T>(r[d / EPW], d);
+          if (CWT && nd == CWT * EPW) {
+#pragma unroll
+            for (int d = 0; d < CWT * EPW; ++d) a += word_elem<T>(r[d / EPW], d);
+          } else {
+            for (int d = 0; d < nd; ++d) a += word_elem<T>(r[d / EPW], d);
+          }
         } else {
           const uint32_t* r = tile + xi * P;
           const int nd = min(dch, W - x - d0);                 // x + d0 + d < W
-          for (int d = 0; d < nd; ++d) a += word_elem<T>(r[d * P + d / EPW], d);
+          if (CWT && nd == CWT * EPW) {
+#pragma unroll
+            for (int d = 0; d < CWT * EPW; ++d) a += word_elem<T>(r[d * (CWT | 1) + d / EPW], d);
+          } else {
+            for (int d = 0; d < nd; ++d) a += word_elem<T>(r[d * P + d / EPW], d);
+          }
         }
         acc[u] = a;
       }
@@ -222,6 +242,49 @@ concat_bwd_row_kernel(const T* __restrict__ gout, T* __restrict__ gl, T* __restr
       if (xi < ntx) dst[x0 + xi] = from_f<T>(acc[u]);
     }
   }
+}
+
+// Left half of the adjoint, gL[x] = sum_{d <= min(x, D-1)} gV[c, x, d]: plain sums of D contiguous elements per
+// pixel -- no shared memory.  Four lanes per pixel take its 16-byte chunks in turn (a warp instruction reads eight
+// pixels x 64 contiguous bytes: whole sectors), all of a lane's loads in flight, two shuffles fold the partial sums
+// (fixed order: deterministic).  Needs D % (16 / sizeof(T)) == 0 and a 16-byte aligned gradient.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+concat_bwd_left_kernel(const T* __restrict__ gout, T* __restrict__ gl, int64_t npix, int C, int H, int W, int D) {
+  constexpr int EPV = 16 / (int)sizeof(T);
+  const int64_t i = ((int64_t)blockIdx.x * kThreads + threadIdx.x) >> 2;     // pixel (n, c, y, x) of gl
+  const int q = threadIdx.x & 3;
+  const bool live = i < npix;
+  const int64_t ii = live ? i : npix - 1;
+  const int64_t r = ii / W;                                                  // (n * C + c) * H + y
+  const int x = (int)(ii - r * W);
+  const int64_t ch = (int64_t)C * H;
+  const int64_t n = r / ch;
+  const T* __restrict__ src = gout + (((n * 2 * C) * H + (r - n * ch)) * W + x) * D;
+  const int nchunk = D / EPV;
+  float a = 0.f;
+  constexpr int U = 4;                                                       // loads in flight per lane
+  for (int c0 = q; c0 < nchunk; c0 += 4 * U) {
+    Vec16<T> v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (c0 + 4 * u < nchunk) v[u] = ldcs16(src + (c0 + 4 * u) * EPV);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (c0 + 4 * u >= nchunk) break;
+      const int d0 = (c0 + 4 * u) * EPV;
+      if (x >= D - 1) {
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) a += to_f(v[u].v[e]);
+      } else {                                                               // the forward's fill region: d <= x only
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) a += d0 + e <= x ? to_f(v[u].v[e]) : 0.f;
+      }
+    }
+  }
+  a += __shfl_xor_sync(0xffffffffu, a, 1);
+  a += __shfl_xor_sync(0xffffffffu, a, 2);
+  if (live && q == 0) gl[i] = from_f<T>(a);
 }
 
 // ============================================================================= interweave
@@ -506,18 +569,41 @@ extern "C" int rsm_concat_bwd(const void* gout, void* gleft, void* gright, int64
       const int CW = DW <= 64 ? DW : 48;                             // words per pixel and disparity chunk
       const int dch = CW * EPW;
       const int P = CW | 1;                                          // odd word pitch
-      int64_t tx = (96 * 1024) / (4 * (int64_t)P) - (dch - 1);       // pixels per tile within 96 KB, halo included
+      int64_t tx = (96 * 1024) / (4 * (int64_t)P) - (dch - 1);       // pixels per tile within 96 KB, halo included (48 KB tiles, five CTAs per SM: the same time)
       tx = tx < 32 ? 32 : tx;
       if (tx > 2 * kThreads) tx = 2 * kThreads;                      // two pixels per thread
       // equal tiles: W = 480 as 2 x 240 measured 0.65 of HBM against 0.61 for 454 + 26; a row that fits is one tile
       tx = ceil_div(W, ceil_div(W, tx));
       const size_t smem = (size_t)(tx + dch - 1) * P * 4;
       if (smem <= 200 * 1024) {
-        auto k = CW == DW ? concat_bwd_row_kernel<T, false> : concat_bwd_row_kernel<T, true>;
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k<<<(unsigned)(N * 2 * C * H), kThreads, smem, st>>>((const T*)gout, (T*)gleft, (T*)gright, (int)C, (int)H,
-                                                             (int)W, (int)D, (int)tx, P, dch);
-        return finish_launch("rsm_concat_bwd");
+        // left half: streaming row sums when the chunks are 16-byte aligned, else through the row kernel as well
+        constexpr int EPV = 16 / (int)sizeof(T);
+        // (pixel rows of >= 192 bytes: at 96 bytes -- D = 48 in 16 bits -- the lanes' chunks do not divide evenly and the
+        // split measured 6-10 % slower than one pass of the row kernel.  A skewed-scatter form of the RIGHT half -- rows read
+        // straight from global memory, element d stored to sS[d][x - d], column sums -- measured slower than the row kernel
+        // too: 447 vs 390 us at cfg3.)
+        const bool split = D % EPV == 0 && D * (int64_t)sizeof(T) >= 192 && aligned_to(gout, 16) &&
+                           grid_ok(ceil_div(4 * total, kThreads));
+        if (split) {
+          concat_bwd_left_kernel<T><<<(unsigned)ceil_div(4 * total, kThreads), kThreads, 0, st>>>(
+              (const T*)gout, (T*)gleft, total, (int)C, (int)H, (int)W, (int)D);
+          if (int rc = finish_launch("rsm_concat_bwd(left)")) return rc;
+        }
+        const unsigned rows = (unsigned)(N * (split ? 1 : 2) * C * H);
+        auto go = [&](auto k) -> int {
+          if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          k<<<rows, kThreads, smem, st>>>((const T*)gout, (T*)gleft, (T*)gright, (int)C, (int)H, (int)W, (int)D, (int)tx, P, dch);
+          return finish_launch("rsm_concat_bwd");
+        };
+        const bool chunked = CW != DW;
+        if (split) {
+          if (CW == 48) return chunked ? go(concat_bwd_row_kernel<T, true, 48, true>) : go(concat_bwd_row_kernel<T, false, 48, true>);
+          if (CW == 24) return go(concat_bwd_row_kernel<T, false, 24, true>);
+          return chunked ? go(concat_bwd_row_kernel<T, true, 0, true>) : go(concat_bwd_row_kernel<T, false, 0, true>);
+        }
+        if (CW == 48) return chunked ? go(concat_bwd_row_kernel<T, true, 48, false>) : go(concat_bwd_row_kernel<T, false, 48, false>);
+        if (CW == 24) return go(concat_bwd_row_kernel<T, false, 24, false>);
+        return chunked ? go(concat_bwd_row_kernel<T, true, 0, false>) : go(concat_bwd_row_kernel<T, false, 0, false>);
       }
     }
     concat_bwd_kernel<T><<<(unsigned)ceil_div(total, kThreads), kThreads, 0, st>>>(

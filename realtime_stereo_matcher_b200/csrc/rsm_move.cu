@@ -287,6 +287,68 @@ concat_bwd_left_kernel(const T* __restrict__ gout, T* __restrict__ gl, int64_t n
   if (live && q == 0) gl[i] = from_f<T>(a);
 }
 
+// Right half of the adjoint for rows that fit shared memory whole, gR[x'] = sum_{d, x'+d < W} gV[C+c, x'+d, d]:
+// one CTA per (n, c, y) row, the contiguous W x D matrix fetched by ONE elected thread with bulk copies (TMA, completion
+// counted on an mbarrier) -- no per-thread copy instructions, no halo, no padding; two or three CTAs per SM overlap
+// one row's sums with the others' copies.  The diagonal of the DENSE matrix would put a warp's reads into two banks
+// (pitch D = 16 mod 32 words); so lane l starts its diagonal at d = l and wraps around: word (x'+d) D + d with x' and d
+// both advancing by one per lane is (2D+1) l + const -- an odd stride, conflict-free.  Sums are deterministic; their
+// order starts at d = lane, not at 0.  (A persistent form -- one CTA per SM walking the rows through a ring of three
+// row buffers -- measured slower: 690 vs 554 us for the whole adjoint at cfg3.)
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+concat_bwd_right_bulk_kernel(const T* __restrict__ gout, T* __restrict__ gr, int C, int H, int W, int D) {
+  extern __shared__ __align__(128) unsigned char sraw[];
+  const T* sM = reinterpret_cast<const T*>(sraw);           // [W][D]
+  const uint32_t bytes = (uint32_t)W * (uint32_t)D * (uint32_t)sizeof(T);
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(sraw + bytes);
+  const int64_t row = blockIdx.x;                          // (n * C + c) * H + y
+  const int64_t nc = row / H;
+  const int64_t grow = ((nc / C) * 2 * C + C + nc % C) * H + row % H;
+  const unsigned char* __restrict__ src = reinterpret_cast<const unsigned char*>(gout + grow * (int64_t)W * D);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sraw);
+    for (uint32_t off = 0; off < bytes; off += 32768u) {
+      const uint32_t n = min(32768u, bytes - off);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(dst + off), "l"(src + off), "r"(n), "r"(bar)
+                   : "memory");
+    }
+  }
+  {   // every thread waits for the bytes (bounded: a wait that expires traps instead of hanging)
+    bool done = false;
+    for (int it = 0; it < (1 << 12) && !done; ++it) {
+      uint32_t ok;
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(ok) : "r"(bar), "r"(0u), "r"(0x989680u) : "memory");
+      done = ok != 0;
+    }
+    if (!done) __trap();
+  }
+  const int NT = blockDim.x;
+  const int rot = (threadIdx.x & 31) % D;
+  T* __restrict__ dst = gr + row * (int64_t)W;
+  for (int x = threadIdx.x; x < W; x += NT) {
+    const int nd = min(D, W - x);                           // x + d < W
+    float a = 0.f;
+    const T* p1 = sM + (int64_t)(x + rot) * D + rot;       // d = rot .. nd - 1
+    const int e1 = nd - rot;
+#pragma unroll 4
+    for (int i = 0; i < e1; ++i) a += to_f(p1[i * (D + 1)]);
+    const T* p2 = sM + (int64_t)x * D;                      // d = 0 .. min(rot, nd) - 1
+    const int e2 = min(rot, nd);
+#pragma unroll 4
+    for (int i = 0; i < e2; ++i) a += to_f(p2[i * (D + 1)]);
+    dst[x] = from_f<T>(a);
+  }
+}
+
 // ============================================================================= interweave
 template <typename T, int VEC>
 __global__ void __launch_bounds__(kThreads)
@@ -588,6 +650,18 @@ extern "C" int rsm_concat_bwd(const void* gout, void* gleft, void* gright, int64
           concat_bwd_left_kernel<T><<<(unsigned)ceil_div(4 * total, kThreads), kThreads, 0, st>>>(
               (const T*)gout, (T*)gleft, total, (int)C, (int)H, (int)W, (int)D);
           if (int rc = finish_launch("rsm_concat_bwd(left)")) return rc;
+        }
+        const int64_t row_bytes = W * D * (int64_t)sizeof(T);
+        if (split && sizeof(T) == 4 && row_bytes % 16 == 0 && row_bytes <= 100 * 1024) {
+          // right half, fp32: whole rows by bulk copy (two or more CTAs per SM), the row in equal passes of <= 256 threads
+          // (16-bit rows: the same time as the row kernel, which keeps the ascending order of the sums)
+          const int64_t passes = ceil_div(W, kThreads);
+          const unsigned nthr = (unsigned)(ceil_div(ceil_div(W, passes), 32) * 32);
+          const size_t smb = (size_t)row_bytes + 16;
+          auto kb = concat_bwd_right_bulk_kernel<T>;
+          if (smb > 48 * 1024) cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb);
+          kb<<<(unsigned)(N * C * H), nthr, smb, st>>>((const T*)gout, (T*)gright, (int)C, (int)H, (int)W, (int)D);
+          return finish_launch("rsm_concat_bwd(right, bulk)");
         }
         const unsigned rows = (unsigned)(N * (split ? 1 : 2) * C * H);
         auto go = [&](auto k) -> int {

@@ -297,15 +297,17 @@ concat_bwd_left_kernel(const T* __restrict__ gout, T* __restrict__ gl, int64_t n
 // row buffers -- measured slower: 690 vs 554 us for the whole adjoint at cfg3.)
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
-concat_bwd_right_bulk_kernel(const T* __restrict__ gout, T* __restrict__ gr, int C, int H, int W, int D) {
+concat_bwd_right_bulk_kernel(const T* __restrict__ gout, T* __restrict__ gr, int C, int H, int W, int D, int TXP) {
   extern __shared__ __align__(128) unsigned char sraw[];
-  const T* sM = reinterpret_cast<const T*>(sraw);           // [W][D]
-  const uint32_t bytes = (uint32_t)W * (uint32_t)D * (uint32_t)sizeof(T);
+  // blockIdx.y = part of the row: output pixels [xa, xb), staged pixels [xa, min(W, xb + D - 1)) (contiguous in memory)
+  const int xa = blockIdx.y * TXP, xb = min(W, xa + TXP), xe = min(W, xb + D - 1);
+  const T* sM = reinterpret_cast<const T*>(sraw) - (int64_t)xa * D;   // [pixel][D], indexed by the row's pixel
+  const uint32_t bytes = (uint32_t)(xe - xa) * (uint32_t)D * (uint32_t)sizeof(T);
   const uint32_t bar = (uint32_t)__cvta_generic_to_shared(sraw + bytes);
   const int64_t row = blockIdx.x;                          // (n * C + c) * H + y
   const int64_t nc = row / H;
   const int64_t grow = ((nc / C) * 2 * C + C + nc % C) * H + row % H;
-  const unsigned char* __restrict__ src = reinterpret_cast<const unsigned char*>(gout + grow * (int64_t)W * D);
+  const unsigned char* __restrict__ src = reinterpret_cast<const unsigned char*>(gout + (grow * (int64_t)W + xa) * D);
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -334,7 +336,7 @@ concat_bwd_right_bulk_kernel(const T* __restrict__ gout, T* __restrict__ gr, int
   const int NT = blockDim.x;
   const int rot = (threadIdx.x & 31) % D;
   T* __restrict__ dst = gr + row * (int64_t)W;
-  for (int x = threadIdx.x; x < W; x += NT) {
+  for (int x = xa + threadIdx.x; x < xb; x += NT) {
     const int nd = min(D, W - x);                           // x + d < W
     float a = 0.f;
     const T* p1 = sM + (int64_t)(x + rot) * D + rot;       // d = rot .. nd - 1
@@ -655,12 +657,19 @@ extern "C" int rsm_concat_bwd(const void* gout, void* gleft, void* gright, int64
         if (split && sizeof(T) == 4 && row_bytes % 16 == 0 && row_bytes <= 100 * 1024) {
           // right half, fp32: whole rows by bulk copy (two or more CTAs per SM), the row in equal passes of <= 256 threads
           // (16-bit rows: the same time as the row kernel, which keeps the ascending order of the sums)
-          const int64_t passes = ceil_div(W, kThreads);
-          const unsigned nthr = (unsigned)(ceil_div(ceil_div(W, passes), 32) * 32);
-          const size_t smb = (size_t)row_bytes + 16;
+          // a row in parts of <= 40 KB with their D-1 pixel halo (re-read from L2): five CTAs per SM instead of three
+          const int64_t pix_bytes = D * (int64_t)sizeof(T);
+          int64_t parts = ceil_div(row_bytes, 40 * 1024);
+          if (parts > 1 && (W % parts != 0 || ((W / parts) * pix_bytes) % 16 != 0 || parts > 65535)) parts = 1;
+          const int64_t txp = W / parts;
+          const int64_t npx = txp + (parts > 1 ? D - 1 : 0) < W ? txp + (parts > 1 ? D - 1 : 0) : W;
+          const int64_t passes = ceil_div(txp, kThreads);
+          const unsigned nthr = (unsigned)(ceil_div(ceil_div(txp, passes), 32) * 32);
+          const size_t smb = (size_t)(npx * pix_bytes) + 16;
           auto kb = concat_bwd_right_bulk_kernel<T>;
           if (smb > 48 * 1024) cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb);
-          kb<<<(unsigned)(N * C * H), nthr, smb, st>>>((const T*)gout, (T*)gright, (int)C, (int)H, (int)W, (int)D);
+          kb<<<dim3((unsigned)(N * C * H), (unsigned)parts), nthr, smb, st>>>((const T*)gout, (T*)gright, (int)C, (int)H, (int)W,
+                                                                             (int)D, (int)txp);
           return finish_launch("rsm_concat_bwd(right, bulk)");
         }
         const unsigned rows = (unsigned)(N * (split ? 1 : 2) * C * H);

@@ -46,7 +46,10 @@ class Guarded:
             assert left == 0, f"{what}: {left} output elements never written"
 
 
-SHAPES = [(2, 12, 5, 67, 19, 3), (1, 16, 3, 130, 70, 4), (1, 32, 2, 240, 48, 8), (3, 5, 4, 9, 13, 5), (1, 8, 1, 1, 3, 2)]
+SHAPES = [(2, 12, 5, 67, 19, 3), (1, 16, 3, 130, 70, 4), (1, 32, 2, 240, 48, 8), (3, 5, 4, 9, 13, 5), (1, 8, 1, 1, 3, 2),
+          # concat adjoint by halves: 16-bit rows of >= 192 bytes (left streaming kernel + right-only row kernel), fp32 rows
+          # fetched by bulk copy whole (W not divisible into parts) -- (1, 32, 2, 240, 48, 8) above takes it in two parts
+          (1, 8, 2, 100, 96, 4), (1, 4, 2, 313, 48, 2)]
 DTYPES = [(torch.float32, 0), (torch.float16, 1), (torch.bfloat16, 2)]
 
 

@@ -629,6 +629,25 @@ def test_concat_bwd_disparity_chunks(rsm, dn):
         close(R.grad, gr, atol)
 
 
+@pytest.mark.parametrize("case", [(1, 4, 3, 313, 48, "fp32"), (1, 3, 2, 50, 192, "fp32"), (1, 2, 2, 1000, 48, "fp32"),
+                                  (2, 6, 2, 100, 96, "bf16"), (1, 4, 2, 100, 96, "fp16"), (1, 2, 3, 64, 48, "bf16"),
+                                  (1, 2, 2, 30, 48, "fp32")])
+def test_concat_bwd_halves(rsm, case):
+    """The concatenation adjoint by halves (pixel rows of >= 192 bytes): left half as streaming row sums, right half from
+    whole rows fetched by bulk copy (fp32: one part, W not divisible into parts, D = 192, D > W) or through the right-only
+    row kernel (16-bit tensors, rows too long for shared memory); 16-bit rows of 96 bytes keep the one-pass kernel.
+    Dyadic gradients: the sums are exact whatever their order, so the comparison with the oracle is bit for bit."""
+    n, c, h, w, d, dn = case
+    rng = np.random.default_rng(75)
+    gout = (rng.integers(-8, 9, (n, 2 * c, h, w, d)) / 8.0).astype(np.float32)
+    gl, gr = oracle.concat_volume_bwd(gout)
+    L = dev(np.zeros((n, c, h, w), np.float32), dn, grad=True)
+    R = dev(np.zeros((n, c, h, w), np.float32), dn, grad=True)
+    rsm.concat_volume(L, R, d).backward(dev(gout, dn))
+    equal(L.grad, round_to(gl, dn))
+    equal(R.grad, round_to(gr, dn))
+
+
 # ------------------------------------------------------------ refinement warp (SURVEY 8f-2)
 @pytest.mark.parametrize("name", names("warp_"))
 def test_warp_goldens(rsm, name):

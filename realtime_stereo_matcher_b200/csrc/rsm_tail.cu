@@ -35,6 +35,18 @@ __device__ __forceinline__ Lin lin_index(int o, float scale, int n_in) {
   return r;
 }
 
+// lin_index(o, 0.25f, n_in) in integers -- the x4 head: src = (o - 1.5) / 4, weights k / 8, all exact in fp32, so the
+// values are the same bit for bit (for o inside the image; rows past it are never stored)
+__device__ __forceinline__ Lin lin_index_x4(int o, int n_in) {
+  Lin r;
+  const int t = o - 2;
+  r.i0 = t < 0 ? 0 : min(t >> 2, n_in - 1);
+  r.i1 = r.i0 + (r.i0 < n_in - 1 ? 1 : 0);
+  r.w1 = t < 0 ? 0.f : 0.125f + 0.25f * (float)(t & 3);
+  r.w0 = 1.f - r.w1;
+  return r;
+}
+
 constexpr int kTX = 32, kTY = 8;   // fine-pixel tile of one CTA (256 threads, one pixel each; 32x16 measured slower)
 constexpr int kNT = kTX * kTY;
 
@@ -380,8 +392,8 @@ upsample_regress_fwd_kernel(const T* __restrict__ cost, T* __restrict__ soft, in
   const TailSmem sm(smem_f, g);
   const int b = blockIdx.z;
   const int x = blockIdx.x * kTX + (threadIdx.x & (kTX - 1)), y = blockIdx.y * kTY + threadIdx.x / kTX;
-  const int cy0 = lin_index(blockIdx.y * kTY, g.sh, g.Hc).i0;
-  const int cx0 = lin_index(blockIdx.x * kTX, g.sw, g.Wc).i0;
+  const int cy0 = ALL4 ? lin_index_x4(blockIdx.y * kTY, g.Hc).i0 : lin_index(blockIdx.y * kTY, g.sh, g.Hc).i0;
+  const int cx0 = ALL4 ? lin_index_x4(blockIdx.x * kTX, g.Wc).i0 : lin_index(blockIdx.x * kTX, g.sw, g.Wc).i0;
   if constexpr (ALL4) stage_tile_all4(cost + (int64_t)b * g.Dc * g.Hc * g.Wc, sm, g, cy0, cx0);
   else stage_tile(cost + (int64_t)b * g.Dc * g.Hc * g.Wc, sm, g, cy0, cx0);
 
@@ -393,7 +405,7 @@ upsample_regress_fwd_kernel(const T* __restrict__ cost, T* __restrict__ soft, in
     const int pi = threadIdx.x & (kNT / 2 - 1), half = threadIdx.x / (kNT / 2);
     const int txp = pi & 15, py = blockIdx.y * kTY + (pi >> 4), px = blockIdx.x * kTX + 2 * txp;
     const bool pvalid = px < g.W && py < g.H;
-    const Lin ly = lin_index(py, g.sh, g.Hc);
+    const Lin ly = lin_index_x4(py, g.Hc);
     const int o0 = min(ly.i0 - cy0, 3) * kTX + 2 * txp, o1 = min(ly.i1 - cy0, 3) * kTX + 2 * txp;
     const float2 ua = *reinterpret_cast<const float2*>(sm.rowmax + o0), ub = *reinterpret_cast<const float2*>(sm.rowmax + o1);
     const float2 la = *reinterpret_cast<const float2*>(sm.rowmax + 4 * kTX + o0),
